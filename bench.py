@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the VPint2 value-propagation path on B200 (BASELINE.json metric:
+VPint2 Mpixel*iter/s and HBM roofline fraction at 1/2/4/8 GPUs vs host-CPU NumPy).
+
+Workload (BASELINE config 3): VPint2 cloud removal on synthetic Sentinel-2-shaped
+256x256x13 patches, `--patches` patches PER GPU (default 512: 6656 independent
+65 536-pixel band problems, 436 Mpx, ~21 GB of fp64 state + weights, far larger
+than the 126 MB L2).  Patches are independent, so ranks shard them with no
+data-path collective (weak scaling).
+
+A "step" is one complete solve of the batch: init (per-band NaN -> mean), weight
+planes, Jacobi sweeps to every problem's own stopping sweep (auto-terminate,
+threshold 1e-4), result gather.  px*it = sum over problems of H*W*sweeps.
+
+  value : device time, inputs (float32 HWB target/features) already resident in HBM
+  e2e   : the same solve through the public host API (vpint_b200.vpint2.solve_bands)
+          from pinned host buffers, H2D + D2H inside the timed region
+  --impl reference : the NumPy oracle port of the reference on the host cores
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, B = 256, 256, 13
+BYTES_WP_F64 = 48.0      # algorithmic bytes per px*it, WP 2-D fp64 (SURVEY 8d / BASELINE.md)
+METRIC = "vpint2_mpixel_iter_per_s"
+UNIT = "Mpx*it/s"
+
+
+# ---------------------------------------------------------------------------
+# synthetic Sentinel-2-shaped patches (SURVEY 8d, config 3 recipe)
+# ---------------------------------------------------------------------------
+def make_patches_numpy(n, seed):
+    """(target, features) float32 (n, H, W, B) as VPint2_interpolator stores them:
+    uint16-quantised reflectances, NaN where the cloud mask (4 discs) hides the target."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    yy /= H
+    xx /= W
+    target = np.empty((n, H, W, B), dtype=np.float32)
+    feats = np.empty((n, H, W, B), dtype=np.float32)
+    for i in range(n):
+        for b in range(B):
+            acc = np.zeros((H, W))
+            for _ in range(6):
+                fy, fx = rng.uniform(0.3, 2.0, 2)
+                py, px = rng.uniform(0, 1, 2)
+                acc += rng.uniform(0.5, 1.0) * np.sin(2 * np.pi * (fy * yy + py)) * np.cos(2 * np.pi * (fx * xx + px))
+            base = 1500.0 + 1200.0 * acc / (np.abs(acc).max() + 1e-9)
+            target[i, :, :, b] = np.round(base + rng.normal(0, 20, (H, W))).clip(1, 65535)
+            feats[i, :, :, b] = np.round(1.1 * base + rng.normal(0, 10, (H, W))).clip(1, 65535)
+        cloud = np.zeros((H, W), dtype=bool)
+        for _ in range(4):
+            cy, cx, r = rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(15, 50) / H
+            cloud |= (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        target[i][cloud, :] = np.nan
+    return target, feats
+
+
+def make_patches_torch(n, seed, device):
+    """Same recipe generated on the device (inputs are synthetic; generation is not timed)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    yy = (torch.arange(H, device=device, dtype=torch.float64) / H).view(1, H, 1, 1)
+    xx = (torch.arange(W, device=device, dtype=torch.float64) / W).view(1, 1, W, 1)
+    target = torch.empty((n, H, W, B), dtype=torch.float32, device=device)
+    feats = torch.empty((n, H, W, B), dtype=torch.float32, device=device)
+    chunk = 32
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        acc = torch.zeros((m, H, W, B), dtype=torch.float64, device=device)
+        for _ in range(6):
+            u = torch.rand((5, m, 1, 1, B), generator=g, device=device, dtype=torch.float64)
+            fy, fx = 0.3 + 1.7 * u[0], 0.3 + 1.7 * u[1]
+            acc += (0.5 + 0.5 * u[4]) * torch.sin(2 * np.pi * (fy * yy + u[2])) * torch.cos(2 * np.pi * (fx * xx + u[3]))
+        base = 1500.0 + 1200.0 * acc / (acc.abs().amax(dim=(1, 2), keepdim=True) + 1e-9)
+        nt = torch.randn((m, H, W, B), generator=g, device=device, dtype=torch.float64)
+        nf = torch.randn((m, H, W, B), generator=g, device=device, dtype=torch.float64)
+        t = torch.round(base + 20.0 * nt).clamp(1, 65535)
+        f = torch.round(1.1 * base + 10.0 * nf).clamp(1, 65535)
+        cloud = torch.zeros((m, H, W, 1), dtype=torch.bool, device=device)
+        for _ in range(4):
+            c = torch.rand((3, m, 1, 1, 1), generator=g, device=device, dtype=torch.float64)
+            r = (15.0 + 35.0 * c[2]) / H
+            cloud |= (yy - c[0]) ** 2 + (xx - c[1]) ** 2 < r * r
+        t = torch.where(cloud, torch.full_like(t, float("nan")), t)
+        target[s:s + m] = t.to(torch.float32)
+        feats[s:s + m] = f.to(torch.float32)
+    return target, feats
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # median over the busier half of the samples = "under load"
+            hi = sorted(sm)[len(sm) // 2:]
+            out["sm_mhz"] = statistics.median(hi)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the NumPy oracle port on host cores
+# ---------------------------------------------------------------------------
+def _oracle_patch(args):
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import vpint_oracle as O
+    target, feats = args
+    _, sweeps = O.vpint2_run(target, feats)
+    return int(sweeps.sum()) * H * W
+
+
+def oracle_rate(target, feats, procs):
+    """Mpx*it/s of the oracle (NumPy restatement of VPint2_interpolator.run) over the given patches."""
+    jobs = [(target[i], feats[i]) for i in range(target.shape[0])]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        pxit = sum(_oracle_patch(j) for j in jobs)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            pxit = sum(pool.map(_oracle_patch, jobs, chunksize=1))
+    dt = time.perf_counter() - t0
+    return pxit / dt / 1e6, pxit, dt
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.ref_patches if args.ref_patches > 0 else max(cores, 2)
+    target, feats = make_patches_numpy(n, 4242)
+    for _ in range(args.warmup and 1):
+        oracle_rate(target[:1], feats[:1], 1)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, pxit, dt = oracle_rate(target, feats, cores)
+        rates.append(r)
+        times.append(dt)
+    val = statistics.median(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: VPint2 256x256x13 patches (bounded sample of %d patches per step)" % n,
+                   "patches": n, "H": H, "W": W, "bands": B},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d patches x 13 bands, auto-terminate; NumPy oracle port of VPint2_interpolator.run, "
+                                   "one forked worker per core" % n},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vpint_b200.engine import Solver
+    from vpint_b200.vpint2 import _band_fill_values, solve_bands
+    from vpint_b200.wp import wp_run_options
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.patches
+    target, feats = make_patches_torch(n, 1003 + rank, dev)
+    torch.cuda.synchronize()
+    opts = wp_run_options()
+    nprob = n * B
+    total_px = nprob * H * W
+
+    # host copies for the e2e leg (pinned)
+    t_host = torch.empty(target.shape, dtype=torch.float32).pin_memory()
+    f_host = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
+    t_host.copy_(target)
+    f_host.copy_(feats)
+    out_host = torch.empty((n, B, H, W), dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    solver = Solver(2, nprob, H, W, nprob_inner=B, planes=True, k_block=args.k_block, device=dev)
+    out_dev = torch.empty((n, B, H, W), dtype=torch.float64, device=dev)
+    fill = _band_fill_values(t_host.numpy()).reshape(-1)      # init values (host NumPy, exact reference semantics)
+
+    def device_step():
+        solver.load(target.permute(0, 3, 1, 2), fill=fill)
+        solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
+        solver.run(opts["iterations"], auto_terminate=True, threshold=opts["threshold"], clip_val=opts["clip_val"],
+                   chunk=args.chunk)
+        _, niter = solver.result(out=out_dev)
+        return niter
+
+    def e2e_step():
+        res, sweeps = solve_bands(t_host, f_host, opts, out_layout="bhw", return_sweeps=True, device=dev,
+                                  k_block=args.k_block, out=out_host, fill=fill)
+        return sweeps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        sweeps_total = 0
+        for _ in range(steps):
+            nit = fn()
+            sweeps_total += int(torch.as_tensor(nit).sum().item())
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+            sw = torch.tensor([sweeps_total], dtype=torch.float64, device=dev)
+            dist.all_reduce(sw, op=dist.ReduceOp.SUM)
+            sweeps_total = float(sw.item())
+        return ms, sweeps_total
+
+    for _ in range(max(args.warmup, 0)):
+        device_step()
+    launches0 = solver.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, sweeps_dev = timed(device_step, args.steps)
+    launches = solver.launches - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    pxit_dev = sweeps_dev * H * W           # whole job (all ranks)
+    value = pxit_dev / (ms_dev * 1e-3) / 1e6
+
+    # e2e through the host API
+    for _ in range(min(max(args.warmup, 0), 2)):
+        e2e_step()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ms_e2e, sweeps_e2e = timed(e2e_step, e2e_steps)
+    e2e_val = sweeps_e2e * H * W / (ms_e2e * 1e-3) / 1e6
+
+    # roofline of the stencil kernel: every problem active, fixed sweeps, CUDA events around the kernel
+    solver.load(target.permute(0, 3, 1, 2), fill=fill)
+    solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
+    solver.begin_run(10 ** 6, auto_terminate=False)
+    kb = solver.k_block
+    for _ in range(3):
+        solver.step_begin(); solver.step_end()
+    times = []
+    for _ in range(args.roofline_launches):
+        times.append(solver.step_profile())
+        solver.step_end()
+    torch.cuda.synchronize()
+    k_ms = statistics.mean(times)
+    alg_bytes = BYTES_WP_F64 * total_px * kb
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    peak, peak_src = peak_hbm()
+    masked_frac = float(torch.isnan(target[..., 0]).double().mean().item())
+    active_tiles, total_tiles = solver.active_tiles, solver.total_tiles
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: VPint2 cloud removal, 256x256x13 Sentinel-2-shaped patches, %d patches per GPU "
+                                   "(%d band problems, %.0f Mpx per GPU), auto-terminate 1e-4" % (n, nprob, total_px / 1e6),
+                       "patches_per_gpu": n, "H": H, "W": W, "bands": B, "k_block": kb, "cloud_fraction": round(masked_frac, 4),
+                       "active_tiles": active_tiles, "total_tiles": total_tiles,
+                       "l2_note": "state+weights %.1f GB per GPU >> 126 MB L2; no flush needed" % (48.0 * total_px / 1e9),
+                       "mean_sweeps_per_problem": sweeps_dev / args.steps / (nprob * world)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "jacobi2d (stencil launch, all problems active)",
+                         "kernel_ms": k_ms, "alg_bytes_per_launch": alg_bytes, "bytes_per_px_it": BYTES_WP_F64},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(t_host.numel() * 4 + f_host.numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 8 + nprob * 4), "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "vpint_b200.vpint2.solve_bands (VPint2 run path), pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+    solver.close()
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cn = args.cpu_patches
+        ct, cf = t_host[:cn].numpy(), f_host[:cn].numpy()
+        r, pxit, dt = oracle_rate(ct, cf, 1)
+        line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "first %d patches (%d band problems) of the same workload, NumPy oracle port, "
+                                          "%.1f s" % (cn, cn * B, dt)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vpint_b200", choices=["vpint_b200", "reference"])
+    ap.add_argument("--patches", type=int, default=512, help="patches per GPU")
+    ap.add_argument("--k-block", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--roofline-launches", type=int, default=20)
+    ap.add_argument("--cpu-patches", type=int, default=8)
+    ap.add_argument("--ref-patches", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/*
+ * vpint_b200.h -- C ABI of the B200-native VPint value-propagation path.
+ *
+ * The reference (LaurensArp/VPint 0.2.4) is pure Python + NumPy and has no
+ * plugin / FFI layer; its boundary for this path is the Python method surface
+ *   SD_SMRP.run   VPint/SD_MRP.py:51      WP_SMRP.run   VPint/WP_MRP.py:82-91
+ *   SD_STMRP.run  VPint/SD_MRP.py:286     WP_STMRP.run  VPint/WP_MRP.py:1289
+ *   VPint2_interpolator.run / run_serial  VPint/VPint2.py:58,109
+ * This header is the C boundary a maintainer would bind (ctypes stub in
+ * INTEGRATION.md) to run those methods on a B200.  Each entry point names the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers and sizes, int status (0 = ok).  No
+ *     exceptions, no torch / Python types.  vpint_last_error() gives the text.
+ *   - every "device pointer" is caller-owned CUDA memory on the current device;
+ *     the library allocates nothing on the device except through the workspace
+ *     the caller binds (vpint_solver_workspace_bytes / vpint_solver_bind).
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as
+ *     void*); only vpint_solver_run blocks the host (it polls one pinned flag
+ *     per chunk of sweeps, never per sweep).
+ *   - arithmetic is IEEE fp64 in both storage modes; VPINT_F32 only changes the
+ *     element type of the device-resident state and weights.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with VPINT_ERR_CUDA.
+ */
+#ifndef VPINT_B200_H
+#define VPINT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPINT_ABI_VERSION 1
+
+/* status codes */
+#define VPINT_OK               0
+#define VPINT_ERR_INVALID      1   /* bad argument / shape / state            */
+#define VPINT_ERR_CUDA         2   /* CUDA runtime error (text in last_error)  */
+#define VPINT_ERR_UNSUPPORTED  3   /* valid request this build cannot serve    */
+#define VPINT_ERR_WORKSPACE    4   /* workspace missing or too small           */
+
+/* element types */
+#define VPINT_F64 0
+#define VPINT_F32 1
+
+/* weight modes */
+#define VPINT_W_SCALAR 0   /* SD_*: per-problem gamma (and tau in 3-D)          */
+#define VPINT_W_PLANES 1   /* WP_*: 4 static planes (2-D) / 4 spatial + 1 temporal (3-D) */
+
+/* pairwise weight methods, WP_SMRP.predict_weight (VPint/WP_MRP.py:396-427) */
+#define VPINT_METHOD_EXACT          0
+#define VPINT_METHOD_COSINE         1
+#define VPINT_METHOD_EXACT_INVERSE  2
+
+/* loop drivers for vpint_solver_run */
+#define VPINT_LOOP_CHUNKED 0   /* host enqueues chunks of launches, polls a pinned flag per chunk */
+#define VPINT_LOOP_GRAPH   1   /* CUDA graph with a device-side WHILE node, one host sync per run */
+
+typedef struct vpint_solver vpint_solver;
+
+/* Shape of one batched solve.  Every problem in the batch has the same shape;
+ * problems are independent (own mask, weights, stopping sweep), which is how
+ * VPint2 bands (VPint/VPint2.py:71-83), patches and hyper-parameter trials map
+ * onto one launch. */
+typedef struct vpint_desc {
+    int32_t ndim;         /* 2: (H, W) grids.  3: (H, W, T) cubes, T contiguous     */
+    int32_t nprob;        /* problems in the batch                                   */
+    int32_t nprob_inner;  /* problem p = outer * nprob_inner + inner for addressing caller arrays
+                             (patch, band); 0 or 1 = flat                            */
+    int32_t H, W, T;      /* T must be 1 when ndim == 2                              */
+    int32_t storage;      /* VPINT_F64 or VPINT_F32 device state                     */
+    int32_t weight_mode;  /* VPINT_W_SCALAR or VPINT_W_PLANES                        */
+    int32_t k_block;      /* sweeps fused per launch (temporal blocking); 0 = default */
+    /* Row-band sharding of ONE global grid across ranks.  For an
+     * unsharded solve leave all four at 0 (then global_H = H, everything owned). */
+    int32_t global_H;     /* rows of the whole grid                                  */
+    int32_t row_offset;   /* global row index of local row 0 (may be negative: never)*/
+    int32_t own_row0;     /* first local row this rank owns                          */
+    int32_t own_rows;     /* number of owned local rows (the rest are halo rows)     */
+} vpint_desc;
+
+/* Arguments of one run() call.  Defaults of the reference in brackets. */
+typedef struct vpint_run_params {
+    int32_t max_iter;        /* sweep cap: `iterations` if >-1, else 5000 (WP 2-D,
+                                VPint/WP_MRP.py:112-115) or 10000 (SD_MRP.py:63-66,296-299) */
+    int32_t auto_terminate;  /* stop when delta <= threshold [True unless iterations>-1] */
+    double  threshold;       /* auto_terminate_threshold [1e-4]                         */
+    double  clip_val;        /* new[new > clip_val] = clip_val [inf], WP_MRP.py:322     */
+    int32_t loop_mode;       /* VPINT_LOOP_*                                            */
+    int32_t chunk;           /* launches per host poll in chunked mode; 0 = default     */
+    double *delta_out;       /* device, [nprob][max_iter] per-sweep delta (track_delta,
+                                SD_MRP.py:140-141) or NULL                              */
+} vpint_run_params;
+
+/* ---- library ---------------------------------------------------------- */
+int         vpint_abi_version(void);
+const char *vpint_last_error(void);              /* thread-local, never NULL */
+int64_t     vpint_row_pitch(int64_t row_elems);  /* padded device row length (elements) */
+
+/* ---- solver life cycle ------------------------------------------------ */
+int    vpint_solver_create(const vpint_desc *desc, vpint_solver **out);
+void   vpint_solver_destroy(vpint_solver *s);
+size_t vpint_solver_workspace_bytes(const vpint_solver *s);
+/* workspace: device memory, 256-byte aligned, >= workspace_bytes.  It must stay
+ * valid until destroy / the next bind. */
+int    vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes);
+
+/* ---- A1 + known-cell bookkeeping --------------------------------------
+ * Replaces the per-run setup around MRP.original_grid / pred_grid
+ * (VPint/MRP.py:47-52, restore at SD_MRP.py:133-134, WP_MRP.py:321,323).
+ *   original : device, dtype `dtype`, NaN marks an unknown cell.
+ *   pred0    : device, same layout, the state run() starts from
+ *              (self.pred_grid); may be NULL, then unknown cells start at
+ *              fill[p] (the init_strategy='mean'/'zero' value computed by the
+ *              caller exactly as MRP.init_pred_grid does, MRP.py:64-82).
+ *   fill     : HOST array [nprob]; only read when pred0 == NULL.
+ *   stride   : 5 element strides {outer problem, inner problem, row, column, t}
+ *              of original/pred0 (t ignored for ndim == 2).  This is how the
+ *              band-interleaved (N, H, W, B) VPint2 arrays are read in place:
+ *              outer = patch, inner = band.
+ * Builds the bit mask of unknown cells, both ping-pong state buffers, the
+ * active-tile list and the sums over known cells the stopping rule needs. */
+int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0,
+                      const double *fill, int dtype, const int64_t *stride, void *stream);
+
+/* ---- A2 weights -------------------------------------------------------
+ * VPINT_W_PLANES only.  feat: device (..., F) features with 5 element strides
+ * {outer problem, inner problem, row, column, feature}; zeros are read as 0.01
+ * (WP_MRP.py:143-145).
+ * 2-D exact:  w_dir = mean_k f[i,j,k] / f[nb_dir,k], missing neighbour -> 0
+ *             (WP_MRP.py:149-170).  method selects predict_weight's variants
+ *             (WP_MRP.py:396-427) with the [min_gamma, max_gamma] clamp, which
+ *             the vectorised exact branch does not apply (pass clamp = 0).
+ * 3-D      :  features are (H, W, F), static in time (WP_MRP.py:1319-1355). */
+int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int64_t *stride,
+                         int F, int method, int clamp, double min_gamma, double max_gamma,
+                         void *stream);
+/* VPINT_W_SCALAR: HOST arrays [nprob]; tau is ignored for ndim == 2
+ * (SD_MRP.py:87, 315-321). */
+int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau);
+
+/* ---- A4 + A5 the loop --------------------------------------------------
+ * Jacobi sweeps with the reference's stopping rule
+ *   delta = nanmean(|new-old|) / nanmean(old) <= threshold   (SD_MRP.py:138-147,
+ *   WP_MRP.py:351-362), commit-then-break, exact stopping sweep (temporal-block
+ * overshoot is rolled back and replayed).  Blocks the host until every problem
+ * stopped or hit max_iter.  Can be called again to continue from the current
+ * state (run(50); run(50) == run(100)). */
+int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream);
+
+/* Split form of ONE launch for callers that put a collective between the
+ * local sums and the stop decision (row-sharded multi-GPU):
+ *   step_begin : k_block sweeps on the local rows + local per-sweep sums
+ *   (caller all-reduces vpint_solver_sums_ptr(): [nprob][k_block][4] doubles,
+ *    and exchanges halo rows of vpint_solver_state_ptr())
+ *   step_end   : stop decision; *active_out (HOST, may be NULL) is only valid
+ *                after the stream is synchronised. */
+int     vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *stream);
+int     vpint_solver_step_begin(vpint_solver *s, void *stream);
+int     vpint_solver_step_end(vpint_solver *s, void *stream);
+/* step_begin with CUDA events around the stencil launch only (on `stream`); synchronises and
+ * returns that kernel's duration in milliseconds.  For roofline measurements. */
+int     vpint_solver_step_profile(vpint_solver *s, void *stream, float *stencil_ms);
+double *vpint_solver_sums_ptr(vpint_solver *s);
+int     vpint_solver_sums_count(const vpint_solver *s);
+void   *vpint_solver_state_ptr(vpint_solver *s, int which);   /* ping-pong buffer 0/1, [nprob][H][pitch] */
+int32_t*vpint_solver_active_ptr(vpint_solver *s);             /* device int32: problems still running   */
+int32_t*vpint_solver_cur_ptr(vpint_solver *s);                /* device int32[nprob]: buffer holding the current state */
+
+/* ---- results -----------------------------------------------------------
+ * out: device, dtype `dtype`, element strides as in load.  This is
+ * self.pred_grid after run().  niter_out: device int32[nprob] sweeps executed
+ * per problem (== len(delta_vec) under track_delta); may be NULL. */
+int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *stride,
+                        int32_t *niter_out, void *stream);
+
+/* Introspection used by benchmarks and tests (host values, valid after load). */
+int64_t vpint_solver_active_tiles(const vpint_solver *s);
+int64_t vpint_solver_total_tiles(const vpint_solver *s);
+int64_t vpint_solver_launches(const vpint_solver *s);   /* kernels launched so far */
+int     vpint_solver_k_block(const vpint_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPINT_B200_H */

@@ -232,7 +232,33 @@ def case_vpint2():
          pred_fix=pred_fix, pred_clip=np.ascontiguousarray(pred_clip))
 
 
+def case_vpint2_ctor():
+    rng = np.random.default_rng(1006)
+    out = {}
+    for tag, (H, W) in (("wide", (12, 20)), ("tall", (20, 12))):
+        B = 2
+        target = rng.uniform(100, 200, (H, W, B))
+        features = rng.uniform(100, 200, (H, W, B))
+        mask = np.zeros((H, W))
+        mask[3, 4] = 1.0
+        mask[H - 2, W - 3] = 0.5
+        mask[H // 2, W - 1] = 0.1      # below the 0.2 default threshold
+        vp = VPint2_interpolator(target, features, mask=mask, buffer_mask=True, mask_buffer_size=3,
+                                 mask_buffer_passes=2)
+        out[tag + "_target"], out[tag + "_features"], out[tag + "_mask"] = target, features, mask
+        out[tag + "_stored"] = vp.target
+        vp1 = VPint2_interpolator(target, features, mask=mask, clip_target=150, clip_features=(110.0, 190.0))
+        out[tag + "_stored_clip"] = vp1.target
+        out[tag + "_features_clip"] = vp1.features
+    tb = np.moveaxis(out["wide_target"], -1, 0)
+    fb = np.moveaxis(out["wide_features"], -1, 0)
+    vp = VPint2_interpolator(tb, fb, mask=out["wide_mask"], bands_first=True, dtype=np.float64, threshold=0.05)
+    out["bf_stored"] = vp.target
+    save("vpint2_ctor", **out)
+
+
 if __name__ == "__main__":
+    case_vpint2_ctor()
     case_sd2d()
     case_wp2d()
     case_wp2d_edge()

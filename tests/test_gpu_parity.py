@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Three layers:
+  1. reference-generated golden fixtures (tests/golden/*.npz),
+  2. the NumPy oracle on the same seeded inputs at sizes it finishes in seconds,
+  3. size-independent properties at larger sizes.
+
+Bar (BASELINE.json north_star): fp64 mode within 1e-9 relative per pixel with the
+SAME iteration count; fp32-storage mode within 1e-4 relative.
+"""
+
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import vpint_oracle as O
+from vpint_b200 import SD_SMRP, SD_STMRP, VPint2_interpolator, VPintError, WP_SMRP, WP_STMRP, run_patches
+from vpint_b200 import solve as solve_mod
+from vpint_b200.batch import sd_trials
+from vpint_b200.engine import Solver
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+RTOL64 = 1e-9     # north_star: fp64 mode
+RTOL32 = 1e-4     # north_star: fp32-storage mode
+K_BLOCKS = [1]
+
+
+def close(a, b, rtol=RTOL64):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    inf = np.isinf(b)
+    assert np.array_equal(np.isinf(a), inf) and np.array_equal(a[inf], b[inf]), "inf pattern differs"
+    ok = ~(np.isnan(b) | inf)
+    err = np.abs(a[ok] - b[ok])
+    bound = rtol * np.abs(b[ok]) + 1e-300
+    assert (err <= bound).all(), "max rel err %.3e" % float(np.max(err / (np.abs(b[ok]) + 1e-300)))
+
+
+@pytest.fixture(params=K_BLOCKS, ids=lambda k: "k%d" % k)
+def kblock(request, monkeypatch):
+    monkeypatch.setattr(solve_mod, "DEFAULT_K_BLOCK", request.param)
+    return request.param
+
+
+# ---- 1. golden fixtures produced by the reference itself --------------------------------------
+def test_golden_sd2d(golden, kblock):
+    g = golden("sd2d")
+    grid = g["grid"]
+    m = SD_SMRP(grid.copy(), gamma=0.9)
+    p, d = m.run(track_delta=True)
+    assert len(d) == len(g["d_auto"])
+    close(p, g["pred_auto"]); close(d, g["d_auto"])
+    assert p is m.pred_grid and p.dtype == np.float64
+    m = SD_SMRP(grid.copy(), gamma=0.73)
+    p, d = m.run(iterations=7, track_delta=True)
+    close(p, g["pred_fix"]); close(d, g["d_fix"])
+    m = SD_SMRP(grid.copy(), gamma=0.9, init_strategy="zero")
+    p, d = m.run(iterations=3, track_delta=True)
+    close(p, g["pred_zero"]); close(d, g["d_zero"])
+    m = SD_SMRP(grid.copy(), gamma=0.73)       # resume: run(3); run(4) == run(7)
+    m.run(iterations=3)
+    close(m.run(iterations=4), g["pred_resume"])
+    m = SD_SMRP(grid.copy(), gamma=0.9)        # reset() leaves NaN in the start state
+    m.reset()
+    p, d = m.run(iterations=4, track_delta=True)
+    close(p, g["pred_reset"]); close(d, g["d_reset"])
+
+
+def test_golden_wp2d(golden, kblock):
+    g = golden("wp2d")
+    grid, feat = g["grid"], g["feat"]
+    m = WP_SMRP(grid.copy(), feat.copy())
+    p, d = m.run(track_delta=True)
+    assert len(d) == len(g["d_auto"]) == 14
+    close(p, g["pred_auto"]); close(d, g["d_auto"])
+    assert m.run_state and m.run_method == "exact"
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(iterations=9, track_delta=True)
+    close(p, g["pred_fix"]); close(d, g["d_fix"])
+    m = WP_SMRP(grid.copy(), feat.copy())
+    p, d = m.run(iterations=6, track_delta=True, clip_val=float(g["clip_val"]))
+    close(p, g["pred_clip"]); close(d, g["d_clip"])
+    assert m.clip_val == float(g["clip_val"])
+    for method in ("cosine_similarity", "exact_inverse"):
+        m = WP_SMRP(grid.copy(), feat.copy(), min_gamma=0.2, max_gamma=1.05)
+        p, d = m.run(iterations=5, method=method, track_delta=True)
+        close(p, g["pred_" + method]); close(d, g["d_" + method])
+
+
+def test_golden_wp2d_edge_cases(golden, kblock):
+    g = golden("wp2d_edge")
+    m = WP_SMRP(g["z_grid"].copy(), g["z_feat"].copy())          # zeros in the features
+    p, d = m.run(iterations=5, track_delta=True)
+    close(p, g["z_pred"]); close(d, g["z_d"])
+    assert np.array_equal(m.feature_grid, g["z_feat_after"])
+    p, d = WP_SMRP(g["f9_grid"].copy(), g["f9_feat"].copy()).run(iterations=4, track_delta=True)
+    close(p, g["f9_pred"]); close(d, g["f9_d"])
+    p, d = WP_SMRP(g["f9_grid"].copy(), g["f19_feat"].copy()).run(iterations=3, track_delta=True)
+    close(p, g["f19_pred"]); close(d, g["f19_d"])
+    for tag in ("col", "row"):                                   # H or W == 1: neighbour count 2 / 0
+        p, d = WP_SMRP(g[tag + "_grid"].copy(), g[tag + "_feat"].copy()).run(iterations=3, track_delta=True)
+        close(p, g[tag + "_pred"]); close(d, g[tag + "_d"])
+    p, d = WP_SMRP(g["inf_grid"].copy(), g["inf_feat"].copy()).run(iterations=8, track_delta=True)   # blow-up to inf / NaN
+    close(p, g["inf_pred"]); close(d, g["inf_d"])
+    p, d = WP_SMRP(g["inf_grid"].copy(), g["inf_feat"].copy()).run(track_delta=True)
+    assert len(d) == 3
+    close(p, g["inf_pred_auto"]); close(d, g["inf_d_auto"])
+
+
+def test_golden_st3d(golden):
+    g = golden("st3d")
+    cube = g["cube"]
+    p, d = SD_STMRP(cube.copy(), gamma=0.9, tau=0.8).run(track_delta=True)
+    assert len(d) == len(g["sd_d_auto"])
+    close(p, g["sd_auto"]); close(d, g["sd_d_auto"])
+    p, d = SD_STMRP(cube.copy(), gamma=0.6, tau=0.95).run(iterations=6, track_delta=True)
+    close(p, g["sd_fix"]); close(d, g["sd_d_fix"])
+    feat = g["feat"]
+    p, d = WP_STMRP(cube.copy(), feat.copy()).run(iterations=5, method="exact", track_delta=True)
+    close(p, g["wp_exact"]); close(d, g["wp_d_exact"])
+    p, d = WP_STMRP(cube.copy(), feat.copy()).run(iterations=4, method="cosine_similarity", track_delta=True)
+    close(p, g["wp_cos"]); close(d, g["wp_d_cos"])
+    p, d = WP_STMRP(cube.copy(), feat.copy()).run(method="exact", track_delta=True)
+    assert len(d) == len(g["wp_d_auto"])
+    close(p, g["wp_auto"]); close(d, g["wp_d_auto"])
+    p, d = SD_STMRP(g["flat"].copy(), gamma=0.9, tau=0.9).run(iterations=3, track_delta=True)
+    close(p, g["sd_flat"]); close(d, g["sd_d_flat"])
+
+
+def test_golden_vpint2(golden, kblock):
+    g = golden("vpint2")
+    vp = VPint2_interpolator(g["target"], g["features"], mask=g["mask"], threshold=10)
+    p = vp.run()
+    assert p.shape == g["pred_par"].shape and p.dtype == np.float64
+    close(p, g["pred_par"])
+    ps = vp.run_serial()
+    assert ps.dtype == np.float32 and ps.flags["C_CONTIGUOUS"]
+    close(ps, g["pred_serial"], rtol=2e-7)     # float32 rounding of an fp64 result within 1e-9
+    close(vp.run_serial(iterations=5), g["pred_fix"], rtol=2e-7)
+    close(vp.run(iterations=4, clip_val=1500.0), g["pred_clip"])
+    from vpint_b200.vpint2 import solve_bands
+    from vpint_b200.wp import wp_run_options
+    _, sweeps = solve_bands(vp.target, vp.features, wp_run_options(), return_sweeps=True)
+    assert list(sweeps) == list(g["sweeps"])
+
+
+# ---- 2. the oracle on seeded inputs ------------------------------------------------------------
+def smooth(rng, shape, lo=300.0, hi=2700.0, modes=5):
+    axes = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+    acc = np.zeros(shape)
+    for _ in range(modes):
+        term = np.ones(shape)
+        for ax in axes:
+            term = term * np.sin(2 * np.pi * (rng.uniform(0.3, 2.0) * ax + rng.uniform()))
+        acc += rng.uniform(0.5, 1.0) * term
+    acc = (acc - acc.min()) / (acc.max() - acc.min() + 1e-12)
+    return lo + (hi - lo) * acc
+
+
+def discs(rng, shape, n, rmin, rmax):
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    m = np.zeros(shape, dtype=bool)
+    for _ in range(n):
+        cy, cx, r = rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(rmin, rmax)
+        m |= (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+    return m
+
+
+def test_oracle_sd2d_config1_shape(kblock):
+    """BASELINE config 1: SD_SMRP on a 100x100 grid, ~20 % uniformly hidden."""
+    rng = np.random.default_rng(1001)
+    grid = smooth(rng, (100, 100), 15, 25) + rng.normal(0, 1.0, (100, 100))
+    grid[rng.uniform(size=grid.shape) < 0.2] = np.nan
+    ref, dref, n = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.9)
+    p, d = SD_SMRP(grid.copy(), gamma=0.9).run(track_delta=True)
+    assert len(d) == n
+    close(p, ref); close(d, dref)
+    ref, dref, _ = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.9, iterations=100)
+    p, d = SD_SMRP(grid.copy(), gamma=0.9).run(iterations=100, track_delta=True)
+    close(p, ref); close(d, dref)
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (130, 203), (67, 300)])
+def test_oracle_wp2d(shape, kblock):
+    """BASELINE config 2 recipe (WP_SMRP, 3 feature layers, disc clouds) at oracle-friendly sizes,
+    including ragged shapes that do not divide the tile or the row pitch."""
+    rng = np.random.default_rng(1002 + shape[1])
+    base = smooth(rng, shape)
+    grid = base + rng.normal(0, 20, shape)
+    feat = np.stack([rng.uniform(0.7, 1.3) * base + rng.normal(0, 10, shape) for _ in range(3)], axis=-1)
+    feat = np.maximum(feat, 50.0)
+    grid[discs(rng, shape, 6, 8, 40)] = np.nan
+    ref, dref, n = O.wp_run_2d(grid, O.init_pred(grid), feat.copy())
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
+    assert len(d) == n, (len(d), n)
+    close(p, ref); close(d, dref)
+    ref, dref, _ = O.wp_run_2d(grid, O.init_pred(grid), feat.copy(), iterations=25, clip_val=2000.0)
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(iterations=25, track_delta=True, clip_val=2000.0)
+    close(p, ref); close(d, dref)
+
+
+def test_oracle_st3d():
+    rng = np.random.default_rng(1005)
+    shape = (24, 20, 12)
+    cube = smooth(rng, shape, 10, 30) + rng.normal(0, 0.3, shape)
+    for t in range(shape[2]):
+        cube[discs(rng, shape[:2], 2, 2, 6), t] = np.nan
+    ref, dref, n = O.sd_run_3d(cube, O.init_pred(cube), gamma=0.9, tau=0.9)
+    p, d = SD_STMRP(cube.copy(), gamma=0.9, tau=0.9).run(track_delta=True)
+    assert len(d) == n
+    close(p, ref); close(d, dref)
+    feat = smooth(rng, shape[:2] + (1,), 1, 3)
+    ref, dref, n = O.wp_run_3d(cube, O.init_pred(cube), feat.copy(), method="exact")
+    p, d = WP_STMRP(cube.copy(), feat.copy()).run(method="exact", track_delta=True)
+    assert len(d) == n
+    close(p, ref); close(d, dref)
+
+
+def make_patch(rng, H=64, W=64, B=4):
+    target = np.stack([np.round(smooth(rng, (H, W))) for _ in range(B)], axis=-1).astype(np.uint16)
+    feats = np.stack([np.round(1.1 * target[:, :, b] + rng.normal(0, 10, (H, W))) for b in range(B)], axis=-1)
+    feats = np.clip(feats, 1, 65535).astype(np.uint16)
+    mask = np.where(discs(rng, (H, W), 3, 4, 14), 100.0, 0.0)
+    return VPint2_interpolator(target, feats, mask=mask, threshold=10)
+
+
+def test_oracle_vpint2_patch_batch(kblock):
+    """BASELINE config 3 recipe: a batch of Sentinel-2-shaped patches, every (patch, band) its own
+    problem with its own stopping sweep."""
+    rng = np.random.default_rng(1003)
+    vps = [make_patch(rng) for _ in range(5)]
+    outs = run_patches(vps)
+    for vp, out in zip(vps, outs):
+        ref, sweeps = O.vpint2_run(vp.target, vp.features)
+        close(out, ref)
+        assert out.shape == ref.shape
+    one = vps[2].run()
+    close(one, outs[2], rtol=0)      # batching must not change a problem's result at all
+    ser = run_patches(vps[:2], serial=True, iterations=12)
+    ref, _ = O.vpint2_run(vps[1].target, vps[1].features, iterations=12)
+    close(ser[1], ref.astype(np.float32), rtol=2e-7)
+
+
+def test_oracle_sweep_counts_per_problem(kblock):
+    rng = np.random.default_rng(77)
+    vp = make_patch(rng, 96, 80, 5)
+    from vpint_b200.vpint2 import solve_bands
+    from vpint_b200.wp import wp_run_options
+    out, sweeps = solve_bands(vp.target, vp.features, wp_run_options(), return_sweeps=True)
+    ref, ref_sweeps = O.vpint2_run(vp.target, vp.features)
+    assert list(sweeps) == list(ref_sweeps)
+    assert len(set(ref_sweeps)) > 1, "fixture should stop bands at different sweeps"
+    close(np.moveaxis(out, 0, -1), ref)
+
+
+def test_find_gamma_batched_trials_match_reference_rng_order():
+    rng = np.random.default_rng(5)
+    grid = smooth(rng, (30, 30), 10, 30)
+    grid[rng.uniform(size=grid.shape) < 0.3] = np.nan
+    np.random.seed(11)
+    m = SD_SMRP(grid.copy())
+    best = m.find_gamma(6, 0.5, sub_iterations=20)
+    # replay the reference's RNG order on the host and score with the oracle
+    np.random.seed(11)
+    sub = grid.copy()
+    for i in range(30):
+        for j in range(30):
+            if not np.isnan(sub[i, j]) and np.random.rand() < 0.5:
+                sub[i, j] = np.nan
+    best_ref, best_loss = 0.9, np.inf
+    for _ in range(6):
+        gam = np.random.uniform(low=0, high=1)
+        pred, _, _ = O.sd_run_2d(sub, O.init_pred(sub), gamma=gam, iterations=20)
+        sel = ~np.isnan(grid) & np.isnan(sub)
+        mae = np.abs(pred[sel] - grid[sel]).sum() / sel.sum()
+        if mae < best_loss:
+            best_ref, best_loss = gam, mae
+    assert isinstance(best, float) and best == best_ref and m.gamma == best_ref
+
+
+# ---- 3. properties at larger sizes ---------------------------------------------------------------
+def test_properties_large_wp(kblock):
+    rng = np.random.default_rng(2024)
+    shape = (1024, 1024)                                    # BASELINE config 2 size
+    base = smooth(rng, shape)
+    feat = np.stack([rng.uniform(0.7, 1.3) * base for _ in range(3)], axis=-1)
+    cloud = discs(rng, shape, 12, 30, 120)
+    grid = base.copy()
+    grid[cloud] = np.nan
+    m = WP_SMRP(grid.copy(), feat.copy())
+    p, d = m.run(iterations=40, track_delta=True)
+    assert np.array_equal(p[~cloud], grid[~cloud]), "known cells must come back bit-exact"
+    assert not np.isnan(p).any() and d[-1] < d[0]
+    # linearity: scaling the target scales the result, the stopping statistic is scale free
+    m2 = WP_SMRP(4.0 * grid, feat.copy())
+    p2, d2 = m2.run(iterations=40, track_delta=True)
+    close(p2, 4.0 * p, rtol=1e-12); close(d2, d, rtol=1e-12)
+    # resume == one longer run
+    m3 = WP_SMRP(grid.copy(), feat.copy())
+    m3.run(iterations=15)
+    close(m3.run(iterations=25), p, rtol=0)
+    # target proportional to a single feature is a fixed point of the exact weights
+    m4 = WP_SMRP(np.where(cloud, np.nan, 0.5 * base), base.copy())
+    m4.pred_grid = 0.5 * base
+    close(m4.run(iterations=3), 0.5 * base, rtol=1e-12)
+
+
+def test_known_answers():
+    g = np.full((3, 3), 2.0)
+    g[1, 1] = np.nan
+    g[0, 1], g[1, 2], g[2, 1], g[1, 0] = 1.0, 2.0, 3.0, 6.0
+    assert SD_SMRP(g, gamma=1.0).run(1)[1, 1] == 3.0          # mean of the 4 neighbours
+    c = np.full((5, 5), 7.0)
+    for (i, j) in ((2, 2), (0, 2), (0, 0)):                   # interior / edge / corner: exactly gamma * c
+        h = c.copy()
+        h[i, j] = np.nan
+        assert SD_SMRP(h, gamma=0.5).run(1)[i, j] == 3.5
+
+
+def test_start_state_differs_from_original_on_known_cells(kblock):
+    """pred_grid edited by the caller: the first sweep reads it, known cells are then restored."""
+    rng = np.random.default_rng(9)
+    grid = smooth(rng, (40, 40), 10, 20)
+    grid[rng.uniform(size=grid.shape) < 0.3] = np.nan
+    start = O.init_pred(grid) * rng.uniform(0.9, 1.1, grid.shape)
+    ref, dref, _ = O.sd_run_2d(grid, start.copy(), gamma=0.8, iterations=6)
+    m = SD_SMRP(grid.copy(), gamma=0.8)
+    m.pred_grid = start.copy()
+    p, d = m.run(iterations=6, track_delta=True)
+    close(p, ref); close(d, dref)
+
+
+def test_fp32_storage_mode():
+    rng = np.random.default_rng(31)
+    shape = (200, 160)
+    base = smooth(rng, shape)
+    grid = base + rng.normal(0, 20, shape)
+    feat = (1.1 * base + rng.normal(0, 10, shape)).reshape(shape + (1,))
+    grid[discs(rng, shape, 5, 8, 30)] = np.nan
+    ref, _, n = O.wp_run_2d(grid, O.init_pred(grid), feat.copy(), iterations=60)
+    res, _, sweeps = solve_mod.propagate(grid, O.init_pred(grid), planes=True, features=feat, max_iter=60,
+                                         auto_terminate=False, threshold=1e-4, storage="float32")
+    assert sweeps == 60
+    close(res, ref, rtol=RTOL32)
+
+
+def test_batched_trials_and_stride0_inputs():
+    rng = np.random.default_rng(8)
+    grid = smooth(rng, (50, 50), 10, 30)
+    grid[rng.uniform(size=grid.shape) < 0.25] = np.nan
+    gammas = np.array([0.3, 0.9, 0.55])
+    out = sd_trials(grid, gammas, 15)
+    for i, gam in enumerate(gammas):
+        ref, _, _ = O.sd_run_2d(grid, O.init_pred(grid), gamma=gam, iterations=15)
+        close(out[i], ref)
+
+
+def test_solver_introspection_and_tile_skipping():
+    import torch
+    grid = np.ones((256, 512))
+    grid[10:20, 10:20] = np.nan                     # one small cloud: most tiles inactive
+    s = Solver(2, 1, 256, 512, planes=False)
+    s.load(torch.from_numpy(grid).cuda().unsqueeze(0), fill=[1.0])
+    assert 0 < s.active_tiles < s.total_tiles
+    s.discounts(0.9)
+    s.run(5, auto_terminate=False)
+    out, niter = s.result()
+    assert int(niter[0]) == 5 and s.launches > 0
+    ref, _, _ = O.sd_run_2d(grid[:, :256].copy(), np.where(np.isnan(grid[:, :256]), 1.0, grid[:, :256]), gamma=0.9, iterations=5)
+    close(out[0].cpu().numpy()[:20, :20], ref[:20, :20])
+    s.close()
+    with pytest.raises(VPintError):
+        WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, resistance=True)

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference interface (constructors, argument handling,
+error behaviour) against reference-generated fixtures.  No GPU needed: run() is
+only checked to fail loudly without a device."""
+
+import numpy as np
+import pytest
+
+import vpint_b200
+from vpint_b200 import SD_SMRP, SD_STMRP, VPint2_interpolator, VPintError, WP_SMRP, WP_STMRP
+from vpint_b200.wp import wp_run_options
+
+try:
+    import torch
+    HAS_CUDA = torch.cuda.is_available()
+except Exception:  # pragma: no cover
+    HAS_CUDA = False
+
+
+def same(a, b):
+    assert a.shape == b.shape and a.dtype == b.dtype
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_reference_module_names_importable():
+    from vpint_b200.SD_MRP import SD_SMRP as A
+    from vpint_b200.WP_MRP import WP_SMRP as B, VPintError as E
+    from vpint_b200.VPint2 import VPint2_interpolator as V
+    from vpint_b200.MRP import MRP, SMRP, STMRP
+    assert A is SD_SMRP and B is WP_SMRP and V is VPint2_interpolator and E is VPintError
+    assert issubclass(SMRP, MRP) and issubclass(STMRP, MRP)
+
+
+def test_init_strategies(golden):
+    g = golden("sd2d")["grid"]
+    m = SD_SMRP(g.copy())
+    same(m.original_grid, g)
+    assert not np.isnan(m.pred_grid).any()
+    assert m.pred_grid[np.isnan(g)][0] == np.nanmean(g)
+    m = SD_SMRP(g.copy(), init_strategy="zero")
+    assert (m.pred_grid[np.isnan(g)] == 0).all()
+    np.random.seed(3)
+    m = SD_SMRP(g.copy(), init_strategy="random")
+    np.random.seed(3)
+    ref = np.random.normal(np.nanmean(g), np.nanstd(g), size=int(np.isnan(g).sum()))
+    assert np.array_equal(m.pred_grid[np.isnan(g)], ref)
+    with pytest.raises(VPintError):
+        SD_SMRP(g.copy(), init_strategy="bogus")
+    m = SD_SMRP(g.copy())
+    m.reset()
+    assert m.pred_grid is m.original_grid
+
+
+def test_float32_mean_init_keeps_dtype():
+    g = np.random.default_rng(0).uniform(1, 2, (9, 9)).astype(np.float32)
+    g[2, 3] = np.nan
+    m = WP_SMRP(g, np.ones((9, 9), dtype=np.float32))
+    assert m.pred_grid.dtype == np.float32 and m.feature_grid.dtype == np.float64
+    assert m.pred_grid[2, 3] == np.nanmean(g)
+    assert m.feature_grid.shape == (9, 9, 1)
+
+
+def test_mrp_apply_mask_reference_quirk():
+    # VPint/MRP.py:100-113 masks cells whose VALUE is 1 and edits the caller's array
+    g = np.array([[1.0, 2.0], [3.0, 1.0]])
+    mask = np.zeros((2, 2))
+    m = SD_SMRP(g, mask=mask)
+    assert np.isnan(m.original_grid[0, 0]) and np.isnan(m.original_grid[1, 1])
+    assert np.isnan(g[0, 0])
+    with pytest.raises(VPintError):
+        SD_SMRP(np.ones((2, 2)), mask=np.zeros((2, 1, 2)))
+
+
+def test_wp_constructor_errors():
+    with pytest.raises(VPintError):
+        WP_SMRP(np.ones((4, 4)), np.ones((4, 5)))
+    with pytest.raises(VPintError):
+        WP_SMRP(np.ones((4, 4, 2)), np.ones((4, 4)))
+    with pytest.raises(VPintError):
+        WP_SMRP(np.ones((4, 4)), np.ones((4, 4, 1, 1)))
+    m = WP_SMRP(np.ones((4, 4, 1)), np.ones((4, 4)))
+    assert m.original_grid.shape == (4, 4)
+
+
+def test_run_option_handling():
+    o = wp_run_options()
+    assert o["iterations"] == 5000 and o["auto_terminate"] and o["method"] == "exact"
+    o = wp_run_options(iterations=7)
+    assert o["iterations"] == 7 and not o["auto_terminate"]
+    for kw in (dict(method="predict"), dict(method="nope"), dict(save_gif=True), dict(auto_adapt=True)):
+        with pytest.raises(VPintError):
+            wp_run_options(**kw)
+    with pytest.raises(TypeError):
+        wp_run_options(no_such_option=1)
+
+
+def test_sd_nonsquare_raises_like_numpy():
+    m = SD_SMRP(np.ones((4, 5)))
+    with pytest.raises(ValueError):
+        m.run(1)
+
+
+def test_zero_iterations_returns_start_state_without_gpu():
+    g = np.ones((5, 5))
+    g[1, 1] = np.nan
+    m = SD_SMRP(g)
+    out = m.run(iterations=0)
+    assert out is m.pred_grid and m.run_state
+    p, d = m.run(iterations=0, track_delta=True)
+    assert d.shape == (0,)
+    c = np.ones((3, 3, 2))
+    assert SD_STMRP(c).run(iterations=0).shape == (3, 3, 2)
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")
+def test_run_fails_loudly_without_cuda():
+    g = np.ones((5, 5))
+    g[1, 1] = np.nan
+    with pytest.raises(VPintError, match="no CPU fallback"):
+        SD_SMRP(g).run(3)
+    with pytest.raises(VPintError, match="no CPU fallback"):
+        WP_SMRP(g, np.ones((5, 5))).run(3)
+    with pytest.raises(VPintError, match="no CPU fallback"):
+        VPint2_interpolator(np.ones((4, 4, 2)), np.ones((4, 4, 2))).run()
+
+
+def test_stmrp_dim_check_and_timesteps():
+    m = SD_STMRP(np.ones((4, 3)))
+    assert m.original_grid.shape == (4, 3, 1)
+    data = {"2020-01-01 00:00:00": np.ones((2, 2)), "2020-01-03 00:00:00": 2 * np.ones((2, 2)),
+            "2020-01-04 00:00:00": 3 * np.ones((2, 2))}
+    m = SD_STMRP(data, auto_timesteps=True)
+    assert m.original_grid.shape == (2, 2, 4) and m.true_time_indices == [0, 2, 3]
+    assert np.isnan(m.original_grid[:, :, 1]).all() and not np.isnan(m.pred_grid).any()
+    w = WP_STMRP(np.ones((3, 3, 2)), np.ones((3, 3, 1)))
+    with pytest.raises(VPintError):
+        w.run(iterations=1)          # default method='predict'
+    with pytest.raises(VPintError):
+        w.run(iterations=1, method="nope")
+
+
+def test_vpint2_constructor_matches_reference(golden):
+    g = golden("vpint2_ctor")
+    for tag in ("wide", "tall"):
+        vp = VPint2_interpolator(g[tag + "_target"], g[tag + "_features"], mask=g[tag + "_mask"], buffer_mask=True,
+                                 mask_buffer_size=3, mask_buffer_passes=2)
+        same(vp.target, g[tag + "_stored"])
+        assert vp.features.dtype == np.float32
+        vp = VPint2_interpolator(g[tag + "_target"], g[tag + "_features"], mask=g[tag + "_mask"], clip_target=150,
+                                 clip_features=(110.0, 190.0))
+        same(vp.target, g[tag + "_stored_clip"])
+        same(vp.features, g[tag + "_features_clip"])
+    vp = VPint2_interpolator(np.moveaxis(g["wide_target"], -1, 0), np.moveaxis(g["wide_features"], -1, 0),
+                             mask=g["wide_mask"], bands_first=True, dtype=np.float64, threshold=0.05)
+    same(vp.target, g["bf_stored"])
+    v = golden("vpint2")
+    vp = VPint2_interpolator(v["target"], v["features"], mask=v["mask"], threshold=10)
+    same(vp.target, v["stored_target"])
+    with pytest.raises(AssertionError):
+        VPint2_interpolator(np.ones((4, 4, 2)), np.ones((4, 4, 3)))
+
+
+def test_package_exports():
+    for name in vpint_b200.__all__:
+        assert hasattr(vpint_b200, name)

@@ -1,0 +1,418 @@
+// C ABI of the vpint_b200 library (declared in include/vpint_b200.h): solver object, workspace carving,
+// and the loop drivers around the stencil / reduction / decision kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "vpint_internal.cuh"
+
+namespace vpint {
+void k1_tile_shape(int ndim, int *th, int *tw);
+void tb_tile_shape(int k_block, int *th, int *tw);
+bool tb_supported(const Geom &g, int storage);
+cudaError_t launch_step2d_tb(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
+                             int64_t *launches);
+}  // namespace vpint
+
+using namespace vpint;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *where) {
+    g_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return VPINT_ERR_CUDA;
+}
+
+#define VP_CUDA(call, where)                                   \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return fail_cuda(e__, where);  \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum Counter { kCntDirty = 0, kCntActiveTiles = 1, kCntActiveProblems = 8, kCntTotal = 16 };
+
+}  // namespace
+
+struct vpint_solver {
+    vpint_desc desc;
+    Geom g;
+    int storage, weight_mode, n_planes;
+    size_t elem;
+    int64_t tiles_total;
+    // workspace offsets
+    size_t off_buf[2], off_mask, off_w[5], off_gamma, off_tau, off_fill, off_rowpart, off_known0, off_known,
+        off_state, off_counters, off_tileflag, off_tiles, off_tilestart, off_partial, off_sums, ws_bytes;
+    char *ws = nullptr;
+    bool loaded = false, weights_ready = false, run_begun = false, first_step_pending = false;
+    bool use_tb = false;
+    int64_t tiles_active = 0;
+    int any_dirty = 0;
+    int64_t launches = 0;
+    int *h_counters = nullptr;   // pinned
+    cudaEvent_t ev = nullptr;
+    vpint_run_params prm;
+
+    template <typename T>
+    T *at(size_t off) const { return reinterpret_cast<T *>(ws + off); }
+};
+
+extern "C" {
+
+int vpint_abi_version(void) { return VPINT_ABI_VERSION; }
+
+const char *vpint_last_error(void) { return g_last_error.c_str(); }
+
+int64_t vpint_row_pitch(int64_t row_elems) {
+    if (row_elems < 1) row_elems = 1;
+    return (row_elems + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+}
+
+int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
+    if (!d || !out) return fail(VPINT_ERR_INVALID, "vpint_solver_create: null argument");
+    *out = nullptr;
+    if (d->ndim != 2 && d->ndim != 3) return fail(VPINT_ERR_INVALID, "ndim must be 2 or 3");
+    if (d->nprob < 1 || d->H < 1 || d->W < 1 || d->T < 1) return fail(VPINT_ERR_INVALID, "nprob, H, W, T must be >= 1");
+    if (d->ndim == 2 && d->T != 1) return fail(VPINT_ERR_INVALID, "T must be 1 for ndim == 2");
+    if (d->storage != VPINT_F64 && d->storage != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad storage type");
+    if (d->weight_mode != VPINT_W_SCALAR && d->weight_mode != VPINT_W_PLANES)
+        return fail(VPINT_ERR_INVALID, "bad weight_mode");
+    if (d->k_block < 0 || d->k_block > kMaxKBlock) return fail(VPINT_ERR_INVALID, "k_block out of range");
+    if (d->nprob_inner < 0 || (d->nprob_inner > 1 && d->nprob % d->nprob_inner != 0))
+        return fail(VPINT_ERR_INVALID, "nprob_inner must divide nprob");
+    if ((int64_t)d->W * d->T > (int64_t)1 << 30) return fail(VPINT_ERR_INVALID, "row too long");
+
+    vpint_solver *s = new (std::nothrow) vpint_solver();
+    if (!s) return fail(VPINT_ERR_INVALID, "out of host memory");
+    s->desc = *d;
+    Geom &g = s->g;
+    g.ndim = d->ndim; g.P = d->nprob; g.H = d->H; g.W = d->W; g.T = d->T;
+    g.Pin = d->nprob_inner > 1 ? d->nprob_inner : 1;
+    g.L = d->W * d->T;
+    g.pitch = (int)vpint_row_pitch(g.L);
+    g.mpitch = g.pitch / kMaskWordBits;
+    g.wpitch = (int)vpint_row_pitch(g.W);
+    if (d->global_H == 0 && d->own_rows == 0 && d->row_offset == 0 && d->own_row0 == 0) {
+        g.global_H = g.H; g.row_offset = 0; g.own_row0 = 0; g.own_rows = g.H;
+    } else {
+        g.global_H = d->global_H; g.row_offset = d->row_offset; g.own_row0 = d->own_row0; g.own_rows = d->own_rows;
+        if (g.own_row0 < 0 || g.own_rows < 1 || g.own_row0 + g.own_rows > g.H || g.row_offset < 0 ||
+            g.row_offset + g.H > g.global_H) {
+            delete s;
+            return fail(VPINT_ERR_INVALID, "inconsistent row sharding (global_H, row_offset, own_row0, own_rows)");
+        }
+    }
+    g.n_cells = (double)g.global_H * (double)g.L;
+    s->storage = d->storage;
+    s->weight_mode = d->weight_mode;
+    s->elem = (d->storage == VPINT_F64) ? 8 : 4;
+    s->n_planes = (d->weight_mode == VPINT_W_PLANES) ? (d->ndim == 2 ? 4 : 5) : 0;
+
+    int kb = d->k_block;
+    if (d->ndim == 3) {
+        if (kb > 1) { delete s; return fail(VPINT_ERR_UNSUPPORTED, "temporal blocking (k_block > 1) is 2-D only"); }
+        kb = 1;
+    }
+    if (kb == 0) kb = 1;
+    g.KB = kb;
+    s->use_tb = (kb > 1);
+    if (s->use_tb) tb_tile_shape(kb, &g.TH, &g.TW);
+    else k1_tile_shape(g.ndim, &g.TH, &g.TW);
+    if (s->use_tb && !tb_supported(g, s->storage)) {
+        delete s;
+        return fail(VPINT_ERR_UNSUPPORTED, "temporally blocked kernel does not support this configuration");
+    }
+    g.tiles_y = (g.own_rows + g.TH - 1) / g.TH;
+    g.tiles_x = (g.L + g.TW - 1) / g.TW;
+    g.tiles_per_prob = g.tiles_y * g.tiles_x;
+    s->tiles_total = (int64_t)g.P * g.tiles_per_prob;
+    if (s->tiles_total >= ((int64_t)1 << 31) - 1024 || (int64_t)g.P * g.H >= ((int64_t)1 << 31) - 1) {
+        delete s;
+        return fail(VPINT_ERR_INVALID, "batch too large for one solver (tile or row count exceeds 2^31)");
+    }
+
+    // workspace layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t plane = (size_t)g.P * g.H * g.pitch * s->elem;
+    s->off_buf[0] = take(plane);
+    s->off_buf[1] = take(plane);
+    s->off_mask = take((size_t)g.P * g.H * g.mpitch * sizeof(uint32_t));
+    const size_t wplane = (d->ndim == 2) ? plane : (size_t)g.P * g.H * g.wpitch * s->elem;
+    for (int i = 0; i < 5; ++i) s->off_w[i] = (i < s->n_planes) ? take(wplane) : 0;
+    s->off_gamma = take((size_t)g.P * sizeof(double));
+    s->off_tau = take((size_t)g.P * sizeof(double));
+    s->off_fill = take((size_t)g.P * sizeof(double));
+    s->off_rowpart = take((size_t)g.P * g.H * 8 * sizeof(double));
+    s->off_known0 = take((size_t)g.P * kSumSlots * sizeof(double));
+    s->off_known = take((size_t)g.P * kSumSlots * sizeof(double));
+    s->off_state = take((size_t)g.P * sizeof(ProbState));
+    s->off_counters = take(kCntTotal * sizeof(int));
+    s->off_tileflag = take((size_t)s->tiles_total * sizeof(int));
+    s->off_tiles = take((size_t)s->tiles_total * sizeof(TileRef));
+    s->off_tilestart = take((size_t)(g.P + 1) * sizeof(int));
+    s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
+    s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
+    s->ws_bytes = off;
+    *out = s;
+    return VPINT_OK;
+}
+
+void vpint_solver_destroy(vpint_solver *s) {
+    if (!s) return;
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->ev) cudaEventDestroy(s->ev);
+    delete s;
+}
+
+size_t vpint_solver_workspace_bytes(const vpint_solver *s) { return s ? s->ws_bytes : 0; }
+
+int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
+    if (!s) return fail(VPINT_ERR_INVALID, "null solver");
+    if (!workspace || bytes < s->ws_bytes) return fail(VPINT_ERR_WORKSPACE, "workspace missing or too small");
+    if ((uintptr_t)workspace % 256 != 0) return fail(VPINT_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if (!s->h_counters) {
+        VP_CUDA(cudaHostAlloc((void **)&s->h_counters, kCntTotal * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
+        VP_CUDA(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    s->ws = static_cast<char *>(workspace);
+    s->loaded = s->weights_ready = s->run_begun = false;
+    return VPINT_OK;
+}
+
+int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, const double *fill, int dtype,
+                      const int64_t *stride, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!original || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_load: null argument");
+    if (!pred0 && !fill) return fail(VPINT_ERR_INVALID, "vpint_solver_load: need pred0 or fill");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geom &g = s->g;
+    if (!pred0)
+        VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_fill), fill, (size_t)g.P * sizeof(double), cudaMemcpyHostToDevice, st),
+                "copy fill");
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
+    VP_CUDA(launch_prepare(g, original, pred0, s->at<double>(s->off_fill), dtype, stride, s->storage,
+                           s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]), s->at<uint32_t>(s->off_mask),
+                           s->at<double>(s->off_rowpart), s->at<double>(s->off_known0), s->at<double>(s->off_known),
+                           s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
+            "prepare");
+    VP_CUDA(launch_tiles(g, s->at<uint32_t>(s->off_mask), s->at<int>(s->off_tileflag), s->at<TileRef>(s->off_tiles),
+                         s->at<int>(s->off_tilestart), s->at<int>(s->off_counters), st, &s->launches),
+            "tile list");
+    VP_CUDA(cudaMemcpyAsync(s->h_counters, s->at<int>(s->off_counters), kCntTotal * sizeof(int), cudaMemcpyDeviceToHost, st),
+            "read counters");
+    VP_CUDA(cudaStreamSynchronize(st), "load sync");
+    s->any_dirty = s->h_counters[kCntDirty];
+    s->tiles_active = s->h_counters[kCntActiveTiles];
+    s->loaded = true;
+    s->run_begun = false;
+    return VPINT_OK;
+}
+
+int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int64_t *stride, int F, int method,
+                         int clamp, double min_gamma, double max_gamma, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (s->weight_mode != VPINT_W_PLANES) return fail(VPINT_ERR_INVALID, "solver was created with scalar weights");
+    if (!feat || !stride || F < 1) return fail(VPINT_ERR_INVALID, "vpint_solver_weights: bad argument");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    if (method != VPINT_METHOD_EXACT && method != VPINT_METHOD_COSINE && method != VPINT_METHOD_EXACT_INVERSE)
+        return fail(VPINT_ERR_INVALID, "bad weight method");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void *planes[5];
+    for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    if (s->g.ndim == 2) {
+        VP_CUDA(launch_weights2d(s->g, feat, dtype, stride, F, method, clamp, min_gamma, max_gamma, s->storage, planes,
+                                 st, &s->launches),
+                "weights2d");
+    } else {
+        if (method == VPINT_METHOD_EXACT_INVERSE)
+            return fail(VPINT_ERR_UNSUPPORTED, "exact_inverse is not a WP_STMRP method (VPint/WP_MRP.py:1443-1468)");
+        VP_CUDA(launch_weights3d(s->g, feat, dtype, stride, F, method, s->storage, planes, st, &s->launches), "weights3d");
+    }
+    s->weights_ready = true;
+    return VPINT_OK;
+}
+
+int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (s->weight_mode != VPINT_W_SCALAR) return fail(VPINT_ERR_INVALID, "solver was created with weight planes");
+    if (!gamma || (s->g.ndim == 3 && !tau)) return fail(VPINT_ERR_INVALID, "vpint_solver_set_discounts: null argument");
+    const size_t bytes = (size_t)s->g.P * sizeof(double);
+    VP_CUDA(cudaMemcpy(s->at<double>(s->off_gamma), gamma, bytes, cudaMemcpyHostToDevice), "copy gamma");
+    if (tau) VP_CUDA(cudaMemcpy(s->at<double>(s->off_tau), tau, bytes, cudaMemcpyHostToDevice), "copy tau");
+    s->weights_ready = true;
+    return VPINT_OK;
+}
+
+int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!prm) return fail(VPINT_ERR_INVALID, "null run params");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (!s->weights_ready) return fail(VPINT_ERR_INVALID, "weights / discounts have not been set");
+    if (prm->max_iter < 0) return fail(VPINT_ERR_INVALID, "max_iter must be >= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    s->prm = *prm;
+    VP_CUDA(launch_init_state(s->g, s->at<ProbState>(s->off_state), s->at<int>(s->off_counters) + kCntActiveProblems,
+                              prm->max_iter, st, &s->launches),
+            "init state");
+    s->run_begun = true;
+    s->first_step_pending = true;
+    return VPINT_OK;
+}
+
+static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms);
+
+int vpint_solver_step_begin(vpint_solver *s, void *stream) { return step_begin_impl(s, stream, nullptr); }
+
+int vpint_solver_step_profile(vpint_solver *s, void *stream, float *stencil_ms) {
+    if (!stencil_ms) return fail(VPINT_ERR_INVALID, "null stencil_ms");
+    return step_begin_impl(s, stream, stencil_ms);
+}
+
+static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
+    if (!s || !s->run_begun) return fail(VPINT_ERR_INVALID, "vpint_solver_begin_run has not been called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stencil_ms) {
+        VP_CUDA(cudaEventCreate(&e0), "event create");
+        VP_CUDA(cudaEventCreate(&e1), "event create");
+        VP_CUDA(cudaEventRecord(e0, st), "event record");
+    }
+    StepArgs a;
+    a.g = s->g;
+    a.tiles = s->at<TileRef>(s->off_tiles);
+    a.state = s->at<ProbState>(s->off_state);
+    a.buf[0] = s->at<void>(s->off_buf[0]);
+    a.buf[1] = s->at<void>(s->off_buf[1]);
+    a.mask = s->at<uint32_t>(s->off_mask);
+    for (int i = 0; i < 5; ++i) a.w[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    a.gamma = s->at<double>(s->off_gamma);
+    a.tau = s->at<double>(s->off_tau);
+    a.partial = s->at<double>(s->off_partial);
+    a.clip = s->prm.clip_val;
+    if (s->g.ndim == 2) {
+        if (s->use_tb)
+            VP_CUDA(launch_step2d_tb(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d_tb");
+        else
+            VP_CUDA(launch_step2d(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d");
+    } else {
+        VP_CUDA(launch_step3d(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step3d");
+    }
+    if (stencil_ms) {
+        VP_CUDA(cudaEventRecord(e1, st), "event record");
+        VP_CUDA(cudaEventSynchronize(e1), "event sync");
+        VP_CUDA(cudaEventElapsedTime(stencil_ms, e0, e1), "event elapsed");
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), s->at<int>(s->off_tilestart),
+                                   s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), st, &s->launches),
+            "reduce partials");
+    return VPINT_OK;
+}
+
+int vpint_solver_step_end(vpint_solver *s, void *stream) {
+    if (!s || !s->run_begun) return fail(VPINT_ERR_INVALID, "vpint_solver_begin_run has not been called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DecideArgs d;
+    d.g = s->g;
+    d.state = s->at<ProbState>(s->off_state);
+    d.sums = s->at<double>(s->off_sums);
+    d.known0 = s->at<double>(s->off_known0);
+    d.known = s->at<double>(s->off_known);
+    d.delta_out = s->prm.delta_out;
+    d.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
+    d.max_iter = s->prm.max_iter;
+    d.auto_terminate = s->prm.auto_terminate;
+    d.threshold = s->prm.threshold;
+    VP_CUDA(launch_decide(d, st, &s->launches), "decide");
+    if (s->first_step_pending) {
+        s->first_step_pending = false;
+        if (s->any_dirty) {
+            void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+            VP_CUDA(launch_restore_known(s->g, s->storage, s->at<ProbState>(s->off_state), bufs,
+                                         s->at<uint32_t>(s->off_mask), st, &s->launches),
+                    "restore known");
+            s->any_dirty = 0;
+        }
+    }
+    return VPINT_OK;
+}
+
+int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+    int rc = vpint_solver_begin_run(s, prm, stream);
+    if (rc != VPINT_OK) return rc;
+    if (prm->loop_mode != VPINT_LOOP_CHUNKED)
+        return fail(VPINT_ERR_UNSUPPORTED, "only VPINT_LOOP_CHUNKED is available in this build");
+    if (prm->max_iter == 0) return VPINT_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int chunk = prm->chunk > 0 ? prm->chunk : 4;
+    const int chunk_cap = prm->chunk > 0 ? prm->chunk : 64;
+    // Every launch either commits >= 1 sweep of every running problem or is its single replay, so
+    // 2 * max_iter + 2 launches always suffice; the bound only guards against a logic error.
+    int64_t budget = 2 * (int64_t)prm->max_iter + 2;
+    while (budget > 0) {
+        for (int i = 0; i < chunk; ++i) {
+            rc = vpint_solver_step_begin(s, stream);
+            if (rc != VPINT_OK) return rc;
+            rc = vpint_solver_step_end(s, stream);
+            if (rc != VPINT_OK) return rc;
+        }
+        budget -= chunk;
+        VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
+                                sizeof(int), cudaMemcpyDeviceToHost, st),
+                "read active count");
+        VP_CUDA(cudaEventRecord(s->ev, st), "event record");
+        VP_CUDA(cudaEventSynchronize(s->ev), "event sync");
+        if (s->h_counters[kCntActiveProblems] <= 0) return VPINT_OK;
+        if (chunk < chunk_cap) chunk = (chunk * 2 < chunk_cap) ? chunk * 2 : chunk_cap;
+    }
+    return fail(VPINT_ERR_INVALID, "internal error: loop did not terminate within its launch budget");
+}
+
+double *vpint_solver_sums_ptr(vpint_solver *s) { return (s && s->ws) ? s->at<double>(s->off_sums) : nullptr; }
+
+int vpint_solver_sums_count(const vpint_solver *s) { return s ? s->g.P * s->g.KB * kSumSlots : 0; }
+
+void *vpint_solver_state_ptr(vpint_solver *s, int which) {
+    return (s && s->ws && (which == 0 || which == 1)) ? s->at<void>(s->off_buf[which]) : nullptr;
+}
+
+int32_t *vpint_solver_active_ptr(vpint_solver *s) {
+    return (s && s->ws) ? s->at<int32_t>(s->off_counters) + kCntActiveProblems : nullptr;
+}
+
+int32_t *vpint_solver_cur_ptr(vpint_solver *s) {
+    // ProbState is 8 int32; `cur` is field 2.  Exposed as a strided view: element p at [p * 8].
+    return (s && s->ws) ? reinterpret_cast<int32_t *>(s->at<ProbState>(s->off_state)) + 2 : nullptr;
+}
+
+int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (!out || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_result: null argument");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    VP_CUDA(launch_result(s->g, s->storage, s->at<ProbState>(s->off_state), bufs, out, dtype, stride, niter_out,
+                          static_cast<cudaStream_t>(stream), &s->launches),
+            "result");
+    return VPINT_OK;
+}
+
+int64_t vpint_solver_active_tiles(const vpint_solver *s) { return s ? s->tiles_active : 0; }
+int64_t vpint_solver_total_tiles(const vpint_solver *s) { return s ? s->tiles_total : 0; }
+int64_t vpint_solver_launches(const vpint_solver *s) { return s ? s->launches : 0; }
+int vpint_solver_k_block(const vpint_solver *s) { return s ? s->g.KB : 0; }
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// Internal declarations shared by the vpint_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/vpint_b200.h"
+
+namespace vpint {
+
+constexpr int kMaskWordBits = 32;
+constexpr int kPitchAlign = 64;     // row pitch in elements: 64-bit mask words stay aligned, rows 512 B (f64) aligned
+constexpr int kMaxKBlock = 16;      // per-launch fused sweeps (register-resident per-sweep sums)
+
+// Sum slots of one sweep: {sum |new-old|, sum old, #NaN in |new-old|, #NaN in old}.
+// Counts are kept as doubles so one buffer can be all-reduced as fp64.
+constexpr int kSumSlots = 4;
+
+// Geometry of a batched solve.  A "row" is the contiguous inner dimension:
+// W cells in 2-D, W*T cells in 3-D (T fastest).
+struct Geom {
+    int ndim, P, H, W, T;
+    int Pin;          // inner problem count: p = outer * Pin + inner when addressing caller arrays
+    int L;            // row length in elements = W * T
+    int pitch;        // padded row length (multiple of kPitchAlign)
+    int mpitch;       // 32-bit mask words per row = pitch / 32
+    int wpitch;       // 3-D only: padded W for the (H, W) weight planes
+    int TH, TW;       // owned tile: rows x row-elements
+    int tiles_y, tiles_x, tiles_per_prob;
+    int KB;           // sweeps per launch
+    int global_H;     // rows of the whole grid (== H when unsharded)
+    int row_offset;   // global row of local row 0
+    int own_row0;     // first owned local row
+    int own_rows;     // owned rows
+    double n_cells;   // cells of the WHOLE grid (global_H * L): nanmean denominators
+};
+
+// Per-problem loop state (device).
+struct ProbState {
+    int iters_done;   // committed sweeps
+    int k_run;        // sweeps the next launch executes for this problem (0 = idle)
+    int cur;          // ping-pong buffer holding the current state
+    int status;       // 0 running, 1 finished
+    int replay;       // 1: next launch replays k_run sweeps after an overshoot, then finishes
+    int dirty;        // 1: known cells of the start state differ from original (first launch runs 1 sweep)
+    int fresh;        // 1: no sweep committed since load (first sweep uses the known0 sums)
+    int pad;
+};
+
+struct TileRef {
+    int p, y0, x0, pad;
+};
+
+// Everything a stencil launch needs.
+struct StepArgs {
+    Geom g;
+    const TileRef *tiles;
+    ProbState *state;
+    void *buf[2];
+    const uint32_t *mask;
+    const void *w[5];        // planes: up, right, down, left (, temporal for 3-D)
+    const double *gamma;     // [P] scalar mode
+    const double *tau;       // [P] scalar mode, 3-D
+    double *partial;         // [tile][KB][kSumSlots]
+    double clip;
+};
+
+struct DecideArgs {
+    Geom g;
+    ProbState *state;
+    const double *sums;      // [P][KB][kSumSlots] (already combined over ranks when sharded)
+    const double *known0;    // [P][kSumSlots] known-cell terms of the first sweep after load
+    const double *known;     // [P][kSumSlots] known-cell terms of every later sweep
+    double *delta_out;       // [P][max_iter] or null
+    int *n_active;
+    int max_iter;
+    int auto_terminate;
+    double threshold;
+};
+
+// ---- host-side launchers (one per .cu) ------------------------------------
+cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
+                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,
+                           uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
+                           int *counters, cudaStream_t st, int64_t *launches);
+cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
+                         int *counters, cudaStream_t st, int64_t *launches);
+cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const int64_t *stride, int F, int method,
+                             int clamp, double min_gamma, double max_gamma, int storage, void *const *planes,
+                             cudaStream_t st, int64_t *launches);
+cudaError_t launch_weights3d(const Geom &g, const void *feat, int dtype, const int64_t *stride, int F, int method,
+                             int storage, void *const *planes, cudaStream_t st, int64_t *launches);
+cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
+                          int64_t *launches);
+cudaError_t launch_step3d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
+                          int64_t *launches);
+cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
+                                   const ProbState *state, double *sums, cudaStream_t st, int64_t *launches);
+cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
+                              int64_t *launches);
+cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,
+                                 const uint32_t *mask, cudaStream_t st, int64_t *launches);
+cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, void *const *buf, void *out,
+                          int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
+                          int64_t *launches);
+
+// ---- device helpers -------------------------------------------------------
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction of NV doubles per thread; result valid in thread 0.
+// `scratch` needs NV * (blockDim.x / 32) doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double acc = scratch[i];
+            for (int w = 1; w < nwarp; ++w) acc += scratch[w * NV + i];
+            v[i] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+// 2 consecutive elements, 128-bit for double / 64-bit for float.
+__device__ __forceinline__ void load2(const double *p, double &a, double &b) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void load2(const float *p, double &a, double &b) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    a = (double)v.x;
+    b = (double)v.y;
+}
+
+template <typename T>
+__device__ __forceinline__ double ld_as_double(const void *base, int64_t idx) {
+    return (double)reinterpret_cast<const T *>(base)[idx];
+}
+
+#endif  // __CUDACC__
+
+}  // namespace vpint

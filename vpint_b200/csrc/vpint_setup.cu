@@ -1,0 +1,404 @@
+// Setup and bookkeeping kernels: state staging (A1), unknown-cell bit mask, active-tile list,
+// per-problem loop state, result gather.  Reference semantics cited per kernel.
+#include "vpint_internal.cuh"
+
+namespace vpint {
+
+namespace {
+
+struct Strides {
+    int64_t sO, sI, sY, sX, sT;
+};
+
+__device__ __forceinline__ int64_t cell_offset(const Geom &g, const Strides &s, int p, int y, int e) {
+    const int po = p / g.Pin, pi = p - po * g.Pin;
+    const int64_t base = (int64_t)po * s.sO + (int64_t)pi * s.sI + (int64_t)y * s.sY;
+    if (g.T == 1) return base + (int64_t)e * s.sX;
+    const int j = e / g.T, t = e - j * g.T;
+    return base + (int64_t)j * s.sX + (int64_t)t * s.sT;
+}
+
+// One block per (problem, row).  Stages the start state of run():
+//   bufA = pred0 (self.pred_grid, VPint/MRP.py:64-91 or whatever the caller left there),
+//   bufB = original at known cells (the restore of VPint/SD_MRP.py:133-134 / WP_MRP.py:321,323 is
+//          materialised once: later sweeps only write unknown cells),
+//   mask = 1 bit per cell, set where original is NaN,
+// and the known-cell terms of the stopping statistic (VPint/SD_MRP.py:139):
+//   rowpart[8] = {sum|orig-pred0|, sum pred0, #NaN of the former, #NaN of the latter,
+//                 sum orig, #inf orig, dirty (pred0 != orig on a known cell), #unknown}.
+template <typename TIn, typename TSt>
+__global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restrict__ original,
+                                                      const TIn *__restrict__ pred0,
+                                                      const double *__restrict__ fill, Strides sd,
+                                                      TSt *__restrict__ bufA,
+                                                      TSt *__restrict__ bufB, uint32_t *__restrict__ mask,
+                                                      double *__restrict__ rowpart) {
+    __shared__ double scratch[8 * 8];
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
+    const size_t row = ((size_t)p * g.H + y) * g.pitch;
+    const size_t mrow = ((size_t)p * g.H + y) * g.mpitch;
+    const bool owned = (y >= g.own_row0) && (y < g.own_row0 + g.own_rows);
+    const double fillv = pred0 ? 0.0 : fill[p];
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) {
+        bool unknown = false;
+        TSt va = (TSt)0, vb = (TSt)0;
+        if (e < g.L) {
+            const int64_t off = cell_offset(g, sd, p, y, e);
+            const double o = (double)original[off];
+            unknown = (o != o);
+            const double v0 = pred0 ? (double)pred0[off] : (unknown ? fillv : o);
+            va = (TSt)v0;
+            vb = unknown ? va : (TSt)o;
+            if (owned) {
+                if (unknown) {
+                    acc[7] += 1.0;
+                } else {
+                    const double os = (double)vb, vs = (double)va;
+                    const double a0 = fabs(os - vs);
+                    if (a0 != a0) acc[2] += 1.0; else acc[0] += a0;
+                    if (vs != vs) acc[3] += 1.0; else acc[1] += vs;
+                    acc[4] += os;
+                    if (isinf(os)) acc[5] += 1.0;
+                    if (!(vs == os)) acc[6] += 1.0;
+                }
+            }
+        }
+        bufA[row + e] = va;
+        bufB[row + e] = vb;
+        const unsigned word = __ballot_sync(0xffffffffu, unknown);   // pitch % 32 == 0: whole warps iterate together
+        if ((threadIdx.x & 31) == 0) mask[mrow + (e >> 5)] = word;
+    }
+    block_sum<8>(acc, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowpart[(size_t)blockIdx.x * 8 + i] = acc[i];
+    }
+}
+
+// One block per problem: fixed-order reduction of the row partials.
+__global__ void __launch_bounds__(256) prepare_reduce_kernel(Geom g, const double *__restrict__ rowpart,
+                                                             double *__restrict__ known0,
+                                                             double *__restrict__ known, ProbState *state,
+                                                             int *counters) {
+    __shared__ double scratch[8 * 8];
+    const int p = blockIdx.x;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int y = threadIdx.x; y < g.H; y += blockDim.x) {
+        const double *r = rowpart + ((size_t)p * g.H + y) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += r[i];
+    }
+    block_sum<8>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double *k0 = known0 + (size_t)p * kSumSlots, *k = known + (size_t)p * kSumSlots;
+        k0[0] = acc[0]; k0[1] = acc[1]; k0[2] = acc[2]; k0[3] = acc[3];
+        k[0] = 0.0; k[1] = acc[4]; k[2] = acc[5]; k[3] = 0.0;
+        ProbState st;
+        st.iters_done = 0; st.k_run = 0; st.cur = 0; st.status = 1; st.replay = 0;
+        st.dirty = acc[6] > 0.0 ? 1 : 0; st.fresh = 1; st.pad = 0;
+        state[p] = st;
+        if (st.dirty) atomicAdd(&counters[0], 1);
+    }
+}
+
+// One warp per tile: does the owned tile contain an unknown cell?
+__global__ void __launch_bounds__(256) tile_flag_kernel(Geom g, const uint32_t *__restrict__ mask,
+                                                        int *__restrict__ tile_flag, int64_t n_tiles) {
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int p = (int)(t / g.tiles_per_prob);
+    const int r = (int)(t - (int64_t)p * g.tiles_per_prob);
+    const int ty = r / g.tiles_x, tx = r - ty * g.tiles_x;
+    const int y0 = g.own_row0 + ty * g.TH, y1 = min(y0 + g.TH, g.own_row0 + g.own_rows);
+    const int x0 = tx * g.TW, x1 = min(x0 + g.TW, g.L);
+    unsigned any = 0;
+    if (x1 > x0) {
+        const int w0 = x0 >> 5, w1 = (x1 - 1) >> 5;
+        for (int y = y0 + lane; y < y1; y += 32) {
+            const uint32_t *mr = mask + ((size_t)p * g.H + y) * g.mpitch;
+            for (int w = w0; w <= w1; ++w) {
+                unsigned bits = mr[w];
+                if (w == w0) bits &= 0xffffffffu << (x0 & 31);
+                if (w == w1 && ((x1 & 31) != 0)) bits &= 0xffffffffu >> (32 - (x1 & 31));
+                any |= bits;
+            }
+        }
+    }
+    const unsigned vote = __ballot_sync(0xffffffffu, any != 0);
+    if (lane == 0) tile_flag[t] = vote ? 1 : 0;
+}
+
+// Single block: ordered compaction of the flagged tiles (problem-major, then row, then column),
+// tile_start[p] = index of problem p's first active tile, counters[1] = number of active tiles.
+__global__ void __launch_bounds__(1024) tile_compact_kernel(Geom g, const int *__restrict__ tile_flag,
+                                                            TileRef *__restrict__ tiles,
+                                                            int *__restrict__ tile_start, int *counters,
+                                                            int64_t n_tiles) {
+    __shared__ int counts[1024];
+    const int tid = threadIdx.x;
+    const int64_t chunk = (n_tiles + 1023) / 1024;
+    const int64_t a = min((int64_t)tid * chunk, n_tiles), b = min(a + chunk, n_tiles);
+    int c = 0;
+    for (int64_t i = a; i < b; ++i) c += tile_flag[i];
+    counts[tid] = c;
+    __syncthreads();
+    // inclusive Hillis-Steele scan over 1024 counts
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = (tid >= off) ? counts[tid - off] : 0;
+        __syncthreads();
+        counts[tid] += v;
+        __syncthreads();
+    }
+    int pos = counts[tid] - c;
+    for (int64_t i = a; i < b; ++i) {
+        const int p = (int)(i / g.tiles_per_prob);
+        const int r = (int)(i - (int64_t)p * g.tiles_per_prob);
+        if (r == 0) tile_start[p] = pos;
+        if (tile_flag[i]) {
+            const int ty = r / g.tiles_x, tx = r - ty * g.tiles_x;
+            TileRef tr;
+            tr.p = p; tr.y0 = g.own_row0 + ty * g.TH; tr.x0 = tx * g.TW; tr.pad = 0;
+            tiles[pos++] = tr;
+        }
+    }
+    if (tid == 1023) {
+        tile_start[g.P] = counts[1023];
+        counters[1] = counts[1023];
+    }
+}
+
+// Start of a run(): `iterations` bookkeeping of VPint/SD_MRP.py:63-66 / WP_MRP.py:112-115 is done by the
+// caller (max_iter, auto_terminate); iterations == 0 returns the start state untouched.
+__global__ void init_state_kernel(Geom g, ProbState *state, int *n_active, int max_iter) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.P) return;
+    ProbState st = state[p];
+    st.iters_done = 0;
+    st.replay = 0;
+    if (max_iter <= 0) {
+        st.status = 1;
+        st.k_run = 0;
+    } else {
+        st.status = 0;
+        st.k_run = st.dirty ? 1 : min(g.KB, max_iter);
+        atomicAdd(n_active, 1);
+    }
+    state[p] = st;
+}
+
+// Block per problem: fixed-order sum of the per-tile partials of the sweeps this launch executed.
+__global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const double *__restrict__ partial,
+                                                              const int *__restrict__ tile_start,
+                                                              const ProbState *__restrict__ state,
+                                                              double *__restrict__ sums) {
+    __shared__ double scratch[kSumSlots * 4];
+    const int p = blockIdx.x;
+    const int kr = state[p].k_run;
+    double *out = sums + (size_t)p * g.KB * kSumSlots;
+    if (kr == 0) {
+        // keep the buffer finite so an external all-reduce never mixes stale values in
+        for (int i = threadIdx.x; i < g.KB * kSumSlots; i += blockDim.x) out[i] = 0.0;
+        return;
+    }
+    const int t0 = tile_start[p], t1 = tile_start[p + 1];
+    for (int j = 0; j < g.KB; ++j) {
+        double acc[kSumSlots] = {0, 0, 0, 0};
+        if (j < kr) {
+            for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+                const double *q = partial + ((size_t)t * g.KB + j) * kSumSlots;
+#pragma unroll
+                for (int i = 0; i < kSumSlots; ++i) acc[i] += q[i];
+            }
+        }
+        block_sum<kSumSlots>(acc, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < kSumSlots; ++i) out[j * kSumSlots + i] = acc[i];
+        }
+    }
+}
+
+// Thread per problem: the stopping rule and the loop bookkeeping.
+//   delta = nanmean(|new - old|) / nanmean(old) over the whole grid (VPint/SD_MRP.py:139,
+//   VPint/WP_MRP.py:352); known cells contribute |orig - orig| (0, or NaN for +-inf) and orig.
+//   delta <= threshold commits the sweep and stops (SD_MRP.py:142-147); an overshoot inside a
+//   temporally blocked launch schedules a replay of exactly `stop` sweeps from the untouched
+//   launch-entry buffer.
+__global__ void decide_kernel(DecideArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.g.P) return;
+    ProbState st = a.state[p];
+    if (st.status != 0 || st.k_run == 0) return;
+    const int kr = st.k_run;
+    if (st.replay) {
+        st.iters_done += kr;
+        st.cur ^= 1;
+        st.status = 1; st.k_run = 0; st.replay = 0; st.fresh = 0;
+        a.state[p] = st;
+        atomicSub(a.n_active, 1);
+        return;
+    }
+    int stop = -1;
+    for (int j = 0; j < kr; ++j) {
+        const double *S = a.sums + ((size_t)p * a.g.KB + j) * kSumSlots;
+        const double *K = ((st.fresh && j == 0) ? a.known0 : a.known) + (size_t)p * kSumSlots;
+        const double s_abs = S[0] + K[0], s_old = S[1] + K[1];
+        const double n_abs = a.g.n_cells - (S[2] + K[2]), n_old = a.g.n_cells - (S[3] + K[3]);
+        const double delta = (s_abs / n_abs) / (s_old / n_old);
+        if (a.delta_out) a.delta_out[(size_t)p * a.max_iter + st.iters_done + j] = delta;
+        if (a.auto_terminate && delta <= a.threshold) {
+            stop = j + 1;
+            break;
+        }
+    }
+    if (stop < 0 || stop == kr) {
+        st.iters_done += kr;
+        st.cur ^= 1;
+        st.fresh = 0;
+        if (stop == kr || st.iters_done >= a.max_iter) {
+            st.status = 1;
+            st.k_run = 0;
+            atomicSub(a.n_active, 1);
+        } else {
+            st.k_run = min(a.g.KB, a.max_iter - st.iters_done);
+        }
+    } else {
+        st.replay = 1;
+        st.k_run = stop;
+    }
+    a.state[p] = st;
+}
+
+// Rare path: the start state disagreed with `original` on known cells (user-edited pred_grid, or a
+// previous resistance run).  The first launch ran one sweep from it; the other ping-pong buffer still
+// holds those stale known cells, so copy the restored ones over.
+template <typename TSt>
+__global__ void __launch_bounds__(256) restore_known_kernel(Geom g, const ProbState *__restrict__ state,
+                                                            TSt *buf0, TSt *buf1,
+                                                            const uint32_t *__restrict__ mask) {
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
+    const ProbState st = state[p];
+    if (!st.dirty || st.fresh) return;
+    const TSt *src = st.cur ? buf1 : buf0;
+    TSt *dst = st.cur ? buf0 : buf1;
+    const size_t row = ((size_t)p * g.H + y) * g.pitch;
+    const uint32_t *mr = mask + ((size_t)p * g.H + y) * g.mpitch;
+    for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) {
+        if (!((mr[e >> 5] >> (e & 31)) & 1u)) dst[row + e] = src[row + e];
+    }
+}
+
+__global__ void clear_dirty_kernel(Geom g, ProbState *state) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < g.P && !state[p].fresh) state[p].dirty = 0;
+}
+
+// self.pred_grid after run(): gather the current ping-pong buffer of every problem into the caller's
+// layout (VPint/SD_MRP.py:149-156; VPint2 reassembles (H, W, B) at VPint/VPint2.py:96-99,112-116).
+template <typename TSt, typename TOut>
+__global__ void __launch_bounds__(256) result_kernel(Geom g, const ProbState *__restrict__ state,
+                                                     const TSt *__restrict__ buf0, const TSt *__restrict__ buf1,
+                                                     TOut *__restrict__ out, Strides sd, int32_t *niter_out) {
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
+    const ProbState st = state[p];
+    const TSt *src = (st.cur ? buf1 : buf0) + ((size_t)p * g.H + y) * g.pitch;
+    for (int e = threadIdx.x; e < g.L; e += blockDim.x)
+        out[cell_offset(g, sd, p, y, e)] = (TOut)src[e];
+    if (niter_out && y == 0 && threadIdx.x == 0) niter_out[p] = st.iters_done;
+}
+
+}  // namespace
+
+#define VP_LAUNCH_CHECK()                         \
+    do {                                          \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) return e__;       \
+        if (launches) ++*launches;                \
+    } while (0)
+
+cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
+                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,
+                           uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
+                           int *counters, cudaStream_t st, int64_t *launches) {
+    const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+#define VP_PREP(TIN, TST)                                                                                  \
+    prepare_kernel<TIN, TST><<<grid, 256, 0, st>>>(g, (const TIN *)original, (const TIN *)pred0, fill_dev, \
+                                                   sd, (TST *)bufA, (TST *)bufB, mask, rowpart)
+    if (dtype == VPINT_F64 && storage == VPINT_F64) VP_PREP(double, double);
+    else if (dtype == VPINT_F32 && storage == VPINT_F64) VP_PREP(float, double);
+    else if (dtype == VPINT_F64 && storage == VPINT_F32) VP_PREP(double, float);
+    else VP_PREP(float, float);
+#undef VP_PREP
+    VP_LAUNCH_CHECK();
+    prepare_reduce_kernel<<<g.P, 256, 0, st>>>(g, rowpart, known0, known, state, counters);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
+                         int *counters, cudaStream_t st, int64_t *launches) {
+    const int64_t n_tiles = (int64_t)g.P * g.tiles_per_prob;
+    const unsigned grid = (unsigned)((n_tiles + 7) / 8);
+    tile_flag_kernel<<<grid, 256, 0, st>>>(g, mask, tile_flag, n_tiles);
+    VP_LAUNCH_CHECK();
+    tile_compact_kernel<<<1, 1024, 0, st>>>(g, tile_flag, tiles, tile_start, counters, n_tiles);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
+                              int64_t *launches) {
+    cudaError_t e = cudaMemsetAsync(n_active, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    init_state_kernel<<<(g.P + 127) / 128, 128, 0, st>>>(g, state, n_active, max_iter);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
+                                   const ProbState *state, double *sums, cudaStream_t st, int64_t *launches) {
+    reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, tile_start, state, sums);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches) {
+    decide_kernel<<<(a.g.P + 127) / 128, 128, 0, st>>>(a);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,
+                                 const uint32_t *mask, cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    if (storage == VPINT_F64)
+        restore_known_kernel<double><<<grid, 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], mask);
+    else
+        restore_known_kernel<float><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], mask);
+    VP_LAUNCH_CHECK();
+    clear_dirty_kernel<<<(g.P + 127) / 128, 128, 0, st>>>(g, state);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, void *const *buf, void *out,
+                          int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
+                          int64_t *launches) {
+    const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+#define VP_RES(TST, TOUT)                                                                                   \
+    result_kernel<TST, TOUT><<<grid, 256, 0, st>>>(g, state, (const TST *)buf[0], (const TST *)buf[1],      \
+                                                   (TOUT *)out, sd, niter_out)
+    if (storage == VPINT_F64 && dtype == VPINT_F64) VP_RES(double, double);
+    else if (storage == VPINT_F64 && dtype == VPINT_F32) VP_RES(double, float);
+    else if (storage == VPINT_F32 && dtype == VPINT_F64) VP_RES(float, double);
+    else VP_RES(float, float);
+#undef VP_RES
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace vpint

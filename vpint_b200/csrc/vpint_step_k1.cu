@@ -1,0 +1,210 @@
+// A4 + A5 (local part): one Jacobi sweep per launch straight from global memory ("k1" kernels).
+//   new = (sum_dir w_dir * P[nb_dir]) / neighbour_count, cells outside the grid read as 0
+//   (VPint/WP_MRP.py:291-319, VPint/SD_MRP.py:112-132, 357-385); clip before the restore
+//   (WP_MRP.py:322); only unknown cells are written, known cells were materialised once at load.
+//   Per tile: {sum |new-old|, sum old, NaN counts} over unknown owned cells (VPint/SD_MRP.py:139).
+// These kernels serve k_block == 1 and the 3-D path; the temporally blocked 2-D kernel lives in
+// vpint_step_tb.cu.
+#include "vpint_internal.cuh"
+
+namespace vpint {
+
+namespace {
+
+constexpr int kTileW2 = 128, kTileH2 = 32;   // 2-D k1 tile: 8 warps as 2 (columns) x 4 (rows), 2 cells x 8 rows per thread
+constexpr int kTileW3 = 256, kTileH3 = 8;    // 3-D k1 tile: 256 row-elements x 8 rows, 1 element x 8 rows per thread
+
+template <typename T>
+struct Acc {
+    double s_abs = 0.0, s_old = 0.0;
+    int c_abs = 0, c_old = 0;
+    __device__ __forceinline__ T commit(double nv, double old) {
+        const T stored = (T)nv;
+        const double d = fabs((double)stored - old);
+        if (d != d) ++c_abs; else s_abs += d;
+        if (old != old) ++c_old; else s_old += old;
+        return stored;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void write_partial(Acc<T> &a, double *partial_tile) {
+    __shared__ double scratch[kSumSlots * 8];
+    double v[kSumSlots] = {a.s_abs, a.s_old, (double)a.c_abs, (double)a.c_old};
+    block_sum<kSumSlots>(v, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kSumSlots; ++i) partial_tile[i] = v[i];
+    }
+}
+
+template <typename T, bool PLANES>
+__global__ void __launch_bounds__(256) jacobi2d_k1_kernel(const StepArgs a) {
+    const TileRef tile = a.tiles[blockIdx.x];
+    const int p = tile.p;
+    const ProbState st = a.state[p];
+    if (st.k_run == 0) return;
+    const Geom &g = a.g;
+    const size_t plane = (size_t)g.H * g.pitch;
+    const T *__restrict__ in = reinterpret_cast<const T *>(a.buf[st.cur]) + (size_t)p * plane;
+    T *__restrict__ out = reinterpret_cast<T *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const T *__restrict__ w_up = PLANES ? reinterpret_cast<const T *>(a.w[0]) + (size_t)p * plane : nullptr;
+    const T *__restrict__ w_rt = PLANES ? reinterpret_cast<const T *>(a.w[1]) + (size_t)p * plane : nullptr;
+    const T *__restrict__ w_dn = PLANES ? reinterpret_cast<const T *>(a.w[2]) + (size_t)p * plane : nullptr;
+    const T *__restrict__ w_lf = PLANES ? reinterpret_cast<const T *>(a.w[3]) + (size_t)p * plane : nullptr;
+    const double gamma = PLANES ? 0.0 : a.gamma[p];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xw = tile.x0 + (warp & 1) * 64;
+    const int x = xw + 2 * lane;
+    const int yb = tile.y0 + (warp >> 1) * 8;
+    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
+    Acc<T> acc;
+    if (xw < g.L) {
+        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
+        const int mp64 = g.mpitch >> 1;
+        for (int r = 0; r < 8; ++r) {
+            const int y = yb + r;
+            if (y >= y_lim) break;
+            const uint64_t bits = m64[(size_t)y * mp64];
+            const unsigned mb = (unsigned)(bits >> (2 * lane)) & 3u;
+            if (mb == 0) continue;
+            const size_t row = (size_t)y * g.pitch;
+            const int yg = y + g.row_offset;
+            const bool has_up = yg > 0, has_dn = yg < g.global_H - 1;
+            double c0, c1, u0 = 0.0, u1 = 0.0, d0 = 0.0, d1 = 0.0, lf = 0.0, rt = 0.0;
+            load2(in + row + x, c0, c1);                       // padding columns hold 0
+            if (has_up) load2(in + row - g.pitch + x, u0, u1);
+            if (has_dn) load2(in + row + g.pitch + x, d0, d1);
+            if (x > 0) lf = (double)in[row + x - 1];
+            if (x + 2 < g.L) rt = (double)in[row + x + 2];
+            double n0, n1;
+            if (PLANES) {
+                double wu0, wu1, wr0, wr1, wd0, wd1, wl0, wl1;
+                load2(w_up + row + x, wu0, wu1);
+                load2(w_rt + row + x, wr0, wr1);
+                load2(w_dn + row + x, wd0, wd1);
+                load2(w_lf + row + x, wl0, wl1);
+                n0 = fma(lf, wl0, fma(d0, wd0, fma(c1, wr0, u0 * wu0)));
+                n1 = fma(c0, wl1, fma(d1, wd1, fma(rt, wr1, u1 * wu1)));
+            } else {
+                n0 = fma(lf, gamma, fma(d0, gamma, fma(c1, gamma, u0 * gamma)));
+                n1 = fma(c0, gamma, fma(d1, gamma, fma(rt, gamma, u1 * gamma)));
+            }
+            const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+            const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+            const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
+            n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
+            n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+            if (n0 > a.clip) n0 = a.clip;
+            if (n1 > a.clip) n1 = a.clip;
+            if (mb & 1u) out[row + x] = acc.commit(n0, c0);
+            if (mb & 2u) out[row + x + 1] = acc.commit(n1, c1);
+        }
+    }
+    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+}
+
+// 3-D: rows are W*T elements with T fastest; element e of a row is (j, t) = (e / T, e % T).
+// Value slots 4 / 5 are the t+1 / t-1 neighbours (VPint/SD_MRP.py:372-378).  Plane mode keeps the
+// reference's pairing: the temporal weight multiplies the t+1 value only where t > 0 and the t-1 value
+// only where t < T-1 (VPint/WP_MRP.py:1344-1353 vs 1406-1412).  Spatial planes are (H, W): features are
+// static in time.
+template <typename T, bool PLANES>
+__global__ void __launch_bounds__(256) jacobi3d_k1_kernel(const StepArgs a) {
+    const TileRef tile = a.tiles[blockIdx.x];
+    const int p = tile.p;
+    const ProbState st = a.state[p];
+    if (st.k_run == 0) return;
+    const Geom &g = a.g;
+    const size_t plane = (size_t)g.H * g.pitch;
+    const size_t wplane = (size_t)g.H * g.wpitch;
+    const T *__restrict__ in = reinterpret_cast<const T *>(a.buf[st.cur]) + (size_t)p * plane;
+    T *__restrict__ out = reinterpret_cast<T *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const double gamma = PLANES ? 0.0 : a.gamma[p];
+    const double tau = PLANES ? 0.0 : a.tau[p];
+    const int e = tile.x0 + threadIdx.x;
+    const int y_lim = min(tile.y0 + kTileH3, g.own_row0 + g.own_rows);
+    Acc<T> acc;
+    if (e < g.L) {
+        const int j = e / g.T, t = e - j * g.T;
+        const uint32_t *mrow = a.mask + (size_t)p * g.H * g.mpitch + (e >> 5);
+        const int ncx = 6 - (j == 0 ? 1 : 0) - (j == g.W - 1 ? 1 : 0) - (t == 0 ? 1 : 0) - (t == g.T - 1 ? 1 : 0);
+        for (int y = tile.y0; y < y_lim; ++y) {
+            if (!((mrow[(size_t)y * g.mpitch] >> (e & 31)) & 1u)) continue;
+            const size_t row = (size_t)y * g.pitch;
+            const int yg = y + g.row_offset;
+            const double c = (double)in[row + e];
+            const double up = (yg > 0) ? (double)in[row - g.pitch + e] : 0.0;
+            const double dn = (yg < g.global_H - 1) ? (double)in[row + g.pitch + e] : 0.0;
+            const double rt = (j < g.W - 1) ? (double)in[row + e + g.T] : 0.0;
+            const double lf = (j > 0) ? (double)in[row + e - g.T] : 0.0;
+            const double nx = (t < g.T - 1) ? (double)in[row + e + 1] : 0.0;
+            const double pv = (t > 0) ? (double)in[row + e - 1] : 0.0;
+            double nv;
+            if (PLANES) {
+                const size_t wi = (size_t)p * wplane + (size_t)y * g.wpitch + j;
+                const double wu = (double)reinterpret_cast<const T *>(a.w[0])[wi];
+                const double wr = (double)reinterpret_cast<const T *>(a.w[1])[wi];
+                const double wd = (double)reinterpret_cast<const T *>(a.w[2])[wi];
+                const double wl = (double)reinterpret_cast<const T *>(a.w[3])[wi];
+                const double wt = (double)reinterpret_cast<const T *>(a.w[4])[wi];
+                const double w4 = (t > 0) ? wt : 0.0, w5 = (t < g.T - 1) ? wt : 0.0;
+                nv = fma(pv, w5, fma(nx, w4, fma(lf, wl, fma(dn, wd, fma(rt, wr, up * wu)))));
+            } else {
+                nv = fma(pv, tau, fma(nx, tau, fma(lf, gamma, fma(dn, gamma, fma(rt, gamma, up * gamma)))));
+            }
+            const int nc = ncx - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+            nv = nv / (double)nc;
+            out[row + e] = acc.commit(nv, c);
+        }
+    }
+    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+}
+
+}  // namespace
+
+void k1_tile_shape(int ndim, int *th, int *tw) {
+    *th = (ndim == 2) ? kTileH2 : kTileH3;
+    *tw = (ndim == 2) ? kTileW2 : kTileW3;
+}
+
+#define VP_LAUNCH_CHECK()                         \
+    do {                                          \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) return e__;       \
+        if (launches) ++*launches;                \
+    } while (0)
+
+cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
+                          int64_t *launches) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)n_tiles;
+    const bool planes = (weight_mode == VPINT_W_PLANES);
+    if (storage == VPINT_F64) {
+        if (planes) jacobi2d_k1_kernel<double, true><<<grid, 256, 0, st>>>(a);
+        else jacobi2d_k1_kernel<double, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (planes) jacobi2d_k1_kernel<float, true><<<grid, 256, 0, st>>>(a);
+        else jacobi2d_k1_kernel<float, false><<<grid, 256, 0, st>>>(a);
+    }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_step3d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
+                          int64_t *launches) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)n_tiles;
+    const bool planes = (weight_mode == VPINT_W_PLANES);
+    if (storage == VPINT_F64) {
+        if (planes) jacobi3d_k1_kernel<double, true><<<grid, 256, 0, st>>>(a);
+        else jacobi3d_k1_kernel<double, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (planes) jacobi3d_k1_kernel<float, true><<<grid, 256, 0, st>>>(a);
+        else jacobi3d_k1_kernel<float, false><<<grid, 256, 0, st>>>(a);
+    }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace vpint

@@ -1,0 +1,275 @@
+"""Device-side driver: owns the workspace (a torch CUDA byte tensor), marshals
+tensors to the C ABI and returns torch tensors.  torch is plumbing only (device
+memory, streams); every kernel lives in libvpint_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as N
+from .errors import VPintError
+
+_DTYPE_CODE = {"float64": N.F64, "float32": N.F32}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise VPintError("vpint_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _code(t):
+    torch = _torch()
+    if t.dtype == torch.float64:
+        return N.F64
+    if t.dtype == torch.float32:
+        return N.F32
+    raise VPintError("unsupported tensor dtype %s (float32 / float64 only)" % t.dtype)
+
+
+def _i64(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def to_device(x, device, dtype=None, non_blocking=False):
+    """numpy array / torch tensor -> CUDA tensor (no copy if already there)."""
+    torch = _torch()
+    if isinstance(x, np.ndarray):
+        if not x.flags.writeable:
+            x = x.copy()
+        x = torch.from_numpy(x)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x.to(device, non_blocking=non_blocking)
+
+
+class Solver:
+    """One batched solve: ``nprob`` independent problems of identical shape.
+
+    Arrays are addressed through a two-level problem index (outer, inner) so
+    that e.g. a ``(N, H, W, B)`` VPint2 batch is read in place with
+    outer = patch and inner = band.  Tensors handed to :meth:`load`,
+    :meth:`weights` and :meth:`result` are viewed as
+    ``(outer, inner, H, W[, T | F])``.
+    """
+
+    def __init__(self, ndim, nprob, H, W, T=1, *, nprob_inner=1, storage="float64", planes=True,
+                 k_block=0, shard=None, device=None):
+        self.lib = N.load_library()
+        self.torch = _torch()
+        self.device = require_cuda(device)
+        self.ndim, self.nprob, self.nprob_inner = int(ndim), int(nprob), int(nprob_inner)
+        self.H, self.W, self.T = int(H), int(W), int(T)
+        self.storage = storage
+        self.planes = bool(planes)
+        d = N.Desc()
+        d.ndim, d.nprob, d.nprob_inner = self.ndim, self.nprob, self.nprob_inner
+        d.H, d.W, d.T = self.H, self.W, self.T
+        d.storage = _DTYPE_CODE[storage]
+        d.weight_mode = N.W_PLANES if planes else N.W_SCALAR
+        d.k_block = int(k_block)
+        if shard is not None:
+            d.global_H, d.row_offset, d.own_row0, d.own_rows = [int(v) for v in shard]
+        self._h = C.c_void_p()
+        N.check(self.lib, self.lib.vpint_solver_create(C.byref(d), C.byref(self._h)), "vpint_solver_create")
+        nbytes = self.lib.vpint_solver_workspace_bytes(self._h)
+        with self.torch.cuda.device(self.device):
+            self.workspace = self.torch.empty(nbytes + 256, dtype=self.torch.uint8, device=self.device)
+        base = self.workspace.data_ptr()
+        self._ws_ptr = (base + 255) // 256 * 256
+        N.check(self.lib, self.lib.vpint_solver_bind(self._h, C.c_void_p(self._ws_ptr), C.c_size_t(nbytes)),
+                "vpint_solver_bind")
+        self.workspace_bytes = int(nbytes)
+        self._keep = []
+        self.delta = None
+        self.max_iter = 0
+
+    # -- helpers -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.vpint_solver_destroy(self._h)
+            self._h = None
+        self.workspace = None
+        self._keep = []
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _strides(self, t, tail):
+        """Element strides {outer, inner, row, column, last} of ``t`` whose shape is
+        ``(nprob,) + tail`` or ``(outer, inner) + tail``; ``tail`` is (H, W) or (H, W, n)."""
+        outer = self.nprob // self.nprob_inner
+        shape = tuple(t.shape)
+        if shape == (self.nprob,) + tail:
+            ps = (t.stride(0) * self.nprob_inner, t.stride(0))
+            rest = [t.stride(i) for i in range(1, t.dim())]
+        elif shape == (outer, self.nprob_inner) + tail:
+            ps = (t.stride(0), t.stride(1))
+            rest = [t.stride(i) for i in range(2, t.dim())]
+        else:
+            raise VPintError("tensor shape %s does not match the solver layout %s" % (shape, (self.nprob,) + tail))
+        if len(rest) == 2:
+            rest.append(0)
+        return [ps[0], ps[1]] + rest
+
+    def _cell_tail(self):
+        return (self.H, self.W) if self.ndim == 2 else (self.H, self.W, self.T)
+
+    # -- C ABI calls ---------------------------------------------------------
+    def load(self, original, pred0=None, fill=None):
+        """Stage the start state.  ``original``: NaN = unknown.  Either ``pred0``
+        (same layout) or ``fill`` (one value per problem for the unknown cells)."""
+        ov = original
+        st = self._strides(ov, self._cell_tail())
+        pptr = None
+        if pred0 is not None:
+            pv = pred0 if pred0.dtype == ov.dtype else pred0.to(ov.dtype)
+            if tuple(pv.shape) != tuple(ov.shape):
+                raise VPintError("pred0 and original must have the same shape")
+            if self._strides(pv, self._cell_tail()) != st:
+                pv = pv.contiguous()
+                ov = ov.contiguous()
+                st = self._strides(ov, self._cell_tail())
+            self._keep.append(pv)
+            pptr = C.c_void_p(pv.data_ptr())
+            fptr = None
+        else:
+            f = np.ascontiguousarray(np.asarray(fill, dtype=np.float64).reshape(-1))
+            if f.size != self.nprob:
+                raise VPintError("fill needs one value per problem")
+            fptr = f.ctypes.data_as(C.POINTER(C.c_double))
+        self._keep.append(ov)
+        N.check(self.lib, self.lib.vpint_solver_load(self._h, C.c_void_p(ov.data_ptr()), pptr, fptr, _code(ov),
+                                                      _i64(st), self._stream()), "vpint_solver_load")
+        return self
+
+    def weights(self, feat, method="exact", clamp=False, min_gamma=0.0, max_gamma=math.inf):
+        """feat viewed as (outer, inner, H, W, F)."""
+        if method not in N.METHODS:
+            raise VPintError("Invalid weight prediction method: " + str(method))
+        F = int(feat.shape[-1])
+        fv = feat
+        st = self._strides(fv, (self.H, self.W, F))
+        self._keep.append(fv)
+        N.check(self.lib, self.lib.vpint_solver_weights(self._h, C.c_void_p(fv.data_ptr()), _code(fv), _i64(st), int(F),
+                                                         N.METHODS[method], int(bool(clamp)), float(min_gamma),
+                                                         float(max_gamma), self._stream()), "vpint_solver_weights")
+        return self
+
+    def discounts(self, gamma, tau=None):
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gamma, dtype=np.float64), (self.nprob,)))
+        gp = g.ctypes.data_as(C.POINTER(C.c_double))
+        tp = None
+        if tau is not None:
+            t = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (self.nprob,)))
+            tp = t.ctypes.data_as(C.POINTER(C.c_double))
+        N.check(self.lib, self.lib.vpint_solver_set_discounts(self._h, gp, tp), "vpint_solver_set_discounts")
+        return self
+
+    def _params(self, max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk):
+        prm = N.RunParams()
+        prm.max_iter = int(max_iter)
+        prm.auto_terminate = int(bool(auto_terminate))
+        prm.threshold = float(threshold)
+        prm.clip_val = float(clip_val)
+        prm.loop_mode = int(loop_mode)
+        prm.chunk = int(chunk)
+        self.max_iter = int(max_iter)
+        if track_delta and max_iter > 0:
+            self.delta = self.torch.zeros((self.nprob, int(max_iter)), dtype=self.torch.float64, device=self.device)
+            prm.delta_out = self.delta.data_ptr()
+        else:
+            self.delta = None
+            prm.delta_out = None
+        return prm
+
+    def run(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False,
+            loop_mode=N.LOOP_CHUNKED, chunk=0):
+        prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk)
+        N.check(self.lib, self.lib.vpint_solver_run(self._h, C.byref(prm), self._stream()), "vpint_solver_run")
+        return self
+
+    def begin_run(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False):
+        prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, N.LOOP_CHUNKED, 0)
+        N.check(self.lib, self.lib.vpint_solver_begin_run(self._h, C.byref(prm), self._stream()), "vpint_solver_begin_run")
+
+    def step_begin(self):
+        N.check(self.lib, self.lib.vpint_solver_step_begin(self._h, self._stream()), "vpint_solver_step_begin")
+
+    def step_profile(self):
+        """step_begin that returns the stencil kernel's duration in ms (CUDA events on this stream)."""
+        ms = C.c_float(0.0)
+        N.check(self.lib, self.lib.vpint_solver_step_profile(self._h, self._stream(), C.byref(ms)),
+                "vpint_solver_step_profile")
+        return float(ms.value)
+
+    def step_end(self):
+        N.check(self.lib, self.lib.vpint_solver_step_end(self._h, self._stream()), "vpint_solver_step_end")
+
+    def result(self, out=None, dtype=None):
+        """Current state of every problem gathered into ``out`` (same layouts as
+        :meth:`load` accepts).  Returns (out, sweeps[int32, nprob])."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty((self.nprob,) + self._cell_tail(), dtype=dtype or torch.float64, device=self.device)
+        st = self._strides(out, self._cell_tail())
+        niter = torch.zeros(self.nprob, dtype=torch.int32, device=self.device)
+        N.check(self.lib, self.lib.vpint_solver_result(self._h, C.c_void_p(out.data_ptr()), _code(out), _i64(st),
+                                                        C.c_void_p(niter.data_ptr()), self._stream()), "vpint_solver_result")
+        return out, niter
+
+    # -- introspection -------------------------------------------------------
+    @property
+    def active_tiles(self):
+        return int(self.lib.vpint_solver_active_tiles(self._h))
+
+    @property
+    def total_tiles(self):
+        return int(self.lib.vpint_solver_total_tiles(self._h))
+
+    @property
+    def launches(self):
+        return int(self.lib.vpint_solver_launches(self._h))
+
+    @property
+    def k_block(self):
+        return int(self.lib.vpint_solver_k_block(self._h))
+
+    def sums_tensor(self):
+        """[nprob][k_block][4] fp64 per-sweep local sums of the last step_begin (a view
+        of workspace memory, for the all-reduce of a row-sharded solve)."""
+        n = int(self.lib.vpint_solver_sums_count(self._h))
+        ptr = int(self.lib.vpint_solver_sums_ptr(self._h))
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off:off + n * 8].view(self.torch.float64).view(self.nprob, -1, 4)
+
+    def state_tensor(self, which):
+        """Ping-pong buffer ``which`` as a [nprob][H][pitch] tensor (workspace view)."""
+        ptr = int(self.lib.vpint_solver_state_ptr(self._h, int(which)))
+        pitch = int(self.lib.vpint_row_pitch(self.W * self.T))
+        dt = self.torch.float64 if self.storage == "float64" else self.torch.float32
+        esz = 8 if self.storage == "float64" else 4
+        off = ptr - self.workspace.data_ptr()
+        n = self.nprob * self.H * pitch
+        return self.workspace[off:off + n * esz].view(dt).view(self.nprob, self.H, pitch)
+
+    def active_count(self):
+        ptr = int(self.lib.vpint_solver_active_ptr(self._h))
+        off = ptr - self.workspace.data_ptr()
+        return int(self.workspace[off:off + 4].view(self.torch.int32).item())

@@ -1,0 +1,245 @@
+"""VPint2 cloud-removal wrapper: drop-in ``VPint2_interpolator``.
+
+Mirrors VPint/VPint2.py.  The reference splits an (H, W, B) scene into B
+independent ``WP_SMRP`` problems and forks one process per band
+(VPint/VPint2.py:58-106); here all bands -- and, through :func:`run_patches`, all
+bands of many patches -- are ONE batched device solve with per-problem stopping.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import Solver, require_cuda, to_device
+from .errors import VPintError
+from .wp import wp_run_options
+
+
+def _band_fill_values(target):
+    """Per-band start value of the unknown cells: ``WP_SMRP(target[:, :, b], ...)``
+    initialises them with ``np.nanmean`` of the band IN THE BAND'S dtype
+    (VPint/VPint2.py:105 -> VPint/MRP.py:73-77).  target: (..., H, W, B)."""
+    lead = target.shape[:-3]
+    B = target.shape[-1]
+    flat = target.reshape((-1,) + target.shape[-3:])
+    out = np.empty((flat.shape[0], B), dtype=np.float64)
+    for n in range(flat.shape[0]):
+        for b in range(B):
+            out[n, b] = np.nanmean(flat[n, :, :, b])
+    return out.reshape(lead + (B,))
+
+
+def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k_block, dev, out, fill):
+    """solve_bands for torch inputs (CPU, ideally pinned, or CUDA) of shape (N, H, W, B):
+    asynchronous H2D, one batched solve, asynchronous D2H into ``out`` when given."""
+    import torch
+    N, H, W, B = target.shape
+    if fill is None:
+        fill = _band_fill_values(target.cpu().numpy()).reshape(-1)
+    solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
+                    k_block=(0 if k_block is None else k_block), device=dev)
+    try:
+        t_dev = target.to(dev, non_blocking=True)
+        f_dev = features.to(dev, non_blocking=True)
+        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)
+        solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
+                       clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
+        solver.run(opts["iterations"], auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
+                   clip_val=opts["clip_val"])
+        if out_layout == "bhw":
+            res_dev = torch.empty((N, B, H, W), dtype=torch.float64, device=dev)
+            _, niter = solver.result(out=res_dev)
+        else:
+            res_dev = torch.empty((N, H, W, B), dtype=out_dtype, device=dev)
+            _, niter = solver.result(out=res_dev.permute(0, 3, 1, 2))
+        if out is not None:
+            out.copy_(res_dev, non_blocking=True)
+            sweeps = niter.cpu()          # synchronises the stream: `out` is complete after this
+            res = out
+        else:
+            res = res_dev.cpu()
+            sweeps = niter.cpu()
+    finally:
+        solver.close()
+    return res, sweeps.to(torch.int64).view(N, B)
+
+
+def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw", storage="float64",
+                k_block=None, device=None, return_sweeps=False, out=None, fill=None):
+    """All bands of one scene (H, W, B) or of a stack of patches (N, H, W, B) as one
+    batched solve.  ``target`` / ``features`` are the interpolator's stored arrays
+    (DTYPE, NaN = cloud).  Returns float64 (..., B, H, W) for out_layout 'bhw' or
+    ``out_dtype`` (..., H, W, B) for 'hwb'.
+
+    torch tensors (e.g. pinned host buffers) of shape (N, H, W, B) are accepted too:
+    then copies are asynchronous, ``out`` (a preallocated, ideally pinned, tensor)
+    receives the result and torch tensors are returned."""
+    dev = require_cuda(device)
+    import torch
+    if isinstance(target, torch.Tensor):
+        if opts["iterations"] == 0:
+            raise VPintError("iterations=0 is handled by the NumPy entry points")
+        tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {np.dtype(np.float32): torch.float32}.get(
+            np.dtype(out_dtype), torch.float64)
+        res, sweeps = _solve_bands_torch(target, features, opts, out_layout, tdt, storage, k_block, dev, out, fill)
+        return (res, sweeps) if return_sweeps else res
+    single = (target.ndim == 3)
+    tgt = target[None] if single else target
+    fts = features[None] if single else features
+    if tgt.dtype not in (np.float32, np.float64):
+        tgt = tgt.astype(np.float64)
+        fts = fts.astype(np.float64)
+    N, H, W, B = tgt.shape
+    max_iter = opts["iterations"]
+    if max_iter == 0:
+        # the reference returns each band's initial pred_grid (NaN -> band mean)
+        fill = _band_fill_values(tgt)
+        res = np.where(np.isnan(tgt), fill[:, None, None, :].astype(tgt.dtype), tgt)
+        if out_layout == "bhw":
+            res = np.ascontiguousarray(np.moveaxis(res, -1, 1)).astype(tgt.dtype)
+        else:
+            res = res.astype(out_dtype)
+        res = res[0] if single else res
+        return (res, np.zeros((N, B), dtype=np.int64)[0 if single else slice(None)]) if return_sweeps else res
+    fill = _band_fill_values(tgt)
+    solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
+                    k_block=(0 if k_block is None else k_block), device=dev)
+    try:
+        t_dev = to_device(np.ascontiguousarray(tgt), dev)                 # (N, H, W, B) as stored
+        f_dev = to_device(np.ascontiguousarray(fts), dev)
+        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill.reshape(-1))     # view (N, B, H, W): no transpose copy
+        solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
+                       clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
+        solver.run(max_iter, auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
+                   clip_val=opts["clip_val"])
+        if out_layout == "bhw":
+            out = torch.empty((N, B, H, W), dtype=torch.float64, device=dev)
+            _, niter = solver.result(out=out)
+        else:
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}.get(np.dtype(out_dtype))
+            out = torch.empty((N, H, W, B), dtype=tdt or torch.float64, device=dev)
+            _, niter = solver.result(out=out.permute(0, 3, 1, 2))
+        res = out.cpu().numpy()
+        if out_layout == "hwb" and res.dtype != np.dtype(out_dtype):
+            res = res.astype(out_dtype)
+        sweeps = niter.cpu().numpy().astype(np.int64).reshape(N, B)
+    finally:
+        solver.close()
+    if single:
+        res, sweeps = res[0], sweeps[0]
+    return (res, sweeps) if return_sweeps else res
+
+
+class VPint2_interpolator():
+    """Reference: VPint/VPint2.py:12-150.  Constructor semantics are unchanged
+    (dtype cast, optional axis move, clipping, cloud mask -> NaN on every band,
+    optional cloud buffering); only the per-pixel Python loops are vectorised."""
+
+    def __init__(self, target, features, mask=None, buffer_mask=False, mask_buffer_size=5, mask_buffer_passes=1,
+                 bands_first=False, clip_target=None, clip_features=None, dtype=None, **kwargs):
+        assert target.shape == features.shape
+        assert len(target.shape) == 3
+        assert len(features.shape) == 3
+
+        self.DTYPE = dtype if dtype is not None else np.float32
+        target = target.astype(self.DTYPE)
+        features = features.astype(self.DTYPE)
+        if bands_first:
+            target = np.moveaxis(target, 0, -1)
+            features = np.moveaxis(features, 0, -1)
+
+        # clip_* : int / float = upper bound only, otherwise (min, max)   (VPint/VPint2.py:30-41)
+        if clip_target is not None:
+            if type(clip_target) == type(2) or type(clip_target) == type(2.1):
+                target = np.clip(target, a_min=-np.inf, a_max=clip_target)
+            else:
+                target = np.clip(target, a_min=clip_target[0], a_max=clip_target[1])
+        if clip_features is not None:
+            if type(clip_features) == type(2) or type(clip_features) == type(2.1):
+                features = np.clip(features, a_min=-np.inf, a_max=clip_features)
+            else:
+                features = np.clip(features, a_min=clip_features[0], a_max=clip_features[1])
+
+        if mask is not None:
+            assert len(mask.shape) == 2
+            assert mask.shape[0] == target.shape[0]
+            assert mask.shape[1] == target.shape[1]
+            self.target = self.apply_mask(target, mask, **kwargs).astype(self.DTYPE)
+        else:
+            self.target = target.astype(self.DTYPE)
+
+        if buffer_mask:
+            self.target = self.buffer_clouds(self.target, buffer_size=mask_buffer_size, passes=mask_buffer_passes)
+
+        self.features = features.astype(self.DTYPE)
+
+    def run(self, **kwargs):
+        """All bands in one batched device solve (the reference forks one process per
+        band, VPint/VPint2.py:58-101).  Returns float64 (H, W, B), a strided view of a
+        (B, H, W) array exactly like the reference's swapaxes result."""
+        opts = wp_run_options(**kwargs)
+        pred_bhw = solve_bands(self.target, self.features, opts, out_layout="bhw")
+        return pred_bhw.swapaxes(0, 2).swapaxes(0, 1)
+
+    def VPint2_single(self, pred_dict, grids, band, **kwargs):
+        """Kept for API compatibility (VPint/VPint2.py:104-106)."""
+        from .wp import WP_SMRP
+        interp = WP_SMRP(grids[0], grids[1])
+        pred_dict[band] = interp.run(**kwargs)
+
+    def run_serial(self, **kwargs):
+        """Same results as :meth:`run`, returned as a DTYPE (H, W, B) array
+        (VPint/VPint2.py:109-119)."""
+        opts = wp_run_options(**kwargs)
+        return solve_bands(self.target, self.features, opts, out_dtype=self.DTYPE, out_layout="hwb")
+
+    def apply_mask(self, target, mask, threshold=0.2):
+        """mask > threshold -> NaN on every band (VPint/VPint2.py:122-132), vectorised."""
+        target_cloudy = target.copy()
+        target_cloudy[np.asarray(mask) > threshold, :] = np.nan
+        return target_cloudy
+
+    def buffer_clouds(self, target, buffer_size=5, passes=1):
+        """Dilate the NaN footprint (VPint/VPint2.py:135-150), vectorised.  Each pixel
+        with a NaN in any band blanks rows [i-b, i+b) and columns [j-b, min(H, j+b)) --
+        the reference bounds the COLUMN range by shape[0] (:146); kept."""
+        img = target.copy()
+        H, W = target.shape[0], target.shape[1]
+        b = int(buffer_size)
+        for _ in range(0, passes):
+            new_img = target.copy()
+            cloudy = np.isnan(img).any(axis=2)
+            grown = np.zeros((H, W), dtype=bool)
+            if b > 0:
+                pad = np.zeros((H + 2 * b, W + 2 * b), dtype=bool)
+                pad[b:b + H, b:b + W] = cloudy
+                # output (y, x) is covered by source (i, j) iff i-b <= y < i+b and j-b <= x < j+b
+                for dy in range(-b + 1, b + 1):
+                    rows = pad[b + dy:b + dy + H, :]
+                    for dx in range(-b + 1, b + 1):
+                        grown |= rows[:, b + dx:b + dx + W]
+                if H < W:
+                    grown[:, H:] = False
+            new_img[grown, :] = np.nan
+            img = new_img
+        return img
+
+
+def run_patches(interpolators, serial=False, **kwargs):
+    """Run many ``VPint2_interpolator`` objects of one shape as ONE batched solve
+    (problem = (patch, band)).  Equivalent to ``[vp.run(**kwargs) for vp in
+    interpolators]`` (or ``run_serial`` with ``serial=True``)."""
+    if not interpolators:
+        return []
+    opts = wp_run_options(**kwargs)
+    shape, dt = interpolators[0].target.shape, interpolators[0].target.dtype
+    for vp in interpolators:
+        if vp.target.shape != shape or vp.target.dtype != dt:
+            raise VPintError("run_patches needs interpolators of one shape and dtype")
+    tgt = np.stack([vp.target for vp in interpolators])
+    fts = np.stack([vp.features for vp in interpolators])
+    if serial:
+        res = solve_bands(tgt, fts, opts, out_dtype=interpolators[0].DTYPE, out_layout="hwb")
+        return [res[i] for i in range(len(interpolators))]
+    res = solve_bands(tgt, fts, opts, out_layout="bhw")
+    return [res[i].swapaxes(0, 2).swapaxes(0, 1) for i in range(len(interpolators))]

@@ -1,0 +1,206 @@
+"""Feature-weighted interpolators: drop-in ``WP_SMRP`` / ``WP_STMRP``.
+
+Mirrors the public surface of VPint/WP_MRP.py for the propagation path: the
+constructors, every ``run`` keyword and its default, the returned arrays and the
+side effects on the object.  Weight precomputation, the Jacobi loop and the
+stopping test run on the B200 through libvpint_b200.so; options that are not on
+the device path yet raise :class:`VPintError` instead of being ignored.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .base import SMRP, STMRP
+from .errors import VPintError
+from .solve import propagate
+
+SPATIAL_CAP = 5000     # VPint/WP_MRP.py:112-115
+TEMPORAL_CAP = 10000   # VPint/WP_MRP.py:1300-1303
+
+_DEVICE_METHODS = ("exact", "cosine_similarity", "exact_inverse")
+
+
+def wp_run_options(iterations=-1, method='exact', auto_terminate=True, auto_terminate_threshold=1e-4,
+                   track_delta=False,
+                   confidence=False, confidence_model=None,
+                   save_gif=False, gif_path="convergence.gif", gif_ms_per_frame=100, store_gif_source=False,
+                   gif_size_up=20, gif_clip_iter=100,
+                   auto_adapt=False, auto_adaptation_epochs=100, auto_adaptation_proportion=0.5,
+                   auto_adaptation_strategy='random', auto_adaptation_max_iter=-1,
+                   auto_adaptation_subsample_strategy='max_contrast',
+                   auto_adaptation_verbose=False,
+                   prioritise_identity=False, priority_intensity=1, known_value_bias=0,
+                   resistance=False, epsilon=0.01, mu=1.0,
+                   clip_val=np.inf):
+    """Normalise the keyword arguments of ``WP_SMRP.run`` (same names and defaults as
+    VPint/WP_MRP.py:82-91; an unknown keyword raises TypeError just as forwarding it to
+    the reference's ``run`` would) and reject what the device path cannot do."""
+    if iterations > -1:          # VPint/WP_MRP.py:112-115
+        auto_terminate = False
+    else:
+        iterations = SPATIAL_CAP
+    if save_gif or store_gif_source:
+        raise VPintError("save_gif / store_gif_source record every sweep on the host and are not supported "
+                         "by the device path")
+    if auto_adapt:
+        raise VPintError("auto_adapt (host-side hyper-parameter search) is not supported by the device path yet")
+    if prioritise_identity or resistance:
+        raise VPintError("prioritise_identity / resistance are not supported by the device path yet")
+    if method not in _DEVICE_METHODS:
+        if method == 'predict':
+            raise VPintError("method='predict' needs a host-side sklearn model and is not supported by the "
+                             "device path; use 'exact', 'cosine_similarity' or 'exact_inverse'")
+        raise VPintError("Invalid weight prediction method: " + str(method))
+    return dict(iterations=iterations, method=method, auto_terminate=auto_terminate,
+                threshold=auto_terminate_threshold, track_delta=track_delta, clip_val=clip_val)
+
+
+class WP_SMRP(SMRP):
+    """2-D value propagation with per-direction weights derived from a feature
+    grid (reference: VPint/WP_MRP.py:13-393)."""
+
+    def __init__(self, grid, feature_grid, model=None, init_strategy='mean', max_gamma=np.inf, min_gamma=0,
+                 mask=None, clip_val=np.inf):
+        # shape rules of VPint/WP_MRP.py:55-79
+        if grid.shape[0] != feature_grid.shape[0] or grid.shape[1] != feature_grid.shape[1]:
+            raise VPintError("Target and feature grids have different shapes: " + str(grid.shape) + " and "
+                             + str(feature_grid.shape))
+        if len(grid.shape) > 2:
+            if grid.shape[2] == 1:
+                grid = grid[:, :, 0]
+            else:
+                raise VPintError("Input grid needs to be two-dimensional, got " + str(grid.shape))
+        super().__init__(grid, init_strategy=init_strategy, mask=mask)
+        if len(feature_grid.shape) == 3:
+            self.feature_grid = feature_grid.copy().astype(float)
+        elif len(feature_grid.shape) == 2:
+            self.feature_grid = feature_grid.copy().astype(float).reshape(
+                (feature_grid.shape[0], feature_grid.shape[1], 1))
+        else:
+            raise VPintError("Improper feature dimensions; expected 2 or 3, got " + str(len(feature_grid.shape)))
+        self.model = model
+        self.max_gamma = max_gamma
+        self.min_gamma = min_gamma
+        self.clip_val = clip_val
+        self._run_state = False
+        self._run_method = "predict"
+
+    def run(self, iterations=-1, method='exact', auto_terminate=True, auto_terminate_threshold=1e-4,
+            track_delta=False,
+            confidence=False, confidence_model=None,
+            save_gif=False, gif_path="convergence.gif", gif_ms_per_frame=100, store_gif_source=False,
+            gif_size_up=20, gif_clip_iter=100,
+            auto_adapt=False, auto_adaptation_epochs=100, auto_adaptation_proportion=0.5,
+            auto_adaptation_strategy='random', auto_adaptation_max_iter=-1,
+            auto_adaptation_subsample_strategy='max_contrast',
+            auto_adaptation_verbose=False,
+            prioritise_identity=False, priority_intensity=1, known_value_bias=0,
+            resistance=False, epsilon=0.01, mu=1.0,
+            clip_val=np.inf):
+        """Same contract as VPint/WP_MRP.py:82-393.
+
+        Device path: ``method`` in {'exact', 'cosine_similarity', 'exact_inverse'},
+        ``iterations``, ``auto_terminate``(+threshold), ``track_delta``, ``clip_val``.
+        ``confidence`` / ``confidence_model`` are accepted and unused, as in the
+        reference.  Not available here (VPintError): ``method='predict'`` (needs the
+        caller's sklearn model on the host), GIF recording, ``auto_adapt``,
+        ``prioritise_identity`` / ``known_value_bias`` and ``resistance``.
+        """
+        opts = wp_run_options(iterations=iterations, method=method, auto_terminate=auto_terminate,
+                              auto_terminate_threshold=auto_terminate_threshold, track_delta=track_delta,
+                              save_gif=save_gif, store_gif_source=store_gif_source, auto_adapt=auto_adapt,
+                              prioritise_identity=prioritise_identity, resistance=resistance, clip_val=clip_val)
+        iterations, auto_terminate = opts["iterations"], opts["auto_terminate"]
+
+        self.clip_val = clip_val
+        if method == 'exact':
+            # the reference replaces zeros in self.feature_grid in place (VPint/WP_MRP.py:143-145)
+            flat = self.feature_grid.reshape(self.feature_grid.size)
+            flat[flat == 0] = 0.01
+        delta_vec = np.zeros(iterations) if track_delta else None
+        if iterations > 0:
+            new_grid, deltas, sweeps = propagate(
+                self.original_grid, self.pred_grid, planes=True, features=self.feature_grid, method=method,
+                clamp=(method != 'exact'), min_gamma=self.min_gamma, max_gamma=self.max_gamma,
+                max_iter=iterations, auto_terminate=auto_terminate, threshold=auto_terminate_threshold,
+                clip_val=clip_val, track_delta=track_delta)
+            self.pred_grid = new_grid
+            if track_delta:
+                delta_vec[:sweeps] = deltas
+                if auto_terminate:
+                    delta_vec = delta_vec[0:sweeps]
+        self.run_state = True
+        self.run_method = method
+        if track_delta:
+            return self.pred_grid, delta_vec
+        return self.pred_grid
+
+    def predict_weight(self, f1, f2, method):
+        """Host utility with the reference's semantics (VPint/WP_MRP.py:396-427); the
+        device computes the same quantity for whole grids."""
+        if method == "predict":
+            f = np.concatenate((f1, f2)).reshape(1, -1)
+            gamma = 1.0
+            try:
+                gamma = self.model.predict(f)[0]
+            except Exception:
+                gamma = 1.0
+        elif method == "cosine_similarity":
+            gamma = np.dot(f1, f2) / max(np.sum(f1) * np.sum(f2), 0.01)
+        elif method == "exact":
+            d = f1.copy()
+            d[d == 0] = 0.01
+            gamma = np.mean(f2 / d)
+        elif method == "exact_inverse":
+            d = f2.copy()
+            d[d == 0] = 0.01
+            gamma = np.mean(f1 / d)
+        else:
+            raise VPintError("Invalid weight prediction method: " + str(method))
+        return max(self.min_gamma, min(gamma, self.max_gamma))
+
+
+class WP_STMRP(STMRP):
+    """(H, W, T) value propagation with feature-derived weights; features are an
+    (H, W, F) grid, static in time (reference: VPint/WP_MRP.py:1254-1468)."""
+
+    def __init__(self, grid, feature_grid, model_spatial=None, model_temporal=None, auto_timesteps=False,
+                 max_gamma=np.inf, min_gamma=0):
+        super(WP_STMRP, self).__init__(grid, auto_timesteps)
+        self.feature_grid = feature_grid.copy().astype(float)
+        self.model_spatial = model_spatial
+        self.model_temporal = model_temporal
+        self.max_gamma = max_gamma
+        self.min_gamma = min_gamma
+
+    def run(self, iterations=-1, method='predict', auto_terminate=True, auto_terminate_threshold=1e-4,
+            track_delta=False):
+        """Same contract as VPint/WP_MRP.py:1289-1440 for ``method`` in
+        {'exact', 'cosine_similarity'}.  The default ``method='predict'`` needs the
+        caller's sklearn models on the host and raises VPintError."""
+        if iterations > -1:
+            auto_terminate = False
+        else:
+            iterations = TEMPORAL_CAP
+        if method == 'predict':
+            raise VPintError("method='predict' needs host-side sklearn models and is not supported by the device "
+                             "path; use 'exact' or 'cosine_similarity'")
+        if method not in ('exact', 'cosine_similarity'):
+            raise VPintError("Invalid method: " + str(method))
+        if self.feature_grid.ndim != 3:
+            raise VPintError("Improper feature dimensions; expected (H, W, F), got " + str(self.feature_grid.shape))
+        delta_vec = np.zeros(iterations) if track_delta else None
+        if iterations > 0:
+            new_grid, deltas, sweeps = propagate(
+                self.original_grid, self.pred_grid, planes=True, features=self.feature_grid, method=method,
+                max_iter=iterations, auto_terminate=auto_terminate, threshold=auto_terminate_threshold,
+                track_delta=track_delta)
+            self.pred_grid = new_grid
+            if track_delta:
+                delta_vec[:sweeps] = deltas
+                if auto_terminate:
+                    delta_vec = delta_vec[0:sweeps]
+        if track_delta:
+            return self.pred_grid, delta_vec
+        return self.pred_grid
