@@ -25,10 +25,13 @@ warnings.filterwarnings("ignore")
 
 RTOL64 = 1e-9     # north_star: fp64 mode
 RTOL32 = 1e-4     # north_star: fp32-storage mode
-K_BLOCKS = [1]
+K_BLOCKS = [1, 4, 8]
+# Per-sweep deltas are ratios of grid means; once a solve has converged to the last ulp the numerator is
+# pure rounding noise (~1e-16 of the state), so deltas get an absolute floor next to the 1e-9 relative bar.
+DELTA_ATOL = 1e-14
 
 
-def close(a, b, rtol=RTOL64):
+def close(a, b, rtol=RTOL64, atol=0.0):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (a.shape, b.shape)
     assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
@@ -36,8 +39,12 @@ def close(a, b, rtol=RTOL64):
     assert np.array_equal(np.isinf(a), inf) and np.array_equal(a[inf], b[inf]), "inf pattern differs"
     ok = ~(np.isnan(b) | inf)
     err = np.abs(a[ok] - b[ok])
-    bound = rtol * np.abs(b[ok]) + 1e-300
+    bound = rtol * np.abs(b[ok]) + atol + 1e-300
     assert (err <= bound).all(), "max rel err %.3e" % float(np.max(err / (np.abs(b[ok]) + 1e-300)))
+
+
+def closed(a, b, rtol=RTOL64):
+    close(a, b, rtol=rtol, atol=DELTA_ATOL)
 
 
 @pytest.fixture(params=K_BLOCKS, ids=lambda k: "k%d" % k)
@@ -53,21 +60,21 @@ def test_golden_sd2d(golden, kblock):
     m = SD_SMRP(grid.copy(), gamma=0.9)
     p, d = m.run(track_delta=True)
     assert len(d) == len(g["d_auto"])
-    close(p, g["pred_auto"]); close(d, g["d_auto"])
+    close(p, g["pred_auto"]); closed(d, g["d_auto"])
     assert p is m.pred_grid and p.dtype == np.float64
     m = SD_SMRP(grid.copy(), gamma=0.73)
     p, d = m.run(iterations=7, track_delta=True)
-    close(p, g["pred_fix"]); close(d, g["d_fix"])
+    close(p, g["pred_fix"]); closed(d, g["d_fix"])
     m = SD_SMRP(grid.copy(), gamma=0.9, init_strategy="zero")
     p, d = m.run(iterations=3, track_delta=True)
-    close(p, g["pred_zero"]); close(d, g["d_zero"])
+    close(p, g["pred_zero"]); closed(d, g["d_zero"])
     m = SD_SMRP(grid.copy(), gamma=0.73)       # resume: run(3); run(4) == run(7)
     m.run(iterations=3)
     close(m.run(iterations=4), g["pred_resume"])
     m = SD_SMRP(grid.copy(), gamma=0.9)        # reset() leaves NaN in the start state
     m.reset()
     p, d = m.run(iterations=4, track_delta=True)
-    close(p, g["pred_reset"]); close(d, g["d_reset"])
+    close(p, g["pred_reset"]); closed(d, g["d_reset"])
 
 
 def test_golden_wp2d(golden, kblock):
@@ -76,38 +83,38 @@ def test_golden_wp2d(golden, kblock):
     m = WP_SMRP(grid.copy(), feat.copy())
     p, d = m.run(track_delta=True)
     assert len(d) == len(g["d_auto"]) == 14
-    close(p, g["pred_auto"]); close(d, g["d_auto"])
+    close(p, g["pred_auto"]); closed(d, g["d_auto"])
     assert m.run_state and m.run_method == "exact"
     p, d = WP_SMRP(grid.copy(), feat.copy()).run(iterations=9, track_delta=True)
-    close(p, g["pred_fix"]); close(d, g["d_fix"])
+    close(p, g["pred_fix"]); closed(d, g["d_fix"])
     m = WP_SMRP(grid.copy(), feat.copy())
     p, d = m.run(iterations=6, track_delta=True, clip_val=float(g["clip_val"]))
-    close(p, g["pred_clip"]); close(d, g["d_clip"])
+    close(p, g["pred_clip"]); closed(d, g["d_clip"])
     assert m.clip_val == float(g["clip_val"])
     for method in ("cosine_similarity", "exact_inverse"):
         m = WP_SMRP(grid.copy(), feat.copy(), min_gamma=0.2, max_gamma=1.05)
         p, d = m.run(iterations=5, method=method, track_delta=True)
-        close(p, g["pred_" + method]); close(d, g["d_" + method])
+        close(p, g["pred_" + method]); closed(d, g["d_" + method])
 
 
 def test_golden_wp2d_edge_cases(golden, kblock):
     g = golden("wp2d_edge")
     m = WP_SMRP(g["z_grid"].copy(), g["z_feat"].copy())          # zeros in the features
     p, d = m.run(iterations=5, track_delta=True)
-    close(p, g["z_pred"]); close(d, g["z_d"])
+    close(p, g["z_pred"]); closed(d, g["z_d"])
     assert np.array_equal(m.feature_grid, g["z_feat_after"])
     p, d = WP_SMRP(g["f9_grid"].copy(), g["f9_feat"].copy()).run(iterations=4, track_delta=True)
-    close(p, g["f9_pred"]); close(d, g["f9_d"])
+    close(p, g["f9_pred"]); closed(d, g["f9_d"])
     p, d = WP_SMRP(g["f9_grid"].copy(), g["f19_feat"].copy()).run(iterations=3, track_delta=True)
-    close(p, g["f19_pred"]); close(d, g["f19_d"])
+    close(p, g["f19_pred"]); closed(d, g["f19_d"])
     for tag in ("col", "row"):                                   # H or W == 1: neighbour count 2 / 0
         p, d = WP_SMRP(g[tag + "_grid"].copy(), g[tag + "_feat"].copy()).run(iterations=3, track_delta=True)
-        close(p, g[tag + "_pred"]); close(d, g[tag + "_d"])
+        close(p, g[tag + "_pred"]); closed(d, g[tag + "_d"])
     p, d = WP_SMRP(g["inf_grid"].copy(), g["inf_feat"].copy()).run(iterations=8, track_delta=True)   # blow-up to inf / NaN
-    close(p, g["inf_pred"]); close(d, g["inf_d"])
+    close(p, g["inf_pred"]); closed(d, g["inf_d"])
     p, d = WP_SMRP(g["inf_grid"].copy(), g["inf_feat"].copy()).run(track_delta=True)
     assert len(d) == 3
-    close(p, g["inf_pred_auto"]); close(d, g["inf_d_auto"])
+    close(p, g["inf_pred_auto"]); closed(d, g["inf_d_auto"])
 
 
 def test_golden_st3d(golden):
@@ -115,19 +122,19 @@ def test_golden_st3d(golden):
     cube = g["cube"]
     p, d = SD_STMRP(cube.copy(), gamma=0.9, tau=0.8).run(track_delta=True)
     assert len(d) == len(g["sd_d_auto"])
-    close(p, g["sd_auto"]); close(d, g["sd_d_auto"])
+    close(p, g["sd_auto"]); closed(d, g["sd_d_auto"])
     p, d = SD_STMRP(cube.copy(), gamma=0.6, tau=0.95).run(iterations=6, track_delta=True)
-    close(p, g["sd_fix"]); close(d, g["sd_d_fix"])
+    close(p, g["sd_fix"]); closed(d, g["sd_d_fix"])
     feat = g["feat"]
     p, d = WP_STMRP(cube.copy(), feat.copy()).run(iterations=5, method="exact", track_delta=True)
-    close(p, g["wp_exact"]); close(d, g["wp_d_exact"])
+    close(p, g["wp_exact"]); closed(d, g["wp_d_exact"])
     p, d = WP_STMRP(cube.copy(), feat.copy()).run(iterations=4, method="cosine_similarity", track_delta=True)
-    close(p, g["wp_cos"]); close(d, g["wp_d_cos"])
+    close(p, g["wp_cos"]); closed(d, g["wp_d_cos"])
     p, d = WP_STMRP(cube.copy(), feat.copy()).run(method="exact", track_delta=True)
     assert len(d) == len(g["wp_d_auto"])
-    close(p, g["wp_auto"]); close(d, g["wp_d_auto"])
+    close(p, g["wp_auto"]); closed(d, g["wp_d_auto"])
     p, d = SD_STMRP(g["flat"].copy(), gamma=0.9, tau=0.9).run(iterations=3, track_delta=True)
-    close(p, g["sd_flat"]); close(d, g["sd_d_flat"])
+    close(p, g["sd_flat"]); closed(d, g["sd_d_flat"])
 
 
 def test_golden_vpint2(golden, kblock):
@@ -177,10 +184,10 @@ def test_oracle_sd2d_config1_shape(kblock):
     ref, dref, n = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.9)
     p, d = SD_SMRP(grid.copy(), gamma=0.9).run(track_delta=True)
     assert len(d) == n
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
     ref, dref, _ = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.9, iterations=100)
     p, d = SD_SMRP(grid.copy(), gamma=0.9).run(iterations=100, track_delta=True)
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
 
 
 @pytest.mark.parametrize("shape", [(256, 256), (130, 203), (67, 300)])
@@ -196,10 +203,10 @@ def test_oracle_wp2d(shape, kblock):
     ref, dref, n = O.wp_run_2d(grid, O.init_pred(grid), feat.copy())
     p, d = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
     assert len(d) == n, (len(d), n)
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
     ref, dref, _ = O.wp_run_2d(grid, O.init_pred(grid), feat.copy(), iterations=25, clip_val=2000.0)
     p, d = WP_SMRP(grid.copy(), feat.copy()).run(iterations=25, track_delta=True, clip_val=2000.0)
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
 
 
 def test_oracle_st3d():
@@ -211,12 +218,12 @@ def test_oracle_st3d():
     ref, dref, n = O.sd_run_3d(cube, O.init_pred(cube), gamma=0.9, tau=0.9)
     p, d = SD_STMRP(cube.copy(), gamma=0.9, tau=0.9).run(track_delta=True)
     assert len(d) == n
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
     feat = smooth(rng, shape[:2] + (1,), 1, 3)
     ref, dref, n = O.wp_run_3d(cube, O.init_pred(cube), feat.copy(), method="exact")
     p, d = WP_STMRP(cube.copy(), feat.copy()).run(method="exact", track_delta=True)
     assert len(d) == n
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
 
 
 def make_patch(rng, H=64, W=64, B=4):
@@ -297,7 +304,7 @@ def test_properties_large_wp(kblock):
     # linearity: scaling the target scales the result, the stopping statistic is scale free
     m2 = WP_SMRP(4.0 * grid, feat.copy())
     p2, d2 = m2.run(iterations=40, track_delta=True)
-    close(p2, 4.0 * p, rtol=1e-12); close(d2, d, rtol=1e-12)
+    close(p2, 4.0 * p, rtol=1e-12); closed(d2, d, rtol=1e-12)
     # resume == one longer run
     m3 = WP_SMRP(grid.copy(), feat.copy())
     m3.run(iterations=15)
@@ -330,7 +337,7 @@ def test_start_state_differs_from_original_on_known_cells(kblock):
     m = SD_SMRP(grid.copy(), gamma=0.8)
     m.pred_grid = start.copy()
     p, d = m.run(iterations=6, track_delta=True)
-    close(p, ref); close(d, dref)
+    close(p, ref); closed(d, dref)
 
 
 def test_fp32_storage_mode():

@@ -11,6 +11,7 @@ import math
 
 import numpy as np
 
+from . import solve as _solve
 from .engine import Solver, require_cuda, to_device
 from .errors import VPintError
 
@@ -33,7 +34,7 @@ def sd_trials(grid, gammas, iterations, taus=None, device=None, k_block=None):
         pred = grid.copy()
         pred[np.isnan(pred)] = np.nanmean(grid)
         return np.broadcast_to(pred, (n,) + grid.shape).copy()
-    solver = Solver(ndim, n, H, W, T, planes=False, k_block=(0 if k_block is None or ndim == 3 else k_block), device=dev)
+    solver = Solver(ndim, n, H, W, T, planes=False, k_block=(0 if ndim == 3 else (_solve.DEFAULT_K_BLOCK if k_block is None else k_block)), device=dev)
     try:
         g_dev = to_device(grid, dev)
         original = g_dev.unsqueeze(0).expand((n,) + tuple(g_dev.shape))      # stride-0 problem axis: no copies

@@ -12,8 +12,10 @@ namespace vpint {
 void k1_tile_shape(int ndim, int *th, int *tw);
 void tb_tile_shape(int k_block, int *th, int *tw);
 bool tb_supported(const Geom &g, int storage);
-cudaError_t launch_step2d_tb(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
-                             int64_t *launches);
+cudaError_t tb_make_maps(const Geom &g, int storage, void *buf0, void *buf1, void *maps_out);
+size_t tb_maps_bytes();
+cudaError_t launch_step2d_tb(const StepArgs &a, const void *maps, int storage, int weight_mode, int64_t n_tiles,
+                             cudaStream_t st, int64_t *launches);
 }  // namespace vpint
 
 using namespace vpint;
@@ -62,6 +64,7 @@ struct vpint_solver {
     int *h_counters = nullptr;   // pinned
     cudaEvent_t ev = nullptr;
     vpint_run_params prm;
+    alignas(64) unsigned char tb_maps[512];   // two CUtensorMap (ping-pong state buffers)
 
     template <typename T>
     T *at(size_t off) const { return reinterpret_cast<T *>(ws + off); }
@@ -187,6 +190,11 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     }
     s->ws = static_cast<char *>(workspace);
     s->loaded = s->weights_ready = s->run_begun = false;
+    if (s->use_tb) {
+        if (tb_maps_bytes() > sizeof(s->tb_maps)) return fail(VPINT_ERR_INVALID, "internal: tensor map storage too small");
+        VP_CUDA(tb_make_maps(s->g, s->storage, s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]), s->tb_maps),
+                "cuTensorMapEncodeTiled");
+    }
     return VPINT_OK;
 }
 
@@ -303,7 +311,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
     a.clip = s->prm.clip_val;
     if (s->g.ndim == 2) {
         if (s->use_tb)
-            VP_CUDA(launch_step2d_tb(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d_tb");
+            VP_CUDA(launch_step2d_tb(a, s->tb_maps, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d_tb");
         else
             VP_CUDA(launch_step2d(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d");
     } else {

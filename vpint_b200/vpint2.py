@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import solve as _solve
 from .engine import Solver, require_cuda, to_device
 from .errors import VPintError
 from .wp import wp_run_options
@@ -37,7 +38,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
     if fill is None:
         fill = _band_fill_values(target.cpu().numpy()).reshape(-1)
     solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
-                    k_block=(0 if k_block is None else k_block), device=dev)
+                    k_block=(_solve.DEFAULT_K_BLOCK if k_block is None else k_block), device=dev)
     try:
         t_dev = target.to(dev, non_blocking=True)
         f_dev = features.to(dev, non_blocking=True)
@@ -103,7 +104,7 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
         return (res, np.zeros((N, B), dtype=np.int64)[0 if single else slice(None)]) if return_sweeps else res
     fill = _band_fill_values(tgt)
     solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
-                    k_block=(0 if k_block is None else k_block), device=dev)
+                    k_block=(_solve.DEFAULT_K_BLOCK if k_block is None else k_block), device=dev)
     try:
         t_dev = to_device(np.ascontiguousarray(tgt), dev)                 # (N, H, W, B) as stored
         f_dev = to_device(np.ascontiguousarray(fts), dev)
