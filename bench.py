@@ -195,6 +195,17 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kb, masked_px):
+    """DRAM bytes per stencil launch, scaled from the committed `ncu --set full` capture of the same kernel
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per unknown cell per launch)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t["k_block"][str(kb)]
+        return e["dram_bytes_per_unknown_cell_per_launch"] * masked_px, e["source"]
+    except Exception:
+        return None, None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -331,10 +342,16 @@ def run_gpu(args):
         solver.step_end()
     torch.cuda.synchronize()
     k_ms = statistics.mean(times)
-    alg_bytes = BYTES_WP_F64 * total_px * kb
+    masked_frac = float(torch.isnan(target).double().mean().item())
+    masked_px = masked_frac * total_px
+    # Units one stencil launch processes = the unknown cells it updates (known cells are constants and are
+    # never touched again after load), kb sweeps each; 48 B per cell-sweep (state in + 4 weights +
+    # state out).  The whole-grid figure the reference's sweep would move is reported beside it.
+    alg_bytes = BYTES_WP_F64 * masked_px * kb
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    full_grid_gbps = BYTES_WP_F64 * total_px * kb / (k_ms * 1e-3) / 1e9
     peak, peak_src = peak_hbm()
-    masked_frac = float(torch.isnan(target[..., 0]).double().mean().item())
+    traffic, traffic_src = ncu_traffic(kb, masked_px)
     active_tiles, total_tiles = solver.active_tiles, solver.total_tiles
 
     line = None
@@ -350,8 +367,11 @@ def run_gpu(args):
                        "l2_note": "state+weights %.1f GB per GPU >> 126 MB L2; no flush needed" % (48.0 * total_px / 1e9),
                        "mean_sweeps_per_problem": sweeps_dev / args.steps / (nprob * world)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "jacobi2d (stencil launch, all problems active)",
-                         "kernel_ms": k_ms, "alg_bytes_per_launch": alg_bytes, "bytes_per_px_it": BYTES_WP_F64},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "jacobi2d_%s (stencil launch, all problems active)" % ("k1" if kb == 1 else "tb"),
+                         "kernel_ms": k_ms, "alg_bytes_per_launch": alg_bytes, "bytes_per_unit": BYTES_WP_F64,
+                         "unit_def": "one unknown cell updated for one sweep (%.0f cells x %d sweeps per launch)" % (masked_px, kb),
+                         "whole_grid_equiv_gbps": full_grid_gbps},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(t_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 8 + nprob * 4), "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps, "api": "vpint_b200.vpint2.solve_bands (VPint2 run path), pinned host buffers"},
