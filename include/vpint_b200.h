@@ -171,6 +171,22 @@ void   *vpint_solver_state_ptr(vpint_solver *s, int which);   /* ping-pong buffe
 int32_t*vpint_solver_active_ptr(vpint_solver *s);             /* device int32: problems still running   */
 int32_t*vpint_solver_cur_ptr(vpint_solver *s);                /* device int32[nprob]: buffer holding the current state */
 
+/* Row-sharded scenes, used between step_end and the next step_begin.
+ *   known_ptr : [2][nprob][4] doubles, the known-cell terms of the stopping rule summed over the OWNED
+ *               rows at load; all-reduce (SUM) once after vpint_solver_load so that every rank divides
+ *               by the statistics of the whole grid (VPint/SD_MRP.py:139).
+ *   halo_pack : copies the `rows` first / last owned rows of every problem's current state into the
+ *               contiguous messages to_up / to_down ([nprob][rows][pitch], storage type; NULL = skip).
+ *   halo_unpack : writes messages received from the upper / lower neighbour into the halo rows just
+ *               above / below the owned band.
+ *   any_dirty : nonzero when the start state differed from `original` on a known cell (such a start
+ *               state must be avoided in sharded runs: ranks would disagree on the first launch). */
+double *vpint_solver_known_ptr(vpint_solver *s);
+int     vpint_solver_known_count(const vpint_solver *s);
+int     vpint_solver_any_dirty(const vpint_solver *s);
+int     vpint_solver_halo_pack(vpint_solver *s, int rows, void *to_up, void *to_down, void *stream);
+int     vpint_solver_halo_unpack(vpint_solver *s, int rows, const void *from_up, const void *from_down, void *stream);
+
 /* ---- results -----------------------------------------------------------
  * out: device, dtype `dtype`, element strides as in load.  This is
  * self.pred_grid after run().  niter_out: device int32[nprob] sweeps executed

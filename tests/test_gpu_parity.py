@@ -381,3 +381,27 @@ def test_solver_introspection_and_tile_skipping():
     s.close()
     with pytest.raises(VPintError):
         WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, resistance=True)
+
+
+# ---- 4. row-sharded scene on one device: shards in lockstep through the CUDA halo kernels ---------
+@pytest.mark.parametrize("world,k", [(2, 1), (3, 4), (4, 8)])
+def test_row_sharded_scene_lockstep(world, k):
+    from vpint_b200.sharded import RowShard, open_shard, run_lockstep, shard_result
+    from vpint_b200.vpint2 import _band_fill_values
+    from vpint_b200.wp import wp_run_options
+    rng = np.random.default_rng(404)
+    vp = make_patch(rng, 150, 90, 3)
+    ref, ref_sweeps = O.vpint2_run(vp.target, vp.features)
+    fill = _band_fill_values(vp.target)
+    shards = [RowShard(150, world, r, halo=k) for r in range(world)]
+    opened = [open_shard(s.local(vp.target), s.local(vp.features), s, fill, wp_run_options(), k_block=k) for s in shards]
+    try:
+        run_lockstep([e for _, e in opened], shards, wp_run_options()["iterations"], poll_every=4)
+        parts = [shard_result(sv, s) for (sv, _), s in zip(opened, shards)]
+    finally:
+        for sv, _ in opened:
+            sv.close()
+    got = np.concatenate([p.cpu().numpy() for p, _ in parts], axis=1)
+    for _, sweeps in parts:
+        assert list(sweeps) == list(ref_sweeps)
+    close(np.moveaxis(got, 0, -1), ref)

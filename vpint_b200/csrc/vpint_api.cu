@@ -58,6 +58,7 @@ struct vpint_solver {
     char *ws = nullptr;
     bool loaded = false, weights_ready = false, run_begun = false, first_step_pending = false;
     bool use_tb = false;
+    int halo_up = 0, halo_down = 0;   // halo rows above / below the owned band (row-sharded scenes)
     int64_t tiles_active = 0;
     int any_dirty = 0;
     int64_t launches = 0;
@@ -116,6 +117,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
         }
     }
     g.n_cells = (double)g.global_H * (double)g.L;
+    s->halo_up = g.own_row0;
+    s->halo_down = g.H - g.own_row0 - g.own_rows;
     s->storage = d->storage;
     s->weight_mode = d->weight_mode;
     s->elem = (d->storage == VPINT_F64) ? 8 : 4;
@@ -134,6 +137,15 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     if (s->use_tb && !tb_supported(g, s->storage)) {
         delete s;
         return fail(VPINT_ERR_UNSUPPORTED, "temporally blocked kernel does not support this configuration");
+    }
+    {
+        // a launch reads KB rows beyond the owned band unless that side is the physical border of the grid
+        const bool top_border = (g.row_offset + g.own_row0 == 0);
+        const bool bottom_border = (g.row_offset + g.own_row0 + g.own_rows == g.global_H);
+        if ((!top_border && s->halo_up < g.KB) || (!bottom_border && s->halo_down < g.KB)) {
+            delete s;
+            return fail(VPINT_ERR_INVALID, "row sharding needs at least k_block halo rows on every interior side");
+        }
     }
     g.tiles_y = (g.own_rows + g.TH - 1) / g.TH;
     g.tiles_x = (g.L + g.TW - 1) / g.TW;
@@ -157,8 +169,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_tau = take((size_t)g.P * sizeof(double));
     s->off_fill = take((size_t)g.P * sizeof(double));
     s->off_rowpart = take((size_t)g.P * g.H * 8 * sizeof(double));
-    s->off_known0 = take((size_t)g.P * kSumSlots * sizeof(double));
-    s->off_known = take((size_t)g.P * kSumSlots * sizeof(double));
+    s->off_known0 = take(2 * (size_t)g.P * kSumSlots * sizeof(double));   // known0 then known, one contiguous block
+    s->off_known = s->off_known0 + (size_t)g.P * kSumSlots * sizeof(double);
     s->off_state = take((size_t)g.P * sizeof(ProbState));
     s->off_counters = take(kCntTotal * sizeof(int));
     s->off_tileflag = take((size_t)s->tiles_total * sizeof(int));
@@ -404,6 +416,38 @@ int32_t *vpint_solver_active_ptr(vpint_solver *s) {
 int32_t *vpint_solver_cur_ptr(vpint_solver *s) {
     // ProbState is 8 int32; `cur` is field 2.  Exposed as a strided view: element p at [p * 8].
     return (s && s->ws) ? reinterpret_cast<int32_t *>(s->at<ProbState>(s->off_state)) + 2 : nullptr;
+}
+
+double *vpint_solver_known_ptr(vpint_solver *s) { return (s && s->ws) ? s->at<double>(s->off_known0) : nullptr; }
+
+int vpint_solver_known_count(const vpint_solver *s) { return s ? 2 * s->g.P * kSumSlots : 0; }
+
+int vpint_solver_any_dirty(const vpint_solver *s) { return s ? s->any_dirty : 0; }
+
+static int halo_impl(vpint_solver *s, int rows, void *up, void *down, bool pack, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    const Geom &g = s->g;
+    if (rows < 1 || rows > g.own_rows) return fail(VPINT_ERR_INVALID, "halo rows out of range");
+    if ((up && rows > s->halo_up) || (down && rows > s->halo_down))
+        return fail(VPINT_ERR_INVALID, "halo message deeper than the halo rows of this shard");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    const ProbState *state = s->at<ProbState>(s->off_state);
+    // pack: the owned rows a neighbour needs; unpack: the halo rows just outside the owned band
+    const int up_row = pack ? g.own_row0 : g.own_row0 - rows;
+    const int down_row = pack ? g.own_row0 + g.own_rows - rows : g.own_row0 + g.own_rows;
+    if (up) VP_CUDA(launch_halo_rows(g, s->storage, state, bufs, up, up_row, rows, pack, st, &s->launches), "halo rows");
+    if (down) VP_CUDA(launch_halo_rows(g, s->storage, state, bufs, down, down_row, rows, pack, st, &s->launches), "halo rows");
+    return VPINT_OK;
+}
+
+int vpint_solver_halo_pack(vpint_solver *s, int rows, void *to_up, void *to_down, void *stream) {
+    return halo_impl(s, rows, to_up, to_down, true, stream);
+}
+
+int vpint_solver_halo_unpack(vpint_solver *s, int rows, const void *from_up, const void *from_down, void *stream) {
+    return halo_impl(s, rows, const_cast<void *>(from_up), const_cast<void *>(from_down), false, stream);
 }
 
 int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out, void *stream) {

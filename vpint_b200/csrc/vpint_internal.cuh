@@ -102,6 +102,8 @@ cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, in
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,
                                  const uint32_t *mask, cudaStream_t st, int64_t *launches);
+cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state, void *const *buf, void *msg,
+                             int first_row, int rows, bool pack, cudaStream_t st, int64_t *launches);
 cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, void *const *buf, void *out,
                           int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
                           int64_t *launches);

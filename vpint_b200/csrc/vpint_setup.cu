@@ -309,6 +309,21 @@ __global__ void __launch_bounds__(256) result_kernel(Geom g, const ProbState *__
     if (niter_out && y == 0 && threadIdx.x == 0) niter_out[p] = st.iters_done;
 }
 
+// Row-sharded scenes: copy `rows` owned boundary rows of every problem's CURRENT buffer into a
+// contiguous [P][rows][pitch] message (pack), or a received message into the halo rows next to the owned
+// band (unpack).  `first_row` is the local row the block of rows starts at.
+template <typename TSt, bool PACK>
+__global__ void __launch_bounds__(256) halo_rows_kernel(Geom g, const ProbState *__restrict__ state, TSt *buf0,
+                                                        TSt *buf1, TSt *msg, int first_row, int rows) {
+    const int p = blockIdx.x / rows, r = blockIdx.x - p * rows;
+    TSt *grid_row = (state[p].cur ? buf1 : buf0) + ((size_t)p * g.H + first_row + r) * g.pitch;
+    TSt *msg_row = msg + ((size_t)p * rows + r) * g.pitch;
+    for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) {
+        if (PACK) msg_row[e] = grid_row[e];
+        else grid_row[e] = msg_row[e];
+    }
+}
+
 }  // namespace
 
 #define VP_LAUNCH_CHECK()                         \
@@ -380,6 +395,20 @@ cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, v
         restore_known_kernel<float><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], mask);
     VP_LAUNCH_CHECK();
     clear_dirty_kernel<<<(g.P + 127) / 128, 128, 0, st>>>(g, state);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state, void *const *buf, void *msg,
+                             int first_row, int rows, bool pack, cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)g.P * rows);
+    if (storage == VPINT_F64) {
+        if (pack) halo_rows_kernel<double, true><<<grid, 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], (double *)msg, first_row, rows);
+        else halo_rows_kernel<double, false><<<grid, 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], (double *)msg, first_row, rows);
+    } else {
+        if (pack) halo_rows_kernel<float, true><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
+        else halo_rows_kernel<float, false><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
+    }
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -259,6 +259,28 @@ class Solver:
         off = ptr - self.workspace.data_ptr()
         return self.workspace[off:off + n * 8].view(self.torch.float64).view(self.nprob, -1, 4)
 
+    def known_tensor(self):
+        """[2][nprob][4] fp64 known-cell sums of the owned rows (workspace view; all-reduced once by a
+        row-sharded run)."""
+        n = int(self.lib.vpint_solver_known_count(self._h))
+        ptr = int(self.lib.vpint_solver_known_ptr(self._h))
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off:off + n * 8].view(self.torch.float64)
+
+    @property
+    def any_dirty(self):
+        return int(self.lib.vpint_solver_any_dirty(self._h))
+
+    def halo_pack(self, rows, to_up, to_down):
+        N.check(self.lib, self.lib.vpint_solver_halo_pack(
+            self._h, int(rows), C.c_void_p(to_up.data_ptr()) if to_up is not None else None,
+            C.c_void_p(to_down.data_ptr()) if to_down is not None else None, self._stream()), "vpint_solver_halo_pack")
+
+    def halo_unpack(self, rows, from_up, from_down):
+        N.check(self.lib, self.lib.vpint_solver_halo_unpack(
+            self._h, int(rows), C.c_void_p(from_up.data_ptr()) if from_up is not None else None,
+            C.c_void_p(from_down.data_ptr()) if from_down is not None else None, self._stream()), "vpint_solver_halo_unpack")
+
     def state_tensor(self, which):
         """Ping-pong buffer ``which`` as a [nprob][H][pitch] tensor (workspace view)."""
         ptr = int(self.lib.vpint_solver_state_ptr(self._h, int(which)))
