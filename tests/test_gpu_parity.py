@@ -25,7 +25,7 @@ warnings.filterwarnings("ignore")
 
 RTOL64 = 1e-9     # north_star: fp64 mode
 RTOL32 = 1e-4     # north_star: fp32-storage mode
-K_BLOCKS = [1, 4, 8]
+K_BLOCKS = [0, 1, 4, 8]    # 0 = library default: cluster-resident solve where a problem fits on chip
 # Per-sweep deltas are ratios of grid means; once a solve has converged to the last ulp the numerator is
 # pure rounding noise (~1e-16 of the state), so deltas get an absolute floor next to the 1e-9 relative bar.
 DELTA_ATOL = 1e-14

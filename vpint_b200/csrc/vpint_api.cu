@@ -2,6 +2,7 @@
 // and the loop drivers around the stencil / reduction / decision kernels.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -59,6 +60,12 @@ struct vpint_solver {
     bool loaded = false, weights_ready = false, run_begun = false, first_step_pending = false;
     bool use_tb = false;
     int halo_up = 0, halo_down = 0;   // halo rows above / below the owned band (row-sharded scenes)
+    // cluster-resident solve (vpint_resident.cu): chosen when k_block == 0 and one problem fits on chip
+    bool res_ok = false;              // plan valid for this solver's weight form
+    ResidentPlan rplan;
+    bool planes_valid = false;        // the 4 (5) weight planes hold current weights
+    bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
+    size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
     int64_t tiles_active = 0;
     int any_dirty = 0;
     int64_t launches = 0;
@@ -123,6 +130,12 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->weight_mode = d->weight_mode;
     s->elem = (d->storage == VPINT_F64) ? 8 : 4;
     s->n_planes = (d->weight_mode == VPINT_W_PLANES) ? (d->ndim == 2 ? 4 : 5) : 0;
+    const bool unsharded = (g.global_H == g.H && g.own_row0 == 0 && g.own_rows == g.H);
+    if (d->k_block == 0 && d->ndim == 2 && d->storage == VPINT_F64 && unsharded && !getenv("VPINT_NO_RESIDENT")) {
+        const int smem_optin = 232448;   // sm_100a: 227 KB per CTA
+        s->res_ok = resident_plan(g, d->weight_mode == VPINT_W_PLANES, smem_optin, &s->rplan);
+        if (s->res_ok && d->weight_mode == VPINT_W_PLANES) s->n_planes = 5;   // + the feature plane
+    }
 
     int kb = d->k_block;
     if (d->ndim == 3) {
@@ -178,6 +191,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_tilestart = take((size_t)(g.P + 1) * sizeof(int));
     s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
+    s->off_flags = take(16 * sizeof(int));
     s->ws_bytes = off;
     *out = s;
     return VPINT_OK;
@@ -202,6 +216,8 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     }
     s->ws = static_cast<char *>(workspace);
     s->loaded = s->weights_ready = s->run_begun = false;
+    s->planes_valid = s->fplane_valid = false;
+    VP_CUDA(cudaMemset(s->at<int>(s->off_flags), 0, 16 * sizeof(int)), "memset flags");
     if (s->use_tb) {
         if (tb_maps_bytes() > sizeof(s->tb_maps)) return fail(VPINT_ERR_INVALID, "internal: tensor map storage too small");
         VP_CUDA(tb_make_maps(s->g, s->storage, s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]), s->tb_maps),
@@ -251,14 +267,24 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void *planes[5];
     for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
-    if (s->g.ndim == 2) {
+    s->planes_valid = s->fplane_valid = false;
+    if (s->g.ndim == 2 && s->res_ok && F == 1 && method == VPINT_METHOD_EXACT && !clamp) {
+        // one feature layer: keep the feature plane only; the ratio planes are derived on demand
+        VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
+        VP_CUDA(launch_fplane(s->g, feat, dtype, stride, s->at<double>(s->off_w[4]), s->at<int>(s->off_flags), st,
+                              &s->launches),
+                "fplane");
+        s->fplane_valid = true;
+    } else if (s->g.ndim == 2) {
         VP_CUDA(launch_weights2d(s->g, feat, dtype, stride, F, method, clamp, min_gamma, max_gamma, s->storage, planes,
                                  st, &s->launches),
                 "weights2d");
+        s->planes_valid = true;
     } else {
         if (method == VPINT_METHOD_EXACT_INVERSE)
             return fail(VPINT_ERR_UNSUPPORTED, "exact_inverse is not a WP_STMRP method (VPint/WP_MRP.py:1443-1468)");
         VP_CUDA(launch_weights3d(s->g, feat, dtype, stride, F, method, s->storage, planes, st, &s->launches), "weights3d");
+        s->planes_valid = true;
     }
     s->weights_ready = true;
     return VPINT_OK;
@@ -308,6 +334,14 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         VP_CUDA(cudaEventCreate(&e0), "event create");
         VP_CUDA(cudaEventCreate(&e1), "event create");
         VP_CUDA(cudaEventRecord(e0, st), "event record");
+    }
+    if (s->weight_mode == VPINT_W_PLANES && !s->planes_valid) {
+        if (!s->fplane_valid) return fail(VPINT_ERR_INVALID, "weights have not been set");
+        void *planes[5];
+        for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+        VP_CUDA(launch_planes_from_fplane(s->g, s->at<double>(s->off_w[4]), s->storage, planes, st, &s->launches),
+                "planes from feature plane");
+        s->planes_valid = true;
     }
     StepArgs a;
     a.g = s->g;
@@ -377,6 +411,39 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         return fail(VPINT_ERR_UNSUPPORTED, "only VPINT_LOOP_CHUNKED is available in this build");
     if (prm->max_iter == 0) return VPINT_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool ratio = (s->weight_mode == VPINT_W_PLANES);
+    if (s->res_ok && !s->any_dirty && (!ratio || s->fplane_valid)) {
+        // whole run() in one launch: a cluster per problem, state resident in shared memory
+        int *flags = s->at<int>(s->off_flags);
+        VP_CUDA(cudaMemsetAsync(flags + 1, 0, sizeof(int), st), "memset queue");
+        ResidentArgs ra;
+        ra.g = s->g;
+        ra.state = s->at<ProbState>(s->off_state);
+        ra.buf[0] = s->at<void>(s->off_buf[0]);
+        ra.buf[1] = s->at<void>(s->off_buf[1]);
+        ra.mask = s->at<uint32_t>(s->off_mask);
+        ra.fplane = ratio ? s->at<double>(s->off_w[4]) : nullptr;
+        ra.gamma = s->at<double>(s->off_gamma);
+        ra.known0 = s->at<double>(s->off_known0);
+        ra.known = s->at<double>(s->off_known);
+        ra.delta_out = prm->delta_out;
+        ra.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
+        ra.queue = flags + 1;
+        ra.bad_flag = ratio ? flags : nullptr;
+        ra.max_iter = prm->max_iter;
+        ra.auto_terminate = prm->auto_terminate;
+        ra.threshold = prm->threshold;
+        ra.clip = prm->clip_val;
+        ra.C = s->rplan.C; ra.R = s->rplan.R; ra.SP = s->rplan.SP; ra.fcap = s->rplan.fcap;
+        VP_CUDA(launch_resident2d(ra, ratio, s->rplan.smem_bytes, 0, st, &s->launches), "resident2d");
+        VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
+                                sizeof(int), cudaMemcpyDeviceToHost, st),
+                "read active count");
+        VP_CUDA(cudaEventRecord(s->ev, st), "event record");
+        VP_CUDA(cudaEventSynchronize(s->ev), "event sync");
+        if (s->h_counters[kCntActiveProblems] <= 0) return VPINT_OK;
+        // the kernel declined (non-finite features): continue on the tiled path from the untouched state
+    }
     int chunk = prm->chunk > 0 ? prm->chunk : 4;
     const int chunk_cap = prm->chunk > 0 ? prm->chunk : 64;
     // Every launch either commits >= 1 sweep of every running problem or is its single replay, so

@@ -79,6 +79,40 @@ struct DecideArgs {
     double threshold;
 };
 
+// ---- cluster-resident solve (vpint_resident.cu) -----------------------------
+constexpr int kResidentThreads = 512;
+constexpr int kResidentMaxPer = 32;   // unknown cells per thread kept in registers
+
+struct ResidentPlan {
+    int C, R, SP, fcap;     // cluster size, rows per CTA, shared-memory row pitch, on-chip feature capacity
+    size_t smem_bytes;      // dynamic shared memory per CTA
+};
+
+struct ResidentArgs {
+    Geom g;
+    ProbState *state;
+    void *buf[2];
+    const uint32_t *mask;
+    const double *fplane;    // RATIO form: [P][H][pitch] features with zeros already replaced
+    const double *gamma;     // SCALAR form: [P]
+    const double *known0, *known;
+    double *delta_out;       // [P][max_iter] or null
+    int *n_active;
+    int *queue;              // zeroed before the launch
+    const int *bad_flag;     // nonzero: decline (non-finite features); null = none
+    int max_iter, auto_terminate;
+    double threshold, clip;
+    int C, R, SP, fcap;
+};
+
+bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);
+cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
+                              int64_t *launches);
+cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
+                          cudaStream_t st, int64_t *launches);
+cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int storage, void *const *planes,
+                                      cudaStream_t st, int64_t *launches);
+
 // ---- host-side launchers (one per .cu) ------------------------------------
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
                            int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,

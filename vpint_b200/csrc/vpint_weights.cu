@@ -194,6 +194,57 @@ __global__ void __launch_bounds__(256) weights_exact_f1_kernel(int P, int H, int
     }
 }
 
+// One feature layer, 'exact' weights: keep the (zero -> 0.01) feature itself as a planar fp64 plane.  The
+// cluster-resident kernel iterates P / f with it (vpint_resident.cu); the four ratio planes are only built
+// from it if a tiled launch is needed (planes_from_fplane_kernel).  bad_flag is raised for a non-finite
+// feature, which sends the solve down the plane path where NaN / inf propagate exactly as in the reference.
+template <typename TIn>
+__global__ void __launch_bounds__(256) fplane_kernel(int Pin, int H, int W, int pitch, const TIn *__restrict__ feat,
+                                                     int64_t sO, int64_t sI, int64_t sY, int64_t sX,
+                                                     double *__restrict__ fplane, int *bad_flag) {
+    const int p = blockIdx.x / H, y = blockIdx.x - p * H;
+    const int po = p / Pin, pi = p - po * Pin;
+    const TIn *frow = feat + (int64_t)po * sO + (int64_t)pi * sI + (int64_t)y * sY;
+    double *out = fplane + ((size_t)p * H + y) * pitch;
+    bool bad = false;
+    for (int x = threadIdx.x; x < pitch; x += blockDim.x) {
+        double f = 1.0;
+        if (x < W) {
+            f = (double)frow[(int64_t)x * sX];
+            if (f == 0.0) f = 0.01;                     // VPint/WP_MRP.py:143-145
+            if (!(fabs(f) <= 1.7976931348623157e308)) bad = true;
+        }
+        out[x] = f;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(bad_flag, 1);
+}
+
+// w_dir = f[i,j] / f[neighbour], missing neighbour -> 0 (VPint/WP_MRP.py:149-170 with one feature layer).
+template <typename TSt>
+__global__ void __launch_bounds__(256) planes_from_fplane_kernel(int H, int W, int pitch, int row_offset, int global_H,
+                                                                 const double *__restrict__ fplane,
+                                                                 TSt *__restrict__ w_up, TSt *__restrict__ w_right,
+                                                                 TSt *__restrict__ w_down, TSt *__restrict__ w_left) {
+    const int p = blockIdx.x / H, y = blockIdx.x - p * H;
+    const size_t row = ((size_t)p * H + y) * pitch;
+    const int yg = y + row_offset;
+    const bool has_up = (yg > 0 && y > 0), has_down = (yg < global_H - 1 && y < H - 1);
+    for (int x = threadIdx.x; x < pitch; x += blockDim.x) {
+        double up = 0.0, right = 0.0, down = 0.0, left = 0.0;
+        if (x < W) {
+            const double c = fplane[row + x];
+            if (has_up) up = c / fplane[row - pitch + x];
+            if (x < W - 1) right = c / fplane[row + x + 1];
+            if (has_down) down = c / fplane[row + pitch + x];
+            if (x > 0) left = c / fplane[row + x - 1];
+        }
+        w_up[row + x] = (TSt)up;
+        w_right[row + x] = (TSt)right;
+        w_down[row + x] = (TSt)down;
+        w_left[row + x] = (TSt)left;
+    }
+}
+
 }  // namespace
 
 #define VP_LAUNCH_CHECK()                         \
@@ -231,6 +282,34 @@ cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const i
     else if (dtype == VPINT_F64 && storage == VPINT_F32) VP_W(double, float);
     else VP_W(float, float);
 #undef VP_W
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
+                          cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    if (dtype == VPINT_F64)
+        fplane_kernel<double><<<grid, 256, 0, st>>>(g.Pin, g.H, g.W, g.pitch, (const double *)feat, stride[0], stride[1],
+                                                    stride[2], stride[3], fplane, bad_flag);
+    else
+        fplane_kernel<float><<<grid, 256, 0, st>>>(g.Pin, g.H, g.W, g.pitch, (const float *)feat, stride[0], stride[1],
+                                                   stride[2], stride[3], fplane, bad_flag);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int storage, void *const *planes,
+                                      cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    if (storage == VPINT_F64)
+        planes_from_fplane_kernel<double><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, fplane,
+                                                                (double *)planes[0], (double *)planes[1],
+                                                                (double *)planes[2], (double *)planes[3]);
+    else
+        planes_from_fplane_kernel<float><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, fplane,
+                                                               (float *)planes[0], (float *)planes[1],
+                                                               (float *)planes[2], (float *)planes[3]);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
