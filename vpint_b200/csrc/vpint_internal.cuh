@@ -81,7 +81,7 @@ struct DecideArgs {
 
 // ---- cluster-resident solve (vpint_resident.cu) -----------------------------
 constexpr int kResidentThreads = 512;
-constexpr int kResidentMaxPer = 32;   // unknown cells per thread kept in registers
+constexpr int kResidentMaxSeg = 8;    // 4-cell segments per thread (new values kept in registers)
 
 struct ResidentPlan {
     int C, R, SP, fcap;     // cluster size, rows per CTA, shared-memory row pitch, on-chip feature capacity
@@ -103,6 +103,7 @@ struct ResidentArgs {
     int max_iter, auto_terminate;
     double threshold, clip;
     int C, R, SP, fcap;
+    int dbg;                 // development switch (VPINT_RES_DBG)
 };
 
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);

@@ -14,14 +14,20 @@
 //           The kernel iterates r = P / f:  r_new = (sum of in-grid neighbour r) / nc, and forms
 //           P = f * r only where the reference's stopping rule and clip need it.  Same iteration in
 //           exact arithmetic; in fp64 it differs from the reference by a few ulp per sweep.
-// Per sweep every CTA does: compute new values of its unknown cells from shared memory (registers hold
-// them), block barrier, store them (own rows + the neighbour CTAs' halo rows through DSMEM) and push its
-// partial {sum|new-old|, sum old, NaN counts} to every CTA of the cluster, ONE cluster barrier, then
-// every CTA adds the C partials in rank order and takes the same stop decision
+//
+// Work unit = a SEGMENT of 4 horizontally adjacent cells (x = 4s .. 4s+3) with at least one unknown cell;
+// the CTA keeps a compact row-major list of its segments.  Per sweep every CTA does: for each of its
+// segments load own row / row above / row below as 128-bit shared-memory vectors, compute the new values
+// of the unknown cells (registers hold them), block barrier, store them (own rows + the neighbour CTAs'
+// halo rows through DSMEM) and push its partial {sum|new-old|, sum old} to every CTA of the cluster, ONE
+// cluster barrier, then every CTA adds the C partials in rank order and takes the same stop decision
 // (delta = nanmean|new-old| / nanmean(old) <= threshold, commit-then-break: VPint/SD_MRP.py:138-147,
 // VPint/WP_MRP.py:351-362).  Halo rows and partials are double buffered by sweep parity, which is what
 // makes one cluster barrier per sweep sufficient.
 #include <cooperative_groups.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "vpint_internal.cuh"
 
@@ -33,15 +39,33 @@ namespace {
 
 constexpr int kThreads = kResidentThreads;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxPer = kResidentMaxPer;   // unknown cells per thread, held in registers across the barrier
+constexpr int kMaxSeg = kResidentMaxSeg;   // segments per thread (4 new values each, in registers)
 constexpr int kMaxC = 8;                   // portable cluster size
+constexpr int kPadL = 2;                   // zero columns left of x = 0 (keeps segments 16-byte aligned)
+
+// list entry: [15:0] plane offset of the segment's first cell, [19:16] unknown-cell nibble,
+// [20] on the first owned row, [21] on the last owned row, [22] touches the grid border (nc < 4 somewhere)
+constexpr unsigned kSegTop = 1u << 20, kSegBot = 1u << 21, kSegEdge = 1u << 22;
+
+// Cluster barrier with release / acquire at cluster scope.
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// fp64 division that the compiler cannot speculate out of a rarely taken branch (an inlined division is
+// ~30 instructions, ~100 with an inf operand such as the default clip_val).
+__device__ __forceinline__ double div_here(double a, double b) {
+    double r;
+    asm volatile("div.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
 
 struct SmemLayout {
-    double *plane;       // [R][SP] owned rows, columns 0 and SP-1 are the zero border
-    double *halo_up;     // [2][SP]  row above the owned band, by sweep parity
-    double *halo_dn;     // [2][SP]  row below
-    double *fcomp;       // [fcap]   feature of the first fcap listed cells (RATIO)
-    unsigned short *list;  // [n]    shared-memory offset (ly * SP + x + 1) of every unknown owned cell, row-major
+    double *plane;       // [R][SP] owned rows; columns < kPadL and > W + 1 are the zero border
+    double *halo_up;     // [2][SP] row above the owned band, by sweep parity
+    double *halo_dn;     // [2][SP] row below
+    double *fseg;        // [fcap][4] features of the first fcap listed segments (RATIO)
+    unsigned *list;      // [n_seg] segment entries, row-major
 };
 
 __device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, int fcap) {
@@ -49,9 +73,151 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, i
     s.plane = reinterpret_cast<double *>(raw);
     s.halo_up = s.plane + (size_t)R * SP;
     s.halo_dn = s.halo_up + 2 * SP;
-    s.fcomp = s.halo_dn + 2 * SP;
-    s.list = reinterpret_cast<unsigned short *>(s.fcomp + fcap);
+    s.fseg = s.halo_dn + 2 * SP;
+    s.list = reinterpret_cast<unsigned *>(s.fseg + (size_t)fcap * 4);
     return s;
+}
+
+struct SweepCtx {
+    double *plane;
+    const double *halo_up, *halo_dn;
+    const double *fseg;
+    const unsigned *list;
+    const double *fp;                 // global feature plane of this problem (segments beyond fcap)
+    double *up_remote, *dn_remote;    // neighbour CTAs' halo rows (DSMEM), null at the physical border
+    int SP, bot_base, fcap, gy0, pitch, tid, n, H, W;
+    double gamma, clip;
+};
+
+__device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    a = v.x; b = v.y;
+}
+
+// One Jacobi sweep over this thread's segments (entries tid + k * kThreads < n, k < KT).  Straight-line
+// code: every k is executed (entries past the end re-read segment n - 1 and are discarded) so the loads
+// and fp64 chains of the KT segments overlap.  New values stay in registers across the block barrier.
+// A NaN or inf anywhere poisons the partial sums, which is how the caller detects data it must leave to
+// the tiled path.
+template <bool RATIO, int KT>
+__device__ __forceinline__ void sweep_segments(const SweepCtx &c, int par, double (*red)[kSumSlots]) {
+    double nr[KT][4];
+    double s_abs = 0.0, s_old = 0.0;
+    const double *halo_up = c.halo_up + par * c.SP, *halo_dn = c.halo_dn + par * c.SP;
+    const int last = c.n - 1;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int i0 = c.tid + k * kThreads;
+        const bool live = i0 <= last;
+        const int i = live ? i0 : last;
+        const unsigned e = c.list[i];
+        const int off = (int)(e & 0xffffu);
+        const unsigned m = live ? ((e >> 16) & 15u) : 0u;
+        const double *row = c.plane + off;
+        const double *upp = (e & kSegTop) ? halo_up + off : row - c.SP;
+        const double *dnp = (e & kSegBot) ? halo_dn + (off - c.bot_base) : row + c.SP;
+        double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
+        ld2(row, c0, c1); ld2(row + 2, c2, c3);
+        ld2(upp, u0, u1); ld2(upp + 2, u2, u3);
+        ld2(dnp, d0, d1); ld2(dnp + 2, d2, d3);
+        const double lf = row[-1], rt = row[4];
+        double r[4];
+        if (RATIO) {
+            r[0] = ((u0 + c1) + d0) + lf;
+            r[1] = ((u1 + c2) + d1) + c0;
+            r[2] = ((u2 + c3) + d2) + c1;
+            r[3] = ((u3 + rt) + d3) + c2;
+        } else {
+            const double g = c.gamma;
+            r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
+            r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
+            r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
+            r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
+        }
+        const bool edge = (e & kSegEdge) != 0;
+        if (__any_sync(0xffffffffu, edge)) {
+            if (edge) {                        // grid border: per-cell neighbour count, true division
+                const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.gy0 + ly;
+                const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = x0 + j;
+                    const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
+                    r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+        }
+        const double cc[4] = {c0, c1, c2, c3};
+        double vn[4], vo[4];
+        if (RATIO) {
+            double f[4];
+            const double *fs = c.fseg + (size_t)min(i, c.fcap - 1) * 4;
+            ld2(fs, f[0], f[1]); ld2(fs + 2, f[2], f[3]);
+            if (i >= c.fcap) {
+                const int ly = off / c.SP;
+                const double *fg = c.fp + (size_t)(c.gy0 + ly) * c.pitch + (off - ly * c.SP - kPadL);
+                ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
+            }
+            bool clipped = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                vn[j] = f[j] * r[j];
+                vo[j] = f[j] * cc[j];
+                clipped |= ((m >> j) & 1u) && (vn[j] > c.clip);
+            }
+            if (__any_sync(0xffffffffu, clipped)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((m >> j) & 1u) && vn[j] > c.clip) { vn[j] = c.clip; r[j] = div_here(c.clip, f[j]); }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (r[j] > c.clip) r[j] = c.clip;
+                vn[j] = r[j];
+                vo[j] = cc[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool unk = (m >> j) & 1u;
+            s_abs += unk ? fabs(vn[j] - vo[j]) : 0.0;
+            s_old += unk ? vo[j] : 0.0;
+            nr[k][j] = unk ? r[j] : cc[j];
+        }
+    }
+    {
+        const int lane = c.tid & 31, warp = c.tid >> 5;
+        const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
+        if (lane == 0) { red[warp][0] = q0; red[warp][1] = q1; }
+    }
+    __syncthreads();                           // every read of the old state is done
+    const int npo = (par ^ 1) * c.SP;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int i = c.tid + k * kThreads;
+        if (i <= last) {
+            const unsigned e = c.list[i];
+            const int off = (int)(e & 0xffffu);
+            const double2 lo = make_double2(nr[k][0], nr[k][1]), hi = make_double2(nr[k][2], nr[k][3]);
+            double2 *row = reinterpret_cast<double2 *>(c.plane + off);
+            row[0] = lo; row[1] = hi;
+            if ((e & kSegTop) && c.up_remote) {
+                double2 *q = reinterpret_cast<double2 *>(c.up_remote + npo + off);
+                q[0] = lo; q[1] = hi;
+            }
+            if ((e & kSegBot) && c.dn_remote) {
+                double2 *q = reinterpret_cast<double2 *>(c.dn_remote + npo + off - c.bot_base);
+                q[0] = lo; q[1] = hi;
+            }
+        }
+    }
 }
 
 template <bool RATIO>
@@ -83,9 +249,9 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
     for (;;) {
         // ---- next problem from the queue (cluster-uniform) ------------------------------------
         if (crank == 0 && tid == 0) next_problem = atomicAdd(a.queue, 1);
-        cluster.sync();
+        cluster_barrier();
         const int p = *next_remote;
-        cluster.sync();                                // everyone has read before rank 0 overwrites or exits
+        cluster_barrier();                             // everyone has read before rank 0 overwrites or exits
         if (p >= g.P) break;
         const ProbState st = a.state[p];
         if (st.status != 0) continue;                  // nothing to run (cluster-uniform)
@@ -102,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
             const bool in_grid = (gy >= 0) && (gy < H);
             for (int lx = lane; lx < SP; lx += 32) {
                 double v = 0.0;
-                const int x = lx - 1;
+                const int x = lx - kPadL;
                 if (in_grid && x >= 0 && x < W) {
                     v = grid[(size_t)gy * g.pitch + x];
                     if (RATIO) v = v / fp[(size_t)gy * g.pitch + x];
@@ -112,12 +278,19 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
             }
         }
 
-        // ---- compact row-major list of the unknown owned cells --------------------------------
+        // ---- compact row-major list of the segments that hold an unknown cell ------------------
+        // A mask word covers 8 segments (nibbles); warps take contiguous row chunks, so the list order
+        // (and with it every partial sum) is fixed.
         const int rows_per_warp = (n_rows + kWarps - 1) / kWarps;
         const int wr0 = min(warp * rows_per_warp, n_rows), wr1 = min(wr0 + rows_per_warp, n_rows);
+        auto nibbles = [](unsigned w) {                // bit 4q set <=> nibble q of w is nonzero
+            unsigned t = w | (w >> 1);
+            t |= t >> 2;
+            return t & 0x11111111u;
+        };
         int cnt = 0;
         for (int ly = wr0; ly < wr1; ++ly)
-            for (int w = lane; w < nwords; w += 32) cnt += __popc(mrow[(size_t)(gy0 + ly) * g.mpitch + w]);
+            for (int w = lane; w < nwords; w += 32) cnt += __popc(nibbles(mrow[(size_t)(gy0 + ly) * g.mpitch + w]));
         cnt = warp_sum(cnt);
         if (lane == 0) wcount[warp] = cnt;
         __syncthreads();
@@ -127,10 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
             n += wcount[w];
         }
         for (int ly = wr0; ly < wr1; ++ly) {
+            const int gy = gy0 + ly;
+            const unsigned row_flags = (ly == 0 ? kSegTop : 0u) | (ly == n_rows - 1 ? kSegBot : 0u);
+            const bool row_edge = (gy == 0) || (gy == H - 1);
             for (int w0 = 0; w0 < nwords; w0 += 32) {
                 const int w = w0 + lane;
-                unsigned word = (w < nwords) ? mrow[(size_t)(gy0 + ly) * g.mpitch + w] : 0u;
-                const int pc = __popc(word);
+                const unsigned word = (w < nwords) ? mrow[(size_t)gy * g.mpitch + w] : 0u;
+                unsigned nz = nibbles(word);
+                const int pc = __popc(nz);
                 int incl = pc;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -139,33 +316,45 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
                 }
                 int pos = base + incl - pc;
                 base += __shfl_sync(0xffffffffu, incl, 31);
-                while (word) {
-                    const int b = __ffs(word) - 1;
-                    word &= word - 1;
-                    const int x = (w << 5) + b;
-                    sm.list[pos] = (unsigned short)(ly * SP + x + 1);
-                    if (RATIO && pos < fcap) sm.fcomp[pos] = fp[(size_t)(gy0 + ly) * g.pitch + x];
-                    ++pos;
+                while (nz) {
+                    const int b = __ffs(nz) - 1;       // bit 4q
+                    nz &= nz - 1;
+                    const int x0 = (w << 5) + b;       // first cell of the segment
+                    const unsigned nib = (word >> b) & 15u;
+                    const bool edge = row_edge || x0 == 0 || (x0 + 3 >= W - 1);
+                    sm.list[pos++] = (unsigned)(ly * SP + x0 + kPadL) | (nib << 16) | row_flags | (edge ? kSegEdge : 0u);
                 }
             }
         }
         __syncthreads();
-
-        // ---- per-thread static facts about its cells (entry i = tid + k * kThreads) -----------
-        const int K = (n > tid) ? (n - tid + kThreads - 1) / kThreads : 0;
-        unsigned top_bits = 0, bot_bits = 0, edge_bits = 0;
-        for (int k = 0; k < K; ++k) {
-            const int off = sm.list[tid + k * kThreads];
-            const int ly = off / SP, x = off - ly * SP - 1, gy = gy0 + ly;
-            if (ly == 0) top_bits |= 1u << k;
-            if (ly == n_rows - 1) bot_bits |= 1u << k;
-            if (gy == 0 || gy == H - 1 || x == 0 || x == W - 1) edge_bits |= 1u << k;
+        if (RATIO) {                                   // features of the listed segments (pad cells read 1.0)
+            for (int i = tid; i < min(n, fcap); i += kThreads) {
+                const int off = (int)(sm.list[i] & 0xffffu);
+                const int ly = off / SP, x0 = off - ly * SP - kPadL;
+                const double *fg = fp + (size_t)(gy0 + ly) * g.pitch + x0;
+                double f0, f1, f2, f3;
+                ld2(fg, f0, f1); ld2(fg + 2, f2, f3);
+                double2 *d = reinterpret_cast<double2 *>(sm.fseg + (size_t)i * 4);
+                d[0] = make_double2(f0, f1); d[1] = make_double2(f2, f3);
+            }
         }
-        const int bot_base = (n_rows - 1) * SP;
+        const int Kmax = (n + kThreads - 1) / kThreads;    // CTA-uniform
+        int kt = kMaxSeg;                                  // smallest unrolled variant >= Kmax
+        {
+            const int kts[6] = {0, 1, 2, 3, 4, 6};
+#pragma unroll
+            for (int q = 5; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
+        }
+        SweepCtx ctx;
+        ctx.plane = sm.plane; ctx.halo_up = sm.halo_up; ctx.halo_dn = sm.halo_dn; ctx.fseg = sm.fseg; ctx.list = sm.list;
+        ctx.fp = fp; ctx.up_remote = up_halo_remote; ctx.dn_remote = dn_halo_remote;
+        ctx.SP = SP; ctx.bot_base = (n_rows - 1) * SP; ctx.fcap = fcap; ctx.gy0 = gy0; ctx.pitch = g.pitch; ctx.tid = tid;
+        ctx.n = n; ctx.H = H; ctx.W = W;
+        ctx.gamma = gamma; ctx.clip = a.clip;
         const double *K0 = a.known0 + (size_t)p * kSumSlots, *K1 = a.known + (size_t)p * kSumSlots;
         const double k0[kSumSlots] = {K0[0], K0[1], K0[2], K0[3]};
         const double k1[kSumSlots] = {K1[0], K1[1], K1[2], K1[3]};
-        cluster.sync();                                // lists and planes of every CTA are in place
+        cluster_barrier();                             // lists and planes of every CTA are in place
 
         // ---- sweeps -----------------------------------------------------------------------------
         int it = 0;
@@ -173,65 +362,19 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
         bool bailed = false;
         bool fresh = (st.fresh != 0);
         for (; it < a.max_iter;) {
-            const double *hu = sm.halo_up + par * SP, *hd = sm.halo_dn + par * SP;
-            double nr[kMaxPer];
-            double s_abs = 0.0, s_old = 0.0;
-            int c_abs = 0, c_old = 0;
-#pragma unroll
-            for (int k = 0; k < kMaxPer; ++k) {
-                if (k < K) {
-                    const int i = tid + k * kThreads;
-                    const int off = sm.list[i];
-                    const double c = sm.plane[off];
-                    const double lf = sm.plane[off - 1], rt = sm.plane[off + 1];
-                    const double up = ((top_bits >> k) & 1u) ? hu[off] : sm.plane[off - SP];
-                    const double dn = ((bot_bits >> k) & 1u) ? hd[off - bot_base] : sm.plane[off + SP];
-                    double s;
-                    if (RATIO) s = ((up + rt) + dn) + lf;
-                    else s = fma(lf, gamma, fma(dn, gamma, fma(rt, gamma, up * gamma)));
-                    double rn;
-                    if ((edge_bits >> k) & 1u) {
-                        const int ly = off / SP, x = off - ly * SP - 1, gy = gy0 + ly;
-                        const int nc = 4 - (gy == 0 ? 1 : 0) - (gy == H - 1 ? 1 : 0) - (x == 0 ? 1 : 0) - (x == W - 1 ? 1 : 0);
-                        rn = s / (double)nc;
-                    } else {
-                        rn = s * 0.25;
-                    }
-                    double vn = rn, vo = c;
-                    if (RATIO) {
-                        const double f = (i < fcap) ? sm.fcomp[i]
-                                                    : fp[(size_t)(gy0 + off / SP) * g.pitch + (off - (off / SP) * SP - 1)];
-                        vn = f * rn;
-                        vo = f * c;
-                        if (vn > a.clip) { vn = a.clip; rn = a.clip / f; }
-                    } else if (vn > a.clip) {
-                        vn = a.clip; rn = a.clip;
-                    }
-                    const double d = fabs(vn - vo);
-                    if (d != d) ++c_abs; else s_abs += d;
-                    if (vo != vo) ++c_old; else s_old += vo;
-                    nr[k] = rn;
-                }
+            switch (kt) {
+                case 0: if (lane == 0) { red[warp][0] = 0.0; red[warp][1] = 0.0; } __syncthreads(); break;
+                case 1: sweep_segments<RATIO, 1>(ctx, par, red); break;
+                case 2: sweep_segments<RATIO, 2>(ctx, par, red); break;
+                case 3: sweep_segments<RATIO, 3>(ctx, par, red); break;
+                case 4: sweep_segments<RATIO, 4>(ctx, par, red); break;
+                case 6: sweep_segments<RATIO, 6>(ctx, par, red); break;
+                default: sweep_segments<RATIO, kMaxSeg>(ctx, par, red); break;
             }
-            {
-                const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
-                const int n0 = warp_sum(c_abs), n1 = warp_sum(c_old);
-                if (lane == 0) { red[warp][0] = q0; red[warp][1] = q1; red[warp][2] = (double)n0; red[warp][3] = (double)n1; }
-            }
-            __syncthreads();                           // every read of the old state is done
             const int npar = par ^ 1;
-#pragma unroll
-            for (int k = 0; k < kMaxPer; ++k) {
-                if (k < K) {
-                    const int off = sm.list[tid + k * kThreads];
-                    sm.plane[off] = nr[k];
-                    if (((top_bits >> k) & 1u) && up_halo_remote) up_halo_remote[npar * SP + off] = nr[k];
-                    if (((bot_bits >> k) & 1u) && dn_halo_remote) dn_halo_remote[npar * SP + off - bot_base] = nr[k];
-                }
-            }
             if (warp == 0) {
                 double part = 0.0;
-                if (lane < kSumSlots) {
+                if (lane < 2) {
                     for (int w = 0; w < kWarps; ++w) part += red[w][lane];
                 }
                 // lane (q * 4 + slot) stores slot of this CTA's partial into CTA q
@@ -239,22 +382,19 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
                 const double val = __shfl_sync(0xffffffffu, part, slot);
                 if (q < C) cluster.map_shared_rank(&cta_part[par][crank][slot], q)[0] = val;
             }
-            cluster.sync();                            // new state, halos and partials visible cluster-wide
-            double S[kSumSlots] = {0.0, 0.0, 0.0, 0.0};
-            for (int q = 0; q < C; ++q) {
-#pragma unroll
-                for (int i = 0; i < kSumSlots; ++i) S[i] += cta_part[par][q][i];
-            }
+            cluster_barrier();                         // new state, halos and partials visible cluster-wide
+            double S0 = 0.0, S1 = 0.0;
+            for (int q = 0; q < C; ++q) { S0 += cta_part[par][q][0]; S1 += cta_part[par][q][1]; }
             // Anything non-finite (NaN start state, overflow of f * r where the reference's w * P would
             // already have overflowed differently, inf inputs): leave this problem, untouched, to the tiled
             // plane path, which reproduces the reference's NaN / inf propagation exactly.
-            if (!(S[2] == 0.0 && S[3] == 0.0 && fabs(S[0]) <= 1.7976931348623157e308 && fabs(S[1]) <= 1.7976931348623157e308)) {
+            if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) {
                 bailed = true;
                 break;
             }
             const double *KK = fresh ? k0 : k1;
-            const double sa = S[0] + KK[0], so = S[1] + KK[1];
-            const double na = n_cells - (S[2] + KK[2]), no = n_cells - (S[3] + KK[3]);
+            const double sa = S0 + KK[0], so = S1 + KK[1];
+            const double na = n_cells - KK[2], no = n_cells - KK[3];
             const double delta = (sa / na) / (so / no);
             if (a.delta_out && crank == 0 && tid == 0) a.delta_out[(size_t)p * a.max_iter + it] = delta;
             fresh = false;
@@ -265,12 +405,18 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
 
         // ---- write the unknown cells back (P = f * r), close the problem ------------------------
         for (int i = tid; i < n && !bailed; i += kThreads) {
-            const int off = sm.list[i];
-            const int ly = off / SP, x = off - ly * SP - 1;
-            const size_t go = (size_t)(gy0 + ly) * g.pitch + x;
-            double v = sm.plane[off];
-            if (RATIO) v = ((i < fcap) ? sm.fcomp[i] : fp[go]) * v;
-            grid[go] = v;
+            const unsigned e = sm.list[i];
+            const int off = (int)(e & 0xffffu);
+            const int ly = off / SP, x0 = off - ly * SP - kPadL;
+            const size_t go = (size_t)(gy0 + ly) * g.pitch + x0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if ((e >> (16 + j)) & 1u) {
+                    double v = sm.plane[off + j];
+                    if (RATIO) v = ((i < fcap) ? sm.fseg[(size_t)i * 4 + j] : fp[go + j]) * v;
+                    grid[go + j] = v;
+                }
+            }
         }
         if (crank == 0 && tid == 0 && !bailed) {
             ProbState ns = st;
@@ -287,24 +433,29 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
 
 // Smallest portable cluster that holds one problem on chip; returns false if none does.
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out) {
-    if (g.ndim != 2 || g.H < 1 || g.L < 1) return false;
-    const int W = g.L, SP = W + 2;
-    const int static_bytes = 2048;   // red, cta_part, wcount, next_problem (+ slack)
+    if (g.ndim != 2 || g.H < 1 || g.L < 1 || (g.H < 2 && g.L < 2)) return false;   // 1x1: neighbour count 0
+    const int W = g.L;
+    const int segs_per_row = (W + 3) / 4;
+    const int SP = 4 * segs_per_row + 4;        // kPadL zero columns left, >= 2 right; even, so rows stay 16-byte aligned
+    if (g.pitch < 4 * segs_per_row) return false;
+    const int static_bytes = 2048;              // red, cta_part, wcount, next_problem (+ slack)
     for (int C = 1; C <= kMaxC; C *= 2) {
         const int R = (g.H + C - 1) / C;
-        if ((g.H + R - 1) / R != C) continue;                       // every CTA must own at least one row
-        if ((int64_t)R * W > (int64_t)kThreads * kMaxPer) continue; // register budget for the new values
-        if ((int64_t)R * SP > 65535) continue;                      // 16-bit shared-memory offsets
-        const int64_t fixed = ((int64_t)R * SP + 4 * SP) * 8 + (((int64_t)R * W * 2 + 15) & ~15LL);
+        if ((g.H + R - 1) / R != C) continue;                                   // every CTA must own at least one row
+        if ((int64_t)R * segs_per_row > (int64_t)kThreads * kMaxSeg) continue;  // register budget for the new values
+        if ((int64_t)R * SP > 65535) continue;                                  // 16-bit shared-memory offsets
+        const int64_t fixed = ((int64_t)R * SP + 4 * SP) * 8 + (int64_t)R * segs_per_row * 4;
         const int64_t room = (int64_t)smem_limit - static_bytes - fixed;
         if (room < 0) continue;
         int fcap = 0;
         if (ratio) {
-            fcap = (int)((room / 8 < (int64_t)R * W) ? room / 8 : (int64_t)R * W);
-            if (fcap * 4 < R * W && C < kMaxC) continue;             // want >= 25 % of the cells' features on chip
+            const int64_t all = (int64_t)R * segs_per_row;
+            fcap = (int)((room / 32 < all) ? room / 32 : all);
+            if (fcap < 1) continue;
+            if (fcap * 4 < all && C < kMaxC) continue;                           // want >= 25 % of the features on chip
         }
         out->C = C; out->R = R; out->SP = SP; out->fcap = fcap;
-        out->smem_bytes = (size_t)(fixed + (int64_t)fcap * 8);
+        out->smem_bytes = (size_t)(fixed + (int64_t)fcap * 32);
         return true;
     }
     return false;
@@ -333,6 +484,9 @@ cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_byt
         if (e != cudaSuccess) return e;
         if (clusters < 1) return cudaErrorLaunchOutOfResources;
     }
+    if (getenv("VPINT_DEBUG"))
+        fprintf(stderr, "[vpint] resident2d: C=%d R=%d SP=%d fcap=%d smem=%zu max_clusters=%d P=%d\n", a.C, a.R, a.SP,
+                a.fcap, smem_bytes, clusters, a.g.P);
     if (clusters > a.g.P) clusters = a.g.P;
     cfg.gridDim = dim3((unsigned)(clusters * a.C), 1, 1);
     e = cudaLaunchKernelEx(&cfg, kern, a);
