@@ -195,13 +195,14 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kb, masked_px):
-    """DRAM bytes per stencil launch, scaled from the committed `ncu --set full` capture of the same kernel
-    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per unknown cell per launch)."""
+def ncu_traffic(key, scale):
+    """DRAM bytes per launch of the dominant kernel, scaled from the committed `ncu --set full` capture of the
+    same kernel (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per unknown cell per
+    launch for the tiled kernels, per problem for the resident kernel)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = t["k_block"][str(kb)]
-        return e["dram_bytes_per_unknown_cell_per_launch"] * masked_px, e["source"]
+        e = t["k_block"][str(key)]
+        return e["dram_bytes_per_unit"] * scale, e["source"]
     except Exception:
         return None, None
 
@@ -329,29 +330,52 @@ def run_gpu(args):
     ms_e2e, sweeps_e2e = timed(e2e_step, e2e_steps)
     e2e_val = sweeps_e2e * H * W / (ms_e2e * 1e-3) / 1e6
 
-    # roofline of the stencil kernel: every problem active, fixed sweeps, CUDA events around the kernel
-    solver.load(target.permute(0, 3, 1, 2), fill=fill)
-    solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
-    solver.begin_run(10 ** 6, auto_terminate=False)
-    kb = solver.k_block
-    for _ in range(3):
-        solver.step_begin(); solver.step_end()
-    times = []
-    for _ in range(args.roofline_launches):
-        times.append(solver.step_profile())
-        solver.step_end()
-    torch.cuda.synchronize()
-    k_ms = statistics.mean(times)
+    # roofline of the dominant kernel, timed alone with CUDA events on the stream it is launched on
     masked_frac = float(torch.isnan(target).double().mean().item())
     masked_px = masked_frac * total_px
-    # Units one stencil launch processes = the unknown cells it updates (known cells are constants and are
-    # never touched again after load), kb sweeps each; 48 B per cell-sweep (state in + 4 weights +
-    # state out).  The whole-grid figure the reference's sweep would move is reported beside it.
-    alg_bytes = BYTES_WP_F64 * masked_px * kb
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    full_grid_gbps = BYTES_WP_F64 * total_px * kb / (k_ms * 1e-3) / 1e9
+    unknown_pp = torch.isnan(target[..., 0]).sum(dim=(1, 2)).double()          # unknown cells per patch (all bands alike)
     peak, peak_src = peak_hbm()
-    traffic, traffic_src = ncu_traffic(kb, masked_px)
+    kb = solver.k_block
+    resident = (args.k_block == 0)
+    if resident:
+        # one launch = the whole run(): a cluster per problem, all sweeps on chip (vpint_resident.cu)
+        times, units = [], 0.0
+        for _ in range(max(2, args.roofline_launches // 4)):
+            solver.load(target.permute(0, 3, 1, 2), fill=fill)
+            solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            solver.run(opts["iterations"], auto_terminate=True, threshold=opts["threshold"], clip_val=opts["clip_val"])
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            _, nit = solver.result(out=out_dev)
+            units = float((nit.view(n, B).double() * unknown_pp.view(n, 1)).sum().item())   # unknown cell x sweep
+        k_ms = statistics.mean(times)
+        kernel_name = "resident2d_kernel<ratio> (one launch = run() of every problem)"
+        unit_def = "one unknown cell updated for one sweep (%.3e per launch: sum over problems of unknown cells x sweeps)" % units
+        traffic, traffic_src = ncu_traffic("resident", nprob)
+    else:
+        solver.load(target.permute(0, 3, 1, 2), fill=fill)
+        solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
+        solver.begin_run(10 ** 6, auto_terminate=False)
+        for _ in range(3):
+            solver.step_begin(); solver.step_end()
+        times = []
+        for _ in range(args.roofline_launches):
+            times.append(solver.step_profile())
+            solver.step_end()
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(times)
+        units = masked_px * kb
+        kernel_name = "jacobi2d_%s (stencil launch, all problems active)" % ("k1" if kb == 1 else "tb")
+        unit_def = "one unknown cell updated for one sweep (%.0f cells x %d sweeps per launch)" % (masked_px, kb)
+        traffic, traffic_src = ncu_traffic(kb, masked_px)
+    # 48 B per unknown cell per sweep (state in + 4 weights + state out); known cells are constants
+    # and are never touched again after load.  The whole-grid figure of the reference's sweep is given beside it.
+    alg_bytes = BYTES_WP_F64 * units
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    full_grid_gbps = achieved / max(masked_frac, 1e-12)
     active_tiles, total_tiles = solver.active_tiles, solver.total_tiles
 
     line = None
@@ -362,16 +386,19 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3: VPint2 cloud removal, 256x256x13 Sentinel-2-shaped patches, %d patches per GPU "
                                    "(%d band problems, %.0f Mpx per GPU), auto-terminate 1e-4" % (n, nprob, total_px / 1e6),
-                       "patches_per_gpu": n, "H": H, "W": W, "bands": B, "k_block": kb, "cloud_fraction": round(masked_frac, 4),
+                       "patches_per_gpu": n, "H": H, "W": W, "bands": B, "k_block": args.k_block,
+                       "path": "cluster-resident (k_block 0)" if args.k_block == 0 else "tiled, %d sweeps per launch" % kb, "cloud_fraction": round(masked_frac, 4),
                        "active_tiles": active_tiles, "total_tiles": total_tiles,
                        "l2_note": "state+weights %.1f GB per GPU >> 126 MB L2; no flush needed" % (48.0 * total_px / 1e9),
                        "mean_sweeps_per_problem": sweeps_dev / args.steps / (nprob * world)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "jacobi2d_%s (stencil launch, all problems active)" % ("k1" if kb == 1 else "tb"),
+                         "kernel": kernel_name,
                          "kernel_ms": k_ms, "alg_bytes_per_launch": alg_bytes, "bytes_per_unit": BYTES_WP_F64,
-                         "unit_def": "one unknown cell updated for one sweep (%.0f cells x %d sweeps per launch)" % (masked_px, kb),
-                         "whole_grid_equiv_gbps": full_grid_gbps},
+                         "unit_def": unit_def, "whole_grid_equiv_gbps": full_grid_gbps,
+                         "note": ("state stays in shared memory for all sweeps: DRAM traffic is one read + one write per "
+                                  "problem, so algorithmic GB/s may exceed the HBM peak" if resident else
+                                  "streams state and weights from HBM every launch")},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(t_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 8 + nprob * 4), "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps, "api": "vpint_b200.vpint2.solve_bands (VPint2 run path), pinned host buffers"},

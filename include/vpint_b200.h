@@ -117,7 +117,10 @@ int    vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes);
  *              (self.pred_grid); may be NULL, then unknown cells start at
  *              fill[p] (the init_strategy='mean'/'zero' value computed by the
  *              caller exactly as MRP.init_pred_grid does, MRP.py:64-82).
- *   fill     : HOST array [nprob]; only read when pred0 == NULL.
+ *   fill     : HOST array [nprob]; only read when pred0 == NULL.  With pred0 == NULL and
+ *              fill == NULL the init_strategy='mean' value is computed on the device:
+ *              np.nanmean of each problem's grid in ITS dtype, bit-identical to NumPy's
+ *              pairwise summation (grids up to 131072 cells; larger grids need fill).
  *   stride   : 5 element strides {outer problem, inner problem, row, column, t}
  *              of original/pred0 (t ignored for ndim == 2).  This is how the
  *              band-interleaved (N, H, W, B) VPint2 arrays are read in place:

@@ -405,3 +405,54 @@ def test_row_sharded_scene_lockstep(world, k):
     for _, sweeps in parts:
         assert list(sweeps) == list(ref_sweeps)
     close(np.moveaxis(got, 0, -1), ref)
+
+
+# ---- 5. A1 on the device and the pipelined host path -----------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(256, 256), (100, 100), (37, 91), (2, 3), (1, 130), (300, 301)])
+def test_device_mean_init_is_numpy_nanmean(shape, dtype):
+    """load(fill=None) must start unknown cells at np.nanmean(band) taken in the band's dtype, bit for bit
+    (VPint/MRP.py:73-77): NumPy's pairwise summation order is reproduced on the device."""
+    import torch
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    B = 3
+    stack = rng.uniform(0, 4000, shape + (B,)).astype(dtype)
+    stack[rng.uniform(size=shape) < 0.3, :] = np.nan
+    stack[0, 0, :] = np.nan                      # at least one unknown and one known cell
+    stack[-1, -1, :] = 1234.5
+    stack[..., 2] = np.round(stack[..., 2])
+    s = Solver(2, B, shape[0], shape[1], nprob_inner=B, planes=False)
+    try:
+        t = torch.from_numpy(stack).cuda()
+        s.load(t.permute(2, 0, 1).unsqueeze(0), fill=None)
+        out, _ = s.result()
+        got = out.cpu().numpy()
+    finally:
+        s.close()
+    for b in range(B):
+        band = stack[:, :, b]
+        want = np.nanmean(band.copy())
+        assert want.dtype == dtype
+        filled = got[b][np.isnan(band)]
+        assert filled.size > 0 and (filled == np.float64(want)).all(), (b, filled[0], want)
+        assert np.array_equal(got[b][~np.isnan(band)], band[~np.isnan(band)].astype(np.float64))
+
+
+def test_pipelined_host_stack_equals_single_solve():
+    import torch
+    from vpint_b200.vpint2 import _solve_bands_torch
+    from vpint_b200.wp import wp_run_options
+    rng = np.random.default_rng(606)
+    vps = [make_patch(rng, 64, 64, 3) for _ in range(7)]
+    tgt = torch.from_numpy(np.stack([v.target for v in vps])).pin_memory()
+    fts = torch.from_numpy(np.stack([v.features for v in vps])).pin_memory()
+    dev = torch.device("cuda", 0)
+    opts = wp_run_options()
+    out = torch.empty((7, 3, 64, 64), dtype=torch.float64).pin_memory()
+    res, sweeps = _solve_bands_torch(tgt, fts, opts, "bhw", torch.float64, "float64", None, dev, out, None, chunk_patches=2)
+    one, sweeps1 = _solve_bands_torch(tgt.cuda(), fts.cuda(), opts, "bhw", torch.float64, "float64", None, dev, None, None)
+    assert torch.equal(sweeps, sweeps1)
+    close(res.numpy(), one.numpy(), rtol=0)
+    ref, ref_sweeps = O.vpint2_run(vps[5].target, vps[5].features)
+    close(np.moveaxis(res.numpy()[5], 0, -1), ref)
+    assert list(sweeps[5].numpy()) == list(ref_sweeps)

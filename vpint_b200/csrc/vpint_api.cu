@@ -230,11 +230,17 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
                       const int64_t *stride, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!original || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_load: null argument");
-    if (!pred0 && !fill) return fail(VPINT_ERR_INVALID, "vpint_solver_load: need pred0 or fill");
+    const bool device_fill = (!pred0 && !fill);
+    if (device_fill && !fill_mean_supported(s->g))
+        return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_load: grid too large for the on-device mean init; pass fill");
+    if (device_fill && (s->g.global_H != s->g.H))
+        return fail(VPINT_ERR_INVALID, "vpint_solver_load: a row shard cannot take the mean of the whole grid; pass fill");
     if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Geom &g = s->g;
-    if (!pred0)
+    if (device_fill)
+        VP_CUDA(launch_fill_mean(g, original, dtype, stride, s->at<double>(s->off_fill), st, &s->launches), "fill mean");
+    else if (!pred0)
         VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_fill), fill, (size_t)g.P * sizeof(double), cudaMemcpyHostToDevice, st),
                 "copy fill");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");

@@ -119,6 +119,9 @@ cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred
                            int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,
                            uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
                            int *counters, cudaStream_t st, int64_t *launches);
+bool fill_mean_supported(const Geom &g);
+cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, const int64_t *stride, double *fill_dev,
+                             cudaStream_t st, int64_t *launches);
 cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
                          int *counters, cudaStream_t st, int64_t *launches);
 cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const int64_t *stride, int F, int method,

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
 #pragma unroll
             for (int q = 5; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
         }
+        if (a.dbg == 1) kt = 0;                            // development: barriers only (timing probe)
         SweepCtx ctx;
         ctx.plane = sm.plane; ctx.halo_up = sm.halo_up; ctx.halo_dn = sm.halo_dn; ctx.fseg = sm.fseg; ctx.list = sm.list;
         ctx.fp = fp; ctx.up_remote = up_halo_remote; ctx.dn_remote = dn_halo_remote;
@@ -461,8 +462,10 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
     return false;
 }
 
-cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
+cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
                               int64_t *launches) {
+    ResidentArgs a = a_in;
+    a.dbg = getenv("VPINT_RES_DBG") ? atoi(getenv("VPINT_RES_DBG")) : 0;
     auto kern = ratio ? resident2d_kernel<true> : resident2d_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;

@@ -18,6 +18,114 @@ __device__ __forceinline__ int64_t cell_offset(const Geom &g, const Strides &s, 
     return base + (int64_t)j * s.sX + (int64_t)t * s.sT;
 }
 
+// A1 on the device: init_strategy='mean' fills unknown cells with np.nanmean(grid) taken in the grid's own
+// dtype (VPint/MRP.py:73-77).  NumPy evaluates it as  dtype( float64(pairwise_sum(grid with NaN -> 0)) /
+// count )  where pairwise_sum is its blocked pairwise summation of the row-major copy (blocks of <= 128
+// elements with 8 running accumulators, halves split at multiples of 8).  This kernel reproduces that
+// summation tree bit for bit (checked against NumPy in tests/test_gpu_parity.py), one block per problem:
+// thread 0 walks the recursion and lists the leaf blocks, 8 lanes per leaf own the 8 accumulators, thread 0
+// combines the leaf sums in recursion order.
+constexpr int kFillMaxLeaves = 2048;        // leaves hold 64..128 elements: grids up to 131072 cells
+
+template <typename TIn>
+__device__ __forceinline__ TIn fill_elem(const Geom &g, const Strides &s, const TIn *base, int p, int64_t idx) {
+    const int y = (int)(idx / g.L), e = (int)(idx - (int64_t)y * g.L);
+    const TIn v = base[cell_offset(g, s, p, y, e)];
+    return (v != v) ? (TIn)0 : v;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__restrict__ original, Strides sd,
+                                                        double *__restrict__ fill) {
+    __shared__ int leaf_lo[kFillMaxLeaves];
+    __shared__ unsigned char leaf_sz[kFillMaxLeaves];
+    __shared__ TIn leaf_sum[kFillMaxLeaves];
+    __shared__ int n_leaves;
+    __shared__ int cnt_part[8];
+    const int p = blockIdx.x;
+    const int64_t n = (int64_t)g.H * g.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {                               // DFS over the recursion, left first
+        int st_lo[40], st_n[40];
+        int sp = 0, nl = 0;
+        st_lo[0] = 0; st_n[0] = (int)n;
+        while (sp >= 0) {
+            const int lo = st_lo[sp], m = st_n[sp];
+            --sp;
+            if (m <= 128) {
+                leaf_lo[nl] = lo; leaf_sz[nl] = (unsigned char)m; ++nl;
+            } else {
+                int h = m / 2;
+                h -= h % 8;
+                ++sp; st_lo[sp] = lo + h; st_n[sp] = m - h;     // right is popped after left
+                ++sp; st_lo[sp] = lo; st_n[sp] = h;
+            }
+        }
+        n_leaves = nl;
+    }
+    __syncthreads();
+    // leaf sums: 8 lanes per leaf = the 8 accumulators of NumPy's unrolled loop
+    const int sub = lane >> 3, j = lane & 7;
+    for (int l0 = warp * 4; l0 < n_leaves; l0 += 8 * 4) {
+        const int l = l0 + sub;
+        TIn res = (TIn)0;
+        if (l < n_leaves) {
+            const int lo = leaf_lo[l], m = leaf_sz[l];
+            if (m < 8) {
+                if (j == 0) {
+                    res = (TIn)0;
+                    for (int i = 0; i < m; ++i) res += fill_elem(g, sd, original, p, (int64_t)lo + i);
+                }
+            } else {
+                TIn r = fill_elem(g, sd, original, p, (int64_t)lo + j);
+                int i = 8;
+                for (; i < m - (m % 8); i += 8) r += fill_elem(g, sd, original, p, (int64_t)lo + i + j);
+                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) within each group of 8 lanes
+                const unsigned grp = 0xffu << (sub * 8);
+                TIn a = r + __shfl_down_sync(grp, r, 1, 8);     // valid in j = 0, 2, 4, 6
+                TIn b = a + __shfl_down_sync(grp, a, 2, 8);     // valid in j = 0, 4
+                TIn c = b + __shfl_down_sync(grp, b, 4, 8);     // valid in j = 0
+                if (j == 0) {
+                    res = c;
+                    for (; i < m; ++i) res += fill_elem(g, sd, original, p, (int64_t)lo + i);
+                }
+            }
+            if (j == 0) leaf_sum[l] = res;
+        }
+    }
+    // count of non-NaN cells
+    int cnt = 0;
+    for (int64_t i = tid; i < n; i += blockDim.x) {
+        const int y = (int)(i / g.L), e = (int)(i - (int64_t)y * g.L);
+        const TIn v = original[cell_offset(g, sd, p, y, e)];
+        cnt += (v == v) ? 1 : 0;
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) cnt_part[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        // combine in recursion order: res(node) = res(left) + res(right)
+        int st_n[40], st_state[40];
+        TIn st_acc[40];
+        int sp = 0, next_leaf = 0;
+        st_n[0] = (int)n; st_state[0] = 0;
+        TIn ret = (TIn)0;
+        while (sp >= 0) {
+            const int m = st_n[sp];
+            if (m <= 128) { ret = leaf_sum[next_leaf++]; --sp; continue; }
+            int h = m / 2;
+            h -= h % 8;
+            if (st_state[sp] == 0) { st_state[sp] = 1; ++sp; st_n[sp] = h; st_state[sp] = 0; }
+            else if (st_state[sp] == 1) { st_acc[sp] = ret; st_state[sp] = 2; ++sp; st_n[sp] = m - h; st_state[sp] = 0; }
+            else { ret = st_acc[sp] + ret; --sp; }
+        }
+        int total = 0;
+        for (int w = 0; w < 8; ++w) total += cnt_part[w];
+        const TIn total_sum = (TIn)0 + ret;                      // add.reduce starts from the identity
+        fill[p] = (double)(TIn)((double)total_sum / (double)total);
+    }
+}
+
 // One block per (problem, row).  Stages the start state of run():
 //   bufA = pred0 (self.pred_grid, VPint/MRP.py:64-91 or whatever the caller left there),
 //   bufB = original at known cells (the restore of VPint/SD_MRP.py:133-134 / WP_MRP.py:321,323 is
@@ -332,6 +440,17 @@ __global__ void __launch_bounds__(256) halo_rows_kernel(Geom g, const ProbState 
         if (e__ != cudaSuccess) return e__;       \
         if (launches) ++*launches;                \
     } while (0)
+
+bool fill_mean_supported(const Geom &g) { return (int64_t)g.H * g.L <= (int64_t)kFillMaxLeaves * 64; }
+
+cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, const int64_t *stride, double *fill_dev,
+                             cudaStream_t st, int64_t *launches) {
+    const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
+    if (dtype == VPINT_F64) fill_mean_kernel<double><<<g.P, 256, 0, st>>>(g, (const double *)original, sd, fill_dev);
+    else fill_mean_kernel<float><<<g.P, 256, 0, st>>>(g, (const float *)original, sd, fill_dev);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
 
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
                            int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,

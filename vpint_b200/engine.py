@@ -149,6 +149,8 @@ class Solver:
             self._keep.append(pv)
             pptr = C.c_void_p(pv.data_ptr())
             fptr = None
+        elif fill is None:
+            fptr = None       # mean init on the device (np.nanmean per problem, NumPy's summation order)
         else:
             f = np.ascontiguousarray(np.asarray(fill, dtype=np.float64).reshape(-1))
             if f.size != self.nprob:

@@ -16,6 +16,11 @@ from .errors import VPintError
 from .wp import wp_run_options
 
 
+# Largest grid whose init_strategy='mean' value the library computes on the device (NumPy-exact pairwise
+# nanmean, csrc/vpint_setup.cu fill_mean_kernel); larger scenes take it on the host.
+DEVICE_FILL_MAX_CELLS = 131072
+
+
 def _band_fill_values(target):
     """Per-band start value of the unknown cells: ``WP_SMRP(target[:, :, b], ...)``
     initialises them with ``np.nanmean`` of the band IN THE BAND'S dtype
@@ -30,39 +35,112 @@ def _band_fill_values(target):
     return out.reshape(lead + (B,))
 
 
-def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k_block, dev, out, fill):
-    """solve_bands for torch inputs (CPU, ideally pinned, or CUDA) of shape (N, H, W, B):
-    asynchronous H2D, one batched solve, asynchronous D2H into ``out`` when given."""
+# Patches per pipeline stage when a host-resident stack is solved chunk by chunk (H2D of chunk i+1 and D2H
+# of chunk i-1 overlap the solve of chunk i).
+PIPELINE_CHUNK_PATCHES = 64
+
+
+def _solve_chunk(solver, t_dev, f_dev, opts, res_dev, out_layout, fill):
+    solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)
+    solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
+                   clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
+    solver.run(opts["iterations"], auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
+               clip_val=opts["clip_val"])          # blocks the host until every problem of the chunk has stopped
+    _, niter = solver.result(out=res_dev if out_layout == "bhw" else res_dev.permute(0, 3, 1, 2))
+    return niter
+
+
+def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k_block, dev, out, fill,
+                       chunk_patches=None):
+    """solve_bands for torch inputs of shape (N, H, W, B).
+
+    CUDA inputs (or a small stack): one batched solve.  Host inputs (ideally pinned): the stack is cut into
+    chunks of ``chunk_patches`` patches and pipelined over three streams -- host->device copy of chunk
+    i+1, solve of chunk i, device->host copy of chunk i-1 -- so the PCIe transfers hide behind the solves.
+    ``out`` (preallocated, ideally pinned) receives the result."""
     import torch
     N, H, W, B = target.shape
-    if fill is None:
+    kb = _solve.DEFAULT_K_BLOCK if k_block is None else k_block
+    if fill is None and H * W > DEVICE_FILL_MAX_CELLS:
         fill = _band_fill_values(target.cpu().numpy()).reshape(-1)
-    solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
-                    k_block=(_solve.DEFAULT_K_BLOCK if k_block is None else k_block), device=dev)
+    fill = None if fill is None else np.asarray(fill, dtype=np.float64).reshape(N, B)
+    chunk = int(chunk_patches or PIPELINE_CHUNK_PATCHES)
+    res_shape = (lambda m: (m, B, H, W)) if out_layout == "bhw" else (lambda m: (m, H, W, B))
+    res_dtype = torch.float64 if out_layout == "bhw" else out_dtype
+
+    if target.device.type != "cpu" or N <= chunk:
+        solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev)
+        try:
+            t_dev = target.to(dev, non_blocking=True)
+            f_dev = features.to(dev, non_blocking=True)
+            res_dev = torch.empty(res_shape(N), dtype=res_dtype, device=dev)
+            niter = _solve_chunk(solver, t_dev, f_dev, opts, res_dev, out_layout, None if fill is None else fill.reshape(-1))
+            if out is not None:
+                out.copy_(res_dev, non_blocking=True)
+                sweeps = niter.cpu()          # synchronises the stream: `out` is complete after this
+                res = out
+            else:
+                res = res_dev.cpu()
+                sweeps = niter.cpu()
+        finally:
+            solver.close()
+        return res, sweeps.to(torch.int64).view(N, B)
+
+    # ---- pipelined path ---------------------------------------------------------------------------
+    if out is None:
+        out = torch.empty(res_shape(N), dtype=res_dtype)
+    sweeps_host = torch.empty(N * B, dtype=torch.int32)
+    if out.is_pinned():
+        sweeps_host = sweeps_host.pin_memory()
+    spans = [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
+    main = torch.cuda.current_stream(dev)
+    s_in, s_run, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+    for st in (s_in, s_run, s_out):
+        st.wait_stream(main)
+    t_slot = [torch.empty((chunk, H, W, B), dtype=target.dtype, device=dev) for _ in range(2)]
+    f_slot = [torch.empty((chunk, H, W, B), dtype=features.dtype, device=dev) for _ in range(2)]
+    r_slot = [torch.empty(res_shape(chunk), dtype=res_dtype, device=dev) for _ in range(2)]
+    solvers = {}
+    ev_in = [None] * len(spans)
+    ev_out = [None] * len(spans)
+
+    def stage(i):
+        a, b = spans[i]
+        with torch.cuda.stream(s_in):
+            t_slot[i % 2][:b - a].copy_(target[a:b], non_blocking=True)
+            f_slot[i % 2][:b - a].copy_(features[a:b], non_blocking=True)
+            ev_in[i] = torch.cuda.Event()
+            ev_in[i].record(s_in)
+
     try:
-        t_dev = target.to(dev, non_blocking=True)
-        f_dev = features.to(dev, non_blocking=True)
-        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)
-        solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
-                       clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
-        solver.run(opts["iterations"], auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
-                   clip_val=opts["clip_val"])
-        if out_layout == "bhw":
-            res_dev = torch.empty((N, B, H, W), dtype=torch.float64, device=dev)
-            _, niter = solver.result(out=res_dev)
-        else:
-            res_dev = torch.empty((N, H, W, B), dtype=out_dtype, device=dev)
-            _, niter = solver.result(out=res_dev.permute(0, 3, 1, 2))
-        if out is not None:
-            out.copy_(res_dev, non_blocking=True)
-            sweeps = niter.cpu()          # synchronises the stream: `out` is complete after this
-            res = out
-        else:
-            res = res_dev.cpu()
-            sweeps = niter.cpu()
+        stage(0)
+        for i, (a, b) in enumerate(spans):
+            m = b - a
+            if i + 1 < len(spans):
+                stage(i + 1)       # its slot was last read by chunk i-1, whose solve has returned
+            if m not in solvers:
+                solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in[i])
+                if i >= 2:
+                    s_run.wait_event(ev_out[i - 2])          # result slot free again
+                niter = _solve_chunk(solvers[m], t_slot[i % 2][:m], f_slot[i % 2][:m], opts, r_slot[i % 2][:m],
+                                     out_layout, None if fill is None else fill[a:b].reshape(-1))
+                done = torch.cuda.Event()
+                done.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out[a:b].copy_(r_slot[i % 2][:m], non_blocking=True)
+                sweeps_host[a * B:b * B].copy_(niter, non_blocking=True)
+                niter.record_stream(s_out)
+                ev_out[i] = torch.cuda.Event()
+                ev_out[i].record(s_out)
+        s_out.synchronize()
+        main.wait_stream(s_run)
     finally:
-        solver.close()
-    return res, sweeps.to(torch.int64).view(N, B)
+        for sv in solvers.values():
+            sv.close()
+    return out, sweeps_host.to(torch.int64).view(N, B)
 
 
 def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw", storage="float64",
@@ -102,13 +180,13 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
             res = res.astype(out_dtype)
         res = res[0] if single else res
         return (res, np.zeros((N, B), dtype=np.int64)[0 if single else slice(None)]) if return_sweeps else res
-    fill = _band_fill_values(tgt)
+    fill = None if H * W <= DEVICE_FILL_MAX_CELLS else _band_fill_values(tgt).reshape(-1)
     solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
                     k_block=(_solve.DEFAULT_K_BLOCK if k_block is None else k_block), device=dev)
     try:
         t_dev = to_device(np.ascontiguousarray(tgt), dev)                 # (N, H, W, B) as stored
         f_dev = to_device(np.ascontiguousarray(fts), dev)
-        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill.reshape(-1))     # view (N, B, H, W): no transpose copy
+        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)                 # view (N, B, H, W): no transpose copy
         solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
                        clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
         solver.run(max_iter, auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
