@@ -69,8 +69,11 @@ class Comm:
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        if dist.is_available() and dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(group)
+        else:                       # single process: nothing to exchange
+            self.rank, self.world = 0, 1
 
     def all_reduce_sum(self, t):
         if self.world > 1:
