@@ -81,7 +81,11 @@ typedef struct vpint_desc {
     int32_t row_offset;   /* global row index of local row 0 (may be negative: never)*/
     int32_t own_row0;     /* first local row this rank owns                          */
     int32_t own_rows;     /* number of owned local rows (the rest are halo rows)     */
+    int32_t features;     /* VPINT_FEAT_* bits: optional workspace the solve will need */
 } vpint_desc;
+
+/* vpint_desc.features */
+#define VPINT_FEAT_RESISTANCE 1   /* keeps a copy of the known values: run() may use `resistance` */
 
 /* Arguments of one run() call.  Defaults of the reference in brackets. */
 typedef struct vpint_run_params {
@@ -94,6 +98,10 @@ typedef struct vpint_run_params {
     int32_t chunk;           /* launches per host poll in chunked mode; 0 = default     */
     double *delta_out;       /* device, [nprob][max_iter] per-sweep delta (track_delta,
                                 SD_MRP.py:140-141) or NULL                              */
+    int32_t resistance;      /* WP_SMRP 'elastic band' damping (WP_MRP.py:327-348): after the restore every
+                                cell -- known ones too -- with new > mu becomes old + (new-old) - epsilon*old
+                                [False].  Needs VPINT_FEAT_RESISTANCE and k_block 1.           */
+    double  epsilon, mu;     /* [0.01, 1.0]                                                     */
 } vpint_run_params;
 
 /* ---- library ---------------------------------------------------------- */
@@ -142,6 +150,16 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0,
 int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int64_t *stride,
                          int F, int method, int clamp, double min_gamma, double max_gamma,
                          void *stream);
+/* prioritise_identity (WP_MRP.py:243-276, 309-315), 2-D VPINT_W_PLANES only, after vpint_solver_weights.
+ * Builds the static priority planes p from the weights (beta == 0: ones with zero borders; otherwise the
+ * reference's two sequential rewrites p>1 -> (1/p)*((1/p)/((1/p)*beta)), then p<1 -> p*(p/((p+0.001)*beta))),
+ * optionally multiplies them by `bias` (device double [nprob][H][W], the known_value_bias sub-solve of
+ * WP_MRP.py:263-276; zeros of the product become 0.01) and folds them into the weights:
+ * w_dir <- w_dir * p_dir / sum(p), with the division by the neighbour count switched off -- the
+ * update new = sum(w*v*p) / sum(p) of WP_MRP.py:311-315.  p_out (device double [nprob][H][W][4], may be
+ * NULL) receives the planes (self.priority_grid). */
+int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, double *p_out, void *stream);
+
 /* VPINT_W_SCALAR: HOST arrays [nprob]; tau is ignored for ndim == 2
  * (SD_MRP.py:87, 315-321). */
 int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau);

@@ -380,7 +380,7 @@ def test_solver_introspection_and_tile_skipping():
     close(out[0].cpu().numpy()[:20, :20], ref[:20, :20])
     s.close()
     with pytest.raises(VPintError):
-        WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, resistance=True)
+        WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, auto_adapt=True)
 
 
 # ---- 4. row-sharded scene on one device: shards in lockstep through the CUDA halo kernels ---------
@@ -456,3 +456,47 @@ def test_pipelined_host_stack_equals_single_solve():
     ref, ref_sweeps = O.vpint2_run(vps[5].target, vps[5].features)
     close(np.moveaxis(res.numpy()[5], 0, -1), ref)
     assert list(sweeps[5].numpy()) == list(ref_sweeps)
+
+
+# ---- 6. in-loop options of WP_SMRP.run: identity priority, known-value bias, resistance -----------
+def test_golden_wp2d_priority_and_resistance(golden, kblock):
+    g = golden("wp2d")
+    grid, feat = g["grid"], g["feat"]
+    for beta, tag in ((0, "0"), (1, "1"), (2.5, "2p5")):
+        m = WP_SMRP(grid.copy(), feat.copy())
+        p, d = m.run(iterations=6, track_delta=True, prioritise_identity=True, priority_intensity=beta)
+        close(p, g["pred_prio_" + tag]); closed(d, g["d_prio_" + tag])
+        assert m.priority_grid.shape == grid.shape + (4,)
+    w = O.weights_exact_2d(feat.astype(float).reshape(feat.shape[0], feat.shape[1], -1).copy())
+    close(m.priority_grid, O.priority_planes(w, 2.5), rtol=1e-14)
+    mu = float(g["res_mu"])
+    m = WP_SMRP(grid.copy(), feat.copy())
+    p, d = m.run(iterations=6, track_delta=True, resistance=True, epsilon=0.02, mu=mu)
+    close(p, g["pred_res"]); closed(d, g["d_res"])
+    assert not np.array_equal(p[~np.isnan(grid)], grid[~np.isnan(grid)]), "resistance moves known cells too"
+    m = WP_SMRP(grid.copy(), feat.copy())
+    p, d = m.run(iterations=5, track_delta=True, resistance=True, epsilon=0.01, mu=mu, prioritise_identity=True,
+                 priority_intensity=1.5, clip_val=2.0 * mu)
+    close(p, g["pred_res_prio"]); closed(d, g["d_res_prio"])
+    p2 = m.run(iterations=2, resistance=True, epsilon=0.01, mu=mu)      # resume from a state whose known cells moved
+    ref, _, _ = O.wp_run_2d(grid, g["pred_res_prio"].copy(), feat.astype(float).reshape(grid.shape + (-1,)).copy(),
+                            iterations=2, resistance=True, epsilon=0.01, mu=mu)
+    close(p2, ref)
+
+
+def test_golden_known_value_bias(golden, kblock):
+    g = golden("wp2d_edge")
+    m = WP_SMRP(g["kvb_grid"].copy(), g["kvb_feat"].copy())
+    p, d = m.run(iterations=5, track_delta=True, prioritise_identity=True, priority_intensity=1, known_value_bias=0.3)
+    close(p, g["kvb_pred"]); closed(d, g["kvb_d"])
+
+
+def test_vpint2_batch_with_priority_and_resistance(kblock):
+    """The notebook's recommended call passes these through VPint2_interpolator.run(**kwargs)."""
+    rng = np.random.default_rng(808)
+    vp = make_patch(rng, 48, 48, 3)
+    kw = dict(iterations=12, prioritise_identity=True, priority_intensity=1, known_value_bias=0.2, resistance=True,
+              epsilon=0.01, mu=1500.0, clip_val=10000)
+    got = vp.run(**kw)
+    ref, _ = O.vpint2_run(vp.target, vp.features, **kw)
+    close(got, ref)

@@ -20,6 +20,7 @@ F64, F32 = 0, 1
 W_SCALAR, W_PLANES = 0, 1
 METHOD_EXACT, METHOD_COSINE, METHOD_EXACT_INVERSE = 0, 1, 2
 LOOP_CHUNKED, LOOP_GRAPH = 0, 1
+FEAT_RESISTANCE = 1
 
 METHODS = {"exact": METHOD_EXACT, "cosine_similarity": METHOD_COSINE, "exact_inverse": METHOD_EXACT_INVERSE}
 
@@ -30,6 +31,7 @@ class Desc(C.Structure):
         ("H", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
         ("storage", C.c_int32), ("weight_mode", C.c_int32), ("k_block", C.c_int32),
         ("global_H", C.c_int32), ("row_offset", C.c_int32), ("own_row0", C.c_int32), ("own_rows", C.c_int32),
+        ("features", C.c_int32),
     ]
 
 
@@ -39,6 +41,7 @@ class RunParams(C.Structure):
         ("threshold", C.c_double), ("clip_val", C.c_double),
         ("loop_mode", C.c_int32), ("chunk", C.c_int32),
         ("delta_out", C.c_void_p),
+        ("resistance", C.c_int32), ("epsilon", C.c_double), ("mu", C.c_double),
     ]
 
 
@@ -55,6 +58,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_int64), C.c_void_p]),
     "vpint_solver_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_double, C.c_void_p]),
+    "vpint_solver_priority": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpint_solver_set_discounts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "vpint_solver_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),
     "vpint_solver_begin_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),

@@ -66,6 +66,9 @@ struct vpint_solver {
     bool planes_valid = false;        // the 4 (5) weight planes hold current weights
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
+    size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
+    bool has_orig = false;
+    bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     int64_t tiles_active = 0;
     int any_dirty = 0;
     int64_t launches = 0;
@@ -192,6 +195,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
     s->off_flags = take(16 * sizeof(int));
+    s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
+    if (s->has_orig) s->off_orig = take(plane);
     s->ws_bytes = off;
     *out = s;
     return VPINT_OK;
@@ -245,7 +250,8 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
                 "copy fill");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
     VP_CUDA(launch_prepare(g, original, pred0, s->at<double>(s->off_fill), dtype, stride, s->storage,
-                           s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]), s->at<uint32_t>(s->off_mask),
+                           s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]),
+                           s->has_orig ? s->at<void>(s->off_orig) : nullptr, s->at<uint32_t>(s->off_mask),
                            s->at<double>(s->off_rowpart), s->at<double>(s->off_known0), s->at<double>(s->off_known),
                            s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
             "prepare");
@@ -274,6 +280,7 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     void *planes[5];
     for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
     s->planes_valid = s->fplane_valid = false;
+    s->no_nc = false;
     if (s->g.ndim == 2 && s->res_ok && F == 1 && method == VPINT_METHOD_EXACT && !clamp) {
         // one feature layer: keep the feature plane only; the ratio planes are derived on demand
         VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
@@ -313,6 +320,10 @@ int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *s
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
     if (!s->weights_ready) return fail(VPINT_ERR_INVALID, "weights / discounts have not been set");
     if (prm->max_iter < 0) return fail(VPINT_ERR_INVALID, "max_iter must be >= 0");
+    if (prm->resistance) {
+        if (!s->has_orig) return fail(VPINT_ERR_INVALID, "resistance needs a solver created with VPINT_FEAT_RESISTANCE");
+        if (s->g.ndim != 2 || s->use_tb) return fail(VPINT_ERR_UNSUPPORTED, "resistance runs on the 2-D one-sweep-per-launch path (k_block 0 or 1)");
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     s->prm = *prm;
     VP_CUDA(launch_init_state(s->g, s->at<ProbState>(s->off_state), s->at<int>(s->off_counters) + kCntActiveProblems,
@@ -324,6 +335,36 @@ int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *s
 }
 
 static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms);
+
+// The four ratio planes are built lazily from the single-layer feature plane (vpint_solver_weights keeps only
+// that plane when the cluster-resident kernel can serve the run).
+static int ensure_planes(vpint_solver *s, cudaStream_t st) {
+    if (s->weight_mode != VPINT_W_PLANES || s->planes_valid) return VPINT_OK;
+    if (!s->fplane_valid) return fail(VPINT_ERR_INVALID, "weights have not been set");
+    void *planes[5];
+    for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    VP_CUDA(launch_planes_from_fplane(s->g, s->at<double>(s->off_w[4]), s->storage, planes, st, &s->launches),
+            "planes from feature plane");
+    s->planes_valid = true;
+    return VPINT_OK;
+}
+
+int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, double *p_out, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (s->weight_mode != VPINT_W_PLANES || s->g.ndim != 2)
+        return fail(VPINT_ERR_INVALID, "prioritise_identity applies to 2-D solvers with weight planes");
+    if (!s->weights_ready) return fail(VPINT_ERR_INVALID, "vpint_solver_weights has not been called");
+    if (s->no_nc) return fail(VPINT_ERR_INVALID, "priority planes are already folded into the weights");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = ensure_planes(s, st);
+    if (rc != VPINT_OK) return rc;
+    void *planes[5];
+    for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    VP_CUDA(launch_priority(s->g, s->storage, planes, beta, bias, p_out, st, &s->launches), "priority");
+    s->fplane_valid = false;          // the ratio form no longer describes these weights
+    s->no_nc = true;
+    return VPINT_OK;
+}
 
 int vpint_solver_step_begin(vpint_solver *s, void *stream) { return step_begin_impl(s, stream, nullptr); }
 
@@ -341,13 +382,9 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         VP_CUDA(cudaEventCreate(&e1), "event create");
         VP_CUDA(cudaEventRecord(e0, st), "event record");
     }
-    if (s->weight_mode == VPINT_W_PLANES && !s->planes_valid) {
-        if (!s->fplane_valid) return fail(VPINT_ERR_INVALID, "weights have not been set");
-        void *planes[5];
-        for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
-        VP_CUDA(launch_planes_from_fplane(s->g, s->at<double>(s->off_w[4]), s->storage, planes, st, &s->launches),
-                "planes from feature plane");
-        s->planes_valid = true;
+    {
+        const int rc = ensure_planes(s, st);
+        if (rc != VPINT_OK) return rc;
     }
     StepArgs a;
     a.g = s->g;
@@ -361,7 +398,14 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
     a.tau = s->at<double>(s->off_tau);
     a.partial = s->at<double>(s->off_partial);
     a.clip = s->prm.clip_val;
-    if (s->g.ndim == 2) {
+    a.no_nc = s->no_nc ? 1 : 0;
+    a.resist = s->prm.resistance ? 1 : 0;
+    a.eps = s->prm.epsilon;
+    a.mu = s->prm.mu;
+    a.orig = s->has_orig ? s->at<void>(s->off_orig) : nullptr;
+    if (a.resist) {
+        VP_CUDA(launch_step2d_resist(a, s->storage, s->weight_mode, st, &s->launches), "step2d_resist");
+    } else if (s->g.ndim == 2) {
         if (s->use_tb)
             VP_CUDA(launch_step2d_tb(a, s->tb_maps, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d_tb");
         else
@@ -377,7 +421,8 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         cudaEventDestroy(e1);
     }
     VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), s->at<int>(s->off_tilestart),
-                                   s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), st, &s->launches),
+                                   s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), s->prm.resistance != 0, st,
+                                   &s->launches),
             "reduce partials");
     return VPINT_OK;
 }
@@ -396,6 +441,7 @@ int vpint_solver_step_end(vpint_solver *s, void *stream) {
     d.max_iter = s->prm.max_iter;
     d.auto_terminate = s->prm.auto_terminate;
     d.threshold = s->prm.threshold;
+    d.all_cells = s->prm.resistance ? 1 : 0;
     VP_CUDA(launch_decide(d, st, &s->launches), "decide");
     if (s->first_step_pending) {
         s->first_step_pending = false;
@@ -418,7 +464,7 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
     if (prm->max_iter == 0) return VPINT_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ratio = (s->weight_mode == VPINT_W_PLANES);
-    if (s->res_ok && !s->any_dirty && (!ratio || s->fplane_valid)) {
+    if (s->res_ok && !s->any_dirty && !prm->resistance && !s->no_nc && (!ratio || s->fplane_valid)) {
         // whole run() in one launch: a cluster per problem, state resident in shared memory
         int *flags = s->at<int>(s->off_flags);
         VP_CUDA(cudaMemsetAsync(flags + 1, 0, sizeof(int), st), "memset queue");

@@ -64,6 +64,10 @@ struct StepArgs {
     const double *tau;       // [P] scalar mode, 3-D
     double *partial;         // [tile][KB][kSumSlots]
     double clip;
+    int no_nc;               // 1: weights already carry the priority normalisation, no division by the neighbour count
+    int resist;              // 1: resistance sweep over ALL cells (vpint_step_k1.cu, jacobi2d_resist_kernel)
+    double eps, mu;
+    const void *orig;        // [P][H][pitch] known values (resistance)
 };
 
 struct DecideArgs {
@@ -77,6 +81,7 @@ struct DecideArgs {
     int max_iter;
     int auto_terminate;
     double threshold;
+    int all_cells;           // 1: the sums already cover every cell (resistance), no known-cell constants
 };
 
 // ---- cluster-resident solve (vpint_resident.cu) -----------------------------
@@ -116,7 +121,7 @@ cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int s
 
 // ---- host-side launchers (one per .cu) ------------------------------------
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
-                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,
+                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB, void *orig_copy,
                            uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
                            int *counters, cudaStream_t st, int64_t *launches);
 bool fill_mean_supported(const Geom &g);
@@ -134,7 +139,11 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
 cudaError_t launch_step3d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
                           int64_t *launches);
 cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
-                                   const ProbState *state, double *sums, cudaStream_t st, int64_t *launches);
+                                   const ProbState *state, double *sums, bool all_tiles, cudaStream_t st,
+                                   int64_t *launches);
+cudaError_t launch_step2d_resist(const StepArgs &a, int storage, int weight_mode, cudaStream_t st, int64_t *launches);
+cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *bias,
+                            double *p_out, cudaStream_t st, int64_t *launches);
 cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
                               int64_t *launches);
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);

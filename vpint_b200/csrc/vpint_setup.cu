@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
                                                       const TIn *__restrict__ pred0,
                                                       const double *__restrict__ fill, Strides sd,
                                                       TSt *__restrict__ bufA,
-                                                      TSt *__restrict__ bufB, uint32_t *__restrict__ mask,
+                                                      TSt *__restrict__ bufB, TSt *__restrict__ orig_copy,
+                                                      uint32_t *__restrict__ mask,
                                                       double *__restrict__ rowpart) {
     __shared__ double scratch[8 * 8];
     const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
         }
         bufA[row + e] = va;
         bufB[row + e] = vb;
+        if (orig_copy) orig_copy[row + e] = vb;
         const unsigned word = __ballot_sync(0xffffffffu, unknown);   // pitch % 32 == 0: whole warps iterate together
         if ((threadIdx.x & 31) == 0) mask[mrow + (e >> 5)] = word;
     }
@@ -300,7 +302,7 @@ __global__ void init_state_kernel(Geom g, ProbState *state, int *n_active, int m
 __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const double *__restrict__ partial,
                                                               const int *__restrict__ tile_start,
                                                               const ProbState *__restrict__ state,
-                                                              double *__restrict__ sums) {
+                                                              double *__restrict__ sums, int all_tiles) {
     __shared__ double scratch[kSumSlots * 4];
     const int p = blockIdx.x;
     const int kr = state[p].k_run;
@@ -310,7 +312,8 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const doub
         for (int i = threadIdx.x; i < g.KB * kSumSlots; i += blockDim.x) out[i] = 0.0;
         return;
     }
-    const int t0 = tile_start[p], t1 = tile_start[p + 1];
+    const int t0 = all_tiles ? p * g.tiles_per_prob : tile_start[p];
+    const int t1 = all_tiles ? t0 + g.tiles_per_prob : tile_start[p + 1];
     for (int j = 0; j < g.KB; ++j) {
         double acc[kSumSlots] = {0, 0, 0, 0};
         if (j < kr) {
@@ -352,8 +355,9 @@ __global__ void decide_kernel(DecideArgs a) {
     for (int j = 0; j < kr; ++j) {
         const double *S = a.sums + ((size_t)p * a.g.KB + j) * kSumSlots;
         const double *K = ((st.fresh && j == 0) ? a.known0 : a.known) + (size_t)p * kSumSlots;
-        const double s_abs = S[0] + K[0], s_old = S[1] + K[1];
-        const double n_abs = a.g.n_cells - (S[2] + K[2]), n_old = a.g.n_cells - (S[3] + K[3]);
+        const double kz = a.all_cells ? 0.0 : 1.0;      // resistance: the sums already cover known cells
+        const double s_abs = a.all_cells ? S[0] : S[0] + K[0], s_old = a.all_cells ? S[1] : S[1] + K[1];
+        const double n_abs = a.g.n_cells - (S[2] + kz * K[2]), n_old = a.g.n_cells - (S[3] + kz * K[3]);
         const double delta = (s_abs / n_abs) / (s_old / n_old);
         if (a.delta_out) a.delta_out[(size_t)p * a.max_iter + st.iters_done + j] = delta;
         if (a.auto_terminate && delta <= a.threshold) {
@@ -453,14 +457,14 @@ cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, con
 }
 
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
-                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB,
+                           int dtype, const int64_t *stride, int storage, void *bufA, void *bufB, void *orig_copy,
                            uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
                            int *counters, cudaStream_t st, int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
     const unsigned grid = (unsigned)((int64_t)g.P * g.H);
 #define VP_PREP(TIN, TST)                                                                                  \
     prepare_kernel<TIN, TST><<<grid, 256, 0, st>>>(g, (const TIN *)original, (const TIN *)pred0, fill_dev, \
-                                                   sd, (TST *)bufA, (TST *)bufB, mask, rowpart)
+                                                   sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart)
     if (dtype == VPINT_F64 && storage == VPINT_F64) VP_PREP(double, double);
     else if (dtype == VPINT_F32 && storage == VPINT_F64) VP_PREP(float, double);
     else if (dtype == VPINT_F64 && storage == VPINT_F32) VP_PREP(double, float);
@@ -493,8 +497,9 @@ cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, in
 }
 
 cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
-                                   const ProbState *state, double *sums, cudaStream_t st, int64_t *launches) {
-    reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, tile_start, state, sums);
+                                   const ProbState *state, double *sums, bool all_tiles, cudaStream_t st,
+                                   int64_t *launches) {
+    reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, tile_start, state, sums, all_tiles ? 1 : 0);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

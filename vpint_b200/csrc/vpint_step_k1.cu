@@ -93,12 +93,73 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_kernel(const StepArgs a) {
             const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
             const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
             const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
-            n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
-            n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+            if (!a.no_nc) {
+                n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
+                n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+            }
             if (n0 > a.clip) n0 = a.clip;
             if (n1 > a.clip) n1 = a.clip;
             if (mb & 1u) out[row + x] = acc.commit(n0, c0);
             if (mb & 2u) out[row + x + 1] = acc.commit(n1, c1);
+        }
+    }
+    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+}
+
+// Resistance sweep (VPint/WP_MRP.py:327-348): the damping  new > mu -> old + (new - old) - epsilon * old  is
+// applied after the restore to EVERY cell, so known cells move too and nothing can be skipped: one block
+// per tile of the full grid (no active-tile list), every cell written, sums over all cells.
+template <typename T, bool PLANES>
+__global__ void __launch_bounds__(256) jacobi2d_resist_kernel(const StepArgs a) {
+    const Geom &g = a.g;
+    const int p = blockIdx.x / g.tiles_per_prob;
+    const int tr = blockIdx.x - p * g.tiles_per_prob;
+    const int ty = tr / g.tiles_x, tx = tr - ty * g.tiles_x;
+    const ProbState st = a.state[p];
+    Acc<T> acc;
+    if (st.k_run != 0) {
+        const size_t plane = (size_t)g.H * g.pitch;
+        const T *__restrict__ in = reinterpret_cast<const T *>(a.buf[st.cur]) + (size_t)p * plane;
+        T *__restrict__ out = reinterpret_cast<T *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+        const T *__restrict__ orig = reinterpret_cast<const T *>(a.orig) + (size_t)p * plane;
+        const uint32_t *mrow = a.mask + (size_t)p * g.H * g.mpitch;
+        const double gamma = PLANES ? 0.0 : a.gamma[p];
+        const int x = tx * kTileW2 + (threadIdx.x & (kTileW2 - 1));
+        const int y_lim = min(g.own_row0 + (ty + 1) * kTileH2, g.own_row0 + g.own_rows);
+        if (x < g.L) {
+            for (int y = g.own_row0 + ty * kTileH2 + (threadIdx.x >> 7); y < y_lim; y += 2) {
+                const size_t row = (size_t)y * g.pitch;
+                const int yg = y + g.row_offset;
+                const double ov = (double)in[row + x];
+                double nv;
+                if ((mrow[(size_t)y * g.mpitch + (x >> 5)] >> (x & 31)) & 1u) {
+                    const double up = (yg > 0) ? (double)in[row - g.pitch + x] : 0.0;
+                    const double dn = (yg < g.global_H - 1) ? (double)in[row + g.pitch + x] : 0.0;
+                    const double lf = (x > 0) ? (double)in[row + x - 1] : 0.0;
+                    const double rt = (x < g.L - 1) ? (double)in[row + x + 1] : 0.0;
+                    if (PLANES) {
+                        const double wu = (double)reinterpret_cast<const T *>(a.w[0])[(size_t)p * plane + row + x];
+                        const double wr = (double)reinterpret_cast<const T *>(a.w[1])[(size_t)p * plane + row + x];
+                        const double wd = (double)reinterpret_cast<const T *>(a.w[2])[(size_t)p * plane + row + x];
+                        const double wl = (double)reinterpret_cast<const T *>(a.w[3])[(size_t)p * plane + row + x];
+                        nv = fma(lf, wl, fma(dn, wd, fma(rt, wr, up * wu)));
+                    } else {
+                        nv = fma(lf, gamma, fma(dn, gamma, fma(rt, gamma, up * gamma)));
+                    }
+                    if (!a.no_nc) {
+                        const int nc = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0) - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+                        nv = (nc == 4) ? nv * 0.25 : nv / (double)nc;
+                    }
+                    if (nv > a.clip) nv = a.clip;
+                } else {
+                    nv = (double)orig[row + x];                // restore (WP_MRP.py:321,323)
+                }
+                const double dy = nv - ov;
+                double t = nv;
+                if (nv <= a.mu) t = ov + dy;                   // WP_MRP.py:340-344
+                if (t > a.mu) t = (ov + dy) - a.eps * ov;      // WP_MRP.py:346-348
+                out[row + x] = acc.commit(t, ov);
+            }
         }
     }
     write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
@@ -186,6 +247,20 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
     } else {
         if (planes) jacobi2d_k1_kernel<float, true><<<grid, 256, 0, st>>>(a);
         else jacobi2d_k1_kernel<float, false><<<grid, 256, 0, st>>>(a);
+    }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_step2d_resist(const StepArgs &a, int storage, int weight_mode, cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)a.g.P * a.g.tiles_per_prob);
+    const bool planes = (weight_mode == VPINT_W_PLANES);
+    if (storage == VPINT_F64) {
+        if (planes) jacobi2d_resist_kernel<double, true><<<grid, 256, 0, st>>>(a);
+        else jacobi2d_resist_kernel<double, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (planes) jacobi2d_resist_kernel<float, true><<<grid, 256, 0, st>>>(a);
+        else jacobi2d_resist_kernel<float, false><<<grid, 256, 0, st>>>(a);
     }
     VP_LAUNCH_CHECK();
     return cudaSuccess;

@@ -162,7 +162,7 @@ jacobi2d_tb_kernel(const StepArgs a, const __grid_constant__ CUtensorMap map0, c
                         else nv = fma(lf, gamma, fma(dn, gamma, fma(rt, gamma, up * gamma)));
                         const int gyg = gyg0 + r;
                         const int nc = ncx - (gyg == 0 ? 1 : 0) - (gyg == g.global_H - 1 ? 1 : 0);
-                        nv = (nc == 4) ? nv * 0.25 : nv / (double)nc;
+                        if (!a.no_nc) nv = (nc == 4) ? nv * 0.25 : nv / (double)nc;
                         if (nv > clip) nv = clip;
                         const T stored = (T)nv;
                         nv = (double)stored;

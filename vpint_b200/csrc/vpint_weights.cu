@@ -245,6 +245,56 @@ __global__ void __launch_bounds__(256) planes_from_fplane_kernel(int H, int W, i
     }
 }
 
+// prioritise_identity (VPint/WP_MRP.py:243-276): static priority planes from the weights, folded back into
+// the weights so that the sweep  new = sum(w * v * p) / sum(p)  (WP_MRP.py:311-315) runs through the ordinary
+// stencil with the neighbour-count division switched off.
+template <typename TSt>
+__global__ void __launch_bounds__(256) priority_kernel(int H, int W, int pitch, int row_offset, int global_H,
+                                                       TSt *__restrict__ w0, TSt *__restrict__ w1,
+                                                       TSt *__restrict__ w2, TSt *__restrict__ w3, double beta,
+                                                       const double *__restrict__ bias, double *__restrict__ p_out) {
+    const int p = blockIdx.x / H, y = blockIdx.x - p * H;
+    const size_t row = ((size_t)p * H + y) * pitch;
+    const int yg = y + row_offset;
+    TSt *wp[4] = {w0, w1, w2, w3};
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        double w[4], pr[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) w[d] = (double)wp[d][row + x];
+        if (beta == 0.0) {                          // ones, zero where the neighbour is missing (:247-255)
+            pr[0] = (yg > 0) ? 1.0 : 0.0;
+            pr[1] = (x < W - 1) ? 1.0 : 0.0;
+            pr[2] = (yg < global_H - 1) ? 1.0 : 0.0;
+            pr[3] = (x > 0) ? 1.0 : 0.0;
+        } else {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {           // two SEQUENTIAL rewrites (:257-259)
+                double q = w[d];
+                if (q > 1.0) { const double a = 1.0 / q; q = a * (a / (a * beta)); }
+                if (q < 1.0) q = q * (q / ((q + 0.001) * beta));
+                pr[d] = q;
+            }
+        }
+        if (p_out) {                                // self.priority_grid is stored before the bias (:260)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) p_out[(((size_t)p * H + y) * W + x) * 4 + d] = pr[d];
+        }
+        if (bias) {                                 // known_value_bias (:263-276)
+            const double b = bias[((size_t)p * H + y) * W + x];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                pr[d] = pr[d] * b;
+                if (pr[d] == 0.0) pr[d] = 0.01;
+            }
+        }
+        const double psum = (((0.0 + pr[0]) + pr[1]) + pr[2]) + pr[3];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            wp[d][row + x] = (TSt)((w[d] * pr[d]) / psum);
+        }
+    }
+}
+
 }  // namespace
 
 #define VP_LAUNCH_CHECK()                         \
@@ -310,6 +360,21 @@ cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int s
         planes_from_fplane_kernel<float><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, fplane,
                                                                (float *)planes[0], (float *)planes[1],
                                                                (float *)planes[2], (float *)planes[3]);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *bias,
+                            double *p_out, cudaStream_t st, int64_t *launches) {
+    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    if (storage == VPINT_F64)
+        priority_kernel<double><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, (double *)planes[0],
+                                                      (double *)planes[1], (double *)planes[2], (double *)planes[3],
+                                                      beta, bias, p_out);
+    else
+        priority_kernel<float><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, (float *)planes[0],
+                                                     (float *)planes[1], (float *)planes[2], (float *)planes[3], beta,
+                                                     bias, p_out);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

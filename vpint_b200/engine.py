@@ -64,7 +64,7 @@ class Solver:
     """
 
     def __init__(self, ndim, nprob, H, W, T=1, *, nprob_inner=1, storage="float64", planes=True,
-                 k_block=0, shard=None, device=None):
+                 k_block=0, shard=None, device=None, resistance=False):
         self.lib = N.load_library()
         self.torch = _torch()
         self.device = require_cuda(device)
@@ -80,6 +80,7 @@ class Solver:
         d.k_block = int(k_block)
         if shard is not None:
             d.global_H, d.row_offset, d.own_row0, d.own_rows = [int(v) for v in shard]
+        d.features = N.FEAT_RESISTANCE if resistance else 0
         self._h = C.c_void_p()
         N.check(self.lib, self.lib.vpint_solver_create(C.byref(d), C.byref(self._h)), "vpint_solver_create")
         nbytes = self.lib.vpint_solver_workspace_bytes(self._h)
@@ -184,8 +185,28 @@ class Solver:
         N.check(self.lib, self.lib.vpint_solver_set_discounts(self._h, gp, tp), "vpint_solver_set_discounts")
         return self
 
-    def _params(self, max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk):
+    def priority(self, beta, bias=None, want_planes=False):
+        """prioritise_identity: fold the priority planes into the weights (after :meth:`weights`).
+        ``bias``: CUDA float64 tensor (nprob, H, W) of the known_value_bias sub-solve, or None.
+        Returns the (nprob, H, W, 4) priority planes when ``want_planes``."""
+        p_out = None
+        if want_planes:
+            p_out = self.torch.empty((self.nprob, self.H, self.W, 4), dtype=self.torch.float64, device=self.device)
+        if bias is not None:
+            bias = bias.to(self.torch.float64).contiguous()
+            if tuple(bias.shape) != (self.nprob, self.H, self.W):
+                raise VPintError("bias must have shape (nprob, H, W)")
+            self._keep.append(bias)
+        N.check(self.lib, self.lib.vpint_solver_priority(
+            self._h, float(beta), C.c_void_p(bias.data_ptr()) if bias is not None else None,
+            C.c_void_p(p_out.data_ptr()) if p_out is not None else None, self._stream()), "vpint_solver_priority")
+        return p_out
+
+    def _params(self, max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk,
+                resistance=None):
         prm = N.RunParams()
+        if resistance is not None:
+            prm.resistance, prm.epsilon, prm.mu = 1, float(resistance[0]), float(resistance[1])
         prm.max_iter = int(max_iter)
         prm.auto_terminate = int(bool(auto_terminate))
         prm.threshold = float(threshold)
@@ -202,8 +223,9 @@ class Solver:
         return prm
 
     def run(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False,
-            loop_mode=N.LOOP_CHUNKED, chunk=0):
-        prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk)
+            loop_mode=N.LOOP_CHUNKED, chunk=0, resistance=None):
+        """``resistance``: None or (epsilon, mu) (solver must have been created with ``resistance=True``)."""
+        prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk, resistance)
         N.check(self.lib, self.lib.vpint_solver_run(self._h, C.byref(prm), self._stream()), "vpint_solver_run")
         return self
 

@@ -40,14 +40,53 @@ def _band_fill_values(target):
 PIPELINE_CHUNK_PATCHES = 64
 
 
+def _known_value_bias(t_dev, kvb, dev):
+    """known_value_bias sub-solve (VPint/WP_MRP.py:263-272) for a stack (N, H, W, B) of patches: SD_SMRP on the
+    known-cell indicator of every band (init 'zero', gamma = 1 - kvb, default run()); (N * B, H, W) float64."""
+    import torch
+    N, H, W, B = t_dev.shape
+    if H != W:      # the reference's SD_SMRP only accepts square grids (VPint/SD_MRP.py:95-96)
+        raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,) " % (H, W))
+    ind = torch.where(torch.isnan(t_dev), t_dev, torch.ones_like(t_dev)).to(torch.float64)
+    sub = Solver(2, N * B, H, W, nprob_inner=B, planes=False, k_block=_solve.DEFAULT_K_BLOCK, device=dev)
+    try:
+        sub.load(ind.permute(0, 3, 1, 2), fill=np.zeros(N * B))
+        sub.discounts(1 - kvb)
+        sub.run(10000, auto_terminate=True, threshold=1e-4)
+        out, _ = sub.result()
+    finally:
+        sub.close()
+    return out
+
+
+def _make_solver(nprob, H, W, B, storage, kb, dev, opts):
+    if opts.get("resistance") and kb not in (0, 1):
+        kb = 1
+    return Solver(2, nprob, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev,
+                  resistance=bool(opts.get("resistance")))
+
+
 def _solve_chunk(solver, t_dev, f_dev, opts, res_dev, out_layout, fill):
     solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)
     solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
                    clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
+    if opts.get("prioritise_identity"):
+        bias = None
+        if opts.get("known_value_bias", 0) > 0:
+            bias = _known_value_bias(t_dev, opts["known_value_bias"], solver.device)
+        solver.priority(opts["priority_intensity"], bias=bias)
     solver.run(opts["iterations"], auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
-               clip_val=opts["clip_val"])          # blocks the host until every problem of the chunk has stopped
+               clip_val=opts["clip_val"],
+               resistance=(opts["epsilon"], opts["mu"]) if opts.get("resistance") else None)
+    # run() blocks the host until every problem of the chunk has stopped
+    if res_dev is None:
+        return None
     _, niter = solver.result(out=res_dev if out_layout == "bhw" else res_dev.permute(0, 3, 1, 2))
     return niter
+
+
+def _solve_chunk_noresult(solver, t_dev, f_dev, opts, fill):
+    return _solve_chunk(solver, t_dev, f_dev, opts, None, None, fill)
 
 
 def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k_block, dev, out, fill,
@@ -69,7 +108,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
     res_dtype = torch.float64 if out_layout == "bhw" else out_dtype
 
     if target.device.type != "cpu" or N <= chunk:
-        solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev)
+        solver = _make_solver(N * B, H, W, B, storage, kb, dev, opts)
         try:
             t_dev = target.to(dev, non_blocking=True)
             f_dev = features.to(dev, non_blocking=True)
@@ -119,7 +158,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
             if i + 1 < len(spans):
                 stage(i + 1)       # its slot was last read by chunk i-1, whose solve has returned
             if m not in solvers:
-                solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev)
+                solvers[m] = _make_solver(m * B, H, W, B, storage, kb, dev, opts)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in[i])
                 if i >= 2:
@@ -181,16 +220,11 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
         res = res[0] if single else res
         return (res, np.zeros((N, B), dtype=np.int64)[0 if single else slice(None)]) if return_sweeps else res
     fill = None if H * W <= DEVICE_FILL_MAX_CELLS else _band_fill_values(tgt).reshape(-1)
-    solver = Solver(2, N * B, H, W, nprob_inner=B, storage=storage, planes=True,
-                    k_block=(_solve.DEFAULT_K_BLOCK if k_block is None else k_block), device=dev)
+    solver = _make_solver(N * B, H, W, B, storage, _solve.DEFAULT_K_BLOCK if k_block is None else k_block, dev, opts)
     try:
         t_dev = to_device(np.ascontiguousarray(tgt), dev)                 # (N, H, W, B) as stored
         f_dev = to_device(np.ascontiguousarray(fts), dev)
-        solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)                 # view (N, B, H, W): no transpose copy
-        solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
-                       clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
-        solver.run(max_iter, auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
-                   clip_val=opts["clip_val"])
+        niter = _solve_chunk_noresult(solver, t_dev, f_dev, opts, fill)   # views (N, B, H, W): no transpose copy
         if out_layout == "bhw":
             out = torch.empty((N, B, H, W), dtype=torch.float64, device=dev)
             _, niter = solver.result(out=out)

@@ -45,15 +45,15 @@ def wp_run_options(iterations=-1, method='exact', auto_terminate=True, auto_term
                          "by the device path")
     if auto_adapt:
         raise VPintError("auto_adapt (host-side hyper-parameter search) is not supported by the device path yet")
-    if prioritise_identity or resistance:
-        raise VPintError("prioritise_identity / resistance are not supported by the device path yet")
     if method not in _DEVICE_METHODS:
         if method == 'predict':
             raise VPintError("method='predict' needs a host-side sklearn model and is not supported by the "
                              "device path; use 'exact', 'cosine_similarity' or 'exact_inverse'")
         raise VPintError("Invalid weight prediction method: " + str(method))
     return dict(iterations=iterations, method=method, auto_terminate=auto_terminate,
-                threshold=auto_terminate_threshold, track_delta=track_delta, clip_val=clip_val)
+                threshold=auto_terminate_threshold, track_delta=track_delta, clip_val=clip_val,
+                prioritise_identity=bool(prioritise_identity), priority_intensity=priority_intensity,
+                known_value_bias=known_value_bias, resistance=bool(resistance), epsilon=epsilon, mu=mu)
 
 
 class WP_SMRP(SMRP):
@@ -103,15 +103,29 @@ class WP_SMRP(SMRP):
         Device path: ``method`` in {'exact', 'cosine_similarity', 'exact_inverse'},
         ``iterations``, ``auto_terminate``(+threshold), ``track_delta``, ``clip_val``.
         ``confidence`` / ``confidence_model`` are accepted and unused, as in the
-        reference.  Not available here (VPintError): ``method='predict'`` (needs the
-        caller's sklearn model on the host), GIF recording, ``auto_adapt``,
-        ``prioritise_identity`` / ``known_value_bias`` and ``resistance``.
+        reference.  ``prioritise_identity`` (+ ``priority_intensity``, ``known_value_bias``) and
+        ``resistance`` (+ ``epsilon``, ``mu``) run on the device as well.  Not available here
+        (VPintError): ``method='predict'`` (needs the caller's sklearn model on the host), GIF
+        recording and ``auto_adapt``.
         """
         opts = wp_run_options(iterations=iterations, method=method, auto_terminate=auto_terminate,
                               auto_terminate_threshold=auto_terminate_threshold, track_delta=track_delta,
                               save_gif=save_gif, store_gif_source=store_gif_source, auto_adapt=auto_adapt,
-                              prioritise_identity=prioritise_identity, resistance=resistance, clip_val=clip_val)
+                              prioritise_identity=prioritise_identity, priority_intensity=priority_intensity,
+                              known_value_bias=known_value_bias, resistance=resistance, epsilon=epsilon, mu=mu,
+                              clip_val=clip_val)
         iterations, auto_terminate = opts["iterations"], opts["auto_terminate"]
+        priority = None
+        if prioritise_identity:
+            bias = None
+            if known_value_bias > 0:
+                # four identical SD_SMRP sub-solves of the known-cell indicator in the reference
+                # (VPint/WP_MRP.py:263-272): solved once here
+                from .sd import SD_SMRP
+                ind = self.original_grid.copy()
+                ind[~np.isnan(ind)] = 1
+                bias = SD_SMRP(ind, init_strategy='zero', gamma=(1 - known_value_bias)).run()
+            priority = dict(beta=priority_intensity, bias=bias, want_planes=True)
 
         self.clip_val = clip_val
         if method == 'exact':
@@ -124,8 +138,11 @@ class WP_SMRP(SMRP):
                 self.original_grid, self.pred_grid, planes=True, features=self.feature_grid, method=method,
                 clamp=(method != 'exact'), min_gamma=self.min_gamma, max_gamma=self.max_gamma,
                 max_iter=iterations, auto_terminate=auto_terminate, threshold=auto_terminate_threshold,
-                clip_val=clip_val, track_delta=track_delta)
+                clip_val=clip_val, track_delta=track_delta, priority=priority,
+                resistance=(epsilon, mu) if resistance else None)
             self.pred_grid = new_grid
+            if priority is not None:
+                self.priority_grid = propagate.last_priority     # debugging access, as in the reference (:260)
             if track_delta:
                 delta_vec[:sweeps] = deltas
                 if auto_terminate:
