@@ -500,3 +500,32 @@ def test_vpint2_batch_with_priority_and_resistance(kblock):
     got = vp.run(**kw)
     ref, _ = O.vpint2_run(vp.target, vp.features, **kw)
     close(got, ref)
+
+
+def test_find_discounts_batched_trials_match_reference_rng_order():
+    """SD_STMRP.find_discounts (VPint/SD_MRP.py:409-476) incl. its reset() quirk: epochs after the first start
+    from the NaN-holding cube."""
+    rng = np.random.default_rng(15)
+    cube = smooth(rng, (10, 9, 5), 10, 30)
+    cube[rng.uniform(size=cube.shape) < 0.15] = np.nan
+    np.random.seed(21)
+    m = SD_STMRP(cube.copy())
+    best = m.find_discounts(4, 0.3, sub_iterations=30)
+    np.random.seed(21)
+    sub = cube.copy()
+    for i in range(10):
+        for j in range(9):
+            for t in range(5):
+                if not np.isnan(sub[i, j, t]) and np.random.rand() < 0.3:
+                    sub[i, j, t] = np.nan
+    best_ref, best_loss = (0.9, 0.9), np.inf
+    state = O.init_pred(sub)
+    for _ in range(4):
+        gam, tau = np.random.rand(), np.random.rand()
+        pred, _, _ = O.sd_run_3d(sub, state, gamma=gam, tau=tau, iterations=30)
+        sel = ~np.isnan(cube) & np.isnan(sub)
+        mae = np.add.accumulate(np.abs(pred[sel] - cube[sel]))[-1] / sel.sum()
+        if mae < best_loss:
+            best_ref, best_loss = (gam, tau), mae
+        state = sub                          # reset(): the next epoch starts from the cube with its NaNs
+    assert best == best_ref and (m.gamma, m.tau) == best_ref

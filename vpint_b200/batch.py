@@ -16,11 +16,13 @@ from .engine import Solver, require_cuda, to_device
 from .errors import VPintError
 
 
-def sd_trials(grid, gammas, iterations, taus=None, device=None, k_block=None):
+def sd_trials(grid, gammas, iterations, taus=None, device=None, k_block=None, nan_start_after_first=False):
     """Run SD_SMRP / SD_STMRP (mean init, fixed ``iterations``) on the SAME grid for
     every discount in ``gammas`` (and ``taus`` for cubes) as one batched solve.
     This is the inner loop of find_gamma / find_discounts (VPint/SD_MRP.py:186-195,
-    441-452).  Returns a float64 array (len(gammas),) + grid.shape."""
+    441-452).  ``nan_start_after_first``: trials after the first start from the grid itself,
+    NaNs included -- what find_discounts does by calling reset() on its one scratch object
+    between epochs (SD_MRP.py:472).  Returns a float64 array (len(gammas),) + grid.shape."""
     dev = require_cuda(device)
     torch = __import__("torch")
     grid = np.ascontiguousarray(np.asarray(grid, dtype=np.float64))
@@ -38,8 +40,16 @@ def sd_trials(grid, gammas, iterations, taus=None, device=None, k_block=None):
     try:
         g_dev = to_device(grid, dev)
         original = g_dev.unsqueeze(0).expand((n,) + tuple(g_dev.shape))      # stride-0 problem axis: no copies
-        fill = np.full(n, np.nanmean(grid))
-        solver.load(original, fill=fill)
+        if nan_start_after_first and n > 1:
+            first = grid.copy()
+            first[np.isnan(first)] = np.nanmean(grid)
+            start = torch.empty((n,) + tuple(g_dev.shape), dtype=g_dev.dtype, device=dev)
+            start[0] = to_device(first, dev)
+            start[1:] = g_dev
+            solver.load(original.contiguous(), pred0=start)
+        else:
+            fill = np.full(n, np.nanmean(grid))
+            solver.load(original, fill=fill)
         solver.discounts(np.asarray(gammas, dtype=np.float64), None if taus is None else np.asarray(taus, dtype=np.float64))
         solver.run(int(iterations), auto_terminate=False)
         out, _ = solver.result()

@@ -79,7 +79,8 @@ class SD_SMRP(SMRP):
             preds = sd_trials(sub_grid, gammas, sub_iterations)
             best_loss = np.inf
             for ep in range(search_epochs):
-                mae = np.sum(np.abs(preds[ep][hide] - self.original_grid[hide])) / int(hide.sum())
+                # the reference accumulates |error| cell by cell in row-major order
+                mae = np.add.accumulate(np.abs(preds[ep][hide] - self.original_grid[hide]))[-1] / int(hide.sum())
                 if mae < best_loss:
                     best_gamma = gammas[ep]
                     best_loss = mae
@@ -101,6 +102,36 @@ class SD_STMRP(STMRP):
 
     def set_tau(self, tau):
         self.tau = tau
+
+    def find_discounts(self, search_epochs, subsample_proportion, sub_iterations=100, ext=None):
+        """Random search for (gamma, tau) on a sub-sampled copy of the cube (reference:
+        VPint/SD_MRP.py:409-476).  The NumPy global RNG is consumed in the reference's order (one
+        ``rand()`` per known cell in (i, j, t) order, then ``rand(), rand()`` per epoch).  The reference
+        reuses ONE scratch interpolator and calls ``reset()`` between epochs, so every epoch after
+        the first starts from the sub-sampled cube with its NaNs; that is reproduced.  All epochs run
+        as one batched device solve."""
+        from .batch import sd_trials
+        if ext is not None:
+            raise NotImplementedError("find_discounts(ext=...) is not implemented by the reference")
+        sub_grid = self.original_grid.copy()
+        known = ~np.isnan(sub_grid)
+        draws = np.random.rand(int(known.sum()))
+        hide = np.zeros(sub_grid.shape, dtype=bool)
+        hide[known] = draws < subsample_proportion
+        sub_grid[hide] = np.nan
+        pairs = [(np.random.rand(), np.random.rand()) for _ in range(search_epochs)]
+        best_gamma, best_tau, best_loss = self.gamma, self.tau, np.inf
+        if search_epochs > 0:
+            preds = sd_trials(sub_grid, [g for g, _ in pairs], sub_iterations, taus=[t for _, t in pairs],
+                              nan_start_after_first=True)
+            n_err = int(hide.sum())
+            for ep, (gamma, tau) in enumerate(pairs):
+                mae = np.add.accumulate(np.abs(preds[ep][hide] - self.original_grid[hide]))[-1] / n_err
+                if mae < best_loss:
+                    best_gamma, best_tau, best_loss = gamma, tau, mae
+        self.gamma = best_gamma
+        self.tau = best_tau
+        return (best_gamma, best_tau)
 
     def run(self, iterations=-1, method='predict', auto_terminate=True, auto_terminate_threshold=1e-4,
             track_delta=False):
