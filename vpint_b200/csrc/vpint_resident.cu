@@ -60,6 +60,47 @@ __device__ __forceinline__ double div_here(double a, double b) {
     return r;
 }
 
+// ---- mbarrier / DSMEM primitives (PTX) --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
+// 16-byte store into another CTA's shared memory that signals that CTA's mbarrier with the bytes written:
+// data and "it has arrived" travel together, no fence and no cluster barrier needed.
+__device__ __forceinline__ void st_async2(uint32_t remote_addr, double a, double b, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "d"(a), "d"(b), "r"(remote_bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "VPR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra VPR_DONE_%=;\n"
+        "bra VPR_WAIT_%=;\n"
+        "VPR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 struct SmemLayout {
     double *plane;       // [R][SP] owned rows; columns < kPadL and > W + 1 are the zero border
     double *halo_up;     // [2][SP] row above the owned band, by sweep parity
@@ -84,9 +125,21 @@ struct SweepCtx {
     const double *fseg;
     const unsigned *list;
     const double *fp;                 // global feature plane of this problem (segments beyond fcap)
-    double *up_remote, *dn_remote;    // neighbour CTAs' halo rows (DSMEM), null at the physical border
+    // neighbour CTAs (shared::cluster addresses): their halo row buffers [2][SP] and their halo barriers [2]
+    uint32_t up_halo, dn_halo, up_bar[2], dn_bar[2];
+    bool has_up, has_dn;
     int SP, bot_base, fcap, gy0, pitch, tid, n, H, W;
     double gamma, clip;
+};
+
+// Per-CTA synchronisation state (static shared memory).
+struct SyncShared {
+    double part[3][kMaxC][2];          // partial {sum|new-old|, sum old} of every CTA of the cluster (16-byte entries)
+    double red[kWarps][2];
+    uint64_t bar_h[2];                 // per sweep parity: this CTA's own stores (kThreads arrivals) + neighbours' halo bytes
+    uint64_t bar_s[3];                 // per sweep mod 3: the C partial sums (C * 16 bytes)
+    int halo_exp[2];                   // bytes per sweep from the upper / lower neighbour
+    int edge_cnt[2];                   // segments on the first / last owned row
 };
 
 __device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
@@ -94,137 +147,210 @@ __device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
     a = v.x; b = v.y;
 }
 
-// One Jacobi sweep over this thread's segments (entries tid + k * kThreads < n, k < KT).  Straight-line
-// code: every k is executed (entries past the end re-read segment n - 1 and are discarded) so the loads
-// and fp64 chains of the KT segments overlap.  New values stay in registers across the block barrier.
-// A NaN or inf anywhere poisons the partial sums, which is how the caller detects data it must leave to
-// the tiled path.
+// Stop decision of one sweep from the C partials (every thread of every CTA computes the same thing):
+// delta = nanmean|new-old| / nanmean(old) with the known-cell constants added (VPint/SD_MRP.py:139).
+// Returns 0 continue, 1 stop, 2 non-finite data (leave the problem to the tiled path).
+__device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned &ph_s, int C, const double *KK, double n_cells,
+                                            const ResidentArgs &a, int p, int sweep, bool writer) {
+    mbar_wait(&sh.bar_s[slot], (ph_s >> slot) & 1u);
+    ph_s ^= 1u << slot;
+    double S0 = 0.0, S1 = 0.0;
+    for (int q = 0; q < C; ++q) { S0 += sh.part[slot][q][0]; S1 += sh.part[slot][q][1]; }
+    if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) return 2;
+    const double sa = S0 + KK[0], so = S1 + KK[1];
+    const double na = n_cells - KK[2], no = n_cells - KK[3];
+    const double delta = (sa / na) / (so / no);
+    if (a.delta_out && writer) a.delta_out[(size_t)p * a.max_iter + sweep] = delta;
+    return (a.auto_terminate && delta <= a.threshold) ? 1 : 0;
+}
+
+// All sweeps of one problem for a CTA whose threads own at most KT segments each (entries tid + k * kThreads).
+//
+// Sweep t:  (1) wait until the state of sweep t-1 is complete in this CTA: own stores + the neighbours' halo
+//               rows (mbarrier bar_h[t & 1]);
+//           (2) compute the new values of the thread's segments into registers -- straight-line code, every
+//               k is executed (entries past the end re-read segment n-1 and are discarded) so the loads and
+//               fp64 chains of the KT segments overlap -- and the warp partial sums;
+//           (3) block barrier: all reads of the old state are done;
+//           (4) stop decision of sweep t-1, whose partial sums have been travelling while (2) ran: if it
+//               stops, sweep t is simply not stored (commit-then-break without a rollback);
+//           (5) warp 0 pushes this CTA's partial of sweep t to every CTA (st.async -> bar_s[t % 3]);
+//           (6) store the new values: own rows with plain stores, first / last owned row also into the
+//               neighbours' halo row of the other parity with st.async (-> their bar_h), then arrive on
+//               the own bar_h of the other parity.
+// A NaN or inf anywhere poisons the partial sums, which is how data for the tiled path is detected.
 template <bool RATIO, int KT>
-__device__ __forceinline__ void sweep_segments(const SweepCtx &c, int par, double (*red)[kSumSlots]) {
-    double nr[KT][4];
-    double s_abs = 0.0, s_old = 0.0;
-    const double *halo_up = c.halo_up + par * c.SP, *halo_dn = c.halo_dn + par * c.SP;
+__device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, const ResidentArgs &a, int p, int C, int crank,
+                                           bool fresh, const double *k0, const double *k1, double n_cells,
+                                           unsigned &ph_h, unsigned &ph_s, int &it_out, bool &bailed_out) {
+    const int lane = c.tid & 31, warp = c.tid >> 5;
     const int last = c.n - 1;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const int i0 = c.tid + k * kThreads;
-        const bool live = i0 <= last;
-        const int i = live ? i0 : last;
-        const unsigned e = c.list[i];
-        const int off = (int)(e & 0xffffu);
-        const unsigned m = live ? ((e >> 16) & 15u) : 0u;
-        const double *row = c.plane + off;
-        const double *upp = (e & kSegTop) ? halo_up + off : row - c.SP;
-        const double *dnp = (e & kSegBot) ? halo_dn + (off - c.bot_base) : row + c.SP;
-        double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
-        ld2(row, c0, c1); ld2(row + 2, c2, c3);
-        ld2(upp, u0, u1); ld2(upp + 2, u2, u3);
-        ld2(dnp, d0, d1); ld2(dnp + 2, d2, d3);
-        const double lf = row[-1], rt = row[4];
-        double r[4];
-        if (RATIO) {
-            r[0] = ((u0 + c1) + d0) + lf;
-            r[1] = ((u1 + c2) + d1) + c0;
-            r[2] = ((u2 + c3) + d2) + c1;
-            r[3] = ((u3 + rt) + d3) + c2;
-        } else {
-            const double g = c.gamma;
-            r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
-            r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
-            r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
-            r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
+    const int T = a.max_iter;
+    const unsigned halo_bytes = (unsigned)((c.has_up ? sh.halo_exp[0] : 0) + (c.has_dn ? sh.halo_exp[1] : 0));
+    const uint32_t my_part = smem_u32(&sh.part[0][0][0]);
+    const uint32_t my_bar_s = smem_u32(&sh.bar_s[0]);
+    const bool writer = (crank == 0 && c.tid == 0);
+    int t = 0, verdict = 0;
+    for (; t < T; ++t) {
+        const int par = t & 1, npar = par ^ 1, slot = t % 3;
+        if (t > 0) {
+            mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+            ph_h ^= 1u << par;
         }
-        const bool edge = (e & kSegEdge) != 0;
-        if (__any_sync(0xffffffffu, edge)) {
-            if (edge) {                        // grid border: per-cell neighbour count, true division
-                const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.gy0 + ly;
-                const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
+        double nr[KT > 0 ? KT : 1][4];
+        double s_abs = 0.0, s_old = 0.0;
+        const double *halo_up = c.halo_up + par * c.SP, *halo_dn = c.halo_dn + par * c.SP;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int x = x0 + j;
-                    const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
-                    r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
+        for (int k = 0; k < KT; ++k) {
+            const int i0 = c.tid + k * kThreads;
+            const bool live = i0 <= last;
+            const int i = live ? i0 : last;
+            const unsigned e = c.list[i];
+            const int off = (int)(e & 0xffffu);
+            const unsigned m = live ? ((e >> 16) & 15u) : 0u;
+            const double *row = c.plane + off;
+            const double *upp = (e & kSegTop) ? halo_up + off : row - c.SP;
+            const double *dnp = (e & kSegBot) ? halo_dn + (off - c.bot_base) : row + c.SP;
+            double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
+            ld2(row, c0, c1); ld2(row + 2, c2, c3);
+            ld2(upp, u0, u1); ld2(upp + 2, u2, u3);
+            ld2(dnp, d0, d1); ld2(dnp + 2, d2, d3);
+            const double lf = row[-1], rt = row[4];
+            double r[4];
+            if (RATIO) {
+                r[0] = ((u0 + c1) + d0) + lf;
+                r[1] = ((u1 + c2) + d1) + c0;
+                r[2] = ((u2 + c3) + d2) + c1;
+                r[3] = ((u3 + rt) + d3) + c2;
+            } else {
+                const double g = c.gamma;
+                r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
+                r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
+                r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
+                r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
+            }
+            const bool edge = (e & kSegEdge) != 0;
+            if (__any_sync(0xffffffffu, edge)) {
+                if (edge) {                        // grid border: per-cell neighbour count, true division
+                    const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.gy0 + ly;
+                    const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int x = x0 + j;
+                        const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
+                        r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r[j] *= 0.25;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) r[j] *= 0.25;
             }
-        } else {
+            const double cc[4] = {c0, c1, c2, c3};
+            double vn[4], vo[4];
+            if (RATIO) {
+                double f[4];
+                const double *fs = c.fseg + (size_t)min(i, c.fcap - 1) * 4;
+                ld2(fs, f[0], f[1]); ld2(fs + 2, f[2], f[3]);
+                if (i >= c.fcap) {
+                    const int ly = off / c.SP;
+                    const double *fg = c.fp + (size_t)(c.gy0 + ly) * c.pitch + (off - ly * c.SP - kPadL);
+                    ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
+                }
+                bool clipped = false;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] *= 0.25;
-        }
-        const double cc[4] = {c0, c1, c2, c3};
-        double vn[4], vo[4];
-        if (RATIO) {
-            double f[4];
-            const double *fs = c.fseg + (size_t)min(i, c.fcap - 1) * 4;
-            ld2(fs, f[0], f[1]); ld2(fs + 2, f[2], f[3]);
-            if (i >= c.fcap) {
-                const int ly = off / c.SP;
-                const double *fg = c.fp + (size_t)(c.gy0 + ly) * c.pitch + (off - ly * c.SP - kPadL);
-                ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
+                for (int j = 0; j < 4; ++j) {
+                    vn[j] = f[j] * r[j];
+                    vo[j] = f[j] * cc[j];
+                    clipped |= ((m >> j) & 1u) && (vn[j] > c.clip);
+                }
+                if (__any_sync(0xffffffffu, clipped)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (((m >> j) & 1u) && vn[j] > c.clip) { vn[j] = c.clip; r[j] = div_here(c.clip, f[j]); }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (r[j] > c.clip) r[j] = c.clip;
+                    vn[j] = r[j];
+                    vo[j] = cc[j];
+                }
             }
-            bool clipped = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                vn[j] = f[j] * r[j];
-                vo[j] = f[j] * cc[j];
-                clipped |= ((m >> j) & 1u) && (vn[j] > c.clip);
-            }
-            if (__any_sync(0xffffffffu, clipped)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (((m >> j) & 1u) && vn[j] > c.clip) { vn[j] = c.clip; r[j] = div_here(c.clip, f[j]); }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (r[j] > c.clip) r[j] = c.clip;
-                vn[j] = r[j];
-                vo[j] = cc[j];
+                const bool unk = (m >> j) & 1u;
+                s_abs += unk ? fabs(vn[j] - vo[j]) : 0.0;
+                s_old += unk ? vo[j] : 0.0;
+                nr[k][j] = unk ? r[j] : cc[j];
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool unk = (m >> j) & 1u;
-            s_abs += unk ? fabs(vn[j] - vo[j]) : 0.0;
-            s_old += unk ? vo[j] : 0.0;
-            nr[k][j] = unk ? r[j] : cc[j];
+        {
+            const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
+            if (lane == 0) { sh.red[warp][0] = q0; sh.red[warp][1] = q1; }
         }
-    }
-    {
-        const int lane = c.tid & 31, warp = c.tid >> 5;
-        const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
-        if (lane == 0) { red[warp][0] = q0; red[warp][1] = q1; }
-    }
-    __syncthreads();                           // every read of the old state is done
-    const int npo = (par ^ 1) * c.SP;
+        __syncthreads();                           // (3) every read of the old state is done; red[] complete
+        if (t > 0) {                               // (4)
+            verdict = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
+            fresh = false;
+            if (verdict != 0) break;
+        }
+        if (warp == 0) {                           // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
+            double v0 = (lane < kWarps) ? sh.red[lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[lane][1] : 0.0;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const int i = c.tid + k * kThreads;
-        if (i <= last) {
-            const unsigned e = c.list[i];
-            const int off = (int)(e & 0xffffu);
-            const double2 lo = make_double2(nr[k][0], nr[k][1]), hi = make_double2(nr[k][2], nr[k][3]);
-            double2 *row = reinterpret_cast<double2 *>(c.plane + off);
-            row[0] = lo; row[1] = hi;
-            if ((e & kSegTop) && c.up_remote) {
-                double2 *q = reinterpret_cast<double2 *>(c.up_remote + npo + off);
-                q[0] = lo; q[1] = hi;
+            for (int o = kWarps / 2; o > 0; o >>= 1) {
+                v0 += __shfl_down_sync(0xffffffffu, v0, o);
+                v1 += __shfl_down_sync(0xffffffffu, v1, o);
             }
-            if ((e & kSegBot) && c.dn_remote) {
-                double2 *q = reinterpret_cast<double2 *>(c.dn_remote + npo + off - c.bot_base);
-                q[0] = lo; q[1] = hi;
+            v0 = __shfl_sync(0xffffffffu, v0, 0);
+            v1 = __shfl_sync(0xffffffffu, v1, 0);
+            if (lane < C)
+                st_async2(map_rank(my_part + (uint32_t)(((slot * kMaxC) + crank) * 16), lane), v0, v1,
+                          map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
+            if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
+        }
+        const uint32_t npo = (uint32_t)(npar * c.SP);   // (6)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int i = c.tid + k * kThreads;
+            if (i <= last) {
+                const unsigned e = c.list[i];
+                const int off = (int)(e & 0xffffu);
+                double2 *row = reinterpret_cast<double2 *>(c.plane + off);
+                row[0] = make_double2(nr[k][0], nr[k][1]);
+                row[1] = make_double2(nr[k][2], nr[k][3]);
+                if ((e & kSegTop) && c.has_up) {   // my first row is the upper CTA's lower halo
+                    const uint32_t dst = c.up_halo + (npo + (uint32_t)off) * 8u;
+                    st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
+                    st_async2(dst + 16u, nr[k][2], nr[k][3], c.up_bar[npar]);
+                }
+                if ((e & kSegBot) && c.has_dn) {   // my last row is the lower CTA's upper halo
+                    const uint32_t dst = c.dn_halo + (npo + (uint32_t)(off - c.bot_base)) * 8u;
+                    st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
+                    st_async2(dst + 16u, nr[k][2], nr[k][3], c.dn_bar[npar]);
+                }
             }
         }
+        if (c.tid == 0) mbar_arrive_tx(&sh.bar_h[npar], halo_bytes);
+        else mbar_arrive(&sh.bar_h[npar]);
     }
+    if (verdict == 0) {                            // ran to max_iter: close the last sweep
+        const int par = T & 1;
+        mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+        ph_h ^= 1u << par;
+        verdict = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
+        if (verdict == 1) verdict = 0;             // stopping at the very last sweep changes nothing
+    }
+    it_out = t;
+    bailed_out = (verdict == 2);
 }
 
 template <bool RATIO>
 __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[kWarps][kSumSlots];
-    __shared__ double cta_part[2][kMaxC][kSumSlots];
+    __shared__ __align__(16) SyncShared sh;
     __shared__ int wcount[kWarps];
     __shared__ int next_problem;
 
@@ -237,8 +363,12 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const SmemLayout sm = carve(smem_raw, R, SP, fcap);
     int *next_remote = cluster.map_shared_rank(&next_problem, 0);
-    double *up_halo_remote = (crank > 0) ? cluster.map_shared_rank(sm.halo_dn, crank - 1) : nullptr;     // my first row -> upper CTA's lower halo
-    double *dn_halo_remote = (crank < C - 1) ? cluster.map_shared_rank(sm.halo_up, crank + 1) : nullptr; // my last row -> lower CTA's upper halo
+    if (tid == 0) {
+        mbar_init(&sh.bar_h[0], kThreads); mbar_init(&sh.bar_h[1], kThreads);
+        mbar_init(&sh.bar_s[0], 1); mbar_init(&sh.bar_s[1], 1); mbar_init(&sh.bar_s[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned ph_h = 0, ph_s = 0;                       // phase parities of bar_h[2] / bar_s[3], carried across problems
 
     const int gy0 = crank * R;                         // first owned grid row
     const int n_rows = max(0, min(R, H - gy0));
@@ -345,64 +475,57 @@ __global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentA
 #pragma unroll
             for (int q = 5; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
         }
-        if (a.dbg == 1) kt = 0;                            // development: barriers only (timing probe)
+        // segments on the first / last owned row: what the neighbours must expect from this CTA per sweep
+        if (tid < 2) sh.edge_cnt[tid] = 0;
+        __syncthreads();
+        {
+            int n_top = 0, n_bot = 0;
+            for (int i = tid; i < n; i += kThreads) {
+                const unsigned e = sm.list[i];
+                n_top += (e & kSegTop) ? 1 : 0;
+                n_bot += (e & kSegBot) ? 1 : 0;
+            }
+            n_top = warp_sum(n_top);
+            n_bot = warp_sum(n_bot);
+            if (lane == 0) { atomicAdd(&sh.edge_cnt[0], n_top); atomicAdd(&sh.edge_cnt[1], n_bot); }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (crank > 0) *cluster.map_shared_rank(&sh.halo_exp[1], crank - 1) = 32 * sh.edge_cnt[0];      // into its lower halo
+            if (crank < C - 1) *cluster.map_shared_rank(&sh.halo_exp[0], crank + 1) = 32 * sh.edge_cnt[1];  // into its upper halo
+        }
         SweepCtx ctx;
         ctx.plane = sm.plane; ctx.halo_up = sm.halo_up; ctx.halo_dn = sm.halo_dn; ctx.fseg = sm.fseg; ctx.list = sm.list;
-        ctx.fp = fp; ctx.up_remote = up_halo_remote; ctx.dn_remote = dn_halo_remote;
+        ctx.fp = fp;
+        ctx.has_up = (crank > 0); ctx.has_dn = (crank < C - 1);
+        ctx.up_halo = ctx.has_up ? map_rank(smem_u32(sm.halo_dn), crank - 1) : 0u;
+        ctx.dn_halo = ctx.has_dn ? map_rank(smem_u32(sm.halo_up), crank + 1) : 0u;
+        for (int q = 0; q < 2; ++q) {
+            ctx.up_bar[q] = ctx.has_up ? map_rank(smem_u32(&sh.bar_h[q]), crank - 1) : 0u;
+            ctx.dn_bar[q] = ctx.has_dn ? map_rank(smem_u32(&sh.bar_h[q]), crank + 1) : 0u;
+        }
         ctx.SP = SP; ctx.bot_base = (n_rows - 1) * SP; ctx.fcap = fcap; ctx.gy0 = gy0; ctx.pitch = g.pitch; ctx.tid = tid;
         ctx.n = n; ctx.H = H; ctx.W = W;
         ctx.gamma = gamma; ctx.clip = a.clip;
         const double *K0 = a.known0 + (size_t)p * kSumSlots, *K1 = a.known + (size_t)p * kSumSlots;
         const double k0[kSumSlots] = {K0[0], K0[1], K0[2], K0[3]};
         const double k1[kSumSlots] = {K1[0], K1[1], K1[2], K1[3]};
-        cluster_barrier();                             // lists and planes of every CTA are in place
+        cluster_barrier();                             // lists, planes and expected byte counts of every CTA are in place
 
         // ---- sweeps -----------------------------------------------------------------------------
         int it = 0;
-        int par = 0;
         bool bailed = false;
-        bool fresh = (st.fresh != 0);
-        for (; it < a.max_iter;) {
-            switch (kt) {
-                case 0: if (lane == 0) { red[warp][0] = 0.0; red[warp][1] = 0.0; } __syncthreads(); break;
-                case 1: sweep_segments<RATIO, 1>(ctx, par, red); break;
-                case 2: sweep_segments<RATIO, 2>(ctx, par, red); break;
-                case 3: sweep_segments<RATIO, 3>(ctx, par, red); break;
-                case 4: sweep_segments<RATIO, 4>(ctx, par, red); break;
-                case 6: sweep_segments<RATIO, 6>(ctx, par, red); break;
-                default: sweep_segments<RATIO, kMaxSeg>(ctx, par, red); break;
-            }
-            const int npar = par ^ 1;
-            if (warp == 0) {
-                double part = 0.0;
-                if (lane < 2) {
-                    for (int w = 0; w < kWarps; ++w) part += red[w][lane];
-                }
-                // lane (q * 4 + slot) stores slot of this CTA's partial into CTA q
-                const int q = lane >> 2, slot = lane & 3;
-                const double val = __shfl_sync(0xffffffffu, part, slot);
-                if (q < C) cluster.map_shared_rank(&cta_part[par][crank][slot], q)[0] = val;
-            }
-            cluster_barrier();                         // new state, halos and partials visible cluster-wide
-            double S0 = 0.0, S1 = 0.0;
-            for (int q = 0; q < C; ++q) { S0 += cta_part[par][q][0]; S1 += cta_part[par][q][1]; }
-            // Anything non-finite (NaN start state, overflow of f * r where the reference's w * P would
-            // already have overflowed differently, inf inputs): leave this problem, untouched, to the tiled
-            // plane path, which reproduces the reference's NaN / inf propagation exactly.
-            if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) {
-                bailed = true;
-                break;
-            }
-            const double *KK = fresh ? k0 : k1;
-            const double sa = S0 + KK[0], so = S1 + KK[1];
-            const double na = n_cells - KK[2], no = n_cells - KK[3];
-            const double delta = (sa / na) / (so / no);
-            if (a.delta_out && crank == 0 && tid == 0) a.delta_out[(size_t)p * a.max_iter + it] = delta;
-            fresh = false;
-            par = npar;
-            ++it;
-            if (a.auto_terminate && delta <= a.threshold) break;
+        const bool fresh = (st.fresh != 0);
+        switch (kt) {
+            case 0: run_sweeps<RATIO, 0>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 1: run_sweeps<RATIO, 1>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 2: run_sweeps<RATIO, 2>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 3: run_sweeps<RATIO, 3>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 4: run_sweeps<RATIO, 4>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 6: run_sweeps<RATIO, 6>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            default: run_sweeps<RATIO, kMaxSeg>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
         }
+        __syncthreads();
 
         // ---- write the unknown cells back (P = f * r), close the problem ------------------------
         for (int i = tid; i < n && !bailed; i += kThreads) {
@@ -439,7 +562,7 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
     const int segs_per_row = (W + 3) / 4;
     const int SP = 4 * segs_per_row + 4;        // kPadL zero columns left, >= 2 right; even, so rows stay 16-byte aligned
     if (g.pitch < 4 * segs_per_row) return false;
-    const int static_bytes = 2048;              // red, cta_part, wcount, next_problem (+ slack)
+    const int static_bytes = 2048;              // SyncShared, wcount, next_problem (+ slack)
     for (int C = 1; C <= kMaxC; C *= 2) {
         const int R = (g.H + C - 1) / C;
         if ((g.H + R - 1) / R != C) continue;                                   // every CTA must own at least one row
