@@ -135,7 +135,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->n_planes = (d->weight_mode == VPINT_W_PLANES) ? (d->ndim == 2 ? 4 : 5) : 0;
     const bool unsharded = (g.global_H == g.H && g.own_row0 == 0 && g.own_rows == g.H);
     if (d->k_block == 0 && d->ndim == 2 && d->storage == VPINT_F64 && unsharded && !getenv("VPINT_NO_RESIDENT")) {
-        const int smem_optin = 232448;   // sm_100a: 227 KB per CTA
+        const int smem_optin = (233472 - kResidentCtasPerSm * 1024) / kResidentCtasPerSm;   // sm_100a: 228 KB per SM, 1 KB reserved per CTA
         s->res_ok = resident_plan(g, d->weight_mode == VPINT_W_PLANES, smem_optin, &s->rplan);
         if (s->res_ok && d->weight_mode == VPINT_W_PLANES) s->n_planes = 5;   // + the feature plane
     }

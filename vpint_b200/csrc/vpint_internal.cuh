@@ -86,6 +86,7 @@ struct DecideArgs {
 
 // ---- cluster-resident solve (vpint_resident.cu) -----------------------------
 constexpr int kResidentThreads = 512;
+constexpr int kResidentCtasPerSm = 1;  // measured: 2 x 256 threads (clusters of 8) and 1 x 1024 threads are both slower than 1 x 512
 constexpr int kResidentMaxSeg = 8;    // 4-cell segments per thread (new values kept in registers)
 
 struct ResidentPlan {

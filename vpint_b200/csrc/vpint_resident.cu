@@ -348,7 +348,7 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
 }
 
 template <bool RATIO>
-__global__ void __launch_bounds__(kThreads, 1) resident2d_kernel(const ResidentArgs a) {
+__global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) SyncShared sh;
     __shared__ int wcount[kWarps];
