@@ -58,7 +58,8 @@ extern "C" {
 
 /* loop drivers for vpint_solver_run */
 #define VPINT_LOOP_CHUNKED 0   /* host enqueues chunks of launches, polls a pinned flag per chunk */
-#define VPINT_LOOP_GRAPH   1   /* CUDA graph with a device-side WHILE node, one host sync per run */
+#define VPINT_LOOP_GRAPH   1   /* CUDA graph with a device-side WHILE node (conditional graph node): one graph
+                                  launch and one host sync per run, no per-sweep host work at all */
 
 typedef struct vpint_solver vpint_solver;
 

@@ -529,3 +529,37 @@ def test_find_discounts_batched_trials_match_reference_rng_order():
             best_ref, best_loss = (gam, tau), mae
         state = sub                          # reset(): the next epoch starts from the cube with its NaNs
     assert best == best_ref and (m.gamma, m.tau) == best_ref
+
+
+# ---- 7. device-side loop: CUDA graph with a conditional WHILE node ----------------------------------------------
+@pytest.mark.parametrize("k", [1, 4])
+def test_graph_loop_mode_matches_chunked(k, monkeypatch):
+    from vpint_b200 import engine, _native
+    monkeypatch.setattr(solve_mod, "DEFAULT_K_BLOCK", k)
+    rng = np.random.default_rng(4242)
+    shape = (130, 203)
+    base = smooth(rng, shape)
+    grid = base + rng.normal(0, 20, shape)
+    feat = np.stack([rng.uniform(0.7, 1.3) * base + rng.normal(0, 10, shape) for _ in range(3)], axis=-1)
+    grid[discs(rng, shape, 6, 8, 40)] = np.nan
+    ref, dref, n = O.wp_run_2d(grid, O.init_pred(grid), feat.copy())
+    p0, d0 = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
+    monkeypatch.setattr(engine, "DEFAULT_LOOP_MODE", _native.LOOP_GRAPH)
+    p1, d1 = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
+    assert len(d1) == n
+    close(p1, ref); closed(d1, dref)
+    close(p1, p0, rtol=0)                       # same kernels, same order: bit-identical to the host-driven loop
+    p2, d2 = WP_SMRP(grid.copy(), feat.copy()).run(iterations=17, track_delta=True)
+    ref2, dref2, _ = O.wp_run_2d(grid, O.init_pred(grid), feat.copy(), iterations=17)
+    close(p2, ref2); closed(d2, dref2)
+    vps = [make_patch(rng, 64, 64, 3) for _ in range(3)]       # batched, per-problem stopping sweeps
+    outs = run_patches(vps)
+    for vp, out in zip(vps, outs):
+        r, _ = O.vpint2_run(vp.target, vp.features)
+        close(out, r)
+    cube = smooth(rng, (12, 10, 6), 10, 30)
+    cube[rng.uniform(size=cube.shape) < 0.2] = np.nan
+    r3, d3, n3 = O.sd_run_3d(cube, O.init_pred(cube), gamma=0.9, tau=0.8)
+    p3, dd3 = SD_STMRP(cube.copy(), gamma=0.9, tau=0.8).run(track_delta=True)
+    assert len(dd3) == n3
+    close(p3, r3)

@@ -456,11 +456,80 @@ int vpint_solver_step_end(vpint_solver *s, void *stream) {
     return VPINT_OK;
 }
 
+// Device-side loop: ONE graph launch runs sweeps until every problem has stopped.  The graph holds a
+// conditional WHILE node whose body is one launch group (stencil, per-problem reduction, stop decision) and
+// a one-thread kernel that re-arms the condition from the "problems still running" counter, so the host
+// neither enqueues per sweep nor polls.
+static int run_graph_loop(vpint_solver *s, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // first launch group outside the graph: it may be followed by the one-off known-cell repair
+    int rc = vpint_solver_step_begin(s, stream);
+    if (rc != VPINT_OK) return rc;
+    rc = vpint_solver_step_end(s, stream);
+    if (rc != VPINT_OK) return rc;
+    int *iter_left = s->at<int>(s->off_flags) + 2;
+    const int budget = 2 * s->prm.max_iter + 2;
+    VP_CUDA(cudaMemcpyAsync(iter_left, &budget, sizeof(int), cudaMemcpyHostToDevice, st), "graph budget");
+
+    cudaGraph_t graph = nullptr, body = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap = nullptr;
+    cudaGraphConditionalHandle handle;
+    int status = VPINT_OK;
+    auto cleanup = [&]() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (cap) cudaStreamDestroy(cap);
+    };
+#define VP_G(call, where)                                                   \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) { cleanup(); return fail_cuda(e__, where); } \
+    } while (0)
+    VP_G(cudaGraphCreate(&graph, 0), "cudaGraphCreate");
+    VP_G(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault), "cudaGraphConditionalHandleCreate");
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    VP_G(cudaGraphAddNode(&node, graph, nullptr, 0, &np), "cudaGraphAddNode(conditional)");
+    body = np.conditional.phGraph_out[0];
+    VP_G(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "cudaStreamCreate");
+    VP_G(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed), "begin capture");
+    status = vpint_solver_step_begin(s, cap);
+    if (status == VPINT_OK) status = vpint_solver_step_end(s, cap);
+    if (status == VPINT_OK) {
+        cudaError_t e = launch_loop_condition(handle, s->at<int>(s->off_counters) + kCntActiveProblems, iter_left, cap,
+                                              &s->launches);
+        if (e != cudaSuccess) status = fail_cuda(e, "loop condition");
+    }
+    {
+        cudaGraph_t captured = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &captured);
+        if (status == VPINT_OK && e != cudaSuccess) status = fail_cuda(e, "end capture");
+    }
+    if (status != VPINT_OK) { cleanup(); return status; }
+    VP_G(cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate");
+    VP_G(cudaGraphLaunch(exec, st), "cudaGraphLaunch");
+    VP_G(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
+                         sizeof(int), cudaMemcpyDeviceToHost, st),
+         "read active count");
+    VP_G(cudaEventRecord(s->ev, st), "event record");
+    VP_G(cudaEventSynchronize(s->ev), "event sync");
+#undef VP_G
+    cleanup();
+    if (s->h_counters[kCntActiveProblems] > 0)
+        return fail(VPINT_ERR_INVALID, "internal error: graph loop did not terminate within its launch budget");
+    return VPINT_OK;
+}
+
 int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
     int rc = vpint_solver_begin_run(s, prm, stream);
     if (rc != VPINT_OK) return rc;
-    if (prm->loop_mode != VPINT_LOOP_CHUNKED)
-        return fail(VPINT_ERR_UNSUPPORTED, "only VPINT_LOOP_CHUNKED is available in this build");
+    if (prm->loop_mode != VPINT_LOOP_CHUNKED && prm->loop_mode != VPINT_LOOP_GRAPH)
+        return fail(VPINT_ERR_INVALID, "bad loop_mode");
     if (prm->max_iter == 0) return VPINT_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ratio = (s->weight_mode == VPINT_W_PLANES);
@@ -496,6 +565,7 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         if (s->h_counters[kCntActiveProblems] <= 0) return VPINT_OK;
         // the kernel declined (non-finite features): continue on the tiled path from the untouched state
     }
+    if (prm->loop_mode == VPINT_LOOP_GRAPH) return run_graph_loop(s, stream);
     int chunk = prm->chunk > 0 ? prm->chunk : 4;
     const int chunk_cap = prm->chunk > 0 ? prm->chunk : 64;
     // Every launch either commits >= 1 sweep of every running problem or is its single replay, so

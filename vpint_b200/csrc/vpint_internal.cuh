@@ -148,6 +148,8 @@ cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, dou
 cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
                               int64_t *launches);
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_loop_condition(cudaGraphConditionalHandle handle, const int *n_active, int *iter_left,
+                                  cudaStream_t st, int64_t *launches);
 cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,
                                  const uint32_t *mask, cudaStream_t st, int64_t *launches);
 cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state, void *const *buf, void *msg,

@@ -383,6 +383,14 @@ __global__ void decide_kernel(DecideArgs a) {
     a.state[p] = st;
 }
 
+// Tail of the WHILE body of the graph loop (vpint_api.cu run_graph_loop): keep looping while a problem is
+// still running and the launch budget lasts.
+__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const int *n_active, int *iter_left) {
+    const int left = *iter_left - 1;
+    *iter_left = left;
+    cudaGraphSetConditional(handle, (*n_active > 0 && left > 0) ? 1u : 0u);
+}
+
 // Rare path: the start state disagreed with `original` on known cells (user-edited pred_grid, or a
 // previous resistance run).  The first launch ran one sweep from it; the other ping-pong buffer still
 // holds those stale known cells, so copy the restored ones over.
@@ -506,6 +514,13 @@ cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const i
 
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches) {
     decide_kernel<<<(a.g.P + 127) / 128, 128, 0, st>>>(a);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_loop_condition(cudaGraphConditionalHandle handle, const int *n_active, int *iter_left,
+                                  cudaStream_t st, int64_t *launches) {
+    loop_condition_kernel<<<1, 1, 0, st>>>(handle, n_active, iter_left);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -15,6 +15,12 @@ from .errors import VPintError
 
 _DTYPE_CODE = {"float64": N.F64, "float32": N.F32}
 
+# Loop driver of the tiled path when the caller does not choose one: N.LOOP_CHUNKED (host enqueues chunks of
+# launches and polls one pinned counter per chunk) or N.LOOP_GRAPH (one CUDA-graph launch with a device-side
+# WHILE node; no host involvement until every problem has stopped).
+import os as _os
+DEFAULT_LOOP_MODE = N.LOOP_GRAPH if _os.environ.get("VPINT_LOOP_MODE", "").lower() == "graph" else N.LOOP_CHUNKED
+
 
 def _torch():
     import torch
@@ -223,8 +229,10 @@ class Solver:
         return prm
 
     def run(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False,
-            loop_mode=N.LOOP_CHUNKED, chunk=0, resistance=None):
+            loop_mode=None, chunk=0, resistance=None):
         """``resistance``: None or (epsilon, mu) (solver must have been created with ``resistance=True``)."""
+        if loop_mode is None:
+            loop_mode = DEFAULT_LOOP_MODE
         prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk, resistance)
         N.check(self.lib, self.lib.vpint_solver_run(self._h, C.byref(prm), self._stream()), "vpint_solver_run")
         return self
