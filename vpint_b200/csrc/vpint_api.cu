@@ -67,8 +67,13 @@ struct vpint_solver {
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
     size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
+    size_t off_extreme = 0;           // double[2]: cells with non-finite / huge values, ... features
     bool has_orig = false;
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
+    // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
+    bool state_ratio = false;         // buffers are in ratio space right now
+    int ratio_verdict = -1;           // -1 not evaluated since load/weights, 0 declined (extreme data), 1 allowed
+    double *h_extreme = nullptr;      // pinned copy of the two range-check counters
     int64_t tiles_active = 0;
     int any_dirty = 0;
     int64_t launches = 0;
@@ -137,8 +142,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     if (d->k_block == 0 && d->ndim == 2 && d->storage == VPINT_F64 && unsharded && !getenv("VPINT_NO_RESIDENT")) {
         const int smem_optin = (233472 - kResidentCtasPerSm * 1024) / kResidentCtasPerSm;   // sm_100a: 228 KB per SM, 1 KB reserved per CTA
         s->res_ok = resident_plan(g, d->weight_mode == VPINT_W_PLANES, smem_optin, &s->rplan);
-        if (s->res_ok && d->weight_mode == VPINT_W_PLANES) s->n_planes = 5;   // + the feature plane
     }
+    if (d->ndim == 2 && d->weight_mode == VPINT_W_PLANES && d->storage == VPINT_F64) s->n_planes = 5;   // + the feature plane
 
     int kb = d->k_block;
     if (d->ndim == 3) {
@@ -185,8 +190,11 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_tau = take((size_t)g.P * sizeof(double));
     s->off_fill = take((size_t)g.P * sizeof(double));
     s->off_rowpart = take((size_t)g.P * g.H * 8 * sizeof(double));
-    s->off_known0 = take(2 * (size_t)g.P * kSumSlots * sizeof(double));   // known0 then known, one contiguous block
+    // known0, known, then two range-check counters (values, features): one contiguous block, all-reduced
+    // as a whole by row-sharded runs
+    s->off_known0 = take((2 * (size_t)g.P * kSumSlots + 2) * sizeof(double));
     s->off_known = s->off_known0 + (size_t)g.P * kSumSlots * sizeof(double);
+    s->off_extreme = s->off_known0 + 2 * (size_t)g.P * kSumSlots * sizeof(double);
     s->off_state = take((size_t)g.P * sizeof(ProbState));
     s->off_counters = take(kCntTotal * sizeof(int));
     s->off_tileflag = take((size_t)s->tiles_total * sizeof(int));
@@ -205,6 +213,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
 void vpint_solver_destroy(vpint_solver *s) {
     if (!s) return;
     if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->h_extreme) cudaFreeHost(s->h_extreme);
     if (s->ev) cudaEventDestroy(s->ev);
     delete s;
 }
@@ -217,6 +226,7 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     if ((uintptr_t)workspace % 256 != 0) return fail(VPINT_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if (!s->h_counters) {
         VP_CUDA(cudaHostAlloc((void **)&s->h_counters, kCntTotal * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
+        VP_CUDA(cudaHostAlloc((void **)&s->h_extreme, 2 * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc");
         VP_CUDA(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming), "cudaEventCreate");
     }
     s->ws = static_cast<char *>(workspace);
@@ -249,11 +259,14 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
         VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_fill), fill, (size_t)g.P * sizeof(double), cudaMemcpyHostToDevice, st),
                 "copy fill");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
+    VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme), 0, sizeof(double), st), "memset range check");
+    s->state_ratio = false;
+    s->ratio_verdict = -1;
     VP_CUDA(launch_prepare(g, original, pred0, s->at<double>(s->off_fill), dtype, stride, s->storage,
                            s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]),
                            s->has_orig ? s->at<void>(s->off_orig) : nullptr, s->at<uint32_t>(s->off_mask),
                            s->at<double>(s->off_rowpart), s->at<double>(s->off_known0), s->at<double>(s->off_known),
-                           s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
+                           s->at<double>(s->off_extreme), s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
             "prepare");
     VP_CUDA(launch_tiles(g, s->at<uint32_t>(s->off_mask), s->at<int>(s->off_tileflag), s->at<TileRef>(s->off_tiles),
                          s->at<int>(s->off_tilestart), s->at<int>(s->off_counters), st, &s->launches),
@@ -279,13 +292,16 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void *planes[5];
     for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    if (s->state_ratio) return fail(VPINT_ERR_INVALID, "vpint_solver_weights: call vpint_solver_load first (a run is in flight)");
     s->planes_valid = s->fplane_valid = false;
     s->no_nc = false;
-    if (s->g.ndim == 2 && s->res_ok && F == 1 && method == VPINT_METHOD_EXACT && !clamp) {
+    s->ratio_verdict = -1;
+    VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme) + 1, 0, sizeof(double), st), "memset range check");
+    if (s->g.ndim == 2 && s->n_planes == 5 && F == 1 && method == VPINT_METHOD_EXACT && !clamp) {
         // one feature layer: keep the feature plane only; the ratio planes are derived on demand
         VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
-        VP_CUDA(launch_fplane(s->g, feat, dtype, stride, s->at<double>(s->off_w[4]), s->at<int>(s->off_flags), st,
-                              &s->launches),
+        VP_CUDA(launch_fplane(s->g, feat, dtype, stride, s->at<double>(s->off_w[4]), s->at<int>(s->off_flags),
+                              s->at<double>(s->off_extreme) + 1, st, &s->launches),
                 "fplane");
         s->fplane_valid = true;
     } else if (s->g.ndim == 2) {
@@ -338,7 +354,40 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms);
 
 // The four ratio planes are built lazily from the single-layer feature plane (vpint_solver_weights keeps only
 // that plane when the cluster-resident kernel can serve the run).
+// ---- ratio form of the tiled path -----------------------------------------------------------------------
+static int leave_ratio(vpint_solver *s, cudaStream_t st) {
+    if (!s->state_ratio) return VPINT_OK;
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    VP_CUDA(launch_from_ratio(s->g, s->at<ProbState>(s->off_state), bufs, s->at<double>(s->off_w[4]),
+                              s->at<double>(s->off_w[0]), s->at<uint32_t>(s->off_mask), st, &s->launches),
+            "from ratio");
+    s->state_ratio = false;
+    return VPINT_OK;
+}
+
+// May this run use the ratio form?  One feature layer with exact weights, fp64, one sweep per launch, and
+// every value / feature of moderate size (counters filled by load and weights; in a row-sharded run the
+// caller has all-reduced them together with the known-cell sums, so every rank answers alike).
+static int ratio_allowed(vpint_solver *s, cudaStream_t st, bool *out) {
+    *out = false;
+    if (s->weight_mode != VPINT_W_PLANES || s->g.ndim != 2 || s->storage != VPINT_F64 || s->use_tb || !s->fplane_valid ||
+        s->no_nc || s->prm.resistance || getenv("VPINT_NO_RATIO_TILES"))
+        return VPINT_OK;
+    if (s->ratio_verdict < 0) {
+        VP_CUDA(cudaMemcpyAsync(s->h_extreme, s->at<double>(s->off_extreme), 2 * sizeof(double), cudaMemcpyDeviceToHost, st),
+                "read range check");
+        VP_CUDA(cudaStreamSynchronize(st), "range check sync");
+        s->ratio_verdict = (s->h_extreme[0] == 0.0 && s->h_extreme[1] == 0.0) ? 1 : 0;
+    }
+    *out = (s->ratio_verdict == 1);
+    return VPINT_OK;
+}
+
 static int ensure_planes(vpint_solver *s, cudaStream_t st) {
+    {
+        const int rc = leave_ratio(s, st);      // the plane slots double as the ratio form's save area
+        if (rc != VPINT_OK) return rc;
+    }
     if (s->weight_mode != VPINT_W_PLANES || s->planes_valid) return VPINT_OK;
     if (!s->fplane_valid) return fail(VPINT_ERR_INVALID, "weights have not been set");
     void *planes[5];
@@ -382,9 +431,22 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         VP_CUDA(cudaEventCreate(&e1), "event create");
         VP_CUDA(cudaEventRecord(e0, st), "event record");
     }
+    bool use_ratio = false;
     {
-        const int rc = ensure_planes(s, st);
+        int rc = ratio_allowed(s, st, &use_ratio);
         if (rc != VPINT_OK) return rc;
+        if (use_ratio) {
+            if (!s->state_ratio) {
+                void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+                VP_CUDA(launch_to_ratio(s->g, bufs, s->at<double>(s->off_w[4]), s->at<double>(s->off_w[0]), st, &s->launches),
+                        "to ratio");
+                s->state_ratio = true;
+                s->planes_valid = false;         // plane slot 0 now holds the saved known values
+            }
+        } else {
+            rc = ensure_planes(s, st);
+            if (rc != VPINT_OK) return rc;
+        }
     }
     StepArgs a;
     a.g = s->g;
@@ -405,6 +467,8 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
     a.orig = s->has_orig ? s->at<void>(s->off_orig) : nullptr;
     if (a.resist) {
         VP_CUDA(launch_step2d_resist(a, s->storage, s->weight_mode, st, &s->launches), "step2d_resist");
+    } else if (use_ratio) {
+        VP_CUDA(launch_step2d_ratio(a, s->tiles_active, st, &s->launches), "step2d_ratio");
     } else if (s->g.ndim == 2) {
         if (s->use_tb)
             VP_CUDA(launch_step2d_tb(a, s->tb_maps, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d_tb");
@@ -535,6 +599,8 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
     const bool ratio = (s->weight_mode == VPINT_W_PLANES);
     if (s->res_ok && !s->any_dirty && !prm->resistance && !s->no_nc && (!ratio || s->fplane_valid)) {
         // whole run() in one launch: a cluster per problem, state resident in shared memory
+        rc = leave_ratio(s, st);                   // a previous tiled run may have left the state in ratio space
+        if (rc != VPINT_OK) return rc;
         int *flags = s->at<int>(s->off_flags);
         VP_CUDA(cudaMemsetAsync(flags + 1, 0, sizeof(int), st), "memset queue");
         ResidentArgs ra;
@@ -609,7 +675,7 @@ int32_t *vpint_solver_cur_ptr(vpint_solver *s) {
 
 double *vpint_solver_known_ptr(vpint_solver *s) { return (s && s->ws) ? s->at<double>(s->off_known0) : nullptr; }
 
-int vpint_solver_known_count(const vpint_solver *s) { return s ? 2 * s->g.P * kSumSlots : 0; }
+int vpint_solver_known_count(const vpint_solver *s) { return s ? 2 * s->g.P * kSumSlots + 2 : 0; }
 
 int vpint_solver_any_dirty(const vpint_solver *s) { return s ? s->any_dirty : 0; }
 
@@ -644,6 +710,10 @@ int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *st
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
     if (!out || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_result: null argument");
     if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    {
+        const int rc = leave_ratio(s, static_cast<cudaStream_t>(stream));
+        if (rc != VPINT_OK) return rc;
+    }
     void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
     VP_CUDA(launch_result(s->g, s->storage, s->at<ProbState>(s->off_state), bufs, out, dtype, stride, niter_out,
                           static_cast<cudaStream_t>(stream), &s->launches),

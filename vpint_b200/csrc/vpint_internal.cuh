@@ -116,15 +116,15 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
 cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
                               int64_t *launches);
 cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
-                          cudaStream_t st, int64_t *launches);
+                          double *extreme, cudaStream_t st, int64_t *launches);
 cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int storage, void *const *planes,
                                       cudaStream_t st, int64_t *launches);
 
 // ---- host-side launchers (one per .cu) ------------------------------------
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
                            int dtype, const int64_t *stride, int storage, void *bufA, void *bufB, void *orig_copy,
-                           uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
-                           int *counters, cudaStream_t st, int64_t *launches);
+                           uint32_t *mask, double *rowpart, double *known0, double *known, double *extreme,
+                           ProbState *state, int *counters, cudaStream_t st, int64_t *launches);
 bool fill_mean_supported(const Geom &g);
 cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, const int64_t *stride, double *fill_dev,
                              cudaStream_t st, int64_t *launches);
@@ -148,6 +148,11 @@ cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, dou
 cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
                               int64_t *launches);
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches);
+cudaError_t launch_to_ratio(const Geom &g, void *const *buf, const double *f, double *save, cudaStream_t st,
+                            int64_t *launches);
+cudaError_t launch_from_ratio(const Geom &g, const ProbState *state, void *const *buf, const double *f,
+                              const double *save, const uint32_t *mask, cudaStream_t st, int64_t *launches);
 cudaError_t launch_loop_condition(cudaGraphConditionalHandle handle, const int *n_active, int *iter_left,
                                   cudaStream_t st, int64_t *launches);
 cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,

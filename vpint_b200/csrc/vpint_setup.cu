@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
                                                       TSt *__restrict__ bufA,
                                                       TSt *__restrict__ bufB, TSt *__restrict__ orig_copy,
                                                       uint32_t *__restrict__ mask,
-                                                      double *__restrict__ rowpart) {
+                                                      double *__restrict__ rowpart, double *__restrict__ extreme) {
     __shared__ double scratch[8 * 8];
+    bool wild = false;        // a non-finite or huge value: the ratio form of the tiled path must not be used
     const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
     const size_t row = ((size_t)p * g.H + y) * g.pitch;
     const size_t mrow = ((size_t)p * g.H + y) * g.mpitch;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
             const double v0 = pred0 ? (double)pred0[off] : (unknown ? fillv : o);
             va = (TSt)v0;
             vb = unknown ? va : (TSt)o;
+            if (!(fabs(v0) < 1e150) || (!unknown && !(fabs(o) < 1e150))) wild = true;
             if (owned) {
                 if (unknown) {
                     acc[7] += 1.0;
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
         const unsigned word = __ballot_sync(0xffffffffu, unknown);   // pitch % 32 == 0: whole warps iterate together
         if ((threadIdx.x & 31) == 0) mask[mrow + (e >> 5)] = word;
     }
+    if (__syncthreads_or(wild) && threadIdx.x == 0) atomicAdd(extreme, 1.0);
     block_sum<8>(acc, scratch);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -383,6 +386,39 @@ __global__ void decide_kernel(DecideArgs a) {
     a.state[p] = st;
 }
 
+// Ratio form of the tiled path (vpint_step_k1.cu, jacobi2d_k1_ratio_kernel): move both state buffers into
+// r = P / f.  `save` keeps buffer 1, which holds the original value of every known cell, for the way back.
+// The form is only used when load / weights found every value and feature finite and of moderate size
+// (|.| < 1e150, |f| > 1e-150), so that f * r cannot overflow where the reference's w * P would not.
+__global__ void __launch_bounds__(256) to_ratio_kernel(Geom g, double *__restrict__ buf0, double *__restrict__ buf1,
+                                                       const double *__restrict__ f, double *__restrict__ save) {
+    const size_t row = (size_t)blockIdx.x * g.pitch;
+    for (int e = threadIdx.x; e < g.L; e += blockDim.x) {
+        const double a = buf0[row + e], b = buf1[row + e], ff = f[row + e];
+        save[row + e] = b;
+        buf0[row + e] = a / ff;
+        buf1[row + e] = b / ff;
+    }
+}
+
+// Back to value space: unknown cells P = f * r of the current buffer, known cells their original value,
+// written to BOTH buffers (the state both hold after any ordinary launch).
+__global__ void __launch_bounds__(256) from_ratio_kernel(Geom g, const ProbState *__restrict__ state, double *buf0,
+                                                         double *buf1, const double *__restrict__ f,
+                                                         const double *__restrict__ save,
+                                                         const uint32_t *__restrict__ mask) {
+    const int p = blockIdx.x / g.H;
+    const size_t row = (size_t)blockIdx.x * g.pitch;
+    const uint32_t *mr = mask + (size_t)blockIdx.x * g.mpitch;
+    const double *cur = state[p].cur ? buf1 : buf0;
+    for (int e = threadIdx.x; e < g.L; e += blockDim.x) {
+        const bool unk = (mr[e >> 5] >> (e & 31)) & 1u;
+        const double v = unk ? f[row + e] * cur[row + e] : save[row + e];
+        buf0[row + e] = v;
+        buf1[row + e] = v;
+    }
+}
+
 // Tail of the WHILE body of the graph loop (vpint_api.cu run_graph_loop): keep looping while a problem is
 // still running and the launch budget lasts.
 __global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const int *n_active, int *iter_left) {
@@ -466,13 +502,13 @@ cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, con
 
 cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred0, const double *fill_dev,
                            int dtype, const int64_t *stride, int storage, void *bufA, void *bufB, void *orig_copy,
-                           uint32_t *mask, double *rowpart, double *known0, double *known, ProbState *state,
-                           int *counters, cudaStream_t st, int64_t *launches) {
+                           uint32_t *mask, double *rowpart, double *known0, double *known, double *extreme,
+                           ProbState *state, int *counters, cudaStream_t st, int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
     const unsigned grid = (unsigned)((int64_t)g.P * g.H);
 #define VP_PREP(TIN, TST)                                                                                  \
     prepare_kernel<TIN, TST><<<grid, 256, 0, st>>>(g, (const TIN *)original, (const TIN *)pred0, fill_dev, \
-                                                   sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart)
+                                                   sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart, extreme)
     if (dtype == VPINT_F64 && storage == VPINT_F64) VP_PREP(double, double);
     else if (dtype == VPINT_F32 && storage == VPINT_F64) VP_PREP(float, double);
     else if (dtype == VPINT_F64 && storage == VPINT_F32) VP_PREP(double, float);
@@ -514,6 +550,21 @@ cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const i
 
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches) {
     decide_kernel<<<(a.g.P + 127) / 128, 128, 0, st>>>(a);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_to_ratio(const Geom &g, void *const *buf, const double *f, double *save, cudaStream_t st,
+                            int64_t *launches) {
+    to_ratio_kernel<<<(unsigned)((int64_t)g.P * g.H), 256, 0, st>>>(g, (double *)buf[0], (double *)buf[1], f, save);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_from_ratio(const Geom &g, const ProbState *state, void *const *buf, const double *f,
+                              const double *save, const uint32_t *mask, cudaStream_t st, int64_t *launches) {
+    from_ratio_kernel<<<(unsigned)((int64_t)g.P * g.H), 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], f, save,
+                                                                       mask);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -106,6 +106,76 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_kernel(const StepArgs a) {
     write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
 }
 
+// Ratio form of the 2-D sweep for ONE feature layer with exact weights (the VPint2 case): the state buffers
+// hold r = P / f, the update is r_new = (sum of in-grid neighbour r) / nc (see vpint_resident.cu for the
+// algebra), and P = f * r is formed only for the stopping statistic and the clip.  Per unknown cell and
+// sweep the kernel moves 8 B state in + 8 B feature + 8 B state out instead of 48 B with weight planes.
+template <int DUMMY>
+__global__ void __launch_bounds__(256) jacobi2d_k1_ratio_kernel(const StepArgs a) {
+    const TileRef tile = a.tiles[blockIdx.x];
+    const int p = tile.p;
+    const ProbState st = a.state[p];
+    if (st.k_run == 0) return;
+    const Geom &g = a.g;
+    const size_t plane = (size_t)g.H * g.pitch;
+    const double *__restrict__ in = reinterpret_cast<const double *>(a.buf[st.cur]) + (size_t)p * plane;
+    double *__restrict__ out = reinterpret_cast<double *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const double *__restrict__ fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xw = tile.x0 + (warp & 1) * 64;
+    const int x = xw + 2 * lane;
+    const int yb = tile.y0 + (warp >> 1) * 8;
+    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
+    double s_abs = 0.0, s_old = 0.0;
+    int c_abs = 0, c_old = 0;
+    if (xw < g.L) {
+        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
+        const int mp64 = g.mpitch >> 1;
+        for (int r = 0; r < 8; ++r) {
+            const int y = yb + r;
+            if (y >= y_lim) break;
+            const uint64_t bits = m64[(size_t)y * mp64];
+            const unsigned mb = (unsigned)(bits >> (2 * lane)) & 3u;
+            if (mb == 0) continue;
+            const size_t row = (size_t)y * g.pitch;
+            const int yg = y + g.row_offset;
+            const bool has_up = yg > 0, has_dn = yg < g.global_H - 1;
+            double c0, c1, u0 = 0.0, u1 = 0.0, d0 = 0.0, d1 = 0.0, lf = 0.0, rt = 0.0, f0, f1;
+            load2(in + row + x, c0, c1);
+            load2(fpl + row + x, f0, f1);
+            if (has_up) load2(in + row - g.pitch + x, u0, u1);
+            if (has_dn) load2(in + row + g.pitch + x, d0, d1);
+            if (x > 0) lf = in[row + x - 1];
+            if (x + 2 < g.L) rt = in[row + x + 2];
+            double n0 = ((u0 + c1) + d0) + lf;
+            double n1 = ((u1 + rt) + d1) + c0;
+            const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+            const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+            const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
+            n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
+            n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+            double v0 = f0 * n0, v1 = f1 * n1;
+            if (v0 > a.clip) { v0 = a.clip; n0 = a.clip / f0; }
+            if (v1 > a.clip) { v1 = a.clip; n1 = a.clip / f1; }
+            if (mb & 1u) {
+                const double o = f0 * c0, d = fabs(v0 - o);
+                if (d != d) ++c_abs; else s_abs += d;
+                if (o != o) ++c_old; else s_old += o;
+                out[row + x] = n0;
+            }
+            if (mb & 2u) {
+                const double o = f1 * c1, d = fabs(v1 - o);
+                if (d != d) ++c_abs; else s_abs += d;
+                if (o != o) ++c_old; else s_old += o;
+                out[row + x + 1] = n1;
+            }
+        }
+    }
+    Acc<double> acc;
+    acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
+    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+}
+
 // Resistance sweep (VPint/WP_MRP.py:327-348): the damping  new > mu -> old + (new - old) - epsilon * old  is
 // applied after the restore to EVERY cell, so known cells move too and nothing can be skipped: one block
 // per tile of the full grid (no active-tile list), every cell written, sums over all cells.
@@ -300,6 +370,13 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
         if (planes) jacobi2d_k1_kernel<float, true><<<grid, 256, 0, st>>>(a);
         else jacobi2d_k1_kernel<float, false><<<grid, 256, 0, st>>>(a);
     }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches) {
+    if (n_tiles <= 0) return cudaSuccess;
+    jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -201,22 +201,25 @@ __global__ void __launch_bounds__(256) weights_exact_f1_kernel(int P, int H, int
 template <typename TIn>
 __global__ void __launch_bounds__(256) fplane_kernel(int Pin, int H, int W, int pitch, const TIn *__restrict__ feat,
                                                      int64_t sO, int64_t sI, int64_t sY, int64_t sX,
-                                                     double *__restrict__ fplane, int *bad_flag) {
+                                                     double *__restrict__ fplane, int *bad_flag,
+                                                     double *__restrict__ extreme) {
     const int p = blockIdx.x / H, y = blockIdx.x - p * H;
     const int po = p / Pin, pi = p - po * Pin;
     const TIn *frow = feat + (int64_t)po * sO + (int64_t)pi * sI + (int64_t)y * sY;
     double *out = fplane + ((size_t)p * H + y) * pitch;
-    bool bad = false;
+    bool bad = false, wild = false;
     for (int x = threadIdx.x; x < pitch; x += blockDim.x) {
         double f = 1.0;
         if (x < W) {
             f = (double)frow[(int64_t)x * sX];
             if (f == 0.0) f = 0.01;                     // VPint/WP_MRP.py:143-145
             if (!(fabs(f) <= 1.7976931348623157e308)) bad = true;
+            if (!(fabs(f) < 1e150) || !(fabs(f) > 1e-150)) wild = true;
         }
         out[x] = f;
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(bad_flag, 1);
+    if (__syncthreads_or(wild) && threadIdx.x == 0) atomicAdd(extreme, 1.0);
 }
 
 // w_dir = f[i,j] / f[neighbour], missing neighbour -> 0 (VPint/WP_MRP.py:149-170 with one feature layer).
@@ -337,14 +340,14 @@ cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const i
 }
 
 cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
-                          cudaStream_t st, int64_t *launches) {
+                          double *extreme, cudaStream_t st, int64_t *launches) {
     const unsigned grid = (unsigned)((int64_t)g.P * g.H);
     if (dtype == VPINT_F64)
         fplane_kernel<double><<<grid, 256, 0, st>>>(g.Pin, g.H, g.W, g.pitch, (const double *)feat, stride[0], stride[1],
-                                                    stride[2], stride[3], fplane, bad_flag);
+                                                    stride[2], stride[3], fplane, bad_flag, extreme);
     else
         fplane_kernel<float><<<grid, 256, 0, st>>>(g.Pin, g.H, g.W, g.pitch, (const float *)feat, stride[0], stride[1],
-                                                   stride[2], stride[3], fplane, bad_flag);
+                                                   stride[2], stride[3], fplane, bad_flag, extreme);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
