@@ -257,6 +257,39 @@ def case_vpint2_ctor():
     save("vpint2_ctor", **out)
 
 
+def case_adapt():
+    """WP_SMRP.run(auto_adapt=True): the host-side search of VPint/WP_MRP.py:212-239, 429-759 with seeded
+    global RNG.  Written to its own file so that the earlier fixtures stay untouched."""
+    rng = np.random.default_rng(1010)
+    shape = (26, 26)
+    base = smooth(rng, shape)
+    grid = base + rng.normal(0, 15, shape)
+    feat = 1.1 * base + rng.normal(0, 8, shape)
+    grid[holes(rng, shape, 0.25)] = np.nan
+    out = {"grid": grid, "feat": feat}
+    runs = {
+        "rand": dict(auto_adaptation_epochs=5, auto_adaptation_strategy='random'),
+        "rand_sub": dict(auto_adaptation_epochs=4, auto_adaptation_strategy='random',
+                         auto_adaptation_subsample_strategy='random', auto_adaptation_proportion=0.3),
+        "diff": dict(auto_adaptation_epochs=3, auto_adaptation_strategy='random',
+                     auto_adaptation_subsample_strategy='max_diff'),
+        "hill": dict(auto_adaptation_epochs=7, auto_adaptation_strategy='hill_climbing', auto_adaptation_max_iter=30),
+        "seq": dict(auto_adaptation_epochs=2, auto_adaptation_strategy='sequential', auto_adaptation_max_iter=15),
+    }
+    for tag, kw in runs.items():
+        np.random.seed(77)
+        m = WP_SMRP(grid.copy(), feat.copy())
+        p, d = m.run(iterations=25, track_delta=True, auto_adapt=True, prioritise_identity=True, resistance=True,
+                     clip_val=5000.0, **kw)
+        out["pred_" + tag], out["d_" + tag] = p, d
+        out["rng_" + tag] = np.array(np.random.rand())        # where the global RNG stands afterwards
+    np.random.seed(78)
+    m = WP_SMRP(grid.copy(), feat.copy())
+    out["pred_beta_only"] = m.run(iterations=10, auto_adapt=True, prioritise_identity=True, auto_adaptation_epochs=4)
+    out["rng_beta_only"] = np.array(np.random.rand())
+    save("adapt", **out)
+
+
 if __name__ == "__main__":
     case_vpint2_ctor()
     case_sd2d()
@@ -264,3 +297,4 @@ if __name__ == "__main__":
     case_wp2d_edge()
     case_st3d()
     case_vpint2()
+    case_adapt()

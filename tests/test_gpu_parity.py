@@ -563,3 +563,53 @@ def test_graph_loop_mode_matches_chunked(k, monkeypatch):
     p3, dd3 = SD_STMRP(cube.copy(), gamma=0.9, tau=0.8).run(track_delta=True)
     assert len(dd3) == n3
     close(p3, r3)
+
+
+# ---- 8. auto_adapt: the reference's host-side parameter search with device trials ---------------------------------
+def test_golden_auto_adapt(golden):
+    """Same picks as the reference under the same seed (incl. its quirks: 'sequential' always fails and falls back
+    to the given parameters), same final result, same position of the global RNG afterwards."""
+    g = golden("adapt")
+    grid, feat = g["grid"], g["feat"]
+    runs = {
+        "rand": dict(auto_adaptation_epochs=5, auto_adaptation_strategy='random'),
+        "rand_sub": dict(auto_adaptation_epochs=4, auto_adaptation_strategy='random',
+                         auto_adaptation_subsample_strategy='random', auto_adaptation_proportion=0.3),
+        "diff": dict(auto_adaptation_epochs=3, auto_adaptation_strategy='random',
+                     auto_adaptation_subsample_strategy='max_diff'),
+        "hill": dict(auto_adaptation_epochs=7, auto_adaptation_strategy='hill_climbing', auto_adaptation_max_iter=30),
+        "seq": dict(auto_adaptation_epochs=2, auto_adaptation_strategy='sequential', auto_adaptation_max_iter=15),
+    }
+    for tag, kw in runs.items():
+        np.random.seed(77)
+        m = WP_SMRP(grid.copy(), feat.copy())
+        p, d = m.run(iterations=25, track_delta=True, auto_adapt=True, prioritise_identity=True, resistance=True,
+                     clip_val=5000.0, **kw)
+        assert np.random.rand() == float(g["rng_" + tag]), tag
+        close(p, g["pred_" + tag]); closed(d, g["d_" + tag])
+    np.random.seed(78)
+    p = WP_SMRP(grid.copy(), feat.copy()).run(iterations=10, auto_adapt=True, prioritise_identity=True,
+                                              auto_adaptation_epochs=4)
+    assert np.random.rand() == float(g["rng_beta_only"])
+    close(p, g["pred_beta_only"])
+
+
+def test_vpint2_auto_adapt_rng_semantics():
+    rng = np.random.default_rng(909)
+    vp = make_patch(rng, 32, 32, 2)
+    kw = dict(iterations=8, auto_adapt=True, auto_adaptation_epochs=3, prioritise_identity=True, resistance=True,
+              mu=1500.0, clip_val=10000)
+    np.random.seed(5)
+    got = vp.run(**kw)
+    assert np.random.rand() == np.random.RandomState(5).rand()      # parent stream untouched, like after fork + join
+    for b in range(2):                                              # every band saw the same stream
+        np.random.seed(5)
+        ref = WP_SMRP(vp.target[:, :, b], vp.features[:, :, b]).run(**kw)
+        close(got[:, :, b], ref, rtol=0)
+    np.random.seed(5)
+    ser = vp.run_serial(**kw)
+    np.random.seed(5)
+    r0 = WP_SMRP(vp.target[:, :, 0], vp.features[:, :, 0]).run(**kw)
+    r1 = WP_SMRP(vp.target[:, :, 1], vp.features[:, :, 1]).run(**kw)    # continues the stream
+    close(ser[:, :, 0], r0.astype(np.float32), rtol=0)
+    close(ser[:, :, 1], r1.astype(np.float32), rtol=0)

@@ -86,9 +86,12 @@ def test_run_option_handling():
     assert o["iterations"] == 5000 and o["auto_terminate"] and o["method"] == "exact"
     o = wp_run_options(iterations=7)
     assert o["iterations"] == 7 and not o["auto_terminate"]
-    for kw in (dict(method="predict"), dict(method="nope"), dict(save_gif=True), dict(auto_adapt=True)):
+    for kw in (dict(method="predict"), dict(method="nope"), dict(save_gif=True), dict(store_gif_source=True)):
         with pytest.raises(VPintError):
             wp_run_options(**kw)
+    o = wp_run_options(auto_adapt=True, prioritise_identity=True, resistance=True, epsilon=0.2)
+    assert o["auto_adapt"] and o["prioritise_identity"] and o["resistance"] and o["epsilon"] == 0.2
+    assert o["auto_adaptation_epochs"] == 100 and o["auto_adaptation_subsample_strategy"] == "max_contrast"
     with pytest.raises(TypeError):
         wp_run_options(no_such_option=1)
 
@@ -162,3 +165,32 @@ def test_vpint2_constructor_matches_reference(golden):
 def test_package_exports():
     for name in vpint_b200.__all__:
         assert hasattr(vpint_b200, name)
+
+
+def test_contrast_map_and_subsampling_match_reference_semantics():
+    """Host-side pieces of auto_adapt (VPint/WP_MRP.py:441-492, 893-940): contrast map incl. the reference's
+    one-short neighbour slices, and which cells the three sub-sampling strategies hide."""
+    from vpint_b200.adapt import _subsample, contrast_map
+    rng = np.random.default_rng(3)
+    g = rng.uniform(1, 9, (7, 6))
+    g[2, 3] = np.nan
+    c = contrast_map(g)
+    assert c.shape == g.shape and np.nanmin(c) == 0.0 and np.nanmax(c) == 1.0
+    # hand evaluation of one interior cell: its right / down planes are shifted by the short slices
+    i, j = 3, 2
+    up, right, down, left = g[i - 1, j], g[i, j + 1], g[i + 1, j], g[i, j - 1]
+    raw = (abs(up - g[i, j]) + abs(right - g[i, j]) + abs(down - g[i, j]) + abs(left - g[i, j])) / 4
+    nb = np.zeros((7, 6, 4)); nb[1:-1, :, 0] = g[0:-2]; nb[:, 0:-2, 1] = g[:, 1:-1]; nb[0:-2, :, 2] = g[1:-1]; nb[:, 1:-1, 3] = g[:, 0:-2]
+    cnt = np.full(g.shape, 4.0); cnt[:, 0] -= 1; cnt[:, -1] -= 1; cnt[0] -= 1; cnt[-1] -= 1
+    full = np.nansum(np.abs(nb - g[:, :, None]), axis=-1) / cnt
+    assert np.isclose(full[i, j], raw)
+    m = WP_SMRP(g.copy(), rng.uniform(1, 2, (7, 6)))
+    np.random.seed(1)
+    s_rand = _subsample(m, 'random', 0.5)
+    np.random.seed(1)
+    assert np.array_equal(np.isnan(s_rand), np.isnan(g) | (np.random.rand(42).reshape(7, 6) < 0.5))
+    for strat in ('max_contrast', 'max_diff'):
+        s = _subsample(m, strat, 0.25)
+        assert np.isnan(s).sum() == 1 + int(0.25 * 41)
+    with pytest.raises(VPintError):
+        _subsample(m, 'bogus', 0.5)

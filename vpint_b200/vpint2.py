@@ -291,8 +291,27 @@ class VPint2_interpolator():
         band, VPint/VPint2.py:58-101).  Returns float64 (H, W, B), a strided view of a
         (B, H, W) array exactly like the reference's swapaxes result."""
         opts = wp_run_options(**kwargs)
+        if opts["auto_adapt"]:
+            return self._run_bands_with_search(kwargs, forked=True).swapaxes(0, 2).swapaxes(0, 1)
         pred_bhw = solve_bands(self.target, self.features, opts, out_layout="bhw")
         return pred_bhw.swapaxes(0, 2).swapaxes(0, 1)
+
+    def _run_bands_with_search(self, kwargs, forked):
+        """auto_adapt=True: every band runs its own host-side parameter search (VPint/WP_MRP.py:212-239), so
+        the bands go through ``WP_SMRP.run`` one after the other (each trial is a device solve).  The
+        reference's ``run`` forks one process per band: every child starts from the SAME global RNG state
+        and the parent's state does not advance; ``run_serial`` shares one advancing stream.  Both are kept."""
+        from .wp import WP_SMRP
+        H, W, B = self.target.shape
+        out = np.empty((B, H, W), dtype=np.float64)
+        state = np.random.get_state()
+        for b in range(B):
+            if forked:
+                np.random.set_state(state)
+            out[b] = WP_SMRP(self.target[:, :, b], self.features[:, :, b]).run(**kwargs)
+        if forked:
+            np.random.set_state(state)
+        return out
 
     def VPint2_single(self, pred_dict, grids, band, **kwargs):
         """Kept for API compatibility (VPint/VPint2.py:104-106)."""
@@ -304,6 +323,9 @@ class VPint2_interpolator():
         """Same results as :meth:`run`, returned as a DTYPE (H, W, B) array
         (VPint/VPint2.py:109-119)."""
         opts = wp_run_options(**kwargs)
+        if opts["auto_adapt"]:
+            pred = self._run_bands_with_search(kwargs, forked=False)
+            return np.ascontiguousarray(np.moveaxis(pred, 0, -1)).astype(self.DTYPE)
         return solve_bands(self.target, self.features, opts, out_dtype=self.DTYPE, out_layout="hwb")
 
     def apply_mask(self, target, mask, threshold=0.2):
@@ -345,6 +367,8 @@ def run_patches(interpolators, serial=False, **kwargs):
     if not interpolators:
         return []
     opts = wp_run_options(**kwargs)
+    if opts["auto_adapt"]:          # per-band searches: no batching across patches
+        return [vp.run_serial(**kwargs) if serial else vp.run(**kwargs) for vp in interpolators]
     shape, dt = interpolators[0].target.shape, interpolators[0].target.dtype
     for vp in interpolators:
         if vp.target.shape != shape or vp.target.dtype != dt:

@@ -43,8 +43,6 @@ def wp_run_options(iterations=-1, method='exact', auto_terminate=True, auto_term
     if save_gif or store_gif_source:
         raise VPintError("save_gif / store_gif_source record every sweep on the host and are not supported "
                          "by the device path")
-    if auto_adapt:
-        raise VPintError("auto_adapt (host-side hyper-parameter search) is not supported by the device path yet")
     if method not in _DEVICE_METHODS:
         if method == 'predict':
             raise VPintError("method='predict' needs a host-side sklearn model and is not supported by the "
@@ -53,7 +51,12 @@ def wp_run_options(iterations=-1, method='exact', auto_terminate=True, auto_term
     return dict(iterations=iterations, method=method, auto_terminate=auto_terminate,
                 threshold=auto_terminate_threshold, track_delta=track_delta, clip_val=clip_val,
                 prioritise_identity=bool(prioritise_identity), priority_intensity=priority_intensity,
-                known_value_bias=known_value_bias, resistance=bool(resistance), epsilon=epsilon, mu=mu)
+                known_value_bias=known_value_bias, resistance=bool(resistance), epsilon=epsilon, mu=mu,
+                auto_adapt=bool(auto_adapt), auto_adaptation_epochs=auto_adaptation_epochs,
+                auto_adaptation_proportion=auto_adaptation_proportion, auto_adaptation_strategy=auto_adaptation_strategy,
+                auto_adaptation_max_iter=auto_adaptation_max_iter,
+                auto_adaptation_subsample_strategy=auto_adaptation_subsample_strategy,
+                auto_adaptation_verbose=auto_adaptation_verbose)
 
 
 class WP_SMRP(SMRP):
@@ -105,16 +108,52 @@ class WP_SMRP(SMRP):
         ``confidence`` / ``confidence_model`` are accepted and unused, as in the
         reference.  ``prioritise_identity`` (+ ``priority_intensity``, ``known_value_bias``) and
         ``resistance`` (+ ``epsilon``, ``mu``) run on the device as well.  Not available here
-        (VPintError): ``method='predict'`` (needs the caller's sklearn model on the host), GIF
-        recording and ``auto_adapt``.
+        (VPintError): ``method='predict'`` (needs the caller's sklearn model on the host) and GIF
+        recording.  ``auto_adapt`` runs the reference's host-side search with every trial on the device.
         """
         opts = wp_run_options(iterations=iterations, method=method, auto_terminate=auto_terminate,
                               auto_terminate_threshold=auto_terminate_threshold, track_delta=track_delta,
-                              save_gif=save_gif, store_gif_source=store_gif_source, auto_adapt=auto_adapt,
+                              save_gif=save_gif, store_gif_source=store_gif_source,
                               prioritise_identity=prioritise_identity, priority_intensity=priority_intensity,
                               known_value_bias=known_value_bias, resistance=resistance, epsilon=epsilon, mu=mu,
                               clip_val=clip_val)
         iterations, auto_terminate = opts["iterations"], opts["auto_terminate"]
+        self.clip_val = clip_val
+        if method == 'exact':
+            # the reference replaces zeros in self.feature_grid in place (VPint/WP_MRP.py:143-145)
+            flat = self.feature_grid.reshape(self.feature_grid.size)
+            flat[flat == 0] = 0.01
+        if auto_adapt:
+            # host-side search (VPint/WP_MRP.py:212-239): every trial is a device solve; any failure is
+            # swallowed and retried three times, then the given parameters are used -- as in the reference
+            params = []
+            if prioritise_identity:
+                params.append('beta')
+            if resistance:
+                params.append('epsilon')
+                params.append('mu')
+            fail_counter = 0
+            while True:
+                if fail_counter >= 3:
+                    print("Auto-adaptation failed 3 times; proceeding with default parameters")
+                    break
+                try:
+                    params_opt = self.auto_adapt(params, auto_adaptation_epochs, auto_adaptation_proportion,
+                                                 search_strategy=auto_adaptation_strategy,
+                                                 max_sub_iter=auto_adaptation_max_iter,
+                                                 subsample_strategy=auto_adaptation_subsample_strategy)
+                    if auto_adaptation_verbose:
+                        print("Best found params: " + str(params_opt))
+                    for k, v in params_opt.items():
+                        if k == 'beta':
+                            priority_intensity = params_opt[k]
+                        elif k == 'epsilon':
+                            epsilon = params_opt[k]
+                        elif k == 'mu':
+                            mu = params_opt[k]
+                    break
+                except Exception:
+                    fail_counter += 1
         priority = None
         if prioritise_identity:
             bias = None
@@ -126,12 +165,6 @@ class WP_SMRP(SMRP):
                 ind[~np.isnan(ind)] = 1
                 bias = SD_SMRP(ind, init_strategy='zero', gamma=(1 - known_value_bias)).run()
             priority = dict(beta=priority_intensity, bias=bias, want_planes=True)
-
-        self.clip_val = clip_val
-        if method == 'exact':
-            # the reference replaces zeros in self.feature_grid in place (VPint/WP_MRP.py:143-145)
-            flat = self.feature_grid.reshape(self.feature_grid.size)
-            flat[flat == 0] = 0.01
         delta_vec = np.zeros(iterations) if track_delta else None
         if iterations > 0:
             new_grid, deltas, sweeps = propagate(
@@ -152,6 +185,20 @@ class WP_SMRP(SMRP):
         if track_delta:
             return self.pred_grid, delta_vec
         return self.pred_grid
+
+    def auto_adapt(self, params, search_epochs, subsample_proportion, search_strategy='random',
+                   subsample_strategy='max_contrast', ranges={}, max_sub_iter=-1, hill_climbing_threshold=5):
+        """Parameter search on a sub-sampled copy of the grid (VPint/WP_MRP.py:429-759); see
+        :mod:`vpint_b200.adapt`."""
+        from .adapt import auto_adapt
+        return auto_adapt(self, params, search_epochs, subsample_proportion, search_strategy=search_strategy,
+                          subsample_strategy=subsample_strategy, ranges=ranges, max_sub_iter=max_sub_iter,
+                          hill_climbing_threshold=hill_climbing_threshold)
+
+    def contrast_map(self, grid):
+        """VPint/WP_MRP.py:893-940."""
+        from .adapt import contrast_map
+        return contrast_map(grid)
 
     def predict_weight(self, f1, f2, method):
         """Host utility with the reference's semantics (VPint/WP_MRP.py:396-427); the
