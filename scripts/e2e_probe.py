@@ -19,10 +19,12 @@ for name, fn in (("h2d", lambda: d.copy_(t_host, non_blocking=True)), ("d2h", la
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
     print(name, "%.1f GB/s" % (t_host.numel() * 4 / dt / 1e9))
 opts = wp_run_options()
-for chunk in (16, 32, 64, 128):
+import itertools
+for workers, chunk in itertools.product((2, 3, 4), (8, 16, 24, 32)):
     V.PIPELINE_CHUNK_PATCHES = chunk
+    V.PIPELINE_WORKERS = workers
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         res, sw = V.solve_bands(t_host, f_host, opts, out_layout="bhw", return_sweeps=True, device=dev, out=out_host)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print("chunk", chunk, "e2e %.1f ms" % (dt * 1e3), "sweeps", int(sw.sum()))
+    print("workers", workers, "chunk", chunk, "e2e %.1f ms" % (dt * 1e3), "sweeps", int(sw.sum()))

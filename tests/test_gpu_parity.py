@@ -380,7 +380,7 @@ def test_solver_introspection_and_tile_skipping():
     close(out[0].cpu().numpy()[:20, :20], ref[:20, :20])
     s.close()
     with pytest.raises(VPintError):
-        WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, auto_adapt=True)
+        WP_SMRP(np.ones((4, 4)), np.ones((4, 4))).run(iterations=1, save_gif=True)
 
 
 # ---- 4. row-sharded scene on one device: shards in lockstep through the CUDA halo kernels ---------

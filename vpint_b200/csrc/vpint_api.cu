@@ -4,8 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "vpint_internal.cuh"
 
@@ -42,6 +44,31 @@ int fail_cuda(cudaError_t e, const char *where) {
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Small pinned host blocks (the per-solver counters the loop drivers poll).  cudaHostAlloc / cudaFreeHost cost
+// milliseconds and the free synchronises the whole device, so blocks are recycled through a process-wide
+// free list and only returned to the driver at process exit.
+constexpr size_t kPinnedBlock = 256;
+std::mutex g_pinned_mutex;
+std::vector<void *> g_pinned_free;
+
+cudaError_t pinned_acquire(void **out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        if (!g_pinned_free.empty()) {
+            *out = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaHostAlloc(out, kPinnedBlock, cudaHostAllocDefault);
+}
+
+void pinned_release(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    g_pinned_free.push_back(p);
+}
 
 enum Counter { kCntDirty = 0, kCntActiveTiles = 1, kCntActiveProblems = 8, kCntTotal = 16 };
 
@@ -212,8 +239,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
 
 void vpint_solver_destroy(vpint_solver *s) {
     if (!s) return;
-    if (s->h_counters) cudaFreeHost(s->h_counters);
-    if (s->h_extreme) cudaFreeHost(s->h_extreme);
+    pinned_release(s->h_counters);
     if (s->ev) cudaEventDestroy(s->ev);
     delete s;
 }
@@ -225,8 +251,11 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     if (!workspace || bytes < s->ws_bytes) return fail(VPINT_ERR_WORKSPACE, "workspace missing or too small");
     if ((uintptr_t)workspace % 256 != 0) return fail(VPINT_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if (!s->h_counters) {
-        VP_CUDA(cudaHostAlloc((void **)&s->h_counters, kCntTotal * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
-        VP_CUDA(cudaHostAlloc((void **)&s->h_extreme, 2 * sizeof(double), cudaHostAllocDefault), "cudaHostAlloc");
+        static_assert(kCntTotal * sizeof(int) + 2 * sizeof(double) <= kPinnedBlock, "pinned block too small");
+        void *blk = nullptr;
+        VP_CUDA(pinned_acquire(&blk), "cudaHostAlloc");
+        s->h_counters = static_cast<int *>(blk);
+        s->h_extreme = reinterpret_cast<double *>(static_cast<char *>(blk) + 128);
         VP_CUDA(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming), "cudaEventCreate");
     }
     s->ws = static_cast<char *>(workspace);

@@ -37,7 +37,9 @@ def _band_fill_values(target):
 
 # Patches per pipeline stage when a host-resident stack is solved chunk by chunk (H2D of chunk i+1 and D2H
 # of chunk i-1 overlap the solve of chunk i).
-PIPELINE_CHUNK_PATCHES = 64
+PIPELINE_CHUNK_PATCHES = 16
+# Host threads (each with its own stream and solver) that take alternate chunks.
+PIPELINE_WORKERS = 3
 
 
 def _known_value_bias(t_dev, kvb, dev):
@@ -126,6 +128,12 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
         return res, sweeps.to(torch.int64).view(N, B)
 
     # ---- pipelined path ---------------------------------------------------------------------------
+    # Two host threads, each with its own stream and solver, take alternate chunks.  A thread blocks in
+    # run() until its chunk has stopped; meanwhile the other thread has already copied in and queued the
+    # next chunk, whose cluster-resident kernel moves onto the SMs as the first one drains (the long-tailed
+    # problems of a chunk no longer leave the GPU idle), and the device->host copy of a finished chunk
+    # overlaps the next solve.
+    import threading
     if out is None:
         out = torch.empty(res_shape(N), dtype=res_dtype)
     sweeps_host = torch.empty(N * B, dtype=torch.int32)
@@ -133,52 +141,45 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
         sweeps_host = sweeps_host.pin_memory()
     spans = [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
     main = torch.cuda.current_stream(dev)
-    s_in, s_run, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-    for st in (s_in, s_run, s_out):
-        st.wait_stream(main)
-    t_slot = [torch.empty((chunk, H, W, B), dtype=target.dtype, device=dev) for _ in range(2)]
-    f_slot = [torch.empty((chunk, H, W, B), dtype=features.dtype, device=dev) for _ in range(2)]
-    r_slot = [torch.empty(res_shape(chunk), dtype=res_dtype, device=dev) for _ in range(2)]
-    solvers = {}
-    ev_in = [None] * len(spans)
-    ev_out = [None] * len(spans)
+    n_workers = PIPELINE_WORKERS
+    errors = []
 
-    def stage(i):
-        a, b = spans[i]
-        with torch.cuda.stream(s_in):
-            t_slot[i % 2][:b - a].copy_(target[a:b], non_blocking=True)
-            f_slot[i % 2][:b - a].copy_(features[a:b], non_blocking=True)
-            ev_in[i] = torch.cuda.Event()
-            ev_in[i].record(s_in)
+    def worker(w):
+        try:
+            with torch.cuda.device(dev):
+                st = torch.cuda.Stream(device=dev)
+                st.wait_stream(main)
+                solvers = {}
+                t_buf = torch.empty((chunk, H, W, B), dtype=target.dtype, device=dev)
+                f_buf = torch.empty((chunk, H, W, B), dtype=features.dtype, device=dev)
+                r_buf = torch.empty(res_shape(chunk), dtype=res_dtype, device=dev)
+                try:
+                    with torch.cuda.stream(st):
+                        for i in range(w, len(spans), n_workers):
+                            a, b = spans[i]
+                            m = b - a
+                            t_buf[:m].copy_(target[a:b], non_blocking=True)
+                            f_buf[:m].copy_(features[a:b], non_blocking=True)
+                            if m not in solvers:
+                                solvers[m] = _make_solver(m * B, H, W, B, storage, kb, dev, opts)
+                            niter = _solve_chunk(solvers[m], t_buf[:m], f_buf[:m], opts, r_buf[:m], out_layout,
+                                                 None if fill is None else fill[a:b].reshape(-1))
+                            out[a:b].copy_(r_buf[:m], non_blocking=True)
+                            sweeps_host[a * B:b * B].copy_(niter, non_blocking=True)
+                            st.synchronize()          # r_buf / niter are reused by this thread's next chunk
+                finally:
+                    for sv in solvers.values():
+                        sv.close()
+        except BaseException as exc:      # surfaced to the caller below
+            errors.append(exc)
 
-    try:
-        stage(0)
-        for i, (a, b) in enumerate(spans):
-            m = b - a
-            if i + 1 < len(spans):
-                stage(i + 1)       # its slot was last read by chunk i-1, whose solve has returned
-            if m not in solvers:
-                solvers[m] = _make_solver(m * B, H, W, B, storage, kb, dev, opts)
-            with torch.cuda.stream(s_run):
-                s_run.wait_event(ev_in[i])
-                if i >= 2:
-                    s_run.wait_event(ev_out[i - 2])          # result slot free again
-                niter = _solve_chunk(solvers[m], t_slot[i % 2][:m], f_slot[i % 2][:m], opts, r_slot[i % 2][:m],
-                                     out_layout, None if fill is None else fill[a:b].reshape(-1))
-                done = torch.cuda.Event()
-                done.record(s_run)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
-                out[a:b].copy_(r_slot[i % 2][:m], non_blocking=True)
-                sweeps_host[a * B:b * B].copy_(niter, non_blocking=True)
-                niter.record_stream(s_out)
-                ev_out[i] = torch.cuda.Event()
-                ev_out[i].record(s_out)
-        s_out.synchronize()
-        main.wait_stream(s_run)
-    finally:
-        for sv in solvers.values():
-            sv.close()
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(min(n_workers, len(spans)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
     return out, sweeps_host.to(torch.int64).view(N, B)
 
 
