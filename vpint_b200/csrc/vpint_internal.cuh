@@ -109,7 +109,6 @@ struct ResidentArgs {
     int max_iter, auto_terminate;
     double threshold, clip;
     int C, R, SP, fcap;
-    int dbg;                 // development switch (VPINT_RES_DBG)
 };
 
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);

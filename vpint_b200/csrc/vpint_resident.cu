@@ -587,8 +587,7 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
 
 cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
                               int64_t *launches) {
-    ResidentArgs a = a_in;
-    a.dbg = getenv("VPINT_RES_DBG") ? atoi(getenv("VPINT_RES_DBG")) : 0;
+    const ResidentArgs &a = a_in;
     auto kern = ratio ? resident2d_kernel<true> : resident2d_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
