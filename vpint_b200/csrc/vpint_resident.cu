@@ -138,6 +138,7 @@ struct SyncShared {
     double red[kWarps][2];
     uint64_t bar_h[2];                 // per sweep parity: this CTA's own stores (kThreads arrivals) + neighbours' halo bytes
     uint64_t bar_s[3];                 // per sweep mod 3: the C partial sums (C * 16 bytes)
+    int verdict;                       // stop decision of the previous sweep, written by warp 0
     int halo_exp[2];                   // bytes per sweep from the upper / lower neighbour
     int edge_cnt[2];                   // segments on the first / last owned row
 };
@@ -147,13 +148,12 @@ __device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
     a = v.x; b = v.y;
 }
 
-// Stop decision of one sweep from the C partials (every thread of every CTA computes the same thing):
+// Stop decision of one sweep from the C partials (warp 0 of every CTA computes the same thing):
 // delta = nanmean|new-old| / nanmean(old) with the known-cell constants added (VPint/SD_MRP.py:139).
 // Returns 0 continue, 1 stop, 2 non-finite data (leave the problem to the tiled path).
-__device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned &ph_s, int C, const double *KK, double n_cells,
+__device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned ph_s, int C, const double *KK, double n_cells,
                                             const ResidentArgs &a, int p, int sweep, bool writer) {
     mbar_wait(&sh.bar_s[slot], (ph_s >> slot) & 1u);
-    ph_s ^= 1u << slot;
     double S0 = 0.0, S1 = 0.0;
     for (int q = 0; q < C; ++q) { S0 += sh.part[slot][q][0]; S1 += sh.part[slot][q][1]; }
     if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) return 2;
@@ -291,10 +291,15 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
             const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
             if (lane == 0) { sh.red[warp][0] = q0; sh.red[warp][1] = q1; }
         }
-        __syncthreads();                           // (3) every read of the old state is done; red[] complete
-        if (t > 0) {                               // (4)
-            verdict = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
+        if (t > 0 && warp == 0) {                  // (4) by one warp; the others pick the verdict up after (3)
+            const int v = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
+            if (lane == 0) sh.verdict = v;
+        }
+        __syncthreads();                           // (3) every read of the old state is done; red[] / verdict complete
+        if (t > 0) {
+            ph_s ^= 1u << ((t - 1) % 3);
             fresh = false;
+            verdict = sh.verdict;
             if (verdict != 0) break;
         }
         if (warp == 0) {                           // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
@@ -340,8 +345,13 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
         const int par = T & 1;
         mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
         ph_h ^= 1u << par;
-        verdict = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
-        if (verdict == 1) verdict = 0;             // stopping at the very last sweep changes nothing
+        if (warp == 0) {
+            const int v = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
+            if (lane == 0) sh.verdict = v;
+        }
+        __syncthreads();
+        ph_s ^= 1u << ((T - 1) % 3);
+        verdict = (sh.verdict == 2) ? 2 : 0;       // stopping at the very last sweep changes nothing
     }
     it_out = t;
     bailed_out = (verdict == 2);
