@@ -613,3 +613,63 @@ def test_vpint2_auto_adapt_rng_semantics():
     r1 = WP_SMRP(vp.target[:, :, 1], vp.features[:, :, 1]).run(**kw)    # continues the stream
     close(ser[:, :, 0], r0.astype(np.float32), rtol=0)
     close(ser[:, :, 1], r1.astype(np.float32), rtol=0)
+
+
+# ---- 9. edge cases of the single-feature (ratio) forms and degenerate grids ----------------------------------------
+@pytest.mark.parametrize("shape", [(37, 91), (130, 203), (64, 5), (3, 300), (300, 301), (2, 2), (9, 1), (1, 9)])
+def test_single_feature_ragged_shapes(shape, kblock):
+    """One feature layer takes the ratio forms (resident kernel for k_block 0, ratio tiles for k_block 1): widths
+    that are not multiples of the 4-cell segments / 64-element pitch, single rows and columns."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    base = smooth(rng, shape, 500, 2500)
+    grid = np.round(base + rng.normal(0, 20, shape))
+    feat = np.round(1.1 * base + rng.normal(0, 10, shape))
+    hide = rng.uniform(size=shape) < 0.35
+    hide.flat[0] = True
+    hide.flat[-1] = False
+    grid[hide] = np.nan
+    ref, dref, n = O.wp_run_2d(grid, O.init_pred(grid), feat.reshape(shape + (1,)).astype(float).copy())
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
+    assert len(d) == n, (len(d), n)
+    close(p, ref); closed(d, dref)
+    assert np.array_equal(p[~hide], grid[~hide])
+    ref, dref, _ = O.wp_run_2d(grid, O.init_pred(grid), feat.reshape(shape + (1,)).astype(float).copy(), iterations=7,
+                               clip_val=1800.0)
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(iterations=7, track_delta=True, clip_val=1800.0)
+    close(p, ref); closed(d, dref)
+
+
+def test_degenerate_grids(kblock):
+    rng = np.random.default_rng(12)
+    full = smooth(rng, (20, 20), 10, 20)                       # nothing to interpolate: one sweep, delta 0
+    p, d = WP_SMRP(full.copy(), full.copy()).run(track_delta=True)
+    ref, dref, n = O.wp_run_2d(full, O.init_pred(full), full.reshape(20, 20, 1).copy())
+    assert len(d) == n == 1 and d[0] == 0.0
+    close(p, ref, rtol=0)
+    p, d = SD_SMRP(full.copy()).run(track_delta=True)
+    assert len(d) == 1 and np.array_equal(p, full)
+    empty = np.full((12, 12), np.nan)                           # nothing known: NaN mean, NaN deltas, never "converges"
+    ref, dref, n = O.sd_run_2d(empty, O.init_pred(empty), gamma=0.9, iterations=3)
+    p, d = SD_SMRP(empty.copy()).run(iterations=3, track_delta=True)
+    close(p, ref); closed(d, dref)
+    one = full.copy()                                           # a single unknown cell in a corner
+    one[0, 0] = np.nan
+    ref, dref, n = O.wp_run_2d(one, O.init_pred(one), full.reshape(20, 20, 1).copy())
+    p, d = WP_SMRP(one.copy(), full.copy()).run(track_delta=True)
+    assert len(d) == n
+    close(p, ref); closed(d, dref)
+
+
+def test_resume_single_feature_paths(kblock):
+    """run(a); run(b) continues from pred_grid on the single-feature paths as well; the ratio forms
+    round-trip through value space between the two calls, so equality with one long run is to ~1 ulp."""
+    rng = np.random.default_rng(33)
+    shape = (70, 90)
+    base = smooth(rng, shape, 500, 2500)
+    grid = base + rng.normal(0, 20, shape)
+    feat = 1.1 * base + rng.normal(0, 10, shape)
+    grid[discs(rng, shape, 4, 6, 20)] = np.nan
+    ref, _, _ = O.wp_run_2d(grid, O.init_pred(grid), feat.reshape(shape + (1,)).copy(), iterations=30)
+    m = WP_SMRP(grid.copy(), feat.copy())
+    m.run(iterations=12)
+    close(m.run(iterations=18), ref)
