@@ -68,7 +68,7 @@ typedef struct vpint_solver vpint_solver;
  * VPint2 bands (VPint/VPint2.py:71-83), patches and hyper-parameter trials map
  * onto one launch. */
 typedef struct vpint_desc {
-    int32_t ndim;         /* 2: (H, W) grids.  3: (H, W, T) cubes, T contiguous     */
+    int32_t ndim;         /* 2: (H, W) grids.  3: (H, W, T) cubes (any strides; device state is time-major) */
     int32_t nprob;        /* problems in the batch                                   */
     int32_t nprob_inner;  /* problem p = outer * nprob_inner + inner for addressing caller arrays
                              (patch, band); 0 or 1 = flat                            */
@@ -189,7 +189,7 @@ int     vpint_solver_step_end(vpint_solver *s, void *stream);
 int     vpint_solver_step_profile(vpint_solver *s, void *stream, float *stencil_ms);
 double *vpint_solver_sums_ptr(vpint_solver *s);
 int     vpint_solver_sums_count(const vpint_solver *s);
-void   *vpint_solver_state_ptr(vpint_solver *s, int which);   /* ping-pong buffer 0/1, [nprob][H][pitch] */
+void   *vpint_solver_state_ptr(vpint_solver *s, int which);   /* ping-pong buffer 0/1, [nprob][H][pitch] (3-D: [nprob][T][H][pitch]) */
 int32_t*vpint_solver_active_ptr(vpint_solver *s);             /* device int32: problems still running   */
 int32_t*vpint_solver_cur_ptr(vpint_solver *s);                /* device int32[nprob]: buffer holding the current state */
 

@@ -136,7 +136,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     if (d->k_block < 0 || d->k_block > kMaxKBlock) return fail(VPINT_ERR_INVALID, "k_block out of range");
     if (d->nprob_inner < 0 || (d->nprob_inner > 1 && d->nprob % d->nprob_inner != 0))
         return fail(VPINT_ERR_INVALID, "nprob_inner must divide nprob");
-    if ((int64_t)d->W * d->T > (int64_t)1 << 30) return fail(VPINT_ERR_INVALID, "row too long");
+    if ((int64_t)d->W > (int64_t)1 << 30 || (int64_t)d->nprob * d->T > (int64_t)1 << 30)
+        return fail(VPINT_ERR_INVALID, "row too long or too many slices");
 
     vpint_solver *s = new (std::nothrow) vpint_solver();
     if (!s) return fail(VPINT_ERR_INVALID, "out of host memory");
@@ -144,10 +145,11 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     Geom &g = s->g;
     g.ndim = d->ndim; g.P = d->nprob; g.H = d->H; g.W = d->W; g.T = d->T;
     g.Pin = d->nprob_inner > 1 ? d->nprob_inner : 1;
-    g.L = d->W * d->T;
+    g.S = (d->ndim == 3) ? d->T : 1;           // time-major slice stack (vpint_internal.cuh, Geom)
+    g.L = d->W;
     g.pitch = (int)vpint_row_pitch(g.L);
     g.mpitch = g.pitch / kMaskWordBits;
-    g.wpitch = (int)vpint_row_pitch(g.W);
+    g.wpitch = g.pitch;
     if (d->global_H == 0 && d->own_rows == 0 && d->row_offset == 0 && d->own_row0 == 0) {
         g.global_H = g.H; g.row_offset = 0; g.own_row0 = 0; g.own_rows = g.H;
     } else {
@@ -158,7 +160,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
             return fail(VPINT_ERR_INVALID, "inconsistent row sharding (global_H, row_offset, own_row0, own_rows)");
         }
     }
-    g.n_cells = (double)g.global_H * (double)g.L;
+    g.n_cells = (double)g.global_H * (double)g.W * (double)g.T;
     s->halo_up = g.own_row0;
     s->halo_down = g.H - g.own_row0 - g.own_rows;
     s->storage = d->storage;
@@ -198,8 +200,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     g.tiles_y = (g.own_rows + g.TH - 1) / g.TH;
     g.tiles_x = (g.L + g.TW - 1) / g.TW;
     g.tiles_per_prob = g.tiles_y * g.tiles_x;
-    s->tiles_total = (int64_t)g.P * g.tiles_per_prob;
-    if (s->tiles_total >= ((int64_t)1 << 31) - 1024 || (int64_t)g.P * g.H >= ((int64_t)1 << 31) - 1) {
+    s->tiles_total = (int64_t)g.P * g.S * g.tiles_per_prob;
+    if (s->tiles_total >= ((int64_t)1 << 31) - 1024 || (int64_t)g.P * g.S * g.H >= ((int64_t)1 << 31) - 1) {
         delete s;
         return fail(VPINT_ERR_INVALID, "batch too large for one solver (tile or row count exceeds 2^31)");
     }
@@ -207,16 +209,16 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t plane = (size_t)g.P * g.H * g.pitch * s->elem;
+    const size_t plane = (size_t)g.P * g.S * g.H * g.pitch * s->elem;
     s->off_buf[0] = take(plane);
     s->off_buf[1] = take(plane);
-    s->off_mask = take((size_t)g.P * g.H * g.mpitch * sizeof(uint32_t));
-    const size_t wplane = (d->ndim == 2) ? plane : (size_t)g.P * g.H * g.wpitch * s->elem;
+    s->off_mask = take((size_t)g.P * g.S * g.H * g.mpitch * sizeof(uint32_t));
+    const size_t wplane = (size_t)g.P * g.H * g.pitch * s->elem;      // (H, W) per problem, also in 3-D
     for (int i = 0; i < 5; ++i) s->off_w[i] = (i < s->n_planes) ? take(wplane) : 0;
     s->off_gamma = take((size_t)g.P * sizeof(double));
     s->off_tau = take((size_t)g.P * sizeof(double));
     s->off_fill = take((size_t)g.P * sizeof(double));
-    s->off_rowpart = take((size_t)g.P * g.H * 8 * sizeof(double));
+    s->off_rowpart = take((size_t)g.P * g.S * g.H * 8 * sizeof(double));
     // known0, known, then two range-check counters (values, features): one contiguous block, all-reduced
     // as a whole by row-sharded runs
     s->off_known0 = take((2 * (size_t)g.P * kSumSlots + 2) * sizeof(double));
@@ -226,7 +228,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_counters = take(kCntTotal * sizeof(int));
     s->off_tileflag = take((size_t)s->tiles_total * sizeof(int));
     s->off_tiles = take((size_t)s->tiles_total * sizeof(TileRef));
-    s->off_tilestart = take((size_t)(g.P + 1) * sizeof(int));
+    s->off_tilestart = take((size_t)(g.P * g.S + 1) * sizeof(int));
     s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
     s->off_flags = take(16 * sizeof(int));

@@ -17,23 +17,25 @@ constexpr int kMaxKBlock = 16;      // per-launch fused sweeps (register-residen
 // Counts are kept as doubles so one buffer can be all-reduced as fp64.
 constexpr int kSumSlots = 4;
 
-// Geometry of a batched solve.  A "row" is the contiguous inner dimension:
-// W cells in 2-D, W*T cells in 3-D (T fastest).
+// Geometry of a batched solve.  Device state is a stack of (H, pitch) SLICES: one per problem in 2-D, T per
+// problem in 3-D (time-major: slice s = p * T + t), so that every slice is an image whose unknown cells are
+// spatially coherent -- whatever the caller's memory order (the reference's cubes are (H, W, T) with T fastest).
 struct Geom {
     int ndim, P, H, W, T;
     int Pin;          // inner problem count: p = outer * Pin + inner when addressing caller arrays
-    int L;            // row length in elements = W * T
+    int S;            // slices per problem: 1 (2-D) or T (3-D)
+    int L;            // row length in elements = W
     int pitch;        // padded row length (multiple of kPitchAlign)
     int mpitch;       // 32-bit mask words per row = pitch / 32
-    int wpitch;       // 3-D only: padded W for the (H, W) weight planes
+    int wpitch;       // == pitch (kept for the (H, W) weight planes of the 3-D plane mode)
     int TH, TW;       // owned tile: rows x row-elements
-    int tiles_y, tiles_x, tiles_per_prob;
+    int tiles_y, tiles_x, tiles_per_prob;   // per SLICE
     int KB;           // sweeps per launch
     int global_H;     // rows of the whole grid (== H when unsharded)
     int row_offset;   // global row of local row 0
     int own_row0;     // first owned local row
     int own_rows;     // owned rows
-    double n_cells;   // cells of the WHOLE grid (global_H * L): nanmean denominators
+    double n_cells;   // cells of the WHOLE grid (global_H * W * T): nanmean denominators
 };
 
 // Per-problem loop state (device).
@@ -49,7 +51,7 @@ struct ProbState {
 };
 
 struct TileRef {
-    int p, y0, x0, pad;
+    int p, y0, x0, pad;      // p = SLICE index (problem * S + t)
 };
 
 // Everything a stencil launch needs.

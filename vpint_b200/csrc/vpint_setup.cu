@@ -10,12 +10,11 @@ struct Strides {
     int64_t sO, sI, sY, sX, sT;
 };
 
-__device__ __forceinline__ int64_t cell_offset(const Geom &g, const Strides &s, int p, int y, int e) {
+// Element offset of cell (row y, column x) of slice `sl` in the caller's array.
+__device__ __forceinline__ int64_t cell_offset(const Geom &g, const Strides &s, int sl, int y, int x) {
+    const int p = sl / g.S, t = sl - p * g.S;
     const int po = p / g.Pin, pi = p - po * g.Pin;
-    const int64_t base = (int64_t)po * s.sO + (int64_t)pi * s.sI + (int64_t)y * s.sY;
-    if (g.T == 1) return base + (int64_t)e * s.sX;
-    const int j = e / g.T, t = e - j * g.T;
-    return base + (int64_t)j * s.sX + (int64_t)t * s.sT;
+    return (int64_t)po * s.sO + (int64_t)pi * s.sI + (int64_t)y * s.sY + (int64_t)x * s.sX + (int64_t)t * s.sT;
 }
 
 // A1 on the device: init_strategy='mean' fills unknown cells with np.nanmean(grid) taken in the grid's own
@@ -144,11 +143,11 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
                                                       double *__restrict__ rowpart, double *__restrict__ extreme) {
     __shared__ double scratch[8 * 8];
     bool wild = false;        // a non-finite or huge value: the ratio form of the tiled path must not be used
-    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;      // p: slice
     const size_t row = ((size_t)p * g.H + y) * g.pitch;
     const size_t mrow = ((size_t)p * g.H + y) * g.mpitch;
     const bool owned = (y >= g.own_row0) && (y < g.own_row0 + g.own_rows);
-    const double fillv = pred0 ? 0.0 : fill[p];
+    const double fillv = pred0 ? 0.0 : fill[p / g.S];
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) {
         bool unknown = false;
@@ -197,8 +196,8 @@ __global__ void __launch_bounds__(256) prepare_reduce_kernel(Geom g, const doubl
     __shared__ double scratch[8 * 8];
     const int p = blockIdx.x;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int y = threadIdx.x; y < g.H; y += blockDim.x) {
-        const double *r = rowpart + ((size_t)p * g.H + y) * 8;
+    for (int y = threadIdx.x; y < g.S * g.H; y += blockDim.x) {      // the rows of every slice of the problem
+        const double *r = rowpart + ((size_t)p * g.S * g.H + y) * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += r[i];
     }
@@ -277,7 +276,7 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(Geom g, const int *_
         }
     }
     if (tid == 1023) {
-        tile_start[g.P] = counts[1023];
+        tile_start[g.P * g.S] = counts[1023];
         counters[1] = counts[1023];
     }
 }
@@ -315,8 +314,8 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const doub
         for (int i = threadIdx.x; i < g.KB * kSumSlots; i += blockDim.x) out[i] = 0.0;
         return;
     }
-    const int t0 = all_tiles ? p * g.tiles_per_prob : tile_start[p];
-    const int t1 = all_tiles ? t0 + g.tiles_per_prob : tile_start[p + 1];
+    const int t0 = all_tiles ? p * g.S * g.tiles_per_prob : tile_start[p * g.S];
+    const int t1 = all_tiles ? t0 + g.S * g.tiles_per_prob : tile_start[(p + 1) * g.S];
     for (int j = 0; j < g.KB; ++j) {
         double acc[kSumSlots] = {0, 0, 0, 0};
         if (j < kr) {
@@ -434,8 +433,8 @@ template <typename TSt>
 __global__ void __launch_bounds__(256) restore_known_kernel(Geom g, const ProbState *__restrict__ state,
                                                             TSt *buf0, TSt *buf1,
                                                             const uint32_t *__restrict__ mask) {
-    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
-    const ProbState st = state[p];
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;      // p: slice
+    const ProbState st = state[p / g.S];
     if (!st.dirty || st.fresh) return;
     const TSt *src = st.cur ? buf1 : buf0;
     TSt *dst = st.cur ? buf0 : buf1;
@@ -457,12 +456,12 @@ template <typename TSt, typename TOut>
 __global__ void __launch_bounds__(256) result_kernel(Geom g, const ProbState *__restrict__ state,
                                                      const TSt *__restrict__ buf0, const TSt *__restrict__ buf1,
                                                      TOut *__restrict__ out, Strides sd, int32_t *niter_out) {
-    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;
-    const ProbState st = state[p];
+    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;      // p: slice
+    const ProbState st = state[p / g.S];
     const TSt *src = (st.cur ? buf1 : buf0) + ((size_t)p * g.H + y) * g.pitch;
     for (int e = threadIdx.x; e < g.L; e += blockDim.x)
         out[cell_offset(g, sd, p, y, e)] = (TOut)src[e];
-    if (niter_out && y == 0 && threadIdx.x == 0) niter_out[p] = st.iters_done;
+    if (niter_out && y == 0 && threadIdx.x == 0 && p % g.S == 0) niter_out[p / g.S] = st.iters_done;
 }
 
 // Row-sharded scenes: copy `rows` owned boundary rows of every problem's CURRENT buffer into a
@@ -489,7 +488,7 @@ __global__ void __launch_bounds__(256) halo_rows_kernel(Geom g, const ProbState 
         if (launches) ++*launches;                \
     } while (0)
 
-bool fill_mean_supported(const Geom &g) { return (int64_t)g.H * g.L <= (int64_t)kFillMaxLeaves * 64; }
+bool fill_mean_supported(const Geom &g) { return g.ndim == 2 && (int64_t)g.H * g.L <= (int64_t)kFillMaxLeaves * 64; }
 
 cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, const int64_t *stride, double *fill_dev,
                              cudaStream_t st, int64_t *launches) {
@@ -505,7 +504,7 @@ cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred
                            uint32_t *mask, double *rowpart, double *known0, double *known, double *extreme,
                            ProbState *state, int *counters, cudaStream_t st, int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
-    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    const unsigned grid = (unsigned)((int64_t)g.P * g.S * g.H);
 #define VP_PREP(TIN, TST)                                                                                  \
     prepare_kernel<TIN, TST><<<grid, 256, 0, st>>>(g, (const TIN *)original, (const TIN *)pred0, fill_dev, \
                                                    sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart, extreme)
@@ -522,7 +521,7 @@ cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred
 
 cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
                          int *counters, cudaStream_t st, int64_t *launches) {
-    const int64_t n_tiles = (int64_t)g.P * g.tiles_per_prob;
+    const int64_t n_tiles = (int64_t)g.P * g.S * g.tiles_per_prob;
     const unsigned grid = (unsigned)((n_tiles + 7) / 8);
     tile_flag_kernel<<<grid, 256, 0, st>>>(g, mask, tile_flag, n_tiles);
     VP_LAUNCH_CHECK();
@@ -578,7 +577,7 @@ cudaError_t launch_loop_condition(cudaGraphConditionalHandle handle, const int *
 
 cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, void *const *buf,
                                  const uint32_t *mask, cudaStream_t st, int64_t *launches) {
-    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    const unsigned grid = (unsigned)((int64_t)g.P * g.S * g.H);
     if (storage == VPINT_F64)
         restore_known_kernel<double><<<grid, 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], mask);
     else
@@ -607,7 +606,7 @@ cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, vo
                           int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
                           int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
-    const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    const unsigned grid = (unsigned)((int64_t)g.P * g.S * g.H);
 #define VP_RES(TST, TOUT)                                                                                   \
     result_kernel<TST, TOUT><<<grid, 256, 0, st>>>(g, state, (const TST *)buf[0], (const TST *)buf[1],      \
                                                    (TOUT *)out, sd, niter_out)

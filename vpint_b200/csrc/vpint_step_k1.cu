@@ -251,95 +251,78 @@ __device__ __forceinline__ double div_small(double x, int n) {
     return x / (double)n;
 }
 
-// 3-D: rows are W*T elements with T fastest; element e of a row is (j, t) = (e / T, e % T).
+// 3-D sweep on the time-major slice stack: slice s = p * T + t is an (H, pitch) image, so the kernel is the
+// 2-D one (same tiles, two cells per thread, 128-bit loads) plus the two temporal neighbours one slice away.
 // Value slots 4 / 5 are the t+1 / t-1 neighbours (VPint/SD_MRP.py:372-378).  Plane mode keeps the
-// reference's pairing: the temporal weight multiplies the t+1 value only where t > 0 and the t-1 value
-// only where t < T-1 (VPint/WP_MRP.py:1344-1353 vs 1406-1412).  Spatial planes are (H, W): features are
+// reference's pairing: the temporal weight multiplies the t+1 value only where t > 0 and the t-1 value only
+// where t < T-1 (VPint/WP_MRP.py:1344-1353 vs 1406-1412).  Weight planes are (H, W) per problem: features are
 // static in time.
-// With T fastest and different clouds in every time slice only a fraction of the lanes of a warp would
-// hold an unknown cell, so the tile first compacts its unknown cells into a shared-memory list (row-major,
-// fixed order) and the threads then walk the list: every lane updates a cell.
 template <typename T, bool PLANES>
 __global__ void __launch_bounds__(256) jacobi3d_k1_kernel(const StepArgs a) {
-    __shared__ unsigned short cells[kTileW3 * kTileH3];     // (row << 8) | column-in-tile
-    __shared__ int row_base[kTileH3][8];
     const TileRef tile = a.tiles[blockIdx.x];
-    const int p = tile.p;
+    const Geom &g = a.g;
+    const int sl = tile.p;
+    const int p = sl / g.S, t = sl - p * g.S;
     const ProbState st = a.state[p];
     if (st.k_run == 0) return;
-    const Geom &g = a.g;
     const size_t plane = (size_t)g.H * g.pitch;
-    const size_t wplane = (size_t)g.H * g.wpitch;
-    const T *__restrict__ in = reinterpret_cast<const T *>(a.buf[st.cur]) + (size_t)p * plane;
-    T *__restrict__ out = reinterpret_cast<T *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const T *__restrict__ in = reinterpret_cast<const T *>(a.buf[st.cur]) + (size_t)sl * plane;
+    T *__restrict__ out = reinterpret_cast<T *>(a.buf[st.cur ^ 1]) + (size_t)sl * plane;
+    const bool has_nx = t < g.S - 1, has_pv = t > 0;
+    const T *__restrict__ in_nx = in + plane, *__restrict__ in_pv = in - plane;      // only dereferenced when they exist
+    const size_t wbase = (size_t)p * plane;
     const double gamma = PLANES ? 0.0 : a.gamma[p];
     const double tau = PLANES ? 0.0 : a.tau[p];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int e0 = tile.x0 + tid;
-    const int y_lim = min(tile.y0 + kTileH3, g.own_row0 + g.own_rows);
-    // ---- compaction: ballots per (row, warp), exclusive offsets in row-major order ------------------
-    unsigned ballots[kTileH3];
-    {
-        const uint32_t *mrow = a.mask + (size_t)p * g.H * g.mpitch + (e0 >> 5);
-#pragma unroll
-        for (int r = 0; r < kTileH3; ++r) {
-            const int y = tile.y0 + r;
-            const bool unk = (e0 < g.L) && (y < y_lim) && ((mrow[(size_t)y * g.mpitch] >> (e0 & 31)) & 1u);
-            ballots[r] = __ballot_sync(0xffffffffu, unk);
-            if (lane == 0) row_base[r][warp] = __popc(ballots[r]);
-        }
-    }
-    __syncthreads();
-    int n = 0;
-    {
-        int run = 0;
-#pragma unroll
-        for (int r = 0; r < kTileH3; ++r) {
-            int my_base = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int c = row_base[r][w];
-                if (w == warp) my_base = run;
-                run += c;
-            }
-            const unsigned b = ballots[r];
-            if ((b >> lane) & 1u) cells[my_base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)((r << 8) | tid);
-        }
-        n = run;
-    }
-    __syncthreads();
-    // ---- dense walk over the unknown cells -----------------------------------------------------------
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xw = tile.x0 + (warp & 1) * 64;
+    const int x = xw + 2 * lane;
+    const int yb = tile.y0 + (warp >> 1) * 8;
+    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
+    const int nct = 6 - (has_nx ? 0 : 1) - (has_pv ? 0 : 1);
     Acc<T> acc;
-    for (int i = tid; i < n; i += 256) {
-        const int code = cells[i];
-        const int y = tile.y0 + (code >> 8), e = tile.x0 + (code & 255);
-        const int j = e / g.T, t = e - j * g.T;
-        const size_t row = (size_t)y * g.pitch;
-        const int yg = y + g.row_offset;
-        const double c = (double)in[row + e];
-        const double up = (yg > 0) ? (double)in[row - g.pitch + e] : 0.0;
-        const double dn = (yg < g.global_H - 1) ? (double)in[row + g.pitch + e] : 0.0;
-        const double rt = (j < g.W - 1) ? (double)in[row + e + g.T] : 0.0;
-        const double lf = (j > 0) ? (double)in[row + e - g.T] : 0.0;
-        const double nx = (t < g.T - 1) ? (double)in[row + e + 1] : 0.0;
-        const double pv = (t > 0) ? (double)in[row + e - 1] : 0.0;
-        double nv;
-        if (PLANES) {
-            const size_t wi = (size_t)p * wplane + (size_t)y * g.wpitch + j;
-            const double wu = (double)reinterpret_cast<const T *>(a.w[0])[wi];
-            const double wr = (double)reinterpret_cast<const T *>(a.w[1])[wi];
-            const double wd = (double)reinterpret_cast<const T *>(a.w[2])[wi];
-            const double wl = (double)reinterpret_cast<const T *>(a.w[3])[wi];
-            const double wt = (double)reinterpret_cast<const T *>(a.w[4])[wi];
-            const double w4 = (t > 0) ? wt : 0.0, w5 = (t < g.T - 1) ? wt : 0.0;
-            nv = fma(pv, w5, fma(nx, w4, fma(lf, wl, fma(dn, wd, fma(rt, wr, up * wu)))));
-        } else {
-            nv = fma(pv, tau, fma(nx, tau, fma(lf, gamma, fma(dn, gamma, fma(rt, gamma, up * gamma)))));
+    if (xw < g.L) {
+        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)sl * g.H * g.mpitch) + (xw >> 6);
+        const int mp64 = g.mpitch >> 1;
+        for (int r = 0; r < 8; ++r) {
+            const int y = yb + r;
+            if (y >= y_lim) break;
+            const uint64_t bits = m64[(size_t)y * mp64];
+            const unsigned mb = (unsigned)(bits >> (2 * lane)) & 3u;
+            if (mb == 0) continue;
+            const size_t row = (size_t)y * g.pitch;
+            const int yg = y + g.row_offset;
+            double c0, c1, u0 = 0.0, u1 = 0.0, d0 = 0.0, d1 = 0.0, lf = 0.0, rt = 0.0, n0 = 0.0, n1 = 0.0, q0 = 0.0, q1 = 0.0;
+            load2(in + row + x, c0, c1);                       // padding columns hold 0
+            if (yg > 0) load2(in + row - g.pitch + x, u0, u1);
+            if (yg < g.global_H - 1) load2(in + row + g.pitch + x, d0, d1);
+            if (x > 0) lf = (double)in[row + x - 1];
+            if (x + 2 < g.L) rt = (double)in[row + x + 2];
+            if (has_nx) load2(in_nx + row + x, n0, n1);
+            if (has_pv) load2(in_pv + row + x, q0, q1);
+            double v0, v1;
+            if (PLANES) {
+                double wu0, wu1, wr0, wr1, wd0, wd1, wl0, wl1, wt0, wt1;
+                load2(reinterpret_cast<const T *>(a.w[0]) + wbase + row + x, wu0, wu1);
+                load2(reinterpret_cast<const T *>(a.w[1]) + wbase + row + x, wr0, wr1);
+                load2(reinterpret_cast<const T *>(a.w[2]) + wbase + row + x, wd0, wd1);
+                load2(reinterpret_cast<const T *>(a.w[3]) + wbase + row + x, wl0, wl1);
+                load2(reinterpret_cast<const T *>(a.w[4]) + wbase + row + x, wt0, wt1);
+                const double w40 = has_pv ? wt0 : 0.0, w41 = has_pv ? wt1 : 0.0;   // slot 4: set where t > 0, applied to t+1
+                const double w50 = has_nx ? wt0 : 0.0, w51 = has_nx ? wt1 : 0.0;   // slot 5: set where t < T-1, applied to t-1
+                v0 = fma(q0, w50, fma(n0, w40, fma(lf, wl0, fma(d0, wd0, fma(c1, wr0, u0 * wu0)))));
+                v1 = fma(q1, w51, fma(n1, w41, fma(c0, wl1, fma(d1, wd1, fma(rt, wr1, u1 * wu1)))));
+            } else {
+                v0 = fma(q0, tau, fma(n0, tau, fma(lf, gamma, fma(d0, gamma, fma(c1, gamma, u0 * gamma)))));
+                v1 = fma(q1, tau, fma(n1, tau, fma(c0, gamma, fma(d1, gamma, fma(rt, gamma, u1 * gamma)))));
+            }
+            const int ncy = nct - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+            const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+            const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
+            v0 = div_small(v0, nc0);
+            v1 = div_small(v1, nc1);
+            if (mb & 1u) out[row + x] = acc.commit(v0, c0);
+            if (mb & 2u) out[row + x + 1] = acc.commit(v1, c1);
         }
-        const int nc = 6 - (j == 0 ? 1 : 0) - (j == g.W - 1 ? 1 : 0) - (t == 0 ? 1 : 0) - (t == g.T - 1 ? 1 : 0)
-                       - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
-        nv = div_small(nv, nc);
-        out[row + e] = acc.commit(nv, c);
     }
     write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
 }
@@ -347,8 +330,9 @@ __global__ void __launch_bounds__(256) jacobi3d_k1_kernel(const StepArgs a) {
 }  // namespace
 
 void k1_tile_shape(int ndim, int *th, int *tw) {
-    *th = (ndim == 2) ? kTileH2 : kTileH3;
-    *tw = (ndim == 2) ? kTileW2 : kTileW3;
+    (void)ndim;                 // 3-D slices use the 2-D tile
+    *th = kTileH2;
+    *tw = kTileW2;
 }
 
 #define VP_LAUNCH_CHECK()                         \

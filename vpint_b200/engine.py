@@ -314,14 +314,16 @@ class Solver:
             C.c_void_p(from_down.data_ptr()) if from_down is not None else None, self._stream()), "vpint_solver_halo_unpack")
 
     def state_tensor(self, which):
-        """Ping-pong buffer ``which`` as a [nprob][H][pitch] tensor (workspace view)."""
+        """Ping-pong buffer ``which`` as a [slices][H][pitch] tensor (workspace view); slices = nprob in 2-D,
+        nprob * T (time-major) in 3-D."""
         ptr = int(self.lib.vpint_solver_state_ptr(self._h, int(which)))
-        pitch = int(self.lib.vpint_row_pitch(self.W * self.T))
+        pitch = int(self.lib.vpint_row_pitch(self.W))
         dt = self.torch.float64 if self.storage == "float64" else self.torch.float32
         esz = 8 if self.storage == "float64" else 4
         off = ptr - self.workspace.data_ptr()
-        n = self.nprob * self.H * pitch
-        return self.workspace[off:off + n * esz].view(dt).view(self.nprob, self.H, pitch)
+        slices = self.nprob * (self.T if self.ndim == 3 else 1)
+        n = slices * self.H * pitch
+        return self.workspace[off:off + n * esz].view(dt).view(slices, self.H, pitch)
 
     def active_count(self):
         ptr = int(self.lib.vpint_solver_active_ptr(self._h))
