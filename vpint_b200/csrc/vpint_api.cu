@@ -95,6 +95,7 @@ struct vpint_solver {
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
     size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
     size_t off_extreme = 0;           // double[2]: cells with non-finite / huge values, ... features
+    size_t off_stage = 0;             // chunk sums of the two-stage per-problem reduction
     bool has_orig = false;
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
@@ -232,6 +233,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
     s->off_flags = take(16 * sizeof(int));
+    s->off_stage = take(reduce_stage_bytes(g));
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
     if (s->has_orig) s->off_orig = take(plane);
     s->ws_bytes = off;
@@ -516,8 +518,8 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         cudaEventDestroy(e1);
     }
     VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), s->at<int>(s->off_tilestart),
-                                   s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), s->prm.resistance != 0, st,
-                                   &s->launches),
+                                   s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), s->at<double>(s->off_stage),
+                                   s->prm.resistance != 0, st, &s->launches),
             "reduce partials");
     return VPINT_OK;
 }

@@ -140,9 +140,10 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
                           int64_t *launches);
 cudaError_t launch_step3d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
                           int64_t *launches);
+size_t reduce_stage_bytes(const Geom &g);
 cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
-                                   const ProbState *state, double *sums, bool all_tiles, cudaStream_t st,
-                                   int64_t *launches);
+                                   const ProbState *state, double *sums, double *stage, bool all_tiles,
+                                   cudaStream_t st, int64_t *launches);
 cudaError_t launch_step2d_resist(const StepArgs &a, int storage, int weight_mode, cudaStream_t st, int64_t *launches);
 cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *bias,
                             double *p_out, cudaStream_t st, int64_t *launches);

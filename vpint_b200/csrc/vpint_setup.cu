@@ -333,6 +333,48 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const doub
     }
 }
 
+// Two-stage form for few problems with very many tiles (one large grid / cube): stage 1 lets kReduceChunks
+// blocks per problem sum contiguous chunks of the tile partials, stage 2 adds the chunk sums in order.
+constexpr int kReduceChunks = 64;
+
+__global__ void __launch_bounds__(128) reduce_partials_stage1_kernel(Geom g, const double *__restrict__ partial,
+                                                                     const int *__restrict__ tile_start,
+                                                                     const ProbState *__restrict__ state,
+                                                                     double *__restrict__ stage, int all_tiles) {
+    __shared__ double scratch[kSumSlots * 4];
+    const int p = blockIdx.x / kReduceChunks, c = blockIdx.x - p * kReduceChunks;
+    const int kr = state[p].k_run;
+    double *out = stage + ((size_t)p * kReduceChunks + c) * g.KB * kSumSlots;
+    const int t0 = all_tiles ? p * g.S * g.tiles_per_prob : tile_start[p * g.S];
+    const int t1 = all_tiles ? t0 + g.S * g.tiles_per_prob : tile_start[(p + 1) * g.S];
+    const int per = (t1 - t0 + kReduceChunks - 1) / kReduceChunks;
+    const int a0 = min(t0 + c * per, t1), a1 = min(a0 + per, t1);
+    for (int j = 0; j < g.KB; ++j) {
+        double acc[kSumSlots] = {0, 0, 0, 0};
+        if (j < kr) {
+            for (int t = a0 + threadIdx.x; t < a1; t += blockDim.x) {
+                const double *q = partial + ((size_t)t * g.KB + j) * kSumSlots;
+#pragma unroll
+                for (int i = 0; i < kSumSlots; ++i) acc[i] += q[i];
+            }
+        }
+        block_sum<kSumSlots>(acc, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < kSumSlots; ++i) out[j * kSumSlots + i] = acc[i];
+        }
+    }
+}
+
+__global__ void reduce_partials_stage2_kernel(Geom g, const double *__restrict__ stage, double *__restrict__ sums) {
+    const int p = blockIdx.x;
+    const int i = threadIdx.x;                      // (j, slot)
+    if (i >= g.KB * kSumSlots) return;
+    double acc = 0.0;
+    for (int c = 0; c < kReduceChunks; ++c) acc += stage[((size_t)p * kReduceChunks + c) * g.KB * kSumSlots + i];
+    sums[(size_t)p * g.KB * kSumSlots + i] = acc;
+}
+
 // Thread per problem: the stopping rule and the loop bookkeeping.
 //   delta = nanmean(|new - old|) / nanmean(old) over the whole grid (VPint/SD_MRP.py:139,
 //   VPint/WP_MRP.py:352); known cells contribute |orig - orig| (0, or NaN for +-inf) and orig.
@@ -539,9 +581,19 @@ cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, in
     return cudaSuccess;
 }
 
+size_t reduce_stage_bytes(const Geom &g) { return (size_t)g.P * kReduceChunks * g.KB * kSumSlots * sizeof(double); }
+
 cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
-                                   const ProbState *state, double *sums, bool all_tiles, cudaStream_t st,
-                                   int64_t *launches) {
+                                   const ProbState *state, double *sums, double *stage, bool all_tiles,
+                                   cudaStream_t st, int64_t *launches) {
+    // one block per problem is enough unless a problem has tens of thousands of tiles
+    if (stage && (int64_t)g.S * g.tiles_per_prob >= 8192) {
+        reduce_partials_stage1_kernel<<<g.P * kReduceChunks, 128, 0, st>>>(g, partial, tile_start, state, stage, all_tiles ? 1 : 0);
+        VP_LAUNCH_CHECK();
+        reduce_partials_stage2_kernel<<<g.P, 64, 0, st>>>(g, stage, sums);
+        VP_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, tile_start, state, sums, all_tiles ? 1 : 0);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
