@@ -386,6 +386,8 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3: VPint2 cloud removal, 256x256x13 Sentinel-2-shaped patches, %d patches per GPU "
                                    "(%d band problems, %.0f Mpx per GPU), auto-terminate 1e-4" % (n, nprob, total_px / 1e6),
+                       "baseline_config": "BASELINE.json configs[2] (the metric is quoted on VPint2; configs[1] is a single "
+                                          "WP_SMRP grid and configs[3] the row-sharded scene of bench_scene.py)",
                        "patches_per_gpu": n, "H": H, "W": W, "bands": B, "k_block": args.k_block,
                        "path": "cluster-resident (k_block 0)" if args.k_block == 0 else "tiled, %d sweeps per launch" % kb, "cloud_fraction": round(masked_frac, 4),
                        "active_tiles": active_tiles, "total_tiles": total_tiles,
