@@ -258,7 +258,7 @@ __device__ __forceinline__ double div_small(double x, int n) {
 // where t < T-1 (VPint/WP_MRP.py:1344-1353 vs 1406-1412).  Weight planes are (H, W) per problem: features are
 // static in time.
 template <typename T, bool PLANES>
-__global__ void __launch_bounds__(256) jacobi3d_k1_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(256, 5) jacobi3d_k1_kernel(const StepArgs a) {
     const TileRef tile = a.tiles[blockIdx.x];
     const Geom &g = a.g;
     const int sl = tile.p;
