@@ -271,7 +271,7 @@ def run_gpu(args):
 
     solver = Solver(2, nprob, H, W, nprob_inner=B, planes=True, k_block=args.k_block, device=dev)
     out_dev = torch.empty((n, B, H, W), dtype=torch.float64, device=dev)
-    fill = _band_fill_values(t_host.numpy()).reshape(-1)      # init values (host NumPy, exact reference semantics)
+    fill = None      # per-band init value (np.nanmean in float32) is computed on the device inside every step
 
     def device_step():
         solver.load(target.permute(0, 3, 1, 2), fill=fill)
