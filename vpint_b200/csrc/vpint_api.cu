@@ -70,7 +70,7 @@ void pinned_release(void *p) {
     g_pinned_free.push_back(p);
 }
 
-enum Counter { kCntDirty = 0, kCntActiveTiles = 1, kCntActiveProblems = 8, kCntTotal = 16 };
+enum Counter { kCntDirty = 0, kCntActiveTiles = 1, kCntTileless = 2, kCntActiveProblems = 8, kCntTotal = 16 };
 
 }  // namespace
 
@@ -96,6 +96,9 @@ struct vpint_solver {
     size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
     size_t off_extreme = 0;           // double[2]: cells with non-finite / huge values, ... features
     size_t off_stage = 0;             // chunk sums of the two-stage per-problem reduction
+    size_t off_done = 0;              // int[P] tickets of the fused finish
+    bool can_fuse = false;
+    int tileless = 0;                 // problems without any unknown cell (decided by the separate kernel)
     bool has_orig = false;
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
@@ -234,6 +237,9 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
     s->off_flags = take(16 * sizeof(int));
     s->off_stage = take(reduce_stage_bytes(g));
+    s->off_done = take((size_t)g.P * sizeof(int));
+    // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
+    s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
     if (s->has_orig) s->off_orig = take(plane);
     s->ws_bytes = off;
@@ -309,6 +315,7 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     VP_CUDA(cudaStreamSynchronize(st), "load sync");
     s->any_dirty = s->h_counters[kCntDirty];
     s->tiles_active = s->h_counters[kCntActiveTiles];
+    s->tileless = s->h_counters[kCntTileless];
     s->loaded = true;
     s->run_begun = false;
     return VPINT_OK;
@@ -378,12 +385,14 @@ int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *s
     VP_CUDA(launch_init_state(s->g, s->at<ProbState>(s->off_state), s->at<int>(s->off_counters) + kCntActiveProblems,
                               prm->max_iter, st, &s->launches),
             "init state");
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_done), 0, (size_t)s->g.P * sizeof(int), st), "memset tickets");
     s->run_begun = true;
     s->first_step_pending = true;
     return VPINT_OK;
 }
 
-static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms);
+static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, bool fused = false);
+static int step_end_impl(vpint_solver *s, void *stream, bool fused);
 
 // The four ratio planes are built lazily from the single-layer feature plane (vpint_solver_weights keeps only
 // that plane when the cluster-resident kernel can serve the run).
@@ -448,14 +457,14 @@ int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, doub
     return VPINT_OK;
 }
 
-int vpint_solver_step_begin(vpint_solver *s, void *stream) { return step_begin_impl(s, stream, nullptr); }
+int vpint_solver_step_begin(vpint_solver *s, void *stream) { return step_begin_impl(s, stream, nullptr, false); }
 
 int vpint_solver_step_profile(vpint_solver *s, void *stream, float *stencil_ms) {
     if (!stencil_ms) return fail(VPINT_ERR_INVALID, "null stencil_ms");
-    return step_begin_impl(s, stream, stencil_ms);
+    return step_begin_impl(s, stream, stencil_ms, false);
 }
 
-static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
+static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, bool fused) {
     if (!s || !s->run_begun) return fail(VPINT_ERR_INVALID, "vpint_solver_begin_run has not been called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -498,6 +507,17 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
     a.eps = s->prm.epsilon;
     a.mu = s->prm.mu;
     a.orig = s->has_orig ? s->at<void>(s->off_orig) : nullptr;
+    a.fused = fused ? 1 : 0;
+    a.done = s->at<int>(s->off_done);
+    a.tile_start = s->at<int>(s->off_tilestart);
+    a.sums = s->at<double>(s->off_sums);
+    a.known0 = s->at<double>(s->off_known0);
+    a.known = s->at<double>(s->off_known);
+    a.delta_out = s->prm.delta_out;
+    a.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
+    a.max_iter = s->prm.max_iter;
+    a.auto_terminate = s->prm.auto_terminate;
+    a.threshold = s->prm.threshold;
     if (a.resist) {
         VP_CUDA(launch_step2d_resist(a, s->storage, s->weight_mode, st, &s->launches), "step2d_resist");
     } else if (use_ratio) {
@@ -517,6 +537,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
+    if (fused) return VPINT_OK;          // the last tile block of every problem has reduced and decided
     VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), s->at<int>(s->off_tilestart),
                                    s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), s->at<double>(s->off_stage),
                                    s->prm.resistance != 0, st, &s->launches),
@@ -524,9 +545,12 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms) {
     return VPINT_OK;
 }
 
-int vpint_solver_step_end(vpint_solver *s, void *stream) {
+int vpint_solver_step_end(vpint_solver *s, void *stream) { return step_end_impl(s, stream, false); }
+
+static int step_end_impl(vpint_solver *s, void *stream, bool fused) {
     if (!s || !s->run_begun) return fail(VPINT_ERR_INVALID, "vpint_solver_begin_run has not been called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!fused) {
     DecideArgs d;
     d.g = s->g;
     d.state = s->at<ProbState>(s->off_state);
@@ -540,6 +564,7 @@ int vpint_solver_step_end(vpint_solver *s, void *stream) {
     d.threshold = s->prm.threshold;
     d.all_cells = s->prm.resistance ? 1 : 0;
     VP_CUDA(launch_decide(d, st, &s->launches), "decide");
+    }
     if (s->first_step_pending) {
         s->first_step_pending = false;
         if (s->any_dirty) {
@@ -560,9 +585,10 @@ int vpint_solver_step_end(vpint_solver *s, void *stream) {
 static int run_graph_loop(vpint_solver *s, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // first launch group outside the graph: it may be followed by the one-off known-cell repair
-    int rc = vpint_solver_step_begin(s, stream);
+    const bool fused = s->can_fuse && s->tileless == 0;
+    int rc = step_begin_impl(s, stream, nullptr, fused);
     if (rc != VPINT_OK) return rc;
-    rc = vpint_solver_step_end(s, stream);
+    rc = step_end_impl(s, stream, fused);
     if (rc != VPINT_OK) return rc;
     int *iter_left = s->at<int>(s->off_flags) + 2;
     const int budget = 2 * s->prm.max_iter + 2;
@@ -595,8 +621,8 @@ static int run_graph_loop(vpint_solver *s, void *stream) {
     body = np.conditional.phGraph_out[0];
     VP_G(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "cudaStreamCreate");
     VP_G(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed), "begin capture");
-    status = vpint_solver_step_begin(s, cap);
-    if (status == VPINT_OK) status = vpint_solver_step_end(s, cap);
+    status = step_begin_impl(s, cap, nullptr, fused);
+    if (status == VPINT_OK) status = step_end_impl(s, cap, fused);
     if (status == VPINT_OK) {
         cudaError_t e = launch_loop_condition(handle, s->at<int>(s->off_counters) + kCntActiveProblems, iter_left, cap,
                                               &s->launches);
@@ -672,9 +698,9 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
     int64_t budget = 2 * (int64_t)prm->max_iter + 2;
     while (budget > 0) {
         for (int i = 0; i < chunk; ++i) {
-            rc = vpint_solver_step_begin(s, stream);
+            rc = step_begin_impl(s, stream, nullptr, s->can_fuse && s->tileless == 0);
             if (rc != VPINT_OK) return rc;
-            rc = vpint_solver_step_end(s, stream);
+            rc = step_end_impl(s, stream, s->can_fuse && s->tileless == 0);
             if (rc != VPINT_OK) return rc;
         }
         budget -= chunk;

@@ -70,6 +70,17 @@ struct StepArgs {
     int resist;              // 1: resistance sweep over ALL cells (vpint_step_k1.cu, jacobi2d_resist_kernel)
     double eps, mu;
     const void *orig;        // [P][H][pitch] known values (resistance)
+    // fused finish (vpint_solver_run on an unsharded solver): the last tile block of a problem reduces the
+    // per-tile partials and takes the stop decision, so a launch group is ONE kernel
+    int fused;
+    int *done;               // [P] tickets of the blocks of this launch
+    const int *tile_start;   // [P * S + 1]
+    double *sums;            // [P][KB][kSumSlots]
+    const double *known0, *known;
+    double *delta_out;
+    int *n_active;
+    int max_iter, auto_terminate;
+    double threshold;
 };
 
 struct DecideArgs {
@@ -213,6 +224,101 @@ __device__ __forceinline__ void load2(const float *p, double &a, double &b) {
     const float2 v = *reinterpret_cast<const float2 *>(p);
     a = (double)v.x;
     b = (double)v.y;
+}
+
+// The stopping rule and the loop bookkeeping of ONE problem from its per-sweep sums S[KB][kSumSlots]:
+//   delta = nanmean(|new - old|) / nanmean(old) over the whole grid (VPint/SD_MRP.py:139,
+//   VPint/WP_MRP.py:352); known cells contribute |orig - orig| (0, or NaN for +-inf) and orig.
+//   delta <= threshold commits the sweep and stops (SD_MRP.py:142-147); an overshoot inside a
+//   temporally blocked launch schedules a replay of exactly `stop` sweeps from the untouched
+//   launch-entry buffer.
+__device__ __forceinline__ void decide_problem(const Geom &g, ProbState *state, int p, const double *sums_p,
+                                               const double *known0, const double *known, double *delta_out,
+                                               int *n_active, int max_iter, int auto_terminate, double threshold,
+                                               int all_cells) {
+    ProbState st = state[p];
+    if (st.status != 0 || st.k_run == 0) return;
+    const int kr = st.k_run;
+    if (st.replay) {
+        st.iters_done += kr;
+        st.cur ^= 1;
+        st.status = 1; st.k_run = 0; st.replay = 0; st.fresh = 0;
+        state[p] = st;
+        atomicSub(n_active, 1);
+        return;
+    }
+    int stop = -1;
+    for (int j = 0; j < kr; ++j) {
+        const double *S = sums_p + (size_t)j * kSumSlots;
+        const double *K = ((st.fresh && j == 0) ? known0 : known) + (size_t)p * kSumSlots;
+        const double kz = all_cells ? 0.0 : 1.0;      // resistance: the sums already cover known cells
+        const double s_abs = all_cells ? S[0] : S[0] + K[0], s_old = all_cells ? S[1] : S[1] + K[1];
+        const double n_abs = g.n_cells - (S[2] + kz * K[2]), n_old = g.n_cells - (S[3] + kz * K[3]);
+        const double delta = (s_abs / n_abs) / (s_old / n_old);
+        if (delta_out) delta_out[(size_t)p * max_iter + st.iters_done + j] = delta;
+        if (auto_terminate && delta <= threshold) {
+            stop = j + 1;
+            break;
+        }
+    }
+    if (stop < 0 || stop == kr) {
+        st.iters_done += kr;
+        st.cur ^= 1;
+        st.fresh = 0;
+        if (stop == kr || st.iters_done >= max_iter) {
+            st.status = 1;
+            st.k_run = 0;
+            atomicSub(n_active, 1);
+        } else {
+            st.k_run = min(g.KB, max_iter - st.iters_done);
+        }
+    } else {
+        st.replay = 1;
+        st.k_run = stop;
+    }
+    state[p] = st;
+}
+
+// Fused finish, called by every thread of a tile block after the block has written its partial sums: the
+// block that takes the last ticket of its problem adds the partials of all the problem's tiles in a fixed
+// order (threads stride over the tiles, then the deterministic block sum) and decides.  kr = sweeps of this
+// launch.  `scratch` needs kSumSlots * (blockDim.x / 32) doubles.
+__device__ __forceinline__ void finish_tile(const StepArgs &a, int p, int kr, double *scratch) {
+    if (!a.fused) return;
+    __shared__ int s_last;
+    const Geom &g = a.g;
+    __threadfence();
+    __syncthreads();
+    int t0, t1;
+    if (a.resist) { t0 = p * g.S * g.tiles_per_prob; t1 = t0 + g.S * g.tiles_per_prob; }
+    else { t0 = a.tile_start[p * g.S]; t1 = a.tile_start[(p + 1) * g.S]; }
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(&a.done[p], 1);
+        s_last = (ticket == t1 - t0 - 1) ? 1 : 0;
+        if (s_last) a.done[p] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double *out = a.sums + (size_t)p * g.KB * kSumSlots;
+    for (int j = 0; j < g.KB; ++j) {
+        double acc[kSumSlots] = {0, 0, 0, 0};
+        if (j < kr) {
+            for (int t = t0 + (int)threadIdx.x; t < t1; t += blockDim.x) {
+                const double *q = a.partial + ((size_t)t * g.KB + j) * kSumSlots;
+#pragma unroll
+                for (int i = 0; i < kSumSlots; ++i) acc[i] += __ldcg(q + i);
+            }
+        }
+        block_sum<kSumSlots>(acc, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < kSumSlots; ++i) out[j * kSumSlots + i] = acc[i];
+        }
+    }
+    if (threadIdx.x == 0)
+        decide_problem(g, a.state, p, out, a.known0, a.known, a.delta_out, a.n_active, a.max_iter, a.auto_terminate,
+                       a.threshold, a.resist);
 }
 
 template <typename T>

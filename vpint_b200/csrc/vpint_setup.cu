@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256) prepare_reduce_kernel(Geom g, const doubl
         st.dirty = acc[6] > 0.0 ? 1 : 0; st.fresh = 1; st.pad = 0;
         state[p] = st;
         if (st.dirty) atomicAdd(&counters[0], 1);
+        if (acc[7] == 0.0) atomicAdd(&counters[2], 1);     // a problem without unknown cells has no tile to finish it
     }
 }
 
@@ -384,47 +385,8 @@ __global__ void reduce_partials_stage2_kernel(Geom g, const double *__restrict__
 __global__ void decide_kernel(DecideArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.g.P) return;
-    ProbState st = a.state[p];
-    if (st.status != 0 || st.k_run == 0) return;
-    const int kr = st.k_run;
-    if (st.replay) {
-        st.iters_done += kr;
-        st.cur ^= 1;
-        st.status = 1; st.k_run = 0; st.replay = 0; st.fresh = 0;
-        a.state[p] = st;
-        atomicSub(a.n_active, 1);
-        return;
-    }
-    int stop = -1;
-    for (int j = 0; j < kr; ++j) {
-        const double *S = a.sums + ((size_t)p * a.g.KB + j) * kSumSlots;
-        const double *K = ((st.fresh && j == 0) ? a.known0 : a.known) + (size_t)p * kSumSlots;
-        const double kz = a.all_cells ? 0.0 : 1.0;      // resistance: the sums already cover known cells
-        const double s_abs = a.all_cells ? S[0] : S[0] + K[0], s_old = a.all_cells ? S[1] : S[1] + K[1];
-        const double n_abs = a.g.n_cells - (S[2] + kz * K[2]), n_old = a.g.n_cells - (S[3] + kz * K[3]);
-        const double delta = (s_abs / n_abs) / (s_old / n_old);
-        if (a.delta_out) a.delta_out[(size_t)p * a.max_iter + st.iters_done + j] = delta;
-        if (a.auto_terminate && delta <= a.threshold) {
-            stop = j + 1;
-            break;
-        }
-    }
-    if (stop < 0 || stop == kr) {
-        st.iters_done += kr;
-        st.cur ^= 1;
-        st.fresh = 0;
-        if (stop == kr || st.iters_done >= a.max_iter) {
-            st.status = 1;
-            st.k_run = 0;
-            atomicSub(a.n_active, 1);
-        } else {
-            st.k_run = min(a.g.KB, a.max_iter - st.iters_done);
-        }
-    } else {
-        st.replay = 1;
-        st.k_run = stop;
-    }
-    a.state[p] = st;
+    decide_problem(a.g, a.state, p, a.sums + (size_t)p * a.g.KB * kSumSlots, a.known0, a.known, a.delta_out, a.n_active,
+                   a.max_iter, a.auto_terminate, a.threshold, a.all_cells);
 }
 
 // Ratio form of the tiled path (vpint_step_k1.cu, jacobi2d_k1_ratio_kernel): move both state buffers into

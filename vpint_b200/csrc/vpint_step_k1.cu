@@ -27,15 +27,18 @@ struct Acc {
     }
 };
 
+// Block sum of the tile's statistics -> its partial; then (fused mode) the problem's finish.
 template <typename T>
-__device__ __forceinline__ void write_partial(Acc<T> &a, double *partial_tile) {
+__device__ __forceinline__ void write_partial(Acc<T> &a, const StepArgs &args, int problem) {
     __shared__ double scratch[kSumSlots * 8];
     double v[kSumSlots] = {a.s_abs, a.s_old, (double)a.c_abs, (double)a.c_old};
     block_sum<kSumSlots>(v, scratch);
     if (threadIdx.x == 0) {
+        double *partial_tile = args.partial + (size_t)blockIdx.x * args.g.KB * kSumSlots;
 #pragma unroll
         for (int i = 0; i < kSumSlots; ++i) partial_tile[i] = v[i];
     }
+    finish_tile(args, problem, 1, scratch);
 }
 
 template <typename T, bool PLANES>
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_kernel(const StepArgs a) {
             if (mb & 2u) out[row + x + 1] = acc.commit(n1, c1);
         }
     }
-    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+    write_partial(acc, a, p);
 }
 
 // Ratio form of the 2-D sweep for ONE feature layer with exact weights (the VPint2 case): the state buffers
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_ratio_kernel(const StepArgs a
     }
     Acc<double> acc;
     acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
-    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+    write_partial(acc, a, p);
 }
 
 // Resistance sweep (VPint/WP_MRP.py:327-348): the damping  new > mu -> old + (new - old) - epsilon * old  is
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256) jacobi2d_resist_kernel(const StepArgs a) 
             }
         }
     }
-    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+    write_partial(acc, a, p);
 }
 
 // x / n for a small positive integer n, correctly rounded like the IEEE division the reference performs:
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(256, 5) jacobi3d_k1_kernel(const StepArgs a) {
             if (mb & 2u) out[row + x + 1] = acc.commit(v1, c1);
         }
     }
-    write_partial(acc, a.partial + (size_t)blockIdx.x * g.KB * kSumSlots);
+    write_partial(acc, a, p);
 }
 
 }  // namespace

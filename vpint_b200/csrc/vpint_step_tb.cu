@@ -206,6 +206,8 @@ jacobi2d_tb_kernel(const StepArgs a, const __grid_constant__ CUtensorMap map0, c
         for (int w = 0; w < kThreads / 32; ++w) acc += red[w * KB * kSumSlots + tid];
         a.partial[(size_t)blockIdx.x * g.KB * kSumSlots + tid] = acc;
     }
+    __syncthreads();
+    finish_tile(a, p, kr, red);           // red: (kThreads / 32) * KB * kSumSlots doubles >= kSumSlots * 16
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
