@@ -99,6 +99,8 @@ struct vpint_solver {
     size_t off_done = 0;              // int[P] tickets of the fused finish
     bool can_fuse = false;
     int tileless = 0;                 // problems without any unknown cell (decided by the separate kernel)
+    int64_t tiles_full = 0;           // active tiles of the full list built at load
+    bool tiles_trimmed = false;       // the list currently covers only the problems that were still running
     bool has_orig = false;
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
@@ -315,6 +317,8 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     VP_CUDA(cudaStreamSynchronize(st), "load sync");
     s->any_dirty = s->h_counters[kCntDirty];
     s->tiles_active = s->h_counters[kCntActiveTiles];
+    s->tiles_full = s->tiles_active;
+    s->tiles_trimmed = false;
     s->tileless = s->h_counters[kCntTileless];
     s->loaded = true;
     s->run_begun = false;
@@ -370,6 +374,8 @@ int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const doubl
     return VPINT_OK;
 }
 
+static int recompact_tiles(vpint_solver *s, cudaStream_t st, bool trim);
+
 int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!prm) return fail(VPINT_ERR_INVALID, "null run params");
@@ -385,6 +391,10 @@ int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *s
     VP_CUDA(launch_init_state(s->g, s->at<ProbState>(s->off_state), s->at<int>(s->off_counters) + kCntActiveProblems,
                               prm->max_iter, st, &s->launches),
             "init state");
+    if (s->tiles_trimmed) {
+        const int rc = recompact_tiles(s, st, false);
+        if (rc != VPINT_OK) return rc;
+    }
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_done), 0, (size_t)s->g.P * sizeof(int), st), "memset tickets");
     s->run_begun = true;
     s->first_step_pending = true;
@@ -396,6 +406,22 @@ static int step_end_impl(vpint_solver *s, void *stream, bool fused);
 
 // The four ratio planes are built lazily from the single-layer feature plane (vpint_solver_weights keeps only
 // that plane when the cluster-resident kernel can serve the run).
+// Rebuild the active-tile list: for the running problems only (trim) or for every problem again (before a
+// new run() on a solver whose list was trimmed).  Synchronises to learn the new launch size.
+static int recompact_tiles(vpint_solver *s, cudaStream_t st, bool trim) {
+    VP_CUDA(launch_recompact_tiles(s->g, s->at<int>(s->off_tileflag), s->at<TileRef>(s->off_tiles),
+                                   s->at<int>(s->off_tilestart), s->at<int>(s->off_counters),
+                                   trim ? s->at<ProbState>(s->off_state) : nullptr, st, &s->launches),
+            "recompact tiles");
+    VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveTiles, s->at<int>(s->off_counters) + kCntActiveTiles, sizeof(int),
+                            cudaMemcpyDeviceToHost, st),
+            "read tile count");
+    VP_CUDA(cudaStreamSynchronize(st), "recompact sync");
+    s->tiles_active = s->h_counters[kCntActiveTiles];
+    s->tiles_trimmed = trim;
+    return VPINT_OK;
+}
+
 // ---- ratio form of the tiled path -----------------------------------------------------------------------
 static int leave_ratio(vpint_solver *s, cudaStream_t st) {
     if (!s->state_ratio) return VPINT_OK;
@@ -696,6 +722,7 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
     // Every launch either commits >= 1 sweep of every running problem or is its single replay, so
     // 2 * max_iter + 2 launches always suffice; the bound only guards against a logic error.
     int64_t budget = 2 * (int64_t)prm->max_iter + 2;
+    int covered = s->g.P;                 // problems the current tile list covers
     while (budget > 0) {
         for (int i = 0; i < chunk; ++i) {
             rc = step_begin_impl(s, stream, nullptr, s->can_fuse && s->tileless == 0);
@@ -710,6 +737,12 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         VP_CUDA(cudaEventRecord(s->ev, st), "event record");
         VP_CUDA(cudaEventSynchronize(s->ev), "event sync");
         if (s->h_counters[kCntActiveProblems] <= 0) return VPINT_OK;
+        if (s->g.P > 1 && !s->prm.resistance && s->h_counters[kCntActiveProblems] * 2 <= covered) {
+            // many problems of the batch have stopped: later launches should not schedule their tiles
+            rc = recompact_tiles(s, st, true);
+            if (rc != VPINT_OK) return rc;
+            covered = s->h_counters[kCntActiveProblems];
+        }
         if (chunk < chunk_cap) chunk = (chunk * 2 < chunk_cap) ? chunk * 2 : chunk_cap;
     }
     return fail(VPINT_ERR_INVALID, "internal error: loop did not terminate within its launch budget");

@@ -142,6 +142,8 @@ cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, con
                              cudaStream_t st, int64_t *launches);
 cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
                          int *counters, cudaStream_t st, int64_t *launches);
+cudaError_t launch_recompact_tiles(const Geom &g, const int *tile_flag, TileRef *tiles, int *tile_start, int *counters,
+                                   const ProbState *state, cudaStream_t st, int64_t *launches);
 cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const int64_t *stride, int F, int method,
                              int clamp, double min_gamma, double max_gamma, int storage, void *const *planes,
                              cudaStream_t st, int64_t *launches);

@@ -245,16 +245,23 @@ __global__ void __launch_bounds__(256) tile_flag_kernel(Geom g, const uint32_t *
 
 // Single block: ordered compaction of the flagged tiles (problem-major, then row, then column),
 // tile_start[p] = index of problem p's first active tile, counters[1] = number of active tiles.
+// With `state` the list is rebuilt for the problems that are still running only (the loop driver does that
+// when many problems of a batch have stopped, so that later launches do not schedule their tiles).
 __global__ void __launch_bounds__(1024) tile_compact_kernel(Geom g, const int *__restrict__ tile_flag,
                                                             TileRef *__restrict__ tiles,
                                                             int *__restrict__ tile_start, int *counters,
-                                                            int64_t n_tiles) {
+                                                            int64_t n_tiles, const ProbState *__restrict__ state) {
     __shared__ int counts[1024];
     const int tid = threadIdx.x;
     const int64_t chunk = (n_tiles + 1023) / 1024;
     const int64_t a = min((int64_t)tid * chunk, n_tiles), b = min(a + chunk, n_tiles);
+    auto live = [&](int64_t i) {
+        if (!tile_flag[i]) return 0;
+        if (!state) return 1;
+        return state[(int)(i / g.tiles_per_prob) / g.S].status == 0 ? 1 : 0;
+    };
     int c = 0;
-    for (int64_t i = a; i < b; ++i) c += tile_flag[i];
+    for (int64_t i = a; i < b; ++i) c += live(i);
     counts[tid] = c;
     __syncthreads();
     // inclusive Hillis-Steele scan over 1024 counts
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(Geom g, const int *_
         const int p = (int)(i / g.tiles_per_prob);
         const int r = (int)(i - (int64_t)p * g.tiles_per_prob);
         if (r == 0) tile_start[p] = pos;
-        if (tile_flag[i]) {
+        if (live(i)) {
             const int ty = r / g.tiles_x, tx = r - ty * g.tiles_x;
             TileRef tr;
             tr.p = p; tr.y0 = g.own_row0 + ty * g.TH; tr.x0 = tx * g.TW; tr.pad = 0;
@@ -529,7 +536,15 @@ cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, Ti
     const unsigned grid = (unsigned)((n_tiles + 7) / 8);
     tile_flag_kernel<<<grid, 256, 0, st>>>(g, mask, tile_flag, n_tiles);
     VP_LAUNCH_CHECK();
-    tile_compact_kernel<<<1, 1024, 0, st>>>(g, tile_flag, tiles, tile_start, counters, n_tiles);
+    tile_compact_kernel<<<1, 1024, 0, st>>>(g, tile_flag, tiles, tile_start, counters, n_tiles, nullptr);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_recompact_tiles(const Geom &g, const int *tile_flag, TileRef *tiles, int *tile_start, int *counters,
+                                   const ProbState *state, cudaStream_t st, int64_t *launches) {
+    const int64_t n_tiles = (int64_t)g.P * g.S * g.tiles_per_prob;
+    tile_compact_kernel<<<1, 1024, 0, st>>>(g, tile_flag, tiles, tile_start, counters, n_tiles, state);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
