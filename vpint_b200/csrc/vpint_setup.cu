@@ -26,12 +26,22 @@ __device__ __forceinline__ int64_t cell_offset(const Geom &g, const Strides &s, 
 // combines the leaf sums in recursion order.
 constexpr int kFillMaxLeaves = 2048;        // leaves hold 64..128 elements: grids up to 131072 cells
 
+// Walks the row-major cell order of one 2-D problem without a division per element.
 template <typename TIn>
-__device__ __forceinline__ TIn fill_elem(const Geom &g, const Strides &s, const TIn *base, int p, int64_t idx) {
-    const int y = (int)(idx / g.L), e = (int)(idx - (int64_t)y * g.L);
-    const TIn v = base[cell_offset(g, s, p, y, e)];
-    return (v != v) ? (TIn)0 : v;
-}
+struct FillCursor {
+    const TIn *base;      // problem origin in the caller's array
+    int64_t sY, sX;
+    int L, y, x;
+    __device__ __forceinline__ void seek(int64_t idx) { y = (int)(idx / L); x = (int)(idx - (int64_t)y * L); }
+    __device__ __forceinline__ void advance(int n) {
+        x += n;
+        while (x >= L) { x -= L; ++y; }
+    }
+    __device__ __forceinline__ TIn get() const {
+        const TIn v = base[(int64_t)y * sY + (int64_t)x * sX];
+        return (v != v) ? (TIn)0 : v;
+    }
+};
 
 template <typename TIn>
 __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__restrict__ original, Strides sd,
@@ -44,6 +54,8 @@ __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__res
     const int p = blockIdx.x;
     const int64_t n = (int64_t)g.H * g.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int po = p / g.Pin, pi = p - po * g.Pin;
+    const TIn *base = original + (int64_t)po * sd.sO + (int64_t)pi * sd.sI;
     if (tid == 0) {                               // DFS over the recursion, left first
         int st_lo[40], st_n[40];
         int sp = 0, nl = 0;
@@ -62,6 +74,17 @@ __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__res
         }
         n_leaves = nl;
     }
+    // count of non-NaN cells (order does not matter): rows x strided columns, no division per cell
+    int cnt = 0;
+    for (int y = 0; y < g.H; ++y) {
+        const TIn *row = base + (int64_t)y * sd.sY;
+        for (int x = tid; x < g.L; x += blockDim.x) {
+            const TIn v = row[(int64_t)x * sd.sX];
+            cnt += (v == v) ? 1 : 0;
+        }
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) cnt_part[warp] = cnt;
     __syncthreads();
     // leaf sums: 8 lanes per leaf = the 8 accumulators of NumPy's unrolled loop
     const int sub = lane >> 3, j = lane & 7;
@@ -70,15 +93,17 @@ __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__res
         TIn res = (TIn)0;
         if (l < n_leaves) {
             const int lo = leaf_lo[l], m = leaf_sz[l];
+            FillCursor<TIn> cur{base, sd.sY, sd.sX, g.L, 0, 0};
             if (m < 8) {
                 if (j == 0) {
-                    res = (TIn)0;
-                    for (int i = 0; i < m; ++i) res += fill_elem(g, sd, original, p, (int64_t)lo + i);
+                    cur.seek(lo);
+                    for (int i = 0; i < m; ++i) { res += cur.get(); cur.advance(1); }
                 }
             } else {
-                TIn r = fill_elem(g, sd, original, p, (int64_t)lo + j);
+                cur.seek((int64_t)lo + j);
+                TIn r = cur.get();
                 int i = 8;
-                for (; i < m - (m % 8); i += 8) r += fill_elem(g, sd, original, p, (int64_t)lo + i + j);
+                for (; i < m - (m % 8); i += 8) { cur.advance(8); r += cur.get(); }
                 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) within each group of 8 lanes
                 const unsigned grp = 0xffu << (sub * 8);
                 TIn a = r + __shfl_down_sync(grp, r, 1, 8);     // valid in j = 0, 2, 4, 6
@@ -86,21 +111,13 @@ __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__res
                 TIn c = b + __shfl_down_sync(grp, b, 4, 8);     // valid in j = 0
                 if (j == 0) {
                     res = c;
-                    for (; i < m; ++i) res += fill_elem(g, sd, original, p, (int64_t)lo + i);
+                    cur.seek((int64_t)lo + i);
+                    for (; i < m; ++i) { res += cur.get(); cur.advance(1); }
                 }
             }
             if (j == 0) leaf_sum[l] = res;
         }
     }
-    // count of non-NaN cells
-    int cnt = 0;
-    for (int64_t i = tid; i < n; i += blockDim.x) {
-        const int y = (int)(i / g.L), e = (int)(i - (int64_t)y * g.L);
-        const TIn v = original[cell_offset(g, sd, p, y, e)];
-        cnt += (v == v) ? 1 : 0;
-    }
-    cnt = warp_sum(cnt);
-    if (lane == 0) cnt_part[warp] = cnt;
     __syncthreads();
     if (tid == 0) {
         // combine in recursion order: res(node) = res(left) + res(right)
