@@ -707,6 +707,7 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         ra.threshold = prm->threshold;
         ra.clip = prm->clip_val;
         ra.C = s->rplan.C; ra.R = s->rplan.R; ra.SP = s->rplan.SP; ra.fcap = s->rplan.fcap;
+        ra.BS = s->rplan.BS; ra.LB = s->rplan.LB;
         VP_CUDA(launch_resident2d(ra, ratio, s->rplan.smem_bytes, 0, st, &s->launches), "resident2d");
         VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
                                 sizeof(int), cudaMemcpyDeviceToHost, st),

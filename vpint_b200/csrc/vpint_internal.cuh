@@ -104,6 +104,7 @@ constexpr int kResidentMaxSeg = 8;    // 4-cell segments per thread (new values 
 
 struct ResidentPlan {
     int C, R, SP, fcap;     // cluster size, rows per CTA, shared-memory row pitch, on-chip feature capacity
+    int BS, LB;             // rows per round-robin block, blocks per CTA (R = BS * LB)
     size_t smem_bytes;      // dynamic shared memory per CTA
 };
 
@@ -121,7 +122,7 @@ struct ResidentArgs {
     const int *bad_flag;     // nonzero: decline (non-finite features); null = none
     int max_iter, auto_terminate;
     double threshold, clip;
-    int C, R, SP, fcap;
+    int C, R, SP, fcap, BS, LB;
 };
 
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);

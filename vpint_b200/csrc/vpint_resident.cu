@@ -15,6 +15,12 @@
 //           P = f * r only where the reference's stopping rule and clip need it.  Same iteration in
 //           exact arithmetic; in fp64 it differs from the reference by a few ulp per sweep.
 //
+// Rows are dealt to the CTAs of a cluster in BLOCKS of kBlockRows rows, round robin (block b belongs to CTA
+// b mod C), not as one contiguous band per CTA: a cloud then spreads over all CTAs of the cluster and the
+// busiest CTA -- which sets the pace of every sweep -- carries ~1.2x the average number of unknown cells
+// instead of ~2x.  The price is a halo row above and below every block; the neighbours of a CTA are always
+// CTA c-1 and c+1 (mod C).
+//
 // Work unit = a SEGMENT of 4 horizontally adjacent cells (x = 4s .. 4s+3) with at least one unknown cell;
 // the CTA keeps a compact row-major list of its segments.  Per sweep every CTA does: for each of its
 // segments load own row / row above / row below as 128-bit shared-memory vectors, compute the new values
@@ -43,9 +49,15 @@ constexpr int kMaxSeg = kResidentMaxSeg;   // segments per thread (4 new values 
 constexpr int kMaxC = 8;                   // portable cluster size
 constexpr int kPadL = 2;                   // zero columns left of x = 0 (keeps segments 16-byte aligned)
 
+constexpr int kBlockRows = 16;             // rows per round-robin block (clusters of more than one CTA)
+constexpr int kMaxBlocks = 8;              // blocks per CTA
+
 // list entry: [15:0] plane offset of the segment's first cell, [19:16] unknown-cell nibble,
-// [20] on the first owned row, [21] on the last owned row, [22] touches the grid border (nc < 4 somewhere)
-constexpr unsigned kSegTop = 1u << 20, kSegBot = 1u << 21, kSegEdge = 1u << 22;
+// [20] first row of its block (row above is a halo row), [21] last row of its block, [22] touches the grid
+// border (nc < 4 somewhere), [23] first row AND a block above exists (row is sent up), [24] last row AND a
+// block below exists (row is sent down), [27:25] local block index
+constexpr unsigned kSegTop = 1u << 20, kSegBot = 1u << 21, kSegEdge = 1u << 22, kSegSendUp = 1u << 23,
+                   kSegSendDn = 1u << 24;
 
 // Cluster barrier with release / acquire at cluster scope.
 __device__ __forceinline__ void cluster_barrier() {
@@ -103,18 +115,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 struct SmemLayout {
     double *plane;       // [R][SP] owned rows; columns < kPadL and > W + 1 are the zero border
-    double *halo_up;     // [2][SP] row above the owned band, by sweep parity
-    double *halo_dn;     // [2][SP] row below
+    double *halo_up;     // [2][LB][SP] row above every owned block, by sweep parity
+    double *halo_dn;     // [2][LB][SP] row below
     double *fseg;        // [fcap][4] features of the first fcap listed segments (RATIO)
     unsigned *list;      // [n_seg] segment entries, row-major
 };
 
-__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, int fcap) {
+__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, int LB, int fcap) {
     SmemLayout s;
     s.plane = reinterpret_cast<double *>(raw);
     s.halo_up = s.plane + (size_t)R * SP;
-    s.halo_dn = s.halo_up + 2 * SP;
-    s.fseg = s.halo_dn + 2 * SP;
+    s.halo_dn = s.halo_up + 2 * LB * SP;
+    s.fseg = s.halo_dn + 2 * LB * SP;
     s.list = reinterpret_cast<unsigned *>(s.fseg + (size_t)fcap * 4);
     return s;
 }
@@ -128,8 +140,16 @@ struct SweepCtx {
     // neighbour CTAs (shared::cluster addresses): their halo row buffers [2][SP] and their halo barriers [2]
     uint32_t up_halo, dn_halo, up_bar[2], dn_bar[2];
     bool has_up, has_dn;
-    int SP, bot_base, fcap, gy0, pitch, tid, n, H, W;
+    int SP, fcap, pitch, tid, n, H, W;
+    int C, crank, BS, LB;             // cluster size / rank, rows per block, blocks per CTA
+    int shift_up, shift_dn;           // local block index of block b-1 / b+1 in the neighbour CTA, relative to mine
+    const int *blk_bot;               // [LB] local row index of the last row of every block
     double gamma, clip;
+    // grid row of local row ly: blocks are dealt round robin
+    __device__ __forceinline__ int grid_row(int ly) const {
+        const int lb = ly / BS;
+        return (lb * C + crank) * BS + (ly - lb * BS);
+    }
 };
 
 // Per-CTA synchronisation state (static shared memory).
@@ -140,6 +160,7 @@ struct SyncShared {
     uint64_t bar_s[3];                 // per sweep mod 3: the C partial sums (C * 16 bytes)
     int verdict;                       // stop decision of the previous sweep, written by warp 0
     int halo_exp[2];                   // bytes per sweep from the upper / lower neighbour
+    int blk_bot[kMaxBlocks];           // local row index of the last row of every block
     int edge_cnt[2];                   // segments on the first / last owned row
 };
 
@@ -199,7 +220,7 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
         }
         double nr[KT > 0 ? KT : 1][4];
         double s_abs = 0.0, s_old = 0.0;
-        const double *halo_up = c.halo_up + par * c.SP, *halo_dn = c.halo_dn + par * c.SP;
+        const double *halo_up = c.halo_up + par * c.LB * c.SP, *halo_dn = c.halo_dn + par * c.LB * c.SP;
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const int i0 = c.tid + k * kThreads;
@@ -209,8 +230,9 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
             const int off = (int)(e & 0xffffu);
             const unsigned m = live ? ((e >> 16) & 15u) : 0u;
             const double *row = c.plane + off;
-            const double *upp = (e & kSegTop) ? halo_up + off : row - c.SP;
-            const double *dnp = (e & kSegBot) ? halo_dn + (off - c.bot_base) : row + c.SP;
+            const int lb = (int)((e >> 25) & 7u);
+            const double *upp = (e & kSegTop) ? halo_up + (lb * c.SP + off - lb * c.BS * c.SP) : row - c.SP;
+            const double *dnp = (e & kSegBot) ? halo_dn + (lb * c.SP + off - c.blk_bot[lb] * c.SP) : row + c.SP;
             double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
             ld2(row, c0, c1); ld2(row + 2, c2, c3);
             ld2(upp, u0, u1); ld2(upp + 2, u2, u3);
@@ -232,7 +254,7 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
             const bool edge = (e & kSegEdge) != 0;
             if (__any_sync(0xffffffffu, edge)) {
                 if (edge) {                        // grid border: per-cell neighbour count, true division
-                    const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.gy0 + ly;
+                    const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.grid_row(ly);
                     const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -256,7 +278,7 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
                 ld2(fs, f[0], f[1]); ld2(fs + 2, f[2], f[3]);
                 if (i >= c.fcap) {
                     const int ly = off / c.SP;
-                    const double *fg = c.fp + (size_t)(c.gy0 + ly) * c.pitch + (off - ly * c.SP - kPadL);
+                    const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + (off - ly * c.SP - kPadL);
                     ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
                 }
                 bool clipped = false;
@@ -316,7 +338,7 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
                           map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
             if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
         }
-        const uint32_t npo = (uint32_t)(npar * c.SP);   // (6)
+        const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const int i = c.tid + k * kThreads;
@@ -326,13 +348,14 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
                 double2 *row = reinterpret_cast<double2 *>(c.plane + off);
                 row[0] = make_double2(nr[k][0], nr[k][1]);
                 row[1] = make_double2(nr[k][2], nr[k][3]);
-                if ((e & kSegTop) && c.has_up) {   // my first row is the upper CTA's lower halo
-                    const uint32_t dst = c.up_halo + (npo + (uint32_t)off) * 8u;
+                const int lb = (int)((e >> 25) & 7u);
+                if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
+                    const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
                     st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
                     st_async2(dst + 16u, nr[k][2], nr[k][3], c.up_bar[npar]);
                 }
-                if ((e & kSegBot) && c.has_dn) {   // my last row is the lower CTA's upper halo
-                    const uint32_t dst = c.dn_halo + (npo + (uint32_t)(off - c.bot_base)) * 8u;
+                if (e & kSegSendDn) {              // last row of my block = upper halo of the block below (CTA c+1)
+                    const uint32_t dst = c.dn_halo + (npo + (uint32_t)((lb + c.shift_dn) * c.SP + off - c.blk_bot[lb] * c.SP)) * 8u;
                     st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
                     st_async2(dst + 16u, nr[k][2], nr[k][3], c.dn_bar[npar]);
                 }
@@ -371,7 +394,8 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
     const Geom &g = a.g;
     const int W = g.L, H = g.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const SmemLayout sm = carve(smem_raw, R, SP, fcap);
+    const int BS = a.BS, LB = a.LB;
+    const SmemLayout sm = carve(smem_raw, R, SP, LB, fcap);
     int *next_remote = cluster.map_shared_rank(&next_problem, 0);
     if (tid == 0) {
         mbar_init(&sh.bar_h[0], kThreads); mbar_init(&sh.bar_h[1], kThreads);
@@ -380,8 +404,14 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
     }
     unsigned ph_h = 0, ph_s = 0;                       // phase parities of bar_h[2] / bar_s[3], carried across problems
 
-    const int gy0 = crank * R;                         // first owned grid row
-    const int n_rows = max(0, min(R, H - gy0));
+    // round-robin blocks: local block lb is grid block lb * C + crank; the local rows that exist are contiguous
+    const int NB = (H + BS - 1) / BS;
+    int n_rows = 0;
+    for (int lb = 0; lb < LB; ++lb) {
+        const int gb = lb * C + crank;
+        if (gb < NB) n_rows += min(BS, H - gb * BS);
+    }
+    auto grid_row = [&](int ly) { const int lb = ly / BS; return (lb * C + crank) * BS + (ly - lb * BS); };
     const size_t plane_elems = (size_t)H * g.pitch;
     const int nwords = (W + 31) >> 5;
     const double n_cells = g.n_cells;
@@ -402,9 +432,24 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         const double gamma = RATIO ? 1.0 : a.gamma[p];
 
         // ---- stage the owned rows and both halo rows (r = P / f in RATIO form) ----------------
-        for (int row = warp; row < n_rows + 2; row += kWarps) {
-            const int gy = gy0 - 1 + row;              // row 0 = upper halo, n_rows + 1 = lower halo
-            double *dst = (row == 0) ? sm.halo_up : (row == n_rows + 1 ? sm.halo_dn : sm.plane + (size_t)(row - 1) * SP);
+        if (tid < LB) {
+            const int gb = tid * C + crank;
+            sh.blk_bot[tid] = tid * BS + ((gb < NB) ? min(BS, H - gb * BS) : BS) - 1;
+        }
+        for (int row = warp; row < n_rows + 2 * LB; row += kWarps) {
+            // rows 0 .. n_rows-1: owned rows; then for every block its upper and its lower halo row
+            int gy;
+            double *dst;
+            const bool is_halo = row >= n_rows;
+            if (!is_halo) {
+                gy = grid_row(row);
+                dst = sm.plane + (size_t)row * SP;
+            } else {
+                const int h = row - n_rows, lb = h >> 1, gb = lb * C + crank;
+                const int rows_in = (gb < NB) ? min(BS, H - gb * BS) : 0;
+                gy = (gb < NB) ? ((h & 1) ? gb * BS + rows_in : gb * BS - 1) : -1;
+                dst = ((h & 1) ? sm.halo_dn : sm.halo_up) + (size_t)lb * SP;
+            }
             const bool in_grid = (gy >= 0) && (gy < H);
             for (int lx = lane; lx < SP; lx += 32) {
                 double v = 0.0;
@@ -414,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
                     if (RATIO) v = v / fp[(size_t)gy * g.pitch + x];
                 }
                 dst[lx] = v;
-                if (row == 0 || row == n_rows + 1) dst[SP + lx] = v;   // second parity copy of a halo row
+                if (is_halo) dst[LB * SP + lx] = v;            // second parity copy of a halo row
             }
         }
 
@@ -430,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         };
         int cnt = 0;
         for (int ly = wr0; ly < wr1; ++ly)
-            for (int w = lane; w < nwords; w += 32) cnt += __popc(nibbles(mrow[(size_t)(gy0 + ly) * g.mpitch + w]));
+            for (int w = lane; w < nwords; w += 32) cnt += __popc(nibbles(mrow[(size_t)grid_row(ly) * g.mpitch + w]));
         cnt = warp_sum(cnt);
         if (lane == 0) wcount[warp] = cnt;
         __syncthreads();
@@ -440,8 +485,11 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
             n += wcount[w];
         }
         for (int ly = wr0; ly < wr1; ++ly) {
-            const int gy = gy0 + ly;
-            const unsigned row_flags = (ly == 0 ? kSegTop : 0u) | (ly == n_rows - 1 ? kSegBot : 0u);
+            const int gy = grid_row(ly);
+            const int lb = ly / BS, gb = lb * C + crank;
+            const bool top = (ly == lb * BS), bot = (ly == lb * BS + min(BS, H - gb * BS) - 1);
+            const unsigned row_flags = (top ? kSegTop : 0u) | (bot ? kSegBot : 0u) | ((top && gb > 0) ? kSegSendUp : 0u) |
+                                       ((bot && gb < NB - 1) ? kSegSendDn : 0u) | ((unsigned)lb << 25);
             const bool row_edge = (gy == 0) || (gy == H - 1);
             for (int w0 = 0; w0 < nwords; w0 += 32) {
                 const int w = w0 + lane;
@@ -471,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
             for (int i = tid; i < min(n, fcap); i += kThreads) {
                 const int off = (int)(sm.list[i] & 0xffffu);
                 const int ly = off / SP, x0 = off - ly * SP - kPadL;
-                const double *fg = fp + (size_t)(gy0 + ly) * g.pitch + x0;
+                const double *fg = fp + (size_t)grid_row(ly) * g.pitch + x0;
                 double f0, f1, f2, f3;
                 ld2(fg, f0, f1); ld2(fg + 2, f2, f3);
                 double2 *d = reinterpret_cast<double2 *>(sm.fseg + (size_t)i * 4);
@@ -492,8 +540,8 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
             int n_top = 0, n_bot = 0;
             for (int i = tid; i < n; i += kThreads) {
                 const unsigned e = sm.list[i];
-                n_top += (e & kSegTop) ? 1 : 0;
-                n_bot += (e & kSegBot) ? 1 : 0;
+                n_top += (e & kSegSendUp) ? 1 : 0;
+                n_bot += (e & kSegSendDn) ? 1 : 0;
             }
             n_top = warp_sum(n_top);
             n_bot = warp_sum(n_bot);
@@ -501,20 +549,27 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         }
         __syncthreads();
         if (tid == 0) {
-            if (crank > 0) *cluster.map_shared_rank(&sh.halo_exp[1], crank - 1) = 32 * sh.edge_cnt[0];      // into its lower halo
-            if (crank < C - 1) *cluster.map_shared_rank(&sh.halo_exp[0], crank + 1) = 32 * sh.edge_cnt[1];  // into its upper halo
+            if (C > 1) {
+                *cluster.map_shared_rank(&sh.halo_exp[1], (crank + C - 1) % C) = 32 * sh.edge_cnt[0];   // into its lower halos
+                *cluster.map_shared_rank(&sh.halo_exp[0], (crank + 1) % C) = 32 * sh.edge_cnt[1];       // into its upper halos
+            }
         }
         SweepCtx ctx;
         ctx.plane = sm.plane; ctx.halo_up = sm.halo_up; ctx.halo_dn = sm.halo_dn; ctx.fseg = sm.fseg; ctx.list = sm.list;
         ctx.fp = fp;
-        ctx.has_up = (crank > 0); ctx.has_dn = (crank < C - 1);
-        ctx.up_halo = ctx.has_up ? map_rank(smem_u32(sm.halo_dn), crank - 1) : 0u;
-        ctx.dn_halo = ctx.has_dn ? map_rank(smem_u32(sm.halo_up), crank + 1) : 0u;
+        ctx.has_up = ctx.has_dn = (C > 1);
+        const int cu = (crank + C - 1) % C, cd = (crank + 1) % C;
+        ctx.up_halo = ctx.has_up ? map_rank(smem_u32(sm.halo_dn), cu) : 0u;
+        ctx.dn_halo = ctx.has_dn ? map_rank(smem_u32(sm.halo_up), cd) : 0u;
         for (int q = 0; q < 2; ++q) {
-            ctx.up_bar[q] = ctx.has_up ? map_rank(smem_u32(&sh.bar_h[q]), crank - 1) : 0u;
-            ctx.dn_bar[q] = ctx.has_dn ? map_rank(smem_u32(&sh.bar_h[q]), crank + 1) : 0u;
+            ctx.up_bar[q] = ctx.has_up ? map_rank(smem_u32(&sh.bar_h[q]), cu) : 0u;
+            ctx.dn_bar[q] = ctx.has_dn ? map_rank(smem_u32(&sh.bar_h[q]), cd) : 0u;
         }
-        ctx.SP = SP; ctx.bot_base = (n_rows - 1) * SP; ctx.fcap = fcap; ctx.gy0 = gy0; ctx.pitch = g.pitch; ctx.tid = tid;
+        ctx.C = C; ctx.crank = crank; ctx.BS = BS; ctx.LB = LB;
+        ctx.shift_up = (crank == 0) ? -1 : 0;       // block b-1 lives in CTA c-1 under the same local index, or one less after the wrap
+        ctx.shift_dn = (crank == C - 1) ? 1 : 0;
+        ctx.blk_bot = sh.blk_bot;
+        ctx.SP = SP; ctx.fcap = fcap; ctx.pitch = g.pitch; ctx.tid = tid;
         ctx.n = n; ctx.H = H; ctx.W = W;
         ctx.gamma = gamma; ctx.clip = a.clip;
         const double *K0 = a.known0 + (size_t)p * kSumSlots, *K1 = a.known + (size_t)p * kSumSlots;
@@ -542,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
             const unsigned e = sm.list[i];
             const int off = (int)(e & 0xffffu);
             const int ly = off / SP, x0 = off - ly * SP - kPadL;
-            const size_t go = (size_t)(gy0 + ly) * g.pitch + x0;
+            const size_t go = (size_t)grid_row(ly) * g.pitch + x0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if ((e >> (16 + j)) & 1u) {
@@ -574,11 +629,16 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
     if (g.pitch < 4 * segs_per_row) return false;
     const int static_bytes = 2048;              // SyncShared, wcount, next_problem (+ slack)
     for (int C = 1; C <= kMaxC; C *= 2) {
-        const int R = (g.H + C - 1) / C;
-        if ((g.H + R - 1) / R != C) continue;                                   // every CTA must own at least one row
+        // one block per CTA when the cluster is a single CTA, round-robin blocks of kBlockRows rows otherwise
+        const int BS = (C == 1) ? g.H : kBlockRows;
+        const int NB = (g.H + BS - 1) / BS;
+        if (NB < C) continue;                                                   // every CTA must own at least one block
+        const int LB = (NB + C - 1) / C;
+        if (LB > kMaxBlocks) continue;
+        const int R = LB * BS;
         if ((int64_t)R * segs_per_row > (int64_t)kThreads * kMaxSeg) continue;  // register budget for the new values
         if ((int64_t)R * SP > 65535) continue;                                  // 16-bit shared-memory offsets
-        const int64_t fixed = ((int64_t)R * SP + 4 * SP) * 8 + (int64_t)R * segs_per_row * 4;
+        const int64_t fixed = ((int64_t)R * SP + 4 * (int64_t)LB * SP) * 8 + (int64_t)R * segs_per_row * 4;
         const int64_t room = (int64_t)smem_limit - static_bytes - fixed;
         if (room < 0) continue;
         int fcap = 0;
@@ -588,7 +648,7 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
             if (fcap < 1) continue;
             if (fcap * 4 < all && C < kMaxC) continue;                           // want >= 25 % of the features on chip
         }
-        out->C = C; out->R = R; out->SP = SP; out->fcap = fcap;
+        out->C = C; out->R = R; out->SP = SP; out->fcap = fcap; out->BS = BS; out->LB = LB;
         out->smem_bytes = (size_t)(fixed + (int64_t)fcap * 32);
         return true;
     }
@@ -620,8 +680,8 @@ cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_
         if (clusters < 1) return cudaErrorLaunchOutOfResources;
     }
     if (getenv("VPINT_DEBUG"))
-        fprintf(stderr, "[vpint] resident2d: C=%d R=%d SP=%d fcap=%d smem=%zu max_clusters=%d P=%d\n", a.C, a.R, a.SP,
-                a.fcap, smem_bytes, clusters, a.g.P);
+        fprintf(stderr, "[vpint] resident2d: C=%d R=%d (blocks of %d rows x %d) SP=%d fcap=%d smem=%zu max_clusters=%d P=%d\n",
+                a.C, a.R, a.BS, a.LB, a.SP, a.fcap, smem_bytes, clusters, a.g.P);
     if (clusters > a.g.P) clusters = a.g.P;
     cfg.gridDim = dim3((unsigned)(clusters * a.C), 1, 1);
     e = cudaLaunchKernelEx(&cfg, kern, a);
