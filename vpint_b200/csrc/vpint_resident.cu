@@ -43,11 +43,13 @@ namespace vpint {
 
 namespace {
 
-constexpr int kThreads = kResidentThreads;
-constexpr int kWarps = kThreads / 32;
+constexpr int kLaunchThreads = kResidentThreads;
+constexpr int kAllWarps = kLaunchThreads / 32;
+constexpr int kThreads = kLaunchThreads - 32;   // worker threads: they own the segments; the last warp only does the
+constexpr int kWarps = kThreads / 32;           // cross-CTA bookkeeping of a sweep (the "sync warp")
+static_assert(kWarps <= 16, "the partial-sum tree below covers 16 warps");
 constexpr int kMaxSeg = kResidentMaxSeg;   // segments per thread (4 new values each, in registers)
 constexpr int kMaxC = 8;                   // portable cluster size
-constexpr int kPadL = 2;                   // zero columns left of x = 0 (keeps segments 16-byte aligned)
 
 constexpr int kBlockRows = 16;             // rows per round-robin block (clusters of more than one CTA)
 constexpr int kMaxBlocks = 8;              // blocks per CTA
@@ -56,8 +58,10 @@ constexpr int kMaxBlocks = 8;              // blocks per CTA
 // [20] first row of its block (row above is a halo row), [21] last row of its block, [22] touches the grid
 // border (nc < 4 somewhere), [23] first row AND a block above exists (row is sent up), [24] last row AND a
 // block below exists (row is sent down), [27:25] local block index
+// [28] first cell is grid column 0, [29] last cell is grid column W-1, [30] first or last grid row (the three
+// border bits drive the branch-free neighbour counts of the fast path)
 constexpr unsigned kSegTop = 1u << 20, kSegBot = 1u << 21, kSegEdge = 1u << 22, kSegSendUp = 1u << 23,
-                   kSegSendDn = 1u << 24;
+                   kSegSendDn = 1u << 24, kSegLeft = 1u << 28, kSegRight = 1u << 29, kSegRowEdge = 1u << 30;
 
 // Cluster barrier with release / acquire at cluster scope.
 __device__ __forceinline__ void cluster_barrier() {
@@ -106,18 +110,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "VPR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra VPR_DONE_%=;\n"
         "bra VPR_WAIT_%=;\n"
         "VPR_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
+}
+
+#ifdef VPINT_RES_TRACE
+// Debug build only: clock64() stamps of the stages of sweeps 10..17 for thread 0 and the first thread of the sync warp of the
+// CTAs of cluster 0 (scripts/res_trace_probe.py).
+__device__ long long g_trace[8][2][8][10];
+#define VPR_TR(k)                                                                                     \
+    do {                                                                                              \
+        if (blockIdx.x < 8 && t >= 10 && t < 18 && (c.tid == 0 || c.tid == kThreads))                 \
+            g_trace[blockIdx.x][c.tid ? 1 : 0][t - 10][k] = clock64();                                \
+    } while (0)
+#else
+#define VPR_TR(k) do { } while (0)
+#endif
+
+// Split-row layout of a state row in shared memory (SP = 4 * nseg + 4 doubles, HALF = SP / 2):
+//   [0, HALF)    pair s = cells (4s, 4s+1) at 2s, s = 0 .. nseg-1, then one zero pair
+//   [HALF, SP)   one zero pair, then pair s = cells (4s+2, 4s+3) at HALF + 2 + 2s
+// A warp whose lanes hold consecutive segments reads each half with 128-bit loads at a 16-byte lane stride --
+// no bank conflicts, where the plain row-major layout (32-byte stride) costs two wavefronts per quarter warp.
+// With off = row * SP + 2s:  cells 0,1 at off; cells 2,3 at off + HALF + 2; the left neighbour (cell 4s-1) at
+// off + HALF + 1; the right neighbour (cell 4s+4) at off + 2; the zero pairs are the grid's left / right border.
+__device__ __forceinline__ int slot_cell(int lx, int half) {       // column held by row offset lx (pads: < 0 or >= 4 * nseg)
+    if (lx < half) return 4 * (lx >> 1) + (lx & 1);
+    const int q = lx - half;
+    return 4 * ((q >> 1) - 1) + 2 + (q & 1);
 }
 
 struct SmemLayout {
-    double *plane;       // [R][SP] owned rows; columns < kPadL and > W + 1 are the zero border
+    double *plane;       // [R][SP] owned rows in the split-row layout described below
     double *halo_up;     // [2][LB][SP] row above every owned block, by sweep parity
     double *halo_dn;     // [2][LB][SP] row below
-    double *fseg;        // [fcap][4] features of the first fcap listed segments (RATIO)
+    double *fseg;        // [2][fcap][2] features of the first fcap listed segments: cells 0,1 then cells 2,3 (RATIO)
     unsigned *list;      // [n_seg] segment entries, row-major
 };
 
@@ -140,11 +170,14 @@ struct SweepCtx {
     // neighbour CTAs (shared::cluster addresses): their halo row buffers [2][SP] and their halo barriers [2]
     uint32_t up_halo, dn_halo, up_bar[2], dn_bar[2];
     bool has_up, has_dn;
-    int SP, fcap, pitch, tid, n, H, W;
+    int SP, half, fcap, pitch, tid, n, H, W;   // half = SP / 2 (split-row layout)
     int C, crank, BS, LB;             // cluster size / rank, rows per block, blocks per CTA
     int shift_up, shift_dn;           // local block index of block b-1 / b+1 in the neighbour CTA, relative to mine
-    const int *blk_bot;               // [LB] local row index of the last row of every block
+    int part_lb, part_rows;           // local index / row count of this CTA's partial block (H % BS rows), or -1
+    const double *zero4;              // four zeros in shared memory (features of segments that must not count)
     double gamma, clip;
+    // local row of the last row of block lb
+    __device__ __forceinline__ int bot_row(int lb) const { return lb * BS + ((lb == part_lb) ? part_rows : BS) - 1; }
     // grid row of local row ly: blocks are dealt round robin
     __device__ __forceinline__ int grid_row(int ly) const {
         const int lb = ly / BS;
@@ -155,12 +188,12 @@ struct SweepCtx {
 // Per-CTA synchronisation state (static shared memory).
 struct SyncShared {
     double part[3][kMaxC][2];          // partial {sum|new-old|, sum old} of every CTA of the cluster (16-byte entries)
-    double red[kWarps][2];
-    uint64_t bar_h[2];                 // per sweep parity: this CTA's own stores (kThreads arrivals) + neighbours' halo bytes
+    double zero4[4];                   // features of segments that must not count (16-byte aligned)
+    double red[2][kWarps][2];          // warp partials by sweep parity (read by the sync warp while the workers go on)
+    uint64_t bar_h[2];                 // per sweep parity: this CTA's own stores (one arrival per warp) + neighbours' halo bytes
     uint64_t bar_s[3];                 // per sweep mod 3: the C partial sums (C * 16 bytes)
-    int verdict;                       // stop decision of the previous sweep, written by warp 0
+    int verdict[2];                    // stop decision of the previous sweep by sweep parity, written by the sync warp
     int halo_exp[2];                   // bytes per sweep from the upper / lower neighbour
-    int blk_bot[kMaxBlocks];           // local row index of the last row of every block
     int edge_cnt[2];                   // segments on the first / last owned row
 };
 
@@ -180,8 +213,16 @@ __device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned p
     if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) return 2;
     const double sa = S0 + KK[0], so = S1 + KK[1];
     const double na = n_cells - KK[2], no = n_cells - KK[3];
-    const double delta = (sa / na) / (so / no);
-    if (a.delta_out && writer) a.delta_out[(size_t)p * a.max_iter + sweep] = delta;
+    // delta = (sa / na) / (so / no) costs three dependent fp64 divisions on the critical path of every sweep.
+    // (sa * no) against threshold * (so * na) gives the same answer unless delta is within 1e-12 (relative) of
+    // the threshold -- the quotient's own rounding error is < 1e-15 -- and only then is it formed exactly.
+    const double x = sa * no, y = so * na, ty = a.threshold * y;
+    const bool sure = (na > 0.0) && (no > 0.0) && (y > 0.0) && (ty <= 1.7976931348623157e308) &&
+                      (fabs(x - ty) > 1e-12 * ty);
+    const bool want_delta = (a.delta_out != nullptr);
+    if (__all_sync(0xffffffffu, sure && !want_delta)) return (a.auto_terminate && x <= ty) ? 1 : 0;
+    const double delta = div_here(div_here(sa, na), div_here(so, no));
+    if (want_delta && writer) a.delta_out[(size_t)p * a.max_iter + sweep] = delta;
     return (a.auto_terminate && delta <= a.threshold) ? 1 : 0;
 }
 
@@ -192,142 +233,184 @@ __device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned p
 //           (2) compute the new values of the thread's segments into registers -- straight-line code, every
 //               k is executed (entries past the end re-read segment n-1 and are discarded) so the loads and
 //               fp64 chains of the KT segments overlap -- and the warp partial sums;
-//           (3) block barrier: all reads of the old state are done;
-//           (4) stop decision of sweep t-1, whose partial sums have been travelling while (2) ran: if it
-//               stops, sweep t is simply not stored (commit-then-break without a rollback);
-//           (5) warp 0 pushes this CTA's partial of sweep t to every CTA (st.async -> bar_s[t % 3]);
+//           (4) meanwhile the SYNC WARP (warp kWarps, owns no segments) forms the stop decision of sweep t-1,
+//               whose partial sums have been travelling since: if it stops, sweep t is simply not stored
+//               (commit-then-break without a rollback);
+//           (3) block barrier: all reads of the old state are done, the verdict is known;
+//           (5) the sync warp adds up the warp partials of sweep t and pushes the CTA's partial to every CTA
+//               (st.async -> bar_s[t % 3]) while the workers go on with (6);
 //           (6) store the new values: own rows with plain stores, first / last owned row also into the
 //               neighbours' halo row of the other parity with st.async (-> their bar_h), then arrive on
 //               the own bar_h of the other parity.
 // A NaN or inf anywhere poisons the partial sums, which is how data for the tiled path is detected.
-template <bool RATIO, int KT>
+template <bool RATIO, int KT, bool FAST>
 __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, const ResidentArgs &a, int p, int C, int crank,
                                            bool fresh, const double *k0, const double *k1, double n_cells,
                                            unsigned &ph_h, unsigned &ph_s, int &it_out, bool &bailed_out) {
     const int lane = c.tid & 31, warp = c.tid >> 5;
+    const bool sync_warp = (warp == kWarps);       // no segments: decides sweep t-1 and publishes the partial of sweep t
     const int last = c.n - 1;
     const int T = a.max_iter;
     const unsigned halo_bytes = (unsigned)((c.has_up ? sh.halo_exp[0] : 0) + (c.has_dn ? sh.halo_exp[1] : 0));
     const uint32_t my_part = smem_u32(&sh.part[0][0][0]);
     const uint32_t my_bar_s = smem_u32(&sh.bar_s[0]);
-    const bool writer = (crank == 0 && c.tid == 0);
+    const bool writer = (crank == 0 && sync_warp && lane == 0);
     int t = 0, verdict = 0;
     for (; t < T; ++t) {
         const int par = t & 1, npar = par ^ 1, slot = t % 3;
-        if (t > 0) {
-            mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
-            ph_h ^= 1u << par;
-        }
+        VPR_TR(0);
         double nr[KT > 0 ? KT : 1][4];
-        double s_abs = 0.0, s_old = 0.0;
-        const double *halo_up = c.halo_up + par * c.LB * c.SP, *halo_dn = c.halo_dn + par * c.LB * c.SP;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            const int i0 = c.tid + k * kThreads;
-            const bool live = i0 <= last;
-            const int i = live ? i0 : last;
-            const unsigned e = c.list[i];
-            const int off = (int)(e & 0xffffu);
-            const unsigned m = live ? ((e >> 16) & 15u) : 0u;
-            const double *row = c.plane + off;
-            const int lb = (int)((e >> 25) & 7u);
-            const double *upp = (e & kSegTop) ? halo_up + (lb * c.SP + off - lb * c.BS * c.SP) : row - c.SP;
-            const double *dnp = (e & kSegBot) ? halo_dn + (lb * c.SP + off - c.blk_bot[lb] * c.SP) : row + c.SP;
-            double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
-            ld2(row, c0, c1); ld2(row + 2, c2, c3);
-            ld2(upp, u0, u1); ld2(upp + 2, u2, u3);
-            ld2(dnp, d0, d1); ld2(dnp + 2, d2, d3);
-            const double lf = row[-1], rt = row[4];
-            double r[4];
-            if (RATIO) {
-                r[0] = ((u0 + c1) + d0) + lf;
-                r[1] = ((u1 + c2) + d1) + c0;
-                r[2] = ((u2 + c3) + d2) + c1;
-                r[3] = ((u3 + rt) + d3) + c2;
-            } else {
-                const double g = c.gamma;
-                r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
-                r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
-                r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
-                r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
+        if (!sync_warp) {
+            if (t > 0) {
+                mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+                ph_h ^= 1u << par;
             }
-            const bool edge = (e & kSegEdge) != 0;
-            if (__any_sync(0xffffffffu, edge)) {
-                if (edge) {                        // grid border: per-cell neighbour count, true division
-                    const int ly = off / c.SP, x0 = off - ly * c.SP - kPadL, gy = c.grid_row(ly);
-                    const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
+            VPR_TR(1);
+            double s_abs = 0.0, s_old = 0.0;
+            const double *halo_up = c.halo_up + par * c.LB * c.SP, *halo_dn = c.halo_dn + par * c.LB * c.SP;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int x = x0 + j;
-                        const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
-                        r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
+            for (int k = 0; k < KT; ++k) {
+                const int i0 = c.tid + k * kThreads;
+                const bool live = i0 <= last;
+                const int i = live ? i0 : last;
+                const unsigned e = c.list[i];
+                const int off = (int)(e & 0xffffu);
+                const unsigned m = live ? ((e >> 16) & 15u) : 0u;
+                const double *row = c.plane + off;
+                const int lb = (int)((e >> 25) & 7u);
+                const double *upp = (e & kSegTop) ? halo_up + (lb * c.SP + off - lb * c.BS * c.SP) : row - c.SP;
+                const double *dnp = (e & kSegBot) ? halo_dn + (lb * c.SP + off - c.bot_row(lb) * c.SP) : row + c.SP;
+                double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
+                const int hb = c.half + 2;             // second half of a segment
+                ld2(row, c0, c1); ld2(row + hb, c2, c3);
+                ld2(upp, u0, u1); ld2(upp + hb, u2, u3);
+                ld2(dnp, d0, d1); ld2(dnp + hb, d2, d3);
+                const double lf = row[hb - 1], rt = row[2];
+                double r[4];
+                if (RATIO) {
+                    r[0] = ((u0 + c1) + d0) + lf;
+                    r[1] = ((u1 + c2) + d1) + c0;
+                    r[2] = ((u2 + c3) + d2) + c1;
+                    r[3] = ((u3 + rt) + d3) + c2;
+                } else {
+                    const double g = c.gamma;
+                    r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
+                    r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
+                    r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
+                    r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
+                }
+                const double cc[4] = {c0, c1, c2, c3};
+                if (FAST) {
+                    // One basic block for all KT segments (no votes, no branches), so that the loads and the fp64
+                    // chains of different segments overlap.  Neighbour count n in {4, 3, 2} from the border bits;
+                    // s / n as q = s * fl(1/n) plus one fma residual step, which is the correctly rounded quotient
+                    // (Markstein; the identity behind div_small() of the tiled kernels; exact no-op for n = 4).
+                    const bool rowe = (e & kSegRowEdge) != 0u, lft = (e & kSegLeft) != 0u, rgt = (e & kSegRight) != 0u;
+                    const double third = 1.0 / 3.0;
+                    const double dm = rowe ? 3.0 : 4.0, im = rowe ? third : 0.25;
+                    const double dl = lft ? dm - 1.0 : dm, il = lft ? (rowe ? 0.5 : third) : im;
+                    const double dr = rgt ? dm - 1.0 : dm, ir = rgt ? (rowe ? 0.5 : third) : im;
+                    const double q0 = r[0] * il, q1 = r[1] * im, q2 = r[2] * im, q3 = r[3] * ir;
+                    r[0] = fma(fma(-dl, q0, r[0]), il, q0);
+                    r[1] = fma(fma(-dm, q1, r[1]), im, q1);
+                    r[2] = fma(fma(-dm, q2, r[2]), im, q2);
+                    r[3] = fma(fma(-dr, q3, r[3]), ir, q3);
+                    if (RATIO) {
+                        // fseg holds f for the unknown cells of a segment and 0 for the known ones
+                        double f[4];
+                        const double *fa = live ? c.fseg + 2 * i : c.zero4;
+                        const double *fb = live ? c.fseg + 2 * (c.fcap + i) : c.zero4 + 2;
+                        ld2(fa, f[0], f[1]); ld2(fb, f[2], f[3]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            s_abs = fma(f[j], fabs(r[j] - cc[j]), s_abs);   // |f r_new - f r_old|
+                            s_old = fma(f[j], cc[j], s_old);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool unk = (m >> j) & 1u;
+                            s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
+                            s_old += unk ? cc[j] : 0.0;
+                        }
                     }
                 } else {
+                    const bool edge = (e & kSegEdge) != 0;
+                    if (__any_sync(0xffffffffu, edge)) {
+                        if (edge) {                    // grid border: per-cell neighbour count, true division
+                            const int ly = off / c.SP, x0 = 2 * (off - ly * c.SP), gy = c.grid_row(ly);
+                            const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                            for (int j = 0; j < 4; ++j) {
+                                const int x = x0 + j;
+                                const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
+                                r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                    }
+                    if (RATIO) {
+                        double f[4];
+                        const int ic = min(i, c.fcap - 1);
+                        ld2(c.fseg + 2 * ic, f[0], f[1]); ld2(c.fseg + 2 * (c.fcap + ic), f[2], f[3]);
+                        if (i >= c.fcap) {
+                            const int ly = off / c.SP;
+                            const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + 2 * (off - ly * c.SP);
+                            ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
+                        }
+                        bool clipped = false;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) clipped |= ((m >> j) & 1u) && (f[j] * r[j] > c.clip);
+                        if (__any_sync(0xffffffffu, clipped)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (((m >> j) & 1u) && f[j] * r[j] > c.clip) r[j] = div_here(c.clip, f[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double fj = ((m >> j) & 1u) ? f[j] : 0.0;
+                            s_abs = fma(fj, fabs(r[j] - cc[j]), s_abs);
+                            s_old = fma(fj, cc[j], s_old);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool unk = (m >> j) & 1u;
+                            if (r[j] > c.clip) r[j] = c.clip;
+                            s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
+                            s_old += unk ? cc[j] : 0.0;
+                        }
+                    }
                 }
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                for (int j = 0; j < 4; ++j) nr[k][j] = ((m >> j) & 1u) ? r[j] : cc[j];
             }
-            const double cc[4] = {c0, c1, c2, c3};
-            double vn[4], vo[4];
-            if (RATIO) {
-                double f[4];
-                const double *fs = c.fseg + (size_t)min(i, c.fcap - 1) * 4;
-                ld2(fs, f[0], f[1]); ld2(fs + 2, f[2], f[3]);
-                if (i >= c.fcap) {
-                    const int ly = off / c.SP;
-                    const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + (off - ly * c.SP - kPadL);
-                    ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
-                }
-                bool clipped = false;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    vn[j] = f[j] * r[j];
-                    vo[j] = f[j] * cc[j];
-                    clipped |= ((m >> j) & 1u) && (vn[j] > c.clip);
-                }
-                if (__any_sync(0xffffffffu, clipped)) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (((m >> j) & 1u) && vn[j] > c.clip) { vn[j] = c.clip; r[j] = div_here(c.clip, f[j]); }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (r[j] > c.clip) r[j] = c.clip;
-                    vn[j] = r[j];
-                    vo[j] = cc[j];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool unk = (m >> j) & 1u;
-                s_abs += unk ? fabs(vn[j] - vo[j]) : 0.0;
-                s_old += unk ? vo[j] : 0.0;
-                nr[k][j] = unk ? r[j] : cc[j];
-            }
-        }
-        {
+            VPR_TR(2);
             const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
-            if (lane == 0) { sh.red[warp][0] = q0; sh.red[warp][1] = q1; }
-        }
-        if (t > 0 && warp == 0) {                  // (4) by one warp; the others pick the verdict up after (3)
+            if (lane == 0) { sh.red[par][warp][0] = q0; sh.red[par][warp][1] = q1; }
+            VPR_TR(3);
+        } else if (t > 0) {                        // (4) runs beside the workers' (2)
             const int v = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
-            if (lane == 0) sh.verdict = v;
+            if (lane == 0) sh.verdict[par] = v;
         }
+        VPR_TR(4);
         __syncthreads();                           // (3) every read of the old state is done; red[] / verdict complete
         if (t > 0) {
             ph_s ^= 1u << ((t - 1) % 3);
             fresh = false;
-            verdict = sh.verdict;
+            verdict = sh.verdict[par];
             if (verdict != 0) break;
         }
-        if (warp == 0) {                           // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
-            double v0 = (lane < kWarps) ? sh.red[lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[lane][1] : 0.0;
+        VPR_TR(5);
+        if (sync_warp) {                           // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
+            double v0 = (lane < kWarps) ? sh.red[par][lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[par][lane][1] : 0.0;
 #pragma unroll
-            for (int o = kWarps / 2; o > 0; o >>= 1) {
+            for (int o = 8; o > 0; o >>= 1) {
                 v0 += __shfl_down_sync(0xffffffffu, v0, o);
                 v1 += __shfl_down_sync(0xffffffffu, v1, o);
             }
@@ -337,54 +420,60 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
                 st_async2(map_rank(my_part + (uint32_t)(((slot * kMaxC) + crank) * 16), lane), v0, v1,
                           map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
             if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
-        }
-        const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
+            VPR_TR(6);
+        } else {
+            const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            const int i = c.tid + k * kThreads;
-            if (i <= last) {
-                const unsigned e = c.list[i];
-                const int off = (int)(e & 0xffffu);
-                double2 *row = reinterpret_cast<double2 *>(c.plane + off);
-                row[0] = make_double2(nr[k][0], nr[k][1]);
-                row[1] = make_double2(nr[k][2], nr[k][3]);
-                const int lb = (int)((e >> 25) & 7u);
-                if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
-                    const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
-                    st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
-                    st_async2(dst + 16u, nr[k][2], nr[k][3], c.up_bar[npar]);
-                }
-                if (e & kSegSendDn) {              // last row of my block = upper halo of the block below (CTA c+1)
-                    const uint32_t dst = c.dn_halo + (npo + (uint32_t)((lb + c.shift_dn) * c.SP + off - c.blk_bot[lb] * c.SP)) * 8u;
-                    st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
-                    st_async2(dst + 16u, nr[k][2], nr[k][3], c.dn_bar[npar]);
+            for (int k = 0; k < KT; ++k) {
+                const int i = c.tid + k * kThreads;
+                if (i <= last) {
+                    const unsigned e = c.list[i];
+                    const int off = (int)(e & 0xffffu);
+                    const int hb = c.half + 2;
+                    *reinterpret_cast<double2 *>(c.plane + off) = make_double2(nr[k][0], nr[k][1]);
+                    *reinterpret_cast<double2 *>(c.plane + off + hb) = make_double2(nr[k][2], nr[k][3]);
+                    const int lb = (int)((e >> 25) & 7u);
+                    if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
+                        const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
+                        st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
+                        st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.up_bar[npar]);
+                    }
+                    if (e & kSegSendDn) {              // last row of my block = upper halo of the block below (CTA c+1)
+                        const uint32_t dst = c.dn_halo + (npo + (uint32_t)((lb + c.shift_dn) * c.SP + off - c.bot_row(lb) * c.SP)) * 8u;
+                        st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
+                        st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.dn_bar[npar]);
+                    }
                 }
             }
+            VPR_TR(7);
+            __syncwarp();                          // the lanes' stores are ordered before lane 0's (release) arrival
+            if (c.tid == 0) mbar_arrive_tx(&sh.bar_h[npar], halo_bytes);
+            else if (lane == 0) mbar_arrive(&sh.bar_h[npar]);
+            VPR_TR(8);
         }
-        if (c.tid == 0) mbar_arrive_tx(&sh.bar_h[npar], halo_bytes);
-        else mbar_arrive(&sh.bar_h[npar]);
     }
     if (verdict == 0) {                            // ran to max_iter: close the last sweep
         const int par = T & 1;
-        mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
-        ph_h ^= 1u << par;
-        if (warp == 0) {
+        if (!sync_warp) {
+            mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+            ph_h ^= 1u << par;
+        } else {
             const int v = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
-            if (lane == 0) sh.verdict = v;
+            if (lane == 0) sh.verdict[par] = v;
         }
         __syncthreads();
         ph_s ^= 1u << ((T - 1) % 3);
-        verdict = (sh.verdict == 2) ? 2 : 0;       // stopping at the very last sweep changes nothing
+        verdict = (sh.verdict[par] == 2) ? 2 : 0;  // stopping at the very last sweep changes nothing
     }
     it_out = t;
     bailed_out = (verdict == 2);
 }
 
 template <bool RATIO>
-__global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kernel(const ResidentArgs a) {
+__global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d_kernel(const ResidentArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) SyncShared sh;
-    __shared__ int wcount[kWarps];
+    __shared__ int wcount[kAllWarps];
     __shared__ int next_problem;
 
     if (a.bad_flag && *a.bad_flag) return;             // grid-uniform: leave everything to the tiled path
@@ -397,8 +486,9 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
     const int BS = a.BS, LB = a.LB;
     const SmemLayout sm = carve(smem_raw, R, SP, LB, fcap);
     int *next_remote = cluster.map_shared_rank(&next_problem, 0);
+    if (tid < 4) sh.zero4[tid] = 0.0;
     if (tid == 0) {
-        mbar_init(&sh.bar_h[0], kThreads); mbar_init(&sh.bar_h[1], kThreads);
+        mbar_init(&sh.bar_h[0], kWarps); mbar_init(&sh.bar_h[1], kWarps);   // one arrival per warp
         mbar_init(&sh.bar_s[0], 1); mbar_init(&sh.bar_s[1], 1); mbar_init(&sh.bar_s[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -432,11 +522,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         const double gamma = RATIO ? 1.0 : a.gamma[p];
 
         // ---- stage the owned rows and both halo rows (r = P / f in RATIO form) ----------------
-        if (tid < LB) {
-            const int gb = tid * C + crank;
-            sh.blk_bot[tid] = tid * BS + ((gb < NB) ? min(BS, H - gb * BS) : BS) - 1;
-        }
-        for (int row = warp; row < n_rows + 2 * LB; row += kWarps) {
+        for (int row = warp; row < n_rows + 2 * LB; row += kAllWarps) {
             // rows 0 .. n_rows-1: owned rows; then for every block its upper and its lower halo row
             int gy;
             double *dst;
@@ -453,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
             const bool in_grid = (gy >= 0) && (gy < H);
             for (int lx = lane; lx < SP; lx += 32) {
                 double v = 0.0;
-                const int x = lx - kPadL;
+                const int x = slot_cell(lx, SP / 2);
                 if (in_grid && x >= 0 && x < W) {
                     v = grid[(size_t)gy * g.pitch + x];
                     if (RATIO) v = v / fp[(size_t)gy * g.pitch + x];
@@ -466,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         // ---- compact row-major list of the segments that hold an unknown cell ------------------
         // A mask word covers 8 segments (nibbles); warps take contiguous row chunks, so the list order
         // (and with it every partial sum) is fixed.
-        const int rows_per_warp = (n_rows + kWarps - 1) / kWarps;
+        const int rows_per_warp = (n_rows + kAllWarps - 1) / kAllWarps;
         const int wr0 = min(warp * rows_per_warp, n_rows), wr1 = min(wr0 + rows_per_warp, n_rows);
         auto nibbles = [](unsigned w) {                // bit 4q set <=> nibble q of w is nonzero
             unsigned t = w | (w >> 1);
@@ -480,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         if (lane == 0) wcount[warp] = cnt;
         __syncthreads();
         int base = 0, n = 0;
-        for (int w = 0; w < kWarps; ++w) {
+        for (int w = 0; w < kAllWarps; ++w) {
             if (w < warp) base += wcount[w];
             n += wcount[w];
         }
@@ -509,36 +595,40 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
                     nz &= nz - 1;
                     const int x0 = (w << 5) + b;       // first cell of the segment
                     const unsigned nib = (word >> b) & 15u;
-                    const bool edge = row_edge || x0 == 0 || (x0 + 3 >= W - 1);
-                    sm.list[pos++] = (unsigned)(ly * SP + x0 + kPadL) | (nib << 16) | row_flags | (edge ? kSegEdge : 0u);
+                    const bool left = (x0 == 0), right = (x0 + 3 >= W - 1);
+                    const bool edge = row_edge || left || right;
+                    sm.list[pos++] = (unsigned)(ly * SP + (x0 >> 1)) | (nib << 16) | row_flags | (edge ? kSegEdge : 0u) |
+                                     (left ? kSegLeft : 0u) | (right ? kSegRight : 0u) | (row_edge ? kSegRowEdge : 0u);
                 }
             }
         }
         __syncthreads();
         if (RATIO) {                                   // features of the listed segments (pad cells read 1.0)
-            for (int i = tid; i < min(n, fcap); i += kThreads) {
-                const int off = (int)(sm.list[i] & 0xffffu);
-                const int ly = off / SP, x0 = off - ly * SP - kPadL;
+            for (int i = tid; i < min(n, fcap); i += kLaunchThreads) {
+                const unsigned e = sm.list[i];
+                const int off = (int)(e & 0xffffu);
+                const int ly = off / SP, x0 = 2 * (off - ly * SP);
                 const double *fg = fp + (size_t)grid_row(ly) * g.pitch + x0;
                 double f0, f1, f2, f3;
                 ld2(fg, f0, f1); ld2(fg + 2, f2, f3);
-                double2 *d = reinterpret_cast<double2 *>(sm.fseg + (size_t)i * 4);
-                d[0] = make_double2(f0, f1); d[1] = make_double2(f2, f3);
+                // 0 for the known cells: they do not count
+                *reinterpret_cast<double2 *>(sm.fseg + 2 * i) = make_double2((e & (1u << 16)) ? f0 : 0.0, (e & (1u << 17)) ? f1 : 0.0);
+                *reinterpret_cast<double2 *>(sm.fseg + 2 * (fcap + i)) = make_double2((e & (1u << 18)) ? f2 : 0.0, (e & (1u << 19)) ? f3 : 0.0);
             }
         }
         const int Kmax = (n + kThreads - 1) / kThreads;    // CTA-uniform
         int kt = kMaxSeg;                                  // smallest unrolled variant >= Kmax
         {
-            const int kts[6] = {0, 1, 2, 3, 4, 6};
+            const int kts[7] = {0, 1, 2, 3, 4, 6, 8};
 #pragma unroll
-            for (int q = 5; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
+            for (int q = 6; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
         }
         // segments on the first / last owned row: what the neighbours must expect from this CTA per sweep
         if (tid < 2) sh.edge_cnt[tid] = 0;
         __syncthreads();
         {
             int n_top = 0, n_bot = 0;
-            for (int i = tid; i < n; i += kThreads) {
+            for (int i = tid; i < n; i += kLaunchThreads) {
                 const unsigned e = sm.list[i];
                 n_top += (e & kSegSendUp) ? 1 : 0;
                 n_bot += (e & kSegSendDn) ? 1 : 0;
@@ -568,8 +658,10 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         ctx.C = C; ctx.crank = crank; ctx.BS = BS; ctx.LB = LB;
         ctx.shift_up = (crank == 0) ? -1 : 0;       // block b-1 lives in CTA c-1 under the same local index, or one less after the wrap
         ctx.shift_dn = (crank == C - 1) ? 1 : 0;
-        ctx.blk_bot = sh.blk_bot;
-        ctx.SP = SP; ctx.fcap = fcap; ctx.pitch = g.pitch; ctx.tid = tid;
+        ctx.part_lb = -1; ctx.part_rows = BS;      // the partial block, if any, is the grid's last one
+        if ((H % BS) != 0 && ((NB - 1) % C) == crank) { ctx.part_lb = (NB - 1) / C; ctx.part_rows = H % BS; }
+        ctx.zero4 = sh.zero4;
+        ctx.SP = SP; ctx.half = SP / 2; ctx.fcap = fcap; ctx.pitch = g.pitch; ctx.tid = tid;
         ctx.n = n; ctx.H = H; ctx.W = W;
         ctx.gamma = gamma; ctx.clip = a.clip;
         const double *K0 = a.known0 + (size_t)p * kSumSlots, *K1 = a.known + (size_t)p * kSumSlots;
@@ -581,28 +673,43 @@ __global__ void __launch_bounds__(kThreads, kResidentCtasPerSm) resident2d_kerne
         int it = 0;
         bool bailed = false;
         const bool fresh = (st.fresh != 0);
+        // The fast sweep needs: no clip_val, every feature of the listed segments on chip, the grid's last column in
+        // the last cell of a segment, and at most one missing neighbour per direction pair (H >= 3, W >= 4).
+        // Each CTA decides for itself -- the protocol between the CTAs does not depend on it.
+        const bool fast = !(a.clip <= 1.7976931348623157e308) && (!RATIO || n <= fcap) && (W & 3) == 0 && H >= 3;
+#define VPR_RUN(KT_)                                                                                              \
+    do {                                                                                                          \
+        if (fast) run_sweeps<RATIO, KT_, true>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed);  \
+        else run_sweeps<RATIO, KT_, false>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed);      \
+    } while (0)
+#ifdef VPR_ONLY_KT
+        VPR_RUN(VPR_ONLY_KT);
+#else
         switch (kt) {
-            case 0: run_sweeps<RATIO, 0>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            case 1: run_sweeps<RATIO, 1>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            case 2: run_sweeps<RATIO, 2>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            case 3: run_sweeps<RATIO, 3>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            case 4: run_sweeps<RATIO, 4>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            case 6: run_sweeps<RATIO, 6>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
-            default: run_sweeps<RATIO, kMaxSeg>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed); break;
+            case 0: VPR_RUN(0); break;
+            case 1: VPR_RUN(1); break;
+            case 2: VPR_RUN(2); break;
+            case 3: VPR_RUN(3); break;
+            case 4: VPR_RUN(4); break;
+            case 6: VPR_RUN(6); break;
+            case 8: VPR_RUN(8); break;
+            default: VPR_RUN(kMaxSeg); break;
         }
+#endif
+#undef VPR_RUN
         __syncthreads();
 
         // ---- write the unknown cells back (P = f * r), close the problem ------------------------
-        for (int i = tid; i < n && !bailed; i += kThreads) {
+        for (int i = tid; i < n && !bailed; i += kLaunchThreads) {
             const unsigned e = sm.list[i];
             const int off = (int)(e & 0xffffu);
-            const int ly = off / SP, x0 = off - ly * SP - kPadL;
+            const int ly = off / SP, x0 = 2 * (off - ly * SP);
             const size_t go = (size_t)grid_row(ly) * g.pitch + x0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if ((e >> (16 + j)) & 1u) {
-                    double v = sm.plane[off + j];
-                    if (RATIO) v = ((i < fcap) ? sm.fseg[(size_t)i * 4 + j] : fp[go + j]) * v;
+                    double v = sm.plane[off + ((j < 2) ? j : SP / 2 + j)];
+                    if (RATIO) v = ((i < fcap) ? sm.fseg[2 * (((j < 2) ? 0 : fcap) + i) + (j & 1)] : fp[go + j]) * v;
                     grid[go + j] = v;
                 }
             }
@@ -625,7 +732,7 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out)
     if (g.ndim != 2 || g.H < 1 || g.L < 1 || (g.H < 2 && g.L < 2)) return false;   // 1x1: neighbour count 0
     const int W = g.L;
     const int segs_per_row = (W + 3) / 4;
-    const int SP = 4 * segs_per_row + 4;        // kPadL zero columns left, >= 2 right; even, so rows stay 16-byte aligned
+    const int SP = 4 * segs_per_row + 4;        // split-row layout: two halves of (segs_per_row + 1) pairs each
     if (g.pitch < 4 * segs_per_row) return false;
     const int static_bytes = 2048;              // SyncShared, wcount, next_problem (+ slack)
     for (int C = 1; C <= kMaxC; C *= 2) {
@@ -662,7 +769,7 @@ cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(kLaunchThreads, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -691,3 +798,9 @@ cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_
 }
 
 }  // namespace vpint
+
+#ifdef VPINT_RES_TRACE
+extern "C" int vpint_debug_trace(long long *host_out, int n_bytes) {
+    return (int)cudaMemcpyFromSymbol(host_out, vpint::g_trace, (size_t)n_bytes);
+}
+#endif
