@@ -243,163 +243,225 @@ __device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned p
 //               neighbours' halo row of the other parity with st.async (-> their bar_h), then arrive on
 //               the own bar_h of the other parity.
 // A NaN or inf anywhere poisons the partial sums, which is how data for the tiled path is detected.
+// Block barrier shared by the two roles below (the worker warps and the sync warp reach it from different code).
+__device__ __forceinline__ void role_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kLaunchThreads) : "memory");
+}
+
+// Worker warps: steps (1), (2), (3), (6) of every sweep.
 template <bool RATIO, int KT, bool FAST>
-__device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, const ResidentArgs &a, int p, int C, int crank,
-                                           bool fresh, const double *k0, const double *k1, double n_cells,
-                                           unsigned &ph_h, unsigned &ph_s, int &it_out, bool &bailed_out) {
+__device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh, int T, unsigned &ph_h, int &it_out,
+                                              bool &bailed_out) {
     const int lane = c.tid & 31, warp = c.tid >> 5;
-    const bool sync_warp = (warp == kWarps);       // no segments: decides sweep t-1 and publishes the partial of sweep t
     const int last = c.n - 1;
-    const int T = a.max_iter;
     const unsigned halo_bytes = (unsigned)((c.has_up ? sh.halo_exp[0] : 0) + (c.has_dn ? sh.halo_exp[1] : 0));
-    const uint32_t my_part = smem_u32(&sh.part[0][0][0]);
-    const uint32_t my_bar_s = smem_u32(&sh.bar_s[0]);
-    const bool writer = (crank == 0 && sync_warp && lane == 0);
     int t = 0, verdict = 0;
     for (; t < T; ++t) {
-        const int par = t & 1, npar = par ^ 1, slot = t % 3;
+        const int par = t & 1, npar = par ^ 1;
         VPR_TR(0);
+        if (t > 0) {
+            mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+            ph_h ^= 1u << par;
+        }
+        VPR_TR(1);
         double nr[KT > 0 ? KT : 1][4];
-        if (!sync_warp) {
-            if (t > 0) {
-                mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
-                ph_h ^= 1u << par;
+        double s_abs = 0.0, s_old = 0.0;
+        const double *halo_up = c.halo_up + par * c.LB * c.SP, *halo_dn = c.halo_dn + par * c.LB * c.SP;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int i0 = c.tid + k * kThreads;
+            const bool live = i0 <= last;
+            const int i = live ? i0 : last;
+            const unsigned e = c.list[i];
+            const int off = (int)(e & 0xffffu);
+            const unsigned m = live ? ((e >> 16) & 15u) : 0u;
+            const double *row = c.plane + off;
+            const int lb = (int)((e >> 25) & 7u);
+            const double *upp = (e & kSegTop) ? halo_up + (lb * c.SP + off - lb * c.BS * c.SP) : row - c.SP;
+            const double *dnp = (e & kSegBot) ? halo_dn + (lb * c.SP + off - c.bot_row(lb) * c.SP) : row + c.SP;
+            double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
+            const int hb = c.half + 2;             // second half of a segment
+            ld2(row, c0, c1); ld2(row + hb, c2, c3);
+            ld2(upp, u0, u1); ld2(upp + hb, u2, u3);
+            ld2(dnp, d0, d1); ld2(dnp + hb, d2, d3);
+            const double lf = row[hb - 1], rt = row[2];
+            double r[4];
+            if (RATIO) {
+                r[0] = ((u0 + c1) + d0) + lf;
+                r[1] = ((u1 + c2) + d1) + c0;
+                r[2] = ((u2 + c3) + d2) + c1;
+                r[3] = ((u3 + rt) + d3) + c2;
+            } else {
+                const double g = c.gamma;
+                r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
+                r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
+                r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
+                r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
             }
-            VPR_TR(1);
-            double s_abs = 0.0, s_old = 0.0;
-            const double *halo_up = c.halo_up + par * c.LB * c.SP, *halo_dn = c.halo_dn + par * c.LB * c.SP;
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                const int i0 = c.tid + k * kThreads;
-                const bool live = i0 <= last;
-                const int i = live ? i0 : last;
-                const unsigned e = c.list[i];
-                const int off = (int)(e & 0xffffu);
-                const unsigned m = live ? ((e >> 16) & 15u) : 0u;
-                const double *row = c.plane + off;
-                const int lb = (int)((e >> 25) & 7u);
-                const double *upp = (e & kSegTop) ? halo_up + (lb * c.SP + off - lb * c.BS * c.SP) : row - c.SP;
-                const double *dnp = (e & kSegBot) ? halo_dn + (lb * c.SP + off - c.bot_row(lb) * c.SP) : row + c.SP;
-                double c0, c1, c2, c3, u0, u1, u2, u3, d0, d1, d2, d3;
-                const int hb = c.half + 2;             // second half of a segment
-                ld2(row, c0, c1); ld2(row + hb, c2, c3);
-                ld2(upp, u0, u1); ld2(upp + hb, u2, u3);
-                ld2(dnp, d0, d1); ld2(dnp + hb, d2, d3);
-                const double lf = row[hb - 1], rt = row[2];
-                double r[4];
+            const double cc[4] = {c0, c1, c2, c3};
+            if (FAST) {
+                // One basic block for all KT segments (no votes, no branches), so that the loads and the fp64
+                // chains of different segments overlap.  Neighbour count n in {4, 3, 2} from the border bits;
+                // s / n as q = s * fl(1/n) plus one fma residual step, which is the correctly rounded quotient
+                // (Markstein; the identity behind div_small() of the tiled kernels; exact no-op for n = 4).
+                const bool rowe = (e & kSegRowEdge) != 0u, lft = (e & kSegLeft) != 0u, rgt = (e & kSegRight) != 0u;
+                const double third = 1.0 / 3.0;
+                const double dm = rowe ? 3.0 : 4.0, im = rowe ? third : 0.25;
+                const double dl = lft ? dm - 1.0 : dm, il = lft ? (rowe ? 0.5 : third) : im;
+                const double dr = rgt ? dm - 1.0 : dm, ir = rgt ? (rowe ? 0.5 : third) : im;
+                const double q0 = r[0] * il, q1 = r[1] * im, q2 = r[2] * im, q3 = r[3] * ir;
+                r[0] = fma(fma(-dl, q0, r[0]), il, q0);
+                r[1] = fma(fma(-dm, q1, r[1]), im, q1);
+                r[2] = fma(fma(-dm, q2, r[2]), im, q2);
+                r[3] = fma(fma(-dr, q3, r[3]), ir, q3);
                 if (RATIO) {
-                    r[0] = ((u0 + c1) + d0) + lf;
-                    r[1] = ((u1 + c2) + d1) + c0;
-                    r[2] = ((u2 + c3) + d2) + c1;
-                    r[3] = ((u3 + rt) + d3) + c2;
-                } else {
-                    const double g = c.gamma;
-                    r[0] = fma(lf, g, fma(d0, g, fma(c1, g, u0 * g)));
-                    r[1] = fma(c0, g, fma(d1, g, fma(c2, g, u1 * g)));
-                    r[2] = fma(c1, g, fma(d2, g, fma(c3, g, u2 * g)));
-                    r[3] = fma(c2, g, fma(d3, g, fma(rt, g, u3 * g)));
-                }
-                const double cc[4] = {c0, c1, c2, c3};
-                if (FAST) {
-                    // One basic block for all KT segments (no votes, no branches), so that the loads and the fp64
-                    // chains of different segments overlap.  Neighbour count n in {4, 3, 2} from the border bits;
-                    // s / n as q = s * fl(1/n) plus one fma residual step, which is the correctly rounded quotient
-                    // (Markstein; the identity behind div_small() of the tiled kernels; exact no-op for n = 4).
-                    const bool rowe = (e & kSegRowEdge) != 0u, lft = (e & kSegLeft) != 0u, rgt = (e & kSegRight) != 0u;
-                    const double third = 1.0 / 3.0;
-                    const double dm = rowe ? 3.0 : 4.0, im = rowe ? third : 0.25;
-                    const double dl = lft ? dm - 1.0 : dm, il = lft ? (rowe ? 0.5 : third) : im;
-                    const double dr = rgt ? dm - 1.0 : dm, ir = rgt ? (rowe ? 0.5 : third) : im;
-                    const double q0 = r[0] * il, q1 = r[1] * im, q2 = r[2] * im, q3 = r[3] * ir;
-                    r[0] = fma(fma(-dl, q0, r[0]), il, q0);
-                    r[1] = fma(fma(-dm, q1, r[1]), im, q1);
-                    r[2] = fma(fma(-dm, q2, r[2]), im, q2);
-                    r[3] = fma(fma(-dr, q3, r[3]), ir, q3);
-                    if (RATIO) {
-                        // fseg holds f for the unknown cells of a segment and 0 for the known ones
-                        double f[4];
-                        const double *fa = live ? c.fseg + 2 * i : c.zero4;
-                        const double *fb = live ? c.fseg + 2 * (c.fcap + i) : c.zero4 + 2;
-                        ld2(fa, f[0], f[1]); ld2(fb, f[2], f[3]);
+                    // fseg holds f for the unknown cells of a segment and 0 for the known ones
+                    double f[4];
+                    const double *fa = live ? c.fseg + 2 * i : c.zero4;
+                    const double *fb = live ? c.fseg + 2 * (c.fcap + i) : c.zero4 + 2;
+                    ld2(fa, f[0], f[1]); ld2(fb, f[2], f[3]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            s_abs = fma(f[j], fabs(r[j] - cc[j]), s_abs);   // |f r_new - f r_old|
-                            s_old = fma(f[j], cc[j], s_old);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const bool unk = (m >> j) & 1u;
-                            s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
-                            s_old += unk ? cc[j] : 0.0;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        s_abs = fma(f[j], fabs(r[j] - cc[j]), s_abs);   // |f r_new - f r_old|
+                        s_old = fma(f[j], cc[j], s_old);
                     }
                 } else {
-                    const bool edge = (e & kSegEdge) != 0;
-                    if (__any_sync(0xffffffffu, edge)) {
-                        if (edge) {                    // grid border: per-cell neighbour count, true division
-                            const int ly = off / c.SP, x0 = 2 * (off - ly * c.SP), gy = c.grid_row(ly);
-                            const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int x = x0 + j;
-                                const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
-                                r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
-                            }
-                        } else {
+                    for (int j = 0; j < 4; ++j) {
+                        const bool unk = (m >> j) & 1u;
+                        s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
+                        s_old += unk ? cc[j] : 0.0;
+                    }
+                }
+            } else {
+                const bool edge = (e & kSegEdge) != 0;
+                if (__any_sync(0xffffffffu, edge)) {
+                    if (edge) {                    // grid border: per-cell neighbour count, true division
+                        const int ly = off / c.SP, x0 = 2 * (off - ly * c.SP), gy = c.grid_row(ly);
+                        const int ncy = 4 - (gy == 0 ? 1 : 0) - (gy == c.H - 1 ? 1 : 0);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                        for (int j = 0; j < 4; ++j) {
+                            const int x = x0 + j;
+                            const int nc = ncy - (x == 0 ? 1 : 0) - (x == c.W - 1 ? 1 : 0);
+                            r[j] = (nc == 4) ? r[j] * 0.25 : div_here(r[j], (double)nc);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) r[j] *= 0.25;
                     }
-                    if (RATIO) {
-                        double f[4];
-                        const int ic = min(i, c.fcap - 1);
-                        ld2(c.fseg + 2 * ic, f[0], f[1]); ld2(c.fseg + 2 * (c.fcap + ic), f[2], f[3]);
-                        if (i >= c.fcap) {
-                            const int ly = off / c.SP;
-                            const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + 2 * (off - ly * c.SP);
-                            ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
-                        }
-                        bool clipped = false;
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) clipped |= ((m >> j) & 1u) && (f[j] * r[j] > c.clip);
-                        if (__any_sync(0xffffffffu, clipped)) {
+                    for (int j = 0; j < 4; ++j) r[j] *= 0.25;
+                }
+                if (RATIO) {
+                    double f[4];
+                    const int ic = min(i, c.fcap - 1);
+                    ld2(c.fseg + 2 * ic, f[0], f[1]); ld2(c.fseg + 2 * (c.fcap + ic), f[2], f[3]);
+                    if (i >= c.fcap) {
+                        const int ly = off / c.SP;
+                        const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + 2 * (off - ly * c.SP);
+                        ld2(fg, f[0], f[1]); ld2(fg + 2, f[2], f[3]);
+                    }
+                    bool clipped = false;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (((m >> j) & 1u) && f[j] * r[j] > c.clip) r[j] = div_here(c.clip, f[j]);
-                        }
+                    for (int j = 0; j < 4; ++j) clipped |= ((m >> j) & 1u) && (f[j] * r[j] > c.clip);
+                    if (__any_sync(0xffffffffu, clipped)) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const double fj = ((m >> j) & 1u) ? f[j] : 0.0;
-                            s_abs = fma(fj, fabs(r[j] - cc[j]), s_abs);
-                            s_old = fma(fj, cc[j], s_old);
-                        }
-                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (((m >> j) & 1u) && f[j] * r[j] > c.clip) r[j] = div_here(c.clip, f[j]);
+                    }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const bool unk = (m >> j) & 1u;
-                            if (r[j] > c.clip) r[j] = c.clip;
-                            s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
-                            s_old += unk ? cc[j] : 0.0;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const double fj = ((m >> j) & 1u) ? f[j] : 0.0;
+                        s_abs = fma(fj, fabs(r[j] - cc[j]), s_abs);
+                        s_old = fma(fj, cc[j], s_old);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool unk = (m >> j) & 1u;
+                        if (r[j] > c.clip) r[j] = c.clip;
+                        s_abs += unk ? fabs(r[j] - cc[j]) : 0.0;
+                        s_old += unk ? cc[j] : 0.0;
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) nr[k][j] = ((m >> j) & 1u) ? r[j] : cc[j];
             }
-            VPR_TR(2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nr[k][j] = ((m >> j) & 1u) ? r[j] : cc[j];
+        }
+        VPR_TR(2);
+        {
             const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
             if (lane == 0) { sh.red[par][warp][0] = q0; sh.red[par][warp][1] = q1; }
-            VPR_TR(3);
-        } else if (t > 0) {                        // (4) runs beside the workers' (2)
+        }
+        VPR_TR(3);
+        role_barrier();                            // (3) every read of the old state is done; red[] / verdict complete
+        if (t > 0) {
+            verdict = sh.verdict[par];
+            if (verdict != 0) break;
+        }
+        VPR_TR(5);
+        const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int i = c.tid + k * kThreads;
+            if (i <= last) {
+                const unsigned e = c.list[i];
+                const int off = (int)(e & 0xffffu);
+                const int hb = c.half + 2;
+                *reinterpret_cast<double2 *>(c.plane + off) = make_double2(nr[k][0], nr[k][1]);
+                *reinterpret_cast<double2 *>(c.plane + off + hb) = make_double2(nr[k][2], nr[k][3]);
+                const int lb = (int)((e >> 25) & 7u);
+                if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
+                    const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
+                    st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
+                    st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.up_bar[npar]);
+                }
+                if (e & kSegSendDn) {              // last row of my block = upper halo of the block below (CTA c+1)
+                    const uint32_t dst = c.dn_halo + (npo + (uint32_t)((lb + c.shift_dn) * c.SP + off - c.bot_row(lb) * c.SP)) * 8u;
+                    st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
+                    st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.dn_bar[npar]);
+                }
+            }
+        }
+        VPR_TR(7);
+        __syncwarp();                              // the lanes' stores are ordered before lane 0's (release) arrival
+        if (c.tid == 0) mbar_arrive_tx(&sh.bar_h[npar], halo_bytes);
+        else if (lane == 0) mbar_arrive(&sh.bar_h[npar]);
+        VPR_TR(8);
+    }
+    if (verdict == 0) {                            // ran to max_iter: close the last sweep
+        const int par = T & 1;
+        mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
+        ph_h ^= 1u << par;
+        role_barrier();
+        verdict = (sh.verdict[par] == 2) ? 2 : 0;  // stopping at the very last sweep changes nothing
+    }
+    it_out = t;
+    bailed_out = (verdict == 2);
+}
+
+// Sync warp: steps (4), (3), (5) of every sweep.
+__device__ __forceinline__ void sync_sweeps(int tid, SyncShared &sh, const ResidentArgs &a, int p, int C, int crank, bool fresh,
+                                            const double *k0, const double *k1, double n_cells, unsigned &ph_s, int &it_out,
+                                            bool &bailed_out) {
+    const int lane = tid & 31;
+    const int T = a.max_iter;
+    const uint32_t my_part = smem_u32(&sh.part[0][0][0]);
+    const uint32_t my_bar_s = smem_u32(&sh.bar_s[0]);
+    const bool writer = (crank == 0 && lane == 0);
+    struct { int tid; } c = {tid};                 // for VPR_TR
+    (void)c;
+    int t = 0, verdict = 0;
+    for (; t < T; ++t) {
+        const int par = t & 1, slot = t % 3;
+        VPR_TR(0);
+        if (t > 0) {                               // (4) runs beside the workers' (2)
             const int v = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
             if (lane == 0) sh.verdict[par] = v;
         }
         VPR_TR(4);
-        __syncthreads();                           // (3) every read of the old state is done; red[] / verdict complete
+        role_barrier();
         if (t > 0) {
             ph_s ^= 1u << ((t - 1) % 3);
             fresh = false;
@@ -407,63 +469,28 @@ __device__ __forceinline__ void run_sweeps(const SweepCtx &c, SyncShared &sh, co
             if (verdict != 0) break;
         }
         VPR_TR(5);
-        if (sync_warp) {                           // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
-            double v0 = (lane < kWarps) ? sh.red[par][lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[par][lane][1] : 0.0;
+        // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
+        double v0 = (lane < kWarps) ? sh.red[par][lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[par][lane][1] : 0.0;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                v0 += __shfl_down_sync(0xffffffffu, v0, o);
-                v1 += __shfl_down_sync(0xffffffffu, v1, o);
-            }
-            v0 = __shfl_sync(0xffffffffu, v0, 0);
-            v1 = __shfl_sync(0xffffffffu, v1, 0);
-            if (lane < C)
-                st_async2(map_rank(my_part + (uint32_t)(((slot * kMaxC) + crank) * 16), lane), v0, v1,
-                          map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
-            if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
-            VPR_TR(6);
-        } else {
-            const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                const int i = c.tid + k * kThreads;
-                if (i <= last) {
-                    const unsigned e = c.list[i];
-                    const int off = (int)(e & 0xffffu);
-                    const int hb = c.half + 2;
-                    *reinterpret_cast<double2 *>(c.plane + off) = make_double2(nr[k][0], nr[k][1]);
-                    *reinterpret_cast<double2 *>(c.plane + off + hb) = make_double2(nr[k][2], nr[k][3]);
-                    const int lb = (int)((e >> 25) & 7u);
-                    if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
-                        const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
-                        st_async2(dst, nr[k][0], nr[k][1], c.up_bar[npar]);
-                        st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.up_bar[npar]);
-                    }
-                    if (e & kSegSendDn) {              // last row of my block = upper halo of the block below (CTA c+1)
-                        const uint32_t dst = c.dn_halo + (npo + (uint32_t)((lb + c.shift_dn) * c.SP + off - c.bot_row(lb) * c.SP)) * 8u;
-                        st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
-                        st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.dn_bar[npar]);
-                    }
-                }
-            }
-            VPR_TR(7);
-            __syncwarp();                          // the lanes' stores are ordered before lane 0's (release) arrival
-            if (c.tid == 0) mbar_arrive_tx(&sh.bar_h[npar], halo_bytes);
-            else if (lane == 0) mbar_arrive(&sh.bar_h[npar]);
-            VPR_TR(8);
+        for (int o = 8; o > 0; o >>= 1) {
+            v0 += __shfl_down_sync(0xffffffffu, v0, o);
+            v1 += __shfl_down_sync(0xffffffffu, v1, o);
         }
+        v0 = __shfl_sync(0xffffffffu, v0, 0);
+        v1 = __shfl_sync(0xffffffffu, v1, 0);
+        if (lane < C)
+            st_async2(map_rank(my_part + (uint32_t)(((slot * kMaxC) + crank) * 16), lane), v0, v1,
+                      map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
+        if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
+        VPR_TR(6);
     }
     if (verdict == 0) {                            // ran to max_iter: close the last sweep
         const int par = T & 1;
-        if (!sync_warp) {
-            mbar_wait(&sh.bar_h[par], (ph_h >> par) & 1u);
-            ph_h ^= 1u << par;
-        } else {
-            const int v = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
-            if (lane == 0) sh.verdict[par] = v;
-        }
-        __syncthreads();
+        const int v = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
+        if (lane == 0) sh.verdict[par] = v;
+        role_barrier();
         ph_s ^= 1u << ((T - 1) % 3);
-        verdict = (sh.verdict[par] == 2) ? 2 : 0;  // stopping at the very last sweep changes nothing
+        verdict = (sh.verdict[par] == 2) ? 2 : 0;
     }
     it_out = t;
     bailed_out = (verdict == 2);
@@ -677,25 +704,29 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         // the last cell of a segment, and at most one missing neighbour per direction pair (H >= 3, W >= 4).
         // Each CTA decides for itself -- the protocol between the CTAs does not depend on it.
         const bool fast = !(a.clip <= 1.7976931348623157e308) && (!RATIO || n <= fcap) && (W & 3) == 0 && H >= 3;
-#define VPR_RUN(KT_)                                                                                              \
-    do {                                                                                                          \
-        if (fast) run_sweeps<RATIO, KT_, true>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed);  \
-        else run_sweeps<RATIO, KT_, false>(ctx, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_h, ph_s, it, bailed);      \
+#define VPR_RUN(KT_)                                                                          \
+    do {                                                                                      \
+        if (fast) worker_sweeps<RATIO, KT_, true>(ctx, sh, a.max_iter, ph_h, it, bailed);     \
+        else worker_sweeps<RATIO, KT_, false>(ctx, sh, a.max_iter, ph_h, it, bailed);         \
     } while (0)
+        if (warp == kWarps) {
+            sync_sweeps(tid, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_s, it, bailed);
+        } else {
 #ifdef VPR_ONLY_KT
-        VPR_RUN(VPR_ONLY_KT);
+            VPR_RUN(VPR_ONLY_KT);
 #else
-        switch (kt) {
-            case 0: VPR_RUN(0); break;
-            case 1: VPR_RUN(1); break;
-            case 2: VPR_RUN(2); break;
-            case 3: VPR_RUN(3); break;
-            case 4: VPR_RUN(4); break;
-            case 6: VPR_RUN(6); break;
-            case 8: VPR_RUN(8); break;
-            default: VPR_RUN(kMaxSeg); break;
-        }
+            switch (kt) {
+                case 0: VPR_RUN(0); break;
+                case 1: VPR_RUN(1); break;
+                case 2: VPR_RUN(2); break;
+                case 3: VPR_RUN(3); break;
+                case 4: VPR_RUN(4); break;
+                case 6: VPR_RUN(6); break;
+                case 8: VPR_RUN(8); break;
+                default: VPR_RUN(kMaxSeg); break;
+            }
 #endif
+        }
 #undef VPR_RUN
         __syncthreads();
 
