@@ -239,6 +239,25 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def bind_to_gpu_node(index, pci=None):
+    """Pin this process (and the threads it starts later) to the CPUs NVML reports as local to GPU `index`, so that
+    the pinned host buffers of the e2e leg are allocated on the GPU's NUMA node.  Without it the e2e number depends
+    on which socket the scheduler happens to pick (PCIe traffic across the socket link runs at half speed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(pci.encode()) if pci else pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs local to GPU %d" % (len(cpus), index)
+    except Exception as exc:                      # NVML missing or affinity not permitted: run unbound
+        return "unbound (%s)" % type(exc).__name__
+    return "unbound"
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -251,6 +270,12 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        pci = None
+    affinity = bind_to_gpu_node(local, pci)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -403,7 +428,8 @@ def run_gpu(args):
                                   "streams state and weights from HBM every launch")},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(t_host.numel() * 4 + f_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 8 + nprob * 4), "steps": e2e_steps,
-                    "ms_per_step": ms_e2e / e2e_steps, "api": "vpint_b200.vpint2.solve_bands (VPint2 run path), pinned host buffers"},
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "vpint_b200.vpint2.solve_bands (VPint2 run path), pinned host buffers",
+                    "cpu_affinity": affinity},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

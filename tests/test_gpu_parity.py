@@ -438,6 +438,35 @@ def test_device_mean_init_is_numpy_nanmean(shape, dtype):
         assert np.array_equal(got[b][~np.isnan(band)], band[~np.isnan(band)].astype(np.float64))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_mean_init_band_interleaved_stack(dtype):
+    """The band-interleaved fast paths (13 bands, several patches, H * W a power of two): same bit-for-bit
+    np.nanmean per band, known cells copied unchanged."""
+    import torch
+    rng = np.random.default_rng(77)
+    N, H, W, B = 3, 64, 128, 13
+    stack = np.round(rng.uniform(0, 9000, (N, H, W, B))).astype(dtype)
+    for i in range(N):
+        stack[i, rng.uniform(size=(H, W)) < 0.1 + 0.3 * i, :] = np.nan
+    stack[:, 0, 0, :] = np.nan
+    stack[:, -1, -1, :] = 4321.0
+    s = Solver(2, N * B, H, W, nprob_inner=B, planes=False)
+    try:
+        t = torch.from_numpy(stack).cuda()
+        s.load(t.permute(0, 3, 1, 2), fill=None)
+        out, _ = s.result()
+        got = out.cpu().numpy().reshape(N, B, H, W)
+    finally:
+        s.close()
+    for i in range(N):
+        for b in range(B):
+            band = stack[i, :, :, b]
+            want = np.nanmean(band.copy())
+            filled = got[i, b][np.isnan(band)]
+            assert filled.size > 0 and (filled == np.float64(want)).all(), (i, b, filled[0], want)
+            assert np.array_equal(got[i, b][~np.isnan(band)], band[~np.isnan(band)].astype(np.float64))
+
+
 def test_pipelined_host_stack_equals_single_solve():
     import torch
     from vpint_b200.vpint2 import _solve_bands_torch

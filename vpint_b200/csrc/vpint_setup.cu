@@ -142,6 +142,78 @@ __global__ void __launch_bounds__(256) fill_mean_kernel(Geom g, const TIn *__res
     }
 }
 
+// The same mean for a band-interleaved stack (N, H, W, B) with B fastest -- VPint2's layout -- and H * W a power of
+// two: one block per patch takes all B bands at once.  A leaf of the summation tree is 128 consecutive cells of a
+// band, i.e. a contiguous run of 128 * B values; a warp stages that run with coalesced loads and then sums it per
+// band the way NumPy does (8 lanes = the 8 accumulators).  With n = 2^k the tree above the leaves is balanced, so
+// the leaf sums are combined level by level in parallel.  (The general kernel reads every band with a stride of B
+// elements and walks the tree on one thread.)
+constexpr int kFillBandsMax = 16;
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) fill_mean_bands_kernel(Geom g, const TIn *__restrict__ original, int64_t sO,
+                                                              double *__restrict__ fill) {
+    extern __shared__ __align__(16) unsigned char fill_raw[];
+    __shared__ int cnt_s[kFillBandsMax];
+    const int B = g.Pin;
+    const int n = g.H * g.L, NL = n / 128, run = 128 * B;
+    TIn *stage = reinterpret_cast<TIn *>(fill_raw);            // [8 warps][128 * B]
+    TIn *leaf = stage + 8 * run;                               // [B][NL]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane >> 3, j = lane & 7;
+    const TIn *base = original + (int64_t)blockIdx.x * sO;
+    if (tid < kFillBandsMax) cnt_s[tid] = 0;
+    __syncthreads();
+    int cnt[kFillBandsMax / 4] = {0, 0, 0, 0};
+    TIn *my = stage + warp * run;
+    for (int l = warp; l < NL; l += 8) {
+        const TIn *src = base + (int64_t)l * run;
+        for (int k = lane; k < run; k += 32) my[k] = src[k];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kFillBandsMax / 4; ++q) {
+            if (q * 4 < B) {                                   // warp-uniform
+                const int b = q * 4 + sub;
+                const bool live = b < B;
+                TIn r = (TIn)0;
+                if (live) {
+                    const TIn *col = my + j * B + b;
+                    TIn v = col[0];
+                    cnt[q] += (v == v) ? 1 : 0;
+                    r = (v != v) ? (TIn)0 : v;
+                    for (int i = 8; i < 128; i += 8) {
+                        v = col[i * B];
+                        cnt[q] += (v == v) ? 1 : 0;
+                        r += (v != v) ? (TIn)0 : v;
+                    }
+                }
+                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) within each group of 8 lanes
+                const TIn a = r + __shfl_down_sync(0xffffffffu, r, 1, 8);
+                const TIn c = a + __shfl_down_sync(0xffffffffu, a, 2, 8);
+                const TIn d = c + __shfl_down_sync(0xffffffffu, c, 4, 8);
+                if (live && j == 0) leaf[b * NL + l] = d;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < kFillBandsMax / 4; ++q)
+        if (q * 4 + sub < B && cnt[q]) atomicAdd(&cnt_s[q * 4 + sub], cnt[q]);
+    __syncthreads();
+    for (int st = 1; st < NL; st <<= 1) {                      // node = left + right, level by level
+        const int pairs = NL / (2 * st);
+        for (int idx = tid; idx < B * pairs; idx += blockDim.x) {
+            const int b = idx / pairs, i = (idx - b * pairs) * 2 * st;
+            leaf[b * NL + i] = leaf[b * NL + i] + leaf[b * NL + i + st];
+        }
+        __syncthreads();
+    }
+    if (tid < B) {
+        const TIn total_sum = (TIn)0 + leaf[tid * NL];          // add.reduce starts from the identity
+        fill[(size_t)blockIdx.x * B + tid] = (double)(TIn)((double)total_sum / (double)cnt_s[tid]);
+    }
+}
+
 // One block per (problem, row).  Stages the start state of run():
 //   bufA = pred0 (self.pred_grid, VPint/MRP.py:64-91 or whatever the caller left there),
 //   bufB = original at known cells (the restore of VPint/SD_MRP.py:133-134 / WP_MRP.py:321,323 is
@@ -203,6 +275,73 @@ __global__ void __launch_bounds__(256) prepare_kernel(Geom g, const TIn *__restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) rowpart[(size_t)blockIdx.x * 8 + i] = acc[i];
     }
+}
+
+// prepare_kernel for a band-interleaved stack (B fastest, no pred0): one warp per (patch, row) stages the row of all
+// B bands with coalesced loads and then writes every band's plane row.  The general kernel reads each band with a
+// stride of B elements and pays a block-wide reduction of 8 values per 256 cells; here the known-cell terms shrink
+// to {sum orig, #inf, #unknown} because pred0 equals orig on every known cell.
+constexpr int kPrepWarps = 4;
+
+template <typename TIn, typename TSt>
+__global__ void __launch_bounds__(kPrepWarps * 32) prepare_bands_kernel(Geom g, const TIn *__restrict__ original,
+                                                                        const double *__restrict__ fill, Strides sd,
+                                                                        TSt *__restrict__ bufA, TSt *__restrict__ bufB,
+                                                                        TSt *__restrict__ orig_copy, uint32_t *__restrict__ mask,
+                                                                        double *__restrict__ rowpart, double *__restrict__ extreme) {
+    extern __shared__ __align__(16) unsigned char prep_raw[];
+    const int B = g.Pin, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kPrepWarps + warp;          // (patch, row)
+    const int64_t n_rows = (int64_t)(g.P / B) * g.H;
+    if (r >= n_rows) return;
+    const int po = (int)(r / g.H), y = (int)(r - (int64_t)po * g.H);
+    TIn *my = reinterpret_cast<TIn *>(prep_raw) + (size_t)warp * g.L * B;
+    const TIn *src = original + (int64_t)po * sd.sO + (int64_t)y * sd.sY;
+    for (int k = lane; k < g.L * B; k += 32) my[k] = src[k];
+    __syncwarp();
+    const bool owned = (y >= g.own_row0) && (y < g.own_row0 + g.own_rows);
+    bool wild = false;
+    for (int b = 0; b < B; ++b) {
+        const int p = po * B + b;
+        const size_t row = ((size_t)p * g.H + y) * g.pitch;
+        const size_t mrow = ((size_t)p * g.H + y) * g.mpitch;
+        const double fillv = fill[p];
+        double sum_o = 0.0;
+        int counts = 0;                                                 // #inf << 16 | #unknown
+        for (int e = lane; e < g.pitch; e += 32) {
+            bool unknown = false;
+            TSt va = (TSt)0, vb = (TSt)0;
+            if (e < g.L) {
+                const double o = (double)my[e * B + b];
+                unknown = (o != o);
+                const double v0 = unknown ? fillv : o;
+                va = (TSt)v0;
+                vb = va;
+                if (!(fabs(v0) < 1e150)) wild = true;
+                if (owned) {
+                    if (unknown) counts += 1;
+                    else {
+                        const double os = (double)vb;
+                        sum_o += os;
+                        if (isinf(os)) counts += 1 << 16;
+                    }
+                }
+            }
+            bufA[row + e] = va;
+            bufB[row + e] = vb;
+            if (orig_copy) orig_copy[row + e] = vb;
+            const unsigned word = __ballot_sync(0xffffffffu, unknown);
+            if (lane == 0) mask[mrow + (e >> 5)] = word;
+        }
+        sum_o = warp_sum(sum_o);
+        counts = warp_sum(counts);
+        if (lane == 0) {
+            double *rp = rowpart + ((size_t)p * g.H + y) * 8;
+            rp[0] = 0.0; rp[1] = sum_o; rp[2] = 0.0; rp[3] = 0.0;
+            rp[4] = sum_o; rp[5] = (double)(counts >> 16); rp[6] = 0.0; rp[7] = (double)(counts & 0xffff);
+        }
+    }
+    if (__any_sync(0xffffffffu, wild) && lane == 0) atomicAdd(extreme, 1.0);
 }
 
 // One block per problem: fixed-order reduction of the row partials.
@@ -521,6 +660,24 @@ bool fill_mean_supported(const Geom &g) { return g.ndim == 2 && (int64_t)g.H * g
 cudaError_t launch_fill_mean(const Geom &g, const void *original, int dtype, const int64_t *stride, double *fill_dev,
                              cudaStream_t st, int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
+    const int64_t n = (int64_t)g.H * g.L;
+    const size_t esz = (dtype == VPINT_F64) ? 8 : 4;
+    const size_t bands_smem = ((size_t)8 * 128 * g.Pin + (size_t)g.Pin * (n / 128)) * esz;
+    if (g.ndim == 2 && g.Pin >= 2 && g.Pin <= kFillBandsMax && sd.sI == 1 && sd.sX == g.Pin && sd.sY == (int64_t)g.L * g.Pin &&
+        n >= 128 && (n & (n - 1)) == 0 && bands_smem <= 200 * 1024) {
+        cudaError_t e;
+        if (dtype == VPINT_F64) {
+            e = cudaFuncSetAttribute(fill_mean_bands_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bands_smem);
+            if (e != cudaSuccess) return e;
+            fill_mean_bands_kernel<double><<<g.P / g.Pin, 256, bands_smem, st>>>(g, (const double *)original, sd.sO, fill_dev);
+        } else {
+            e = cudaFuncSetAttribute(fill_mean_bands_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bands_smem);
+            if (e != cudaSuccess) return e;
+            fill_mean_bands_kernel<float><<<g.P / g.Pin, 256, bands_smem, st>>>(g, (const float *)original, sd.sO, fill_dev);
+        }
+        VP_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     if (dtype == VPINT_F64) fill_mean_kernel<double><<<g.P, 256, 0, st>>>(g, (const double *)original, sd, fill_dev);
     else fill_mean_kernel<float><<<g.P, 256, 0, st>>>(g, (const float *)original, sd, fill_dev);
     VP_LAUNCH_CHECK();
@@ -533,6 +690,29 @@ cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred
                            ProbState *state, int *counters, cudaStream_t st, int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
     const unsigned grid = (unsigned)((int64_t)g.P * g.S * g.H);
+    const size_t esz = (dtype == VPINT_F64) ? 8 : 4;
+    const size_t bands_smem = (size_t)kPrepWarps * g.L * g.Pin * esz;
+    if (g.ndim == 2 && !pred0 && g.Pin >= 2 && sd.sI == 1 && sd.sX == g.Pin && g.L <= 32768 && bands_smem <= 100 * 1024) {
+        const int64_t n_rows = (int64_t)(g.P / g.Pin) * g.H;
+        const unsigned bgrid = (unsigned)((n_rows + kPrepWarps - 1) / kPrepWarps);
+#define VP_PREPB(TIN, TST)                                                                                          \
+    do {                                                                                                            \
+        cudaError_t e__ = cudaFuncSetAttribute(prepare_bands_kernel<TIN, TST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)bands_smem);                                                    \
+        if (e__ != cudaSuccess) return e__;                                                                         \
+        prepare_bands_kernel<TIN, TST><<<bgrid, kPrepWarps * 32, bands_smem, st>>>(                                 \
+            g, (const TIN *)original, fill_dev, sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart, extreme); \
+    } while (0)
+        if (dtype == VPINT_F64 && storage == VPINT_F64) VP_PREPB(double, double);
+        else if (dtype == VPINT_F32 && storage == VPINT_F64) VP_PREPB(float, double);
+        else if (dtype == VPINT_F64 && storage == VPINT_F32) VP_PREPB(double, float);
+        else VP_PREPB(float, float);
+#undef VP_PREPB
+        VP_LAUNCH_CHECK();
+        prepare_reduce_kernel<<<g.P, 256, 0, st>>>(g, rowpart, known0, known, state, counters);
+        VP_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
 #define VP_PREP(TIN, TST)                                                                                  \
     prepare_kernel<TIN, TST><<<grid, 256, 0, st>>>(g, (const TIN *)original, (const TIN *)pred0, fill_dev, \
                                                    sd, (TST *)bufA, (TST *)bufB, (TST *)orig_copy, mask, rowpart, extreme)

@@ -39,7 +39,7 @@ def _band_fill_values(target):
 # of chunk i-1 overlap the solve of chunk i).
 PIPELINE_CHUNK_PATCHES = 16
 # Host threads (each with its own stream and solver) that take alternate chunks.
-PIPELINE_WORKERS = 3
+PIPELINE_WORKERS = 6
 
 
 def _known_value_bias(t_dev, kvb, dev):
@@ -128,7 +128,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
         return res, sweeps.to(torch.int64).view(N, B)
 
     # ---- pipelined path ---------------------------------------------------------------------------
-    # Two host threads, each with its own stream and solver, take alternate chunks.  A thread blocks in
+    # PIPELINE_WORKERS host threads, each with its own stream and solver, take alternate chunks.  A thread blocks in
     # run() until its chunk has stopped; meanwhile the other thread has already copied in and queued the
     # next chunk, whose cluster-resident kernel moves onto the SMs as the first one drains (the long-tailed
     # problems of a chunk no longer leave the GPU idle), and the device->host copy of a finished chunk
