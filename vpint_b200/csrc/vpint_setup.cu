@@ -619,16 +619,29 @@ __global__ void clear_dirty_kernel(Geom g, ProbState *state) {
 
 // self.pred_grid after run(): gather the current ping-pong buffer of every problem into the caller's
 // layout (VPint/SD_MRP.py:149-156; VPint2 reassembles (H, W, B) at VPint/VPint2.py:96-99,112-116).
+// One warp per row; rows that are contiguous in the caller's array move as 16-byte vectors.
+constexpr int kResultWarps = 8;
+
 template <typename TSt, typename TOut>
-__global__ void __launch_bounds__(256) result_kernel(Geom g, const ProbState *__restrict__ state,
-                                                     const TSt *__restrict__ buf0, const TSt *__restrict__ buf1,
-                                                     TOut *__restrict__ out, Strides sd, int32_t *niter_out) {
-    const int p = blockIdx.x / g.H, y = blockIdx.x - p * g.H;      // p: slice
+__global__ void __launch_bounds__(kResultWarps * 32) result_kernel(Geom g, const ProbState *__restrict__ state,
+                                                                   const TSt *__restrict__ buf0, const TSt *__restrict__ buf1,
+                                                                   TOut *__restrict__ out, Strides sd, int32_t *niter_out,
+                                                                   int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kResultWarps + (threadIdx.x >> 5);
+    if (r >= (int64_t)g.P * g.S * g.H) return;
+    const int p = (int)(r / g.H), y = (int)(r - (int64_t)p * g.H);      // p: slice
     const ProbState st = state[p / g.S];
     const TSt *src = (st.cur ? buf1 : buf0) + ((size_t)p * g.H + y) * g.pitch;
-    for (int e = threadIdx.x; e < g.L; e += blockDim.x)
-        out[cell_offset(g, sd, p, y, e)] = (TOut)src[e];
-    if (niter_out && y == 0 && threadIdx.x == 0 && p % g.S == 0) niter_out[p / g.S] = st.iters_done;
+    TOut *dst = out + cell_offset(g, sd, p, y, 0);
+    if (vec_ok && sizeof(TSt) == 8 && sizeof(TOut) == 8) {              // unit stride, even length, 16-byte aligned rows
+        const double2 *s2 = reinterpret_cast<const double2 *>(src);
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        for (int e = lane; e < g.L / 2; e += 32) d2[e] = s2[e];
+    } else {
+        for (int e = lane; e < g.L; e += 32) dst[(int64_t)e * sd.sX] = (TOut)src[e];
+    }
+    if (niter_out && y == 0 && lane == 0 && p % g.S == 0) niter_out[p / g.S] = st.iters_done;
 }
 
 // Row-sharded scenes: copy `rows` owned boundary rows of every problem's CURRENT buffer into a
@@ -832,10 +845,13 @@ cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, vo
                           int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
                           int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3], (g.ndim == 3) ? stride[4] : 0};
-    const unsigned grid = (unsigned)((int64_t)g.P * g.S * g.H);
-#define VP_RES(TST, TOUT)                                                                                   \
-    result_kernel<TST, TOUT><<<grid, 256, 0, st>>>(g, state, (const TST *)buf[0], (const TST *)buf[1],      \
-                                                   (TOUT *)out, sd, niter_out)
+    const unsigned grid = (unsigned)(((int64_t)g.P * g.S * g.H + kResultWarps - 1) / kResultWarps);
+    // 16-byte vectors need unit stride along the row, an even row length and every row start on a 16-byte boundary
+    const int vec_ok = (sd.sX == 1 && (g.L & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (sd.sO & 1) == 0 &&
+                        (sd.sI & 1) == 0 && (sd.sY & 1) == 0 && (sd.sT & 1) == 0 && (g.pitch & 1) == 0) ? 1 : 0;
+#define VP_RES(TST, TOUT)                                                                                              \
+    result_kernel<TST, TOUT><<<grid, kResultWarps * 32, 0, st>>>(g, state, (const TST *)buf[0], (const TST *)buf[1],   \
+                                                                 (TOUT *)out, sd, niter_out, vec_ok)
     if (storage == VPINT_F64 && dtype == VPINT_F64) VP_RES(double, double);
     else if (storage == VPINT_F64 && dtype == VPINT_F32) VP_RES(double, float);
     else if (storage == VPINT_F32 && dtype == VPINT_F64) VP_RES(float, double);

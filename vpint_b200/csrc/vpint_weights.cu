@@ -222,6 +222,42 @@ __global__ void __launch_bounds__(256) fplane_kernel(int Pin, int H, int W, int 
     if (__syncthreads_or(wild) && threadIdx.x == 0) atomicAdd(extreme, 1.0);
 }
 
+// fplane_kernel for a band-interleaved stack (band fastest): one warp per (patch, row) stages the row of all bands
+// with coalesced loads and writes every band's plane row from shared memory.
+constexpr int kFplaneWarps = 4;
+
+template <typename TIn>
+__global__ void __launch_bounds__(kFplaneWarps * 32) fplane_bands_kernel(int n_patches, int Pin, int H, int W, int pitch,
+                                                                         const TIn *__restrict__ feat, int64_t sO, int64_t sY,
+                                                                         double *__restrict__ fplane, int *bad_flag,
+                                                                         double *__restrict__ extreme) {
+    extern __shared__ __align__(16) unsigned char fp_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kFplaneWarps + warp;
+    if (r >= (int64_t)n_patches * H) return;
+    const int po = (int)(r / H), y = (int)(r - (int64_t)po * H);
+    TIn *my = reinterpret_cast<TIn *>(fp_raw) + (size_t)warp * W * Pin;
+    const TIn *src = feat + (int64_t)po * sO + (int64_t)y * sY;
+    for (int k = lane; k < W * Pin; k += 32) my[k] = src[k];
+    __syncwarp();
+    bool bad = false, wild = false;
+    for (int b = 0; b < Pin; ++b) {
+        double *out = fplane + ((size_t)(po * Pin + b) * H + y) * pitch;
+        for (int x = lane; x < pitch; x += 32) {
+            double f = 1.0;
+            if (x < W) {
+                f = (double)my[x * Pin + b];
+                if (f == 0.0) f = 0.01;                 // VPint/WP_MRP.py:143-145
+                if (!(fabs(f) <= 1.7976931348623157e308)) bad = true;
+                if (!(fabs(f) < 1e150) || !(fabs(f) > 1e-150)) wild = true;
+            }
+            out[x] = f;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(bad_flag, 1);
+    if (__any_sync(0xffffffffu, wild) && lane == 0) atomicAdd(extreme, 1.0);
+}
+
 // w_dir = f[i,j] / f[neighbour], missing neighbour -> 0 (VPint/WP_MRP.py:149-170 with one feature layer).
 template <typename TSt>
 __global__ void __launch_bounds__(256) planes_from_fplane_kernel(int H, int W, int pitch, int row_offset, int global_H,
@@ -342,6 +378,25 @@ cudaError_t launch_weights2d(const Geom &g, const void *feat, int dtype, const i
 cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
                           double *extreme, cudaStream_t st, int64_t *launches) {
     const unsigned grid = (unsigned)((int64_t)g.P * g.H);
+    const size_t bands_smem = (size_t)kFplaneWarps * g.W * g.Pin * ((dtype == VPINT_F64) ? 8 : 4);
+    if (g.Pin >= 2 && stride[1] == 1 && stride[3] == g.Pin && bands_smem <= 100 * 1024) {
+        const int n_patches = g.P / g.Pin;
+        const unsigned bgrid = (unsigned)(((int64_t)n_patches * g.H + kFplaneWarps - 1) / kFplaneWarps);
+        cudaError_t e;
+        if (dtype == VPINT_F64) {
+            e = cudaFuncSetAttribute(fplane_bands_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bands_smem);
+            if (e != cudaSuccess) return e;
+            fplane_bands_kernel<double><<<bgrid, kFplaneWarps * 32, bands_smem, st>>>(
+                n_patches, g.Pin, g.H, g.W, g.pitch, (const double *)feat, stride[0], stride[2], fplane, bad_flag, extreme);
+        } else {
+            e = cudaFuncSetAttribute(fplane_bands_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bands_smem);
+            if (e != cudaSuccess) return e;
+            fplane_bands_kernel<float><<<bgrid, kFplaneWarps * 32, bands_smem, st>>>(
+                n_patches, g.Pin, g.H, g.W, g.pitch, (const float *)feat, stride[0], stride[2], fplane, bad_flag, extreme);
+        }
+        VP_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     if (dtype == VPINT_F64)
         fplane_kernel<double><<<grid, 256, 0, st>>>(g.Pin, g.H, g.W, g.pitch, (const double *)feat, stride[0], stride[1],
                                                     stride[2], stride[3], fplane, bad_flag, extreme);
