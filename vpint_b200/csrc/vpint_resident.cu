@@ -137,12 +137,6 @@ __device__ long long g_trace[8][2][8][10];
 // no bank conflicts, where the plain row-major layout (32-byte stride) costs two wavefronts per quarter warp.
 // With off = row * SP + 2s:  cells 0,1 at off; cells 2,3 at off + HALF + 2; the left neighbour (cell 4s-1) at
 // off + HALF + 1; the right neighbour (cell 4s+4) at off + 2; the zero pairs are the grid's left / right border.
-__device__ __forceinline__ int slot_cell(int lx, int half) {       // column held by row offset lx (pads: < 0 or >= 4 * nseg)
-    if (lx < half) return 4 * (lx >> 1) + (lx & 1);
-    const int q = lx - half;
-    return 4 * ((q >> 1) - 1) + 2 + (q & 1);
-}
-
 struct SmemLayout {
     double *plane;       // [R][SP] owned rows in the split-row layout described below
     double *halo_up;     // [2][LB][SP] row above every owned block, by sweep parity
@@ -564,15 +558,35 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 dst = ((h & 1) ? sm.halo_dn : sm.halo_up) + (size_t)lb * SP;
             }
             const bool in_grid = (gy >= 0) && (gy < H);
-            for (int lx = lane; lx < SP; lx += 32) {
-                double v = 0.0;
-                const int x = slot_cell(lx, SP / 2);
-                if (in_grid && x >= 0 && x < W) {
-                    v = grid[(size_t)gy * g.pitch + x];
-                    if (RATIO) v = v / fp[(size_t)gy * g.pitch + x];
+            const int half = SP / 2, ncell = 2 * half - 4;          // 4 * segments per row
+            if (lane < 2) {                                         // the zero pairs (grid border left / right)
+                dst[ncell / 2 + lane] = 0.0; dst[half + lane] = 0.0;
+                if (is_halo) { dst[LB * SP + ncell / 2 + lane] = 0.0; dst[LB * SP + half + lane] = 0.0; }
+            }
+            // coalesced reads, 8 independent loads (and divisions) in flight per lane
+            constexpr int kU = 8;
+            const double *grow = grid + (size_t)max(gy, 0) * g.pitch;
+            const double *frow = RATIO ? fp + (size_t)max(gy, 0) * g.pitch : nullptr;
+            for (int x0 = 0; x0 < ncell; x0 += 32 * kU) {
+                double v[kU], f[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int x = x0 + u * 32 + lane;
+                    const bool ok = in_grid && x < W;
+                    v[u] = ok ? grow[x] : 0.0;
+                    f[u] = (RATIO && ok) ? frow[x] : 1.0;
                 }
-                dst[lx] = v;
-                if (is_halo) dst[LB * SP + lx] = v;            // second parity copy of a halo row
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int x = x0 + u * 32 + lane;
+                    if (RATIO) v[u] = v[u] / f[u];
+                    if (x < ncell) {
+                        const int sg = x >> 2, j = x & 3;
+                        const int slot = (j < 2) ? 2 * sg + j : half + 2 * sg + j;
+                        dst[slot] = v[u];
+                        if (is_halo) dst[LB * SP + slot] = v[u];    // second parity copy of a halo row
+                    }
+                }
             }
         }
 
