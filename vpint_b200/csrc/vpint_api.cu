@@ -93,6 +93,7 @@ struct vpint_solver {
     bool planes_valid = false;        // the 4 (5) weight planes hold current weights
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
+    size_t off_order = 0;             // int[P]: queue order of the resident kernel
     size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
     size_t off_extreme = 0;           // double[2]: cells with non-finite / huge values, ... features
     size_t off_stage = 0;             // chunk sums of the two-stage per-problem reduction
@@ -240,6 +241,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_flags = take(16 * sizeof(int));
     s->off_stage = take(reduce_stage_bytes(g));
     s->off_done = take((size_t)g.P * sizeof(int));
+    s->off_order = take((size_t)g.P * sizeof(int));
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
@@ -701,6 +703,12 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         ra.delta_out = prm->delta_out;
         ra.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
         ra.queue = flags + 1;
+        ra.order = nullptr;
+        if (s->g.P > 2 * 33 && s->g.P <= kResidentOrderMax && !getenv("VPINT_NO_QUEUE_ORDER")) {
+            // longest problems first: big clouds need the most sweeps, so they must not start last
+            VP_CUDA(launch_resident_order(s->g, ra.state, s->at<int>(s->off_order), st, &s->launches), "queue order");
+            ra.order = s->at<int>(s->off_order);
+        }
         ra.bad_flag = ratio ? flags : nullptr;
         ra.max_iter = prm->max_iter;
         ra.auto_terminate = prm->auto_terminate;

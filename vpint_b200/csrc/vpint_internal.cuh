@@ -47,7 +47,7 @@ struct ProbState {
     int replay;       // 1: next launch replays k_run sweeps after an overshoot, then finishes
     int dirty;        // 1: known cells of the start state differ from original (first launch runs 1 sweep)
     int fresh;        // 1: no sweep committed since load (first sweep uses the known0 sums)
-    int pad;
+    int n_unknown;    // unknown cells of the problem (set by load; orders the resident kernel's queue)
 };
 
 struct TileRef {
@@ -119,6 +119,7 @@ struct ResidentArgs {
     double *delta_out;       // [P][max_iter] or null
     int *n_active;
     int *queue;              // zeroed before the launch
+    const int *order;        // queue position -> problem, largest clouds first; null = index order
     const int *bad_flag;     // nonzero: decline (non-finite features); null = none
     int max_iter, auto_terminate;
     double threshold, clip;
@@ -128,6 +129,8 @@ struct ResidentArgs {
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);
 cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
                               int64_t *launches);
+constexpr int kResidentOrderMax = 32768;   // problems per solver up to which the queue is ordered (rank by counting)
+cudaError_t launch_resident_order(const Geom &g, const ProbState *state, int *order, cudaStream_t st, int64_t *launches);
 cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
                           double *extreme, cudaStream_t st, int64_t *launches);
 cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int storage, void *const *planes,

@@ -531,9 +531,10 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         // ---- next problem from the queue (cluster-uniform) ------------------------------------
         if (crank == 0 && tid == 0) next_problem = atomicAdd(a.queue, 1);
         cluster_barrier();
-        const int p = *next_remote;
+        const int qi = *next_remote;
         cluster_barrier();                             // everyone has read before rank 0 overwrites or exits
-        if (p >= g.P) break;
+        if (qi >= g.P) break;
+        const int p = a.order ? a.order[qi] : qi;
         const ProbState st = a.state[p];
         if (st.status != 0) continue;                  // nothing to run (cluster-uniform)
 
@@ -773,6 +774,34 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
 }  // namespace
 
 // Smallest portable cluster that holds one problem on chip; returns false if none does.
+// order[rank] = p with the problems ranked by descending unknown-cell count (ties by index): every thread counts
+// the problems that come before its own.  P <= kResidentOrderMax keeps the quadratic scan in the microseconds.
+__global__ void __launch_bounds__(256) resident_order_kernel(int P, const ProbState *__restrict__ state, int *__restrict__ order) {
+    __shared__ int keys[1024];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int mine = (p < P) ? state[p].n_unknown : 0;
+    int rank = 0;
+    for (int q0 = 0; q0 < P; q0 += 1024) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) keys[i] = (q0 + i < P) ? state[q0 + i].n_unknown : -1;
+        __syncthreads();
+        const int m = min(1024, P - q0);
+        for (int i = 0; i < m; ++i) {
+            const int k = keys[i];
+            rank += (k > mine || (k == mine && q0 + i < p)) ? 1 : 0;
+        }
+    }
+    if (p < P) order[rank] = p;
+}
+
+cudaError_t launch_resident_order(const Geom &g, const ProbState *state, int *order, cudaStream_t st, int64_t *launches) {
+    resident_order_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, state, order);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    return cudaSuccess;
+}
+
 bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out) {
     if (g.ndim != 2 || g.H < 1 || g.L < 1 || (g.H < 2 && g.L < 2)) return false;   // 1x1: neighbour count 0
     const int W = g.L;

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256) prepare_reduce_kernel(Geom g, const doubl
         k[0] = 0.0; k[1] = acc[4]; k[2] = acc[5]; k[3] = 0.0;
         ProbState st;
         st.iters_done = 0; st.k_run = 0; st.cur = 0; st.status = 1; st.replay = 0;
-        st.dirty = acc[6] > 0.0 ? 1 : 0; st.fresh = 1; st.pad = 0;
+        st.dirty = acc[6] > 0.0 ? 1 : 0; st.fresh = 1; st.n_unknown = (int)acc[7];
         state[p] = st;
         if (st.dirty) atomicAdd(&counters[0], 1);
         if (acc[7] == 0.0) atomicAdd(&counters[2], 1);     // a problem without unknown cells has no tile to finish it
