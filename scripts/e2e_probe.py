@@ -1,7 +1,8 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
-from bench import make_patches_torch, H, W, B
+from bench import make_patches_torch, H, W, B, bind_to_gpu_node
+print("affinity:", bind_to_gpu_node(0))
 import vpint_b200.vpint2 as V
 from vpint_b200.wp import wp_run_options
 dev = torch.device("cuda", 0)
@@ -20,7 +21,7 @@ for name, fn in (("h2d", lambda: d.copy_(t_host, non_blocking=True)), ("d2h", la
     print(name, "%.1f GB/s" % (t_host.numel() * 4 / dt / 1e9))
 opts = wp_run_options()
 import itertools
-for workers, chunk in itertools.product((3, 4, 6), (8, 16, 32)):
+for workers, chunk in itertools.product((4, 6, 8), (16, 32, 64)):
     V.PIPELINE_CHUNK_PATCHES = chunk
     V.PIPELINE_WORKERS = workers
     for rep in range(3):

@@ -668,6 +668,33 @@ def test_single_feature_ragged_shapes(shape, kblock):
     close(p, ref); closed(d, dref)
 
 
+@pytest.mark.parametrize("shape", [(3, 4), (4, 8), (5, 260), (16, 16), (48, 64), (64, 256), (129, 128), (256, 256)])
+def test_resident_fast_sweep_borders(shape):
+    """Grids the resident kernel's branch-free sweep takes (W % 4 == 0, H >= 3, no clip_val) with unknown cells on
+    every border and in every corner: neighbour counts 2 and 3 go through the multiply + fma-residual division,
+    which must equal the reference's true division; row blocks are dealt round robin to the CTAs of a cluster."""
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    base = smooth(rng, shape, 500, 2500)
+    grid = np.round(base + rng.normal(0, 20, shape))
+    feat = np.round(1.1 * base + rng.normal(0, 10, shape))
+    hide = rng.uniform(size=shape) < 0.3
+    hide[0, :] = True; hide[-1, :] = True; hide[:, 0] = True; hide[:, -1] = True
+    hide[shape[0] // 2, 1:-1] = False                             # something known in every column
+    if shape[0] * shape[1] > 4000:
+        hide |= discs(rng, shape, 3, 5, min(shape) // 3)
+        hide[shape[0] // 2, 1:-1] = False
+    grid[hide] = np.nan
+    ref, dref, n = O.wp_run_2d(grid, O.init_pred(grid), feat.reshape(shape + (1,)).astype(float).copy())
+    p, d = WP_SMRP(grid.copy(), feat.copy()).run(track_delta=True)
+    assert len(d) == n, (len(d), n)
+    close(p, ref); closed(d, dref)
+    assert np.array_equal(p[~hide], grid[~hide])
+    if shape[0] == shape[1]:                                      # SD_SMRP.run needs square grids (NumPy broadcast)
+        ref, dref, n = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.93, iterations=40, auto_terminate=False)
+        p, d = SD_SMRP(grid.copy(), gamma=0.93).run(iterations=40, track_delta=True)
+        close(p, ref); closed(d, dref)
+
+
 def test_degenerate_grids(kblock):
     rng = np.random.default_rng(12)
     full = smooth(rng, (20, 20), 10, 20)                       # nothing to interpolate: one sweep, delta 0
