@@ -658,7 +658,11 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 *reinterpret_cast<double2 *>(sm.fseg + 2 * (fcap + i)) = make_double2((e & (1u << 18)) ? f2 : 0.0, (e & (1u << 19)) ? f3 : 0.0);
             }
         }
-        const int Kmax = (n + kThreads - 1) / kThreads;    // CTA-uniform
+        // Segments per thread of THIS warp (entries tid + k * kThreads): the warps that hold no entry of the last
+        // round run a shorter variant, so a list slightly longer than a multiple of kThreads costs a few warps one
+        // more segment instead of all of them.  Every variant meets the same barriers.
+        const int w_first = warp * 32;                     // lowest entry index of the warp's first round
+        const int Kmax = (n > w_first) ? (n - 1 - w_first) / kThreads + 1 : 0;   // warp-uniform
         int kt = kMaxSeg;                                  // smallest unrolled variant >= Kmax
         {
             const int kts[7] = {0, 1, 2, 3, 4, 6, 8};
