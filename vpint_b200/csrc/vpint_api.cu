@@ -92,7 +92,7 @@ struct vpint_solver {
     ResidentPlan rplan;
     bool planes_valid = false;        // the 4 (5) weight planes hold current weights
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
-    size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue
+    size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue, [2] sweeps left (graph loop), [3] a feature that is not a float32 value
     size_t off_order = 0;             // int[P]: queue order of the resident kernel
     size_t off_orig = 0;              // copy of the known values (VPINT_FEAT_RESISTANCE)
     size_t off_extreme = 0;           // double[2]: cells with non-finite / huge values, ... features
@@ -346,6 +346,7 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     if (s->g.ndim == 2 && s->n_planes == 5 && F == 1 && method == VPINT_METHOD_EXACT && !clamp) {
         // one feature layer: keep the feature plane only; the ratio planes are derived on demand
         VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
+        VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags) + 3, 0, sizeof(int), st), "memset flag");
         VP_CUDA(launch_fplane(s->g, feat, dtype, stride, s->at<double>(s->off_w[4]), s->at<int>(s->off_flags),
                               s->at<double>(s->off_extreme) + 1, st, &s->launches),
                 "fplane");
@@ -710,6 +711,7 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
             ra.order = s->at<int>(s->off_order);
         }
         ra.bad_flag = ratio ? flags : nullptr;
+        ra.f32_flag = ratio ? flags + 3 : nullptr;
         ra.max_iter = prm->max_iter;
         ra.auto_terminate = prm->auto_terminate;
         ra.threshold = prm->threshold;

@@ -121,6 +121,7 @@ struct ResidentArgs {
     int *queue;              // zeroed before the launch
     const int *order;        // queue position -> problem, largest clouds first; null = index order
     const int *bad_flag;     // nonzero: decline (non-finite features); null = none
+    const int *f32_flag;     // zero: every feature is exactly a float32 value; null = unknown (keep fp64 on chip)
     int max_iter, auto_terminate;
     double threshold, clip;
     int C, R, SP, fcap, BS, LB;

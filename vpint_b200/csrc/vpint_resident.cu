@@ -141,7 +141,8 @@ struct SmemLayout {
     double *plane;       // [R][SP] owned rows in the split-row layout described below
     double *halo_up;     // [2][LB][SP] row above every owned block, by sweep parity
     double *halo_dn;     // [2][LB][SP] row below
-    double *fseg;        // [2][fcap][2] features of the first fcap listed segments: cells 0,1 then cells 2,3 (RATIO)
+    double *fseg;        // [2][fcap][2] features of the first fcap listed segments: cells 0,1 then cells 2,3 (RATIO);
+                         // as float pairs (twice the capacity in the same bytes) when every feature is a float32 value
     unsigned *list;      // [n_seg] segment entries, row-major
 };
 
@@ -243,7 +244,21 @@ __device__ __forceinline__ void role_barrier() {
 }
 
 // Worker warps: steps (1), (2), (3), (6) of every sweep.
-template <bool RATIO, int KT, bool FAST>
+// Features of listed segment i (or four zeros): fp64 pairs, or float pairs when F32.
+template <bool F32>
+__device__ __forceinline__ void load_fseg(const double *fseg, const double *zero4, int fcap, int i, bool live, double (&f)[4]) {
+    if (F32) {
+        const float2 *q = reinterpret_cast<const float2 *>(fseg), *z = reinterpret_cast<const float2 *>(zero4);
+        const float2 a = *(live ? q + i : z), b = *(live ? q + fcap + i : z);
+        f[0] = (double)a.x; f[1] = (double)a.y; f[2] = (double)b.x; f[3] = (double)b.y;
+    } else {
+        const double *fa = live ? fseg + 2 * i : zero4;
+        const double *fb = live ? fseg + 2 * (fcap + i) : zero4 + 2;
+        ld2(fa, f[0], f[1]); ld2(fb, f[2], f[3]);
+    }
+}
+
+template <bool RATIO, int KT, bool FAST, bool F32>
 __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh, int T, unsigned &ph_h, int &it_out,
                                               bool &bailed_out) {
     const int lane = c.tid & 31, warp = c.tid >> 5;
@@ -311,9 +326,7 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
                 if (RATIO) {
                     // fseg holds f for the unknown cells of a segment and 0 for the known ones
                     double f[4];
-                    const double *fa = live ? c.fseg + 2 * i : c.zero4;
-                    const double *fb = live ? c.fseg + 2 * (c.fcap + i) : c.zero4 + 2;
-                    ld2(fa, f[0], f[1]); ld2(fb, f[2], f[3]);
+                    load_fseg<F32>(c.fseg, c.zero4, c.fcap, i, live, f);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         s_abs = fma(f[j], fabs(r[j] - cc[j]), s_abs);   // |f r_new - f r_old|
@@ -349,8 +362,7 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
                 }
                 if (RATIO) {
                     double f[4];
-                    const int ic = min(i, c.fcap - 1);
-                    ld2(c.fseg + 2 * ic, f[0], f[1]); ld2(c.fseg + 2 * (c.fcap + ic), f[2], f[3]);
+                    load_fseg<F32>(c.fseg, c.zero4, c.fcap, min(i, c.fcap - 1), true, f);
                     if (i >= c.fcap) {
                         const int ly = off / c.SP;
                         const double *fg = c.fp + (size_t)c.grid_row(ly) * c.pitch + 2 * (off - ly * c.SP);
@@ -500,12 +512,15 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
     if (a.bad_flag && *a.bad_flag) return;             // grid-uniform: leave everything to the tiled path
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
-    const int C = a.C, R = a.R, SP = a.SP, fcap = a.fcap;
+    const int C = a.C, R = a.R, SP = a.SP;
+    // every feature of the batch is a float32 value (VPint2's inputs are): keep them on chip as floats, twice as many
+    const bool f32 = RATIO && a.f32_flag && (*a.f32_flag == 0);
+    const int fcap = f32 ? 2 * a.fcap : a.fcap;
     const Geom &g = a.g;
     const int W = g.L, H = g.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BS = a.BS, LB = a.LB;
-    const SmemLayout sm = carve(smem_raw, R, SP, LB, fcap);
+    const SmemLayout sm = carve(smem_raw, R, SP, LB, a.fcap);
     int *next_remote = cluster.map_shared_rank(&next_problem, 0);
     if (tid < 4) sh.zero4[tid] = 0.0;
     if (tid == 0) {
@@ -654,8 +669,16 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 double f0, f1, f2, f3;
                 ld2(fg, f0, f1); ld2(fg + 2, f2, f3);
                 // 0 for the known cells: they do not count
-                *reinterpret_cast<double2 *>(sm.fseg + 2 * i) = make_double2((e & (1u << 16)) ? f0 : 0.0, (e & (1u << 17)) ? f1 : 0.0);
-                *reinterpret_cast<double2 *>(sm.fseg + 2 * (fcap + i)) = make_double2((e & (1u << 18)) ? f2 : 0.0, (e & (1u << 19)) ? f3 : 0.0);
+                f0 = (e & (1u << 16)) ? f0 : 0.0; f1 = (e & (1u << 17)) ? f1 : 0.0;
+                f2 = (e & (1u << 18)) ? f2 : 0.0; f3 = (e & (1u << 19)) ? f3 : 0.0;
+                if (f32) {
+                    float2 *q = reinterpret_cast<float2 *>(sm.fseg);
+                    q[i] = make_float2((float)f0, (float)f1);
+                    q[fcap + i] = make_float2((float)f2, (float)f3);
+                } else {
+                    *reinterpret_cast<double2 *>(sm.fseg + 2 * i) = make_double2(f0, f1);
+                    *reinterpret_cast<double2 *>(sm.fseg + 2 * (fcap + i)) = make_double2(f2, f3);
+                }
             }
         }
         // Segments per thread of THIS warp (entries tid + k * kThreads): the warps that hold no entry of the last
@@ -723,10 +746,15 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         // the last cell of a segment, and at most one missing neighbour per direction pair (H >= 3, W >= 4).
         // Each CTA decides for itself -- the protocol between the CTAs does not depend on it.
         const bool fast = !(a.clip <= 1.7976931348623157e308) && (!RATIO || n <= fcap) && (W & 3) == 0 && H >= 3;
-#define VPR_RUN(KT_)                                                                          \
-    do {                                                                                      \
-        if (fast) worker_sweeps<RATIO, KT_, true>(ctx, sh, a.max_iter, ph_h, it, bailed);     \
-        else worker_sweeps<RATIO, KT_, false>(ctx, sh, a.max_iter, ph_h, it, bailed);         \
+#define VPR_RUN(KT_)                                                                                   \
+    do {                                                                                               \
+        if (RATIO && f32) {                                                                            \
+            if (fast) worker_sweeps<RATIO, KT_, true, RATIO>(ctx, sh, a.max_iter, ph_h, it, bailed);   \
+            else worker_sweeps<RATIO, KT_, false, RATIO>(ctx, sh, a.max_iter, ph_h, it, bailed);       \
+        } else {                                                                                       \
+            if (fast) worker_sweeps<RATIO, KT_, true, false>(ctx, sh, a.max_iter, ph_h, it, bailed);   \
+            else worker_sweeps<RATIO, KT_, false, false>(ctx, sh, a.max_iter, ph_h, it, bailed);       \
+        }                                                                                              \
     } while (0)
         if (warp == kWarps) {
             sync_sweeps(tid, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_s, it, bailed);
@@ -759,7 +787,12 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
             for (int j = 0; j < 4; ++j) {
                 if ((e >> (16 + j)) & 1u) {
                     double v = sm.plane[off + ((j < 2) ? j : SP / 2 + j)];
-                    if (RATIO) v = ((i < fcap) ? sm.fseg[2 * (((j < 2) ? 0 : fcap) + i) + (j & 1)] : fp[go + j]) * v;
+                    if (RATIO) {
+                        const int fi = 2 * (((j < 2) ? 0 : fcap) + i) + (j & 1);
+                        const double fj = (i >= fcap) ? fp[go + j]
+                                                      : (f32 ? (double)reinterpret_cast<const float *>(sm.fseg)[fi] : sm.fseg[fi]);
+                        v = fj * v;
+                    }
                     grid[go + j] = v;
                 }
             }

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) fplane_kernel(int Pin, int H, int W, int 
     const int po = p / Pin, pi = p - po * Pin;
     const TIn *frow = feat + (int64_t)po * sO + (int64_t)pi * sI + (int64_t)y * sY;
     double *out = fplane + ((size_t)p * H + y) * pitch;
-    bool bad = false, wild = false;
+    bool bad = false, wild = false, wide = false;
     for (int x = threadIdx.x; x < pitch; x += blockDim.x) {
         double f = 1.0;
         if (x < W) {
@@ -215,10 +215,12 @@ __global__ void __launch_bounds__(256) fplane_kernel(int Pin, int H, int W, int 
             if (f == 0.0) f = 0.01;                     // VPint/WP_MRP.py:143-145
             if (!(fabs(f) <= 1.7976931348623157e308)) bad = true;
             if (!(fabs(f) < 1e150) || !(fabs(f) > 1e-150)) wild = true;
+            if ((double)(float)f != f) wide = true;      // not a float32 value (0.01 is not): fp64 on chip
         }
         out[x] = f;
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(bad_flag, 1);
+    if (__syncthreads_or(wide) && threadIdx.x == 0) atomicExch(bad_flag + 3, 1);
     if (__syncthreads_or(wild) && threadIdx.x == 0) atomicAdd(extreme, 1.0);
 }
 
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kFplaneWarps * 32) fplane_bands_kernel(int n_p
     const TIn *src = feat + (int64_t)po * sO + (int64_t)y * sY;
     for (int k = lane; k < W * Pin; k += 32) my[k] = src[k];
     __syncwarp();
-    bool bad = false, wild = false;
+    bool bad = false, wild = false, wide = false;
     for (int b = 0; b < Pin; ++b) {
         double *out = fplane + ((size_t)(po * Pin + b) * H + y) * pitch;
         for (int x = lane; x < pitch; x += 32) {
@@ -250,11 +252,13 @@ __global__ void __launch_bounds__(kFplaneWarps * 32) fplane_bands_kernel(int n_p
                 if (f == 0.0) f = 0.01;                 // VPint/WP_MRP.py:143-145
                 if (!(fabs(f) <= 1.7976931348623157e308)) bad = true;
                 if (!(fabs(f) < 1e150) || !(fabs(f) > 1e-150)) wild = true;
+                if ((double)(float)f != f) wide = true;  // not a float32 value (0.01 is not): fp64 on chip
             }
             out[x] = f;
         }
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(bad_flag, 1);
+    if (__any_sync(0xffffffffu, wide) && lane == 0) atomicExch(bad_flag + 3, 1);
     if (__any_sync(0xffffffffu, wild) && lane == 0) atomicAdd(extreme, 1.0);
 }
 
