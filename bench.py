@@ -124,6 +124,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def ready(self):
+        """True once nvidia-smi has written its first sample (or cannot run)."""
+        if self.proc is None or self.proc.poll() is not None:
+            return True
+        try:
+            return os.path.getsize(self.path) > 0
+        except OSError:
+            return False
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
@@ -337,11 +346,19 @@ def run_gpu(args):
         return ms, sweeps_total
 
     for _ in range(max(args.warmup, 0)):
-        device_step()
-    launches0 = solver.launches
+        int(torch.as_tensor(device_step()).sum().item())     # the same host-side reduction a timed step ends with
+    extra_warmup = 0
     sampler = ClockSampler(local)
     if rank == 0:
+        # nvidia-smi takes a few hundred ms to initialise NVML; keep the GPU busy with untimed steps meanwhile so that
+        # neither its start-up nor a clock ramp after an idle wait falls into the timed region (it then samples every
+        # 100 ms during the timed region)
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.ready() and time.perf_counter() - t_wait < 5.0:
+            device_step()
+            extra_warmup += 1
+    launches0 = solver.launches
     ms_dev, sweeps_dev = timed(device_step, args.steps)
     launches = solver.launches - launches0
     clocks = sampler.stop() if rank == 0 else {}
@@ -350,7 +367,7 @@ def run_gpu(args):
 
     # e2e through the host API
     for _ in range(min(max(args.warmup, 0), 2)):
-        e2e_step()
+        int(torch.as_tensor(e2e_step()).sum().item())
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ms_e2e, sweeps_e2e = timed(e2e_step, e2e_steps)
     e2e_val = sweeps_e2e * H * W / (ms_e2e * 1e-3) / 1e6
@@ -417,7 +434,8 @@ def run_gpu(args):
                        "path": "cluster-resident (k_block 0)" if args.k_block == 0 else "tiled, %d sweeps per launch" % kb, "cloud_fraction": round(masked_frac, 4),
                        "active_tiles": active_tiles, "total_tiles": total_tiles,
                        "l2_note": "state+weights %.1f GB per GPU >> 126 MB L2; no flush needed" % (48.0 * total_px / 1e9),
-                       "mean_sweeps_per_problem": sweeps_dev / args.steps / (nprob * world)},
+                       "mean_sweeps_per_problem": sweeps_dev / args.steps / (nprob * world),
+                       "extra_warmup_steps": extra_warmup},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": kernel_name,

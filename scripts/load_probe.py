@@ -26,3 +26,14 @@ out = torch.empty((n, B, H, W), dtype=torch.float64, device=dev)
 print("result %.3f ms" % timed(lambda: s.result(out=out)))
 gb = n * B * H * W * 8 / 1e9
 print("state plane = %.2f GB" % gb)
+# one full step with events between the phases
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+for rep in range(3):
+    torch.cuda.synchronize()
+    ev[0].record(); s.load(tp, fill=None)
+    ev[1].record(); s.weights(fp, method="exact")
+    ev[2].record(); s.run(5000, auto_terminate=True)
+    ev[3].record(); s.result(out=out)
+    ev[4].record(); torch.cuda.synchronize()
+    print("step: load %.3f weights %.3f run %.3f result %.3f total %.3f ms" % tuple(
+        [ev[i].elapsed_time(ev[i + 1]) for i in range(4)] + [ev[0].elapsed_time(ev[4])]))

@@ -16,7 +16,7 @@ KS = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 4
 REPS = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 for k in KS:
     t = rng.uniform(1000, 2000, (P, H, W))
-    f = rng.uniform(1000, 2000, (P, H, W, 1))
+    f = np.round(rng.uniform(1000, 2000, (P, H, W, 1)))   # float32-exact, like VPint2 features
     if k:
         t[:, :, 4:4 + 4 * k] = np.nan
     else:
