@@ -22,14 +22,21 @@
 // CTA c-1 and c+1 (mod C).
 //
 // Work unit = a SEGMENT of 4 horizontally adjacent cells (x = 4s .. 4s+3) with at least one unknown cell;
-// the CTA keeps a compact row-major list of its segments.  Per sweep every CTA does: for each of its
-// segments load own row / row above / row below as 128-bit shared-memory vectors, compute the new values
-// of the unknown cells (registers hold them), block barrier, store them (own rows + the neighbour CTAs'
-// halo rows through DSMEM) and push its partial {sum|new-old|, sum old} to every CTA of the cluster, ONE
-// cluster barrier, then every CTA adds the C partials in rank order and takes the same stop decision
-// (delta = nanmean|new-old| / nanmean(old) <= threshold, commit-then-break: VPint/SD_MRP.py:138-147,
-// VPint/WP_MRP.py:351-362).  Halo rows and partials are double buffered by sweep parity, which is what
-// makes one cluster barrier per sweep sufficient.
+// the CTA keeps a compact row-major list of its segments.  15 WORKER warps own the segments; per sweep they
+// wait for the state of the previous sweep (an mbarrier that counts their own arrivals and the bytes of the
+// neighbours' boundary rows), compute the new values of their unknown cells into registers (own row / row above
+// / row below as 128-bit shared-memory vectors), meet at a block barrier, store the values (own rows, and the
+// block-boundary rows into the neighbour CTAs' halo rows with st.async through DSMEM) and arrive.  The 16th
+// warp, the SYNC WARP, owns no segments: it adds up the warp partials {sum|new-old|, sum old} of a sweep,
+// pushes them to every CTA of the cluster (st.async + mbarrier as well) and takes the stop decision of sweep
+// t-1 while the workers compute sweep t (delta = nanmean|new-old| / nanmean(old) <= threshold,
+// commit-then-break: VPint/SD_MRP.py:138-147, VPint/WP_MRP.py:351-362) -- if it stops, sweep t is not stored.
+// There is no cluster barrier inside the sweep loop; halo rows are double buffered by sweep parity, partials
+// triple buffered.
+//
+// State rows live in shared memory in a split layout (see SmemLayout) that keeps the 128-bit accesses of a
+// warp free of bank conflicts; the features of the listed segments live there too, as float pairs when every
+// feature is a float32 value.
 #include <cooperative_groups.h>
 
 #include <cstdio>
@@ -759,7 +766,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         if (warp == kWarps) {
             sync_sweeps(tid, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_s, it, bailed);
         } else {
-#ifdef VPR_ONLY_KT
+#ifdef VPR_ONLY_KT                                  // build-time triage: one variant only, for per-variant ptxas -v / SASS
             VPR_RUN(VPR_ONLY_KT);
 #else
             switch (kt) {
