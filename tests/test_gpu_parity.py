@@ -668,7 +668,8 @@ def test_single_feature_ragged_shapes(shape, kblock):
     close(p, ref); closed(d, dref)
 
 
-@pytest.mark.parametrize("shape", [(3, 4), (4, 8), (5, 260), (16, 16), (48, 64), (64, 256), (129, 128), (256, 256)])
+@pytest.mark.parametrize("shape", [(3, 4), (4, 8), (5, 260), (16, 16), (48, 64), (64, 256), (129, 128), (256, 256),
+                                   (200, 512), (384, 384)])
 def test_resident_fast_sweep_borders(shape):
     """Grids the resident kernel's branch-free sweep takes (W % 4 == 0, H >= 3, no clip_val) with unknown cells on
     every border and in every corner: neighbour counts 2 and 3 go through the multiply + fma-residual division,
@@ -693,6 +694,35 @@ def test_resident_fast_sweep_borders(shape):
         ref, dref, n = O.sd_run_2d(grid, O.init_pred(grid), gamma=0.93, iterations=40, auto_terminate=False)
         p, d = SD_SMRP(grid.copy(), gamma=0.93).run(iterations=40, track_delta=True)
         close(p, ref); closed(d, dref)
+
+
+def test_resident_feature_width_switch_on_one_solver():
+    """The resident kernel keeps features on chip as floats when every feature of the batch is a float32 value and
+    as doubles otherwise; the flag behind that choice is re-evaluated by every weights() call (also when a zero
+    feature is replaced by 0.01, which is not a float32 value)."""
+    import torch
+    rng = np.random.default_rng(909)
+    shape = (96, 128)
+    base = smooth(rng, shape, 500, 2500)
+    grid = np.round(base + rng.normal(0, 20, shape))
+    grid[discs(rng, shape, 4, 6, 25)] = np.nan
+    feats = {"float32 values": np.round(1.1 * base + rng.normal(0, 10, shape)),
+             "fp64 values": 1.1 * base + rng.normal(0, 10, shape),
+             "float32 values with zeros": np.round(1.1 * base + rng.normal(0, 10, shape))}
+    feats["float32 values with zeros"][rng.uniform(size=shape) < 0.02] = 0.0
+    s = Solver(2, 1, shape[0], shape[1], planes=True, k_block=0)
+    try:
+        for name in ("float32 values", "fp64 values", "float32 values with zeros", "float32 values"):
+            f = feats[name]
+            ref, _, n = O.wp_run_2d(grid, O.init_pred(grid), f.reshape(shape + (1,)).astype(float).copy())
+            s.load(torch.from_numpy(grid).cuda().unsqueeze(0), fill=[float(np.nanmean(grid))])
+            s.weights(torch.from_numpy(f.reshape((1,) + shape + (1,))).cuda(), method="exact")
+            s.run(5000, auto_terminate=True)
+            out, niter = s.result()
+            assert int(niter[0]) == n, (name, int(niter[0]), n)
+            close(out[0].cpu().numpy(), ref)
+    finally:
+        s.close()
 
 
 def test_degenerate_grids(kblock):
