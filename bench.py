@@ -397,7 +397,25 @@ def run_gpu(args):
         kernel_name = "resident2d_kernel<ratio> (one launch = run() of every problem)"
         unit_def = "one unknown cell updated for one sweep (%.3e per launch: sum over problems of unknown cells x sweeps)" % units
         traffic, traffic_src = ncu_traffic("resident", nprob)
+        # what bounds a kernel whose state never leaves the chip: shared-memory wavefronts and issue slots, scaled
+        # from the committed ncu capture (per problem and sweep) to the sweeps of this launch
+        try:
+            e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_block"]["resident"]
+            psw = float(nit.double().sum().item())
+            clk = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+            sms = e["sms_with_a_cta"]
+            onchip = {"problem_sweeps_per_launch": psw,
+                      "smem_wavefronts_per_s": e["smem_wavefronts_per_problem_sweep"] * psw / (k_ms * 1e-3),
+                      "smem_peak_wavefronts_per_s": sms * clk,
+                      "warp_instructions_per_s": e["warp_instructions_per_problem_sweep"] * psw / (k_ms * 1e-3),
+                      "issue_peak_per_s": 4 * sms * clk,
+                      "source": e["source"] + " (per problem-sweep counts of the capture x sweeps of this launch)"}
+            onchip["smem_frac"] = onchip["smem_wavefronts_per_s"] / onchip["smem_peak_wavefronts_per_s"]
+            onchip["issue_frac"] = onchip["warp_instructions_per_s"] / onchip["issue_peak_per_s"]
+        except Exception:
+            onchip = None
     else:
+        onchip = None
         solver.load(target.permute(0, 3, 1, 2), fill=fill)
         solver.weights(feats.permute(0, 3, 1, 2).unsqueeze(-1), method="exact")
         solver.begin_run(10 ** 6, auto_terminate=False)
@@ -440,7 +458,7 @@ def run_gpu(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": kernel_name,
                          "kernel_ms": k_ms, "alg_bytes_per_launch": alg_bytes, "bytes_per_unit": BYTES_WP_F64,
-                         "unit_def": unit_def, "whole_grid_equiv_gbps": full_grid_gbps,
+                         "unit_def": unit_def, "whole_grid_equiv_gbps": full_grid_gbps, "onchip": onchip,
                          "note": ("state stays in shared memory for all sweeps: DRAM traffic is one read + one write per "
                                   "problem, so algorithmic GB/s may exceed the HBM peak" if resident else
                                   "streams state and weights from HBM every launch")},

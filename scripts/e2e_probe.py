@@ -19,9 +19,22 @@ for name, fn in (("h2d", lambda: d.copy_(t_host, non_blocking=True)), ("d2h", la
     for _ in range(3): fn()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
     print(name, "%.1f GB/s" % (t_host.numel() * 4 / dt / 1e9))
+# both directions at once (what the pipeline asks of the link): 3.49 GB in + 3.49 GB out
+d_in = torch.empty((n, H, W, B), dtype=torch.float32, device=dev); d_in2 = torch.empty_like(d_in)
+d_out = torch.empty((n, B, H, W), dtype=torch.float64, device=dev)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+for rep in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    with torch.cuda.stream(s1):
+        d_in.copy_(t_host, non_blocking=True); d_in2.copy_(f_host, non_blocking=True)
+    with torch.cuda.stream(s2):
+        out_host.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("bidirectional: 3.49 GB in + 3.49 GB out in %.1f ms (%.1f GB/s per direction)" % (dt * 1e3, t_host.numel() * 8 / dt / 1e9))
+del d_in, d_in2, d_out
 opts = wp_run_options()
 import itertools
-for workers, chunk in itertools.product((4, 6, 8), (16, 32, 64)):
+for workers, chunk in itertools.product((6,), (16,)):
     V.PIPELINE_CHUNK_PATCHES = chunk
     V.PIPELINE_WORKERS = workers
     for rep in range(3):
