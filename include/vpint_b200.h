@@ -87,6 +87,9 @@ typedef struct vpint_desc {
 
 /* vpint_desc.features */
 #define VPINT_FEAT_RESISTANCE 1   /* keeps a copy of the known values: run() may use `resistance` */
+#define VPINT_FEAT_BLOCKING_WAIT 2 /* host waits of load() and of the cluster-resident run() sleep instead of
+                                      spinning: for callers that drive several solvers from several host threads
+                                      (the pipelined VPint2 path), where spinning threads would fight for cores */
 
 /* Arguments of one run() call.  Defaults of the reference in brackets. */
 typedef struct vpint_run_params {

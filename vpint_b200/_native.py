@@ -21,6 +21,7 @@ W_SCALAR, W_PLANES = 0, 1
 METHOD_EXACT, METHOD_COSINE, METHOD_EXACT_INVERSE = 0, 1, 2
 LOOP_CHUNKED, LOOP_GRAPH = 0, 1
 FEAT_RESISTANCE = 1
+FEAT_BLOCKING_WAIT = 2
 
 METHODS = {"exact": METHOD_EXACT, "cosine_similarity": METHOD_COSINE, "exact_inverse": METHOD_EXACT_INVERSE}
 

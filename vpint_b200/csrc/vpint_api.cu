@@ -103,6 +103,7 @@ struct vpint_solver {
     int64_t tiles_full = 0;           // active tiles of the full list built at load
     bool tiles_trimmed = false;       // the list currently covers only the problems that were still running
     bool has_orig = false;
+    bool blocking_wait = false;       // VPINT_FEAT_BLOCKING_WAIT: s->ev sleeps, load() waits on it
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
     bool state_ratio = false;         // buffers are in ratio space right now
@@ -245,6 +246,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
+    s->blocking_wait = (d->features & VPINT_FEAT_BLOCKING_WAIT) != 0;
     if (s->has_orig) s->off_orig = take(plane);
     s->ws_bytes = off;
     *out = s;
@@ -270,7 +272,8 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
         VP_CUDA(pinned_acquire(&blk), "cudaHostAlloc");
         s->h_counters = static_cast<int *>(blk);
         s->h_extreme = reinterpret_cast<double *>(static_cast<char *>(blk) + 128);
-        VP_CUDA(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming), "cudaEventCreate");
+        VP_CUDA(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming | (s->blocking_wait ? cudaEventBlockingSync : 0)),
+                "cudaEventCreate");
     }
     s->ws = static_cast<char *>(workspace);
     s->loaded = s->weights_ready = s->run_begun = false;
@@ -316,7 +319,12 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
             "tile list");
     VP_CUDA(cudaMemcpyAsync(s->h_counters, s->at<int>(s->off_counters), kCntTotal * sizeof(int), cudaMemcpyDeviceToHost, st),
             "read counters");
-    VP_CUDA(cudaStreamSynchronize(st), "load sync");
+    if (s->blocking_wait) {
+        VP_CUDA(cudaEventRecord(s->ev, st), "event record");
+        VP_CUDA(cudaEventSynchronize(s->ev), "load sync");
+    } else {
+        VP_CUDA(cudaStreamSynchronize(st), "load sync");
+    }
     s->any_dirty = s->h_counters[kCntDirty];
     s->tiles_active = s->h_counters[kCntActiveTiles];
     s->tiles_full = s->tiles_active;

@@ -70,7 +70,7 @@ class Solver:
     """
 
     def __init__(self, ndim, nprob, H, W, T=1, *, nprob_inner=1, storage="float64", planes=True,
-                 k_block=0, shard=None, device=None, resistance=False):
+                 k_block=0, shard=None, device=None, resistance=False, blocking_wait=False):
         self.lib = N.load_library()
         self.torch = _torch()
         self.device = require_cuda(device)
@@ -86,7 +86,7 @@ class Solver:
         d.k_block = int(k_block)
         if shard is not None:
             d.global_H, d.row_offset, d.own_row0, d.own_rows = [int(v) for v in shard]
-        d.features = N.FEAT_RESISTANCE if resistance else 0
+        d.features = (N.FEAT_RESISTANCE if resistance else 0) | (N.FEAT_BLOCKING_WAIT if blocking_wait else 0)
         self._h = C.c_void_p()
         N.check(self.lib, self.lib.vpint_solver_create(C.byref(d), C.byref(self._h)), "vpint_solver_create")
         nbytes = self.lib.vpint_solver_workspace_bytes(self._h)

@@ -8,6 +8,8 @@ bands of many patches -- are ONE batched device solve with per-problem stopping.
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import solve as _solve
@@ -42,6 +44,22 @@ PIPELINE_CHUNK_PATCHES = 16
 PIPELINE_WORKERS = 6
 
 
+def _pipeline_blocking_waits(n_workers):
+    """Should the pipeline threads sleep in their device waits instead of spinning?  Spinning answers a few
+    microseconds sooner, but only while every waiting thread has a core of its own: with several ranks per node
+    (LOCAL_WORLD_SIZE) the spinning threads of all ranks would fight for the cores the process may run on.
+    VPINT_PIPELINE_BLOCKING=0/1 overrides."""
+    env = os.environ.get("VPINT_PIPELINE_BLOCKING")
+    if env in ("0", "1"):
+        return env == "1"
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return (n_workers + 1) * ranks > cores
+
+
 def _known_value_bias(t_dev, kvb, dev):
     """known_value_bias sub-solve (VPint/WP_MRP.py:263-272) for a stack (N, H, W, B) of patches: SD_SMRP on the
     known-cell indicator of every band (init 'zero', gamma = 1 - kvb, default run()); (N * B, H, W) float64."""
@@ -61,11 +79,11 @@ def _known_value_bias(t_dev, kvb, dev):
     return out
 
 
-def _make_solver(nprob, H, W, B, storage, kb, dev, opts):
+def _make_solver(nprob, H, W, B, storage, kb, dev, opts, blocking_wait=False):
     if opts.get("resistance") and kb not in (0, 1):
         kb = 1
     return Solver(2, nprob, H, W, nprob_inner=B, storage=storage, planes=True, k_block=kb, device=dev,
-                  resistance=bool(opts.get("resistance")))
+                  resistance=bool(opts.get("resistance")), blocking_wait=blocking_wait)
 
 
 def _solve_chunk(solver, t_dev, f_dev, opts, res_dev, out_layout, fill):
@@ -142,6 +160,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
     spans = [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
     main = torch.cuda.current_stream(dev)
     n_workers = PIPELINE_WORKERS
+    blocking = _pipeline_blocking_waits(n_workers)
     errors = []
 
     def worker(w):
@@ -153,6 +172,7 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
                 t_buf = torch.empty((chunk, H, W, B), dtype=target.dtype, device=dev)
                 f_buf = torch.empty((chunk, H, W, B), dtype=features.dtype, device=dev)
                 r_buf = torch.empty(res_shape(chunk), dtype=res_dtype, device=dev)
+                done = torch.cuda.Event(blocking=True)
                 try:
                     with torch.cuda.stream(st):
                         for i in range(w, len(spans), n_workers):
@@ -161,12 +181,16 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
                             t_buf[:m].copy_(target[a:b], non_blocking=True)
                             f_buf[:m].copy_(features[a:b], non_blocking=True)
                             if m not in solvers:
-                                solvers[m] = _make_solver(m * B, H, W, B, storage, kb, dev, opts)
+                                solvers[m] = _make_solver(m * B, H, W, B, storage, kb, dev, opts, blocking_wait=blocking)
                             niter = _solve_chunk(solvers[m], t_buf[:m], f_buf[:m], opts, r_buf[:m], out_layout,
                                                  None if fill is None else fill[a:b].reshape(-1))
                             out[a:b].copy_(r_buf[:m], non_blocking=True)
                             sweeps_host[a * B:b * B].copy_(niter, non_blocking=True)
-                            st.synchronize()          # r_buf / niter are reused by this thread's next chunk
+                            if blocking:              # r_buf / niter are reused by this thread's next chunk
+                                done.record(st)
+                                done.synchronize()
+                            else:
+                                st.synchronize()
                 finally:
                     for sv in solvers.values():
                         sv.close()
