@@ -186,6 +186,29 @@ cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, vo
 // ---- device helpers -------------------------------------------------------
 #if defined(__CUDACC__)
 
+// Coalesced copy of `count` elements from global to (this warp's) shared memory: 16-byte vectors, several
+// independent loads in flight per lane, when source and length allow; element-wise otherwise.
+template <typename T>
+__device__ __forceinline__ void warp_stage(T *dst, const T *__restrict__ src, int count, int lane) {
+    constexpr int kPer = 16 / (int)sizeof(T);
+    if ((count % kPer) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int4 *s4 = reinterpret_cast<const int4 *>(src);
+        int4 *d4 = reinterpret_cast<int4 *>(dst);
+        const int n4 = count / kPer;
+        int k = lane;
+        for (; k + 7 * 32 < n4; k += 8 * 32) {
+            int4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = s4[k + u * 32];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d4[k + u * 32] = v[u];
+        }
+        for (; k < n4; k += 32) d4[k] = s4[k];
+    } else {
+        for (int k = lane; k < count; k += 32) dst[k] = src[k];
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) fill_mean_bands_kernel(Geom g, const TIn 
     TIn *my = stage + warp * run;
     for (int l = warp; l < NL; l += 8) {
         const TIn *src = base + (int64_t)l * run;
-        for (int k = lane; k < run; k += 32) my[k] = src[k];
+        warp_stage(my, src, run, lane);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < kFillBandsMax / 4; ++q) {
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) prepare_bands_kernel(Geom g, 
     const int po = (int)(r / g.H), y = (int)(r - (int64_t)po * g.H);
     TIn *my = reinterpret_cast<TIn *>(prep_raw) + (size_t)warp * g.L * B;
     const TIn *src = original + (int64_t)po * sd.sO + (int64_t)y * sd.sY;
-    for (int k = lane; k < g.L * B; k += 32) my[k] = src[k];
+    warp_stage(my, src, g.L * B, lane);
     __syncwarp();
     const bool owned = (y >= g.own_row0) && (y < g.own_row0 + g.own_rows);
     bool wild = false;

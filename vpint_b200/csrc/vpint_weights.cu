@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kFplaneWarps * 32) fplane_bands_kernel(int n_p
     const int po = (int)(r / H), y = (int)(r - (int64_t)po * H);
     TIn *my = reinterpret_cast<TIn *>(fp_raw) + (size_t)warp * W * Pin;
     const TIn *src = feat + (int64_t)po * sO + (int64_t)y * sY;
-    for (int k = lane; k < W * Pin; k += 32) my[k] = src[k];
+    warp_stage(my, src, W * Pin, lane);
     __syncwarp();
     bool bad = false, wild = false, wide = false;
     for (int b = 0; b < Pin; ++b) {
