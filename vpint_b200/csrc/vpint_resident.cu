@@ -415,15 +415,19 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
         }
         VPR_TR(5);
         const uint32_t npo = (uint32_t)(npar * c.LB * c.SP);   // (6)
+        // the rows the neighbour CTAs wait for go out first, the local stores follow
+        unsigned ek[KT > 0 ? KT : 1];
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const int i = c.tid + k * kThreads;
-            if (i <= last) {
-                const unsigned e = c.list[i];
+            ek[k] = (i <= last) ? c.list[i] : 0u;
+        }
+        const int hb = c.half + 2;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const unsigned e = ek[k];
+            if (e & (kSegSendUp | kSegSendDn)) {
                 const int off = (int)(e & 0xffffu);
-                const int hb = c.half + 2;
-                *reinterpret_cast<double2 *>(c.plane + off) = make_double2(nr[k][0], nr[k][1]);
-                *reinterpret_cast<double2 *>(c.plane + off + hb) = make_double2(nr[k][2], nr[k][3]);
                 const int lb = (int)((e >> 25) & 7u);
                 if (e & kSegSendUp) {              // first row of my block = lower halo of the block above (CTA c-1)
                     const uint32_t dst = c.up_halo + (npo + (uint32_t)((lb + c.shift_up) * c.SP + off - lb * c.BS * c.SP)) * 8u;
@@ -435,6 +439,15 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
                     st_async2(dst, nr[k][0], nr[k][1], c.dn_bar[npar]);
                     st_async2(dst + (uint32_t)hb * 8u, nr[k][2], nr[k][3], c.dn_bar[npar]);
                 }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int i = c.tid + k * kThreads;
+            if (i <= last) {
+                const int off = (int)(ek[k] & 0xffffu);
+                *reinterpret_cast<double2 *>(c.plane + off) = make_double2(nr[k][0], nr[k][1]);
+                *reinterpret_cast<double2 *>(c.plane + off + hb) = make_double2(nr[k][2], nr[k][3]);
             }
         }
         VPR_TR(7);
