@@ -194,3 +194,38 @@ def test_contrast_map_and_subsampling_match_reference_semantics():
         assert np.isnan(s).sum() == 1 + int(0.25 * 41)
     with pytest.raises(VPintError):
         _subsample(m, 'bogus', 0.5)
+
+
+def test_pipeline_wait_policy(monkeypatch):
+    """Pipeline threads spin in their device waits only while every one of them can have a core
+    (vpint_b200/vpint2.py:_pipeline_blocking_waits); VPINT_PIPELINE_BLOCKING overrides."""
+    import os
+    from vpint_b200 import vpint2 as V
+    monkeypatch.delenv("VPINT_PIPELINE_BLOCKING", raising=False)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(16)), raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert V._pipeline_blocking_waits(6) is False
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert V._pipeline_blocking_waits(6) is True
+    monkeypatch.setenv("VPINT_PIPELINE_BLOCKING", "0")
+    assert V._pipeline_blocking_waits(6) is False
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    monkeypatch.setenv("VPINT_PIPELINE_BLOCKING", "1")
+    assert V._pipeline_blocking_waits(6) is True
+
+
+def test_bench_numa_binding_degrades_gracefully():
+    """bench.bind_to_gpu_node must never raise: without NVML (this container) it reports 'unbound'."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    msg = bench.bind_to_gpu_node(0)
+    assert isinstance(msg, str) and msg
+    if msg.startswith("unbound"):
+        assert os.sched_getaffinity(0) == before
+    else:                                         # a box with NVML: restore for the tests that follow
+        os.sched_setaffinity(0, before)
