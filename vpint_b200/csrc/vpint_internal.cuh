@@ -98,7 +98,7 @@ struct DecideArgs {
 };
 
 // ---- cluster-resident solve (vpint_resident.cu) -----------------------------
-constexpr int kResidentThreads = 512;
+constexpr int kResidentThreads = 512;   // 15 worker warps + the sync warp
 constexpr int kResidentCtasPerSm = 1;  // measured: 2 x 256 threads (clusters of 8) and 1 x 1024 threads are both slower than 1 x 512
 constexpr int kResidentMaxSeg = 9;    // 4-cell segments per worker thread (new values kept in registers); 480 x 9 >= 64 rows x 64 segments
 

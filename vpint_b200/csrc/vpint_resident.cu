@@ -204,7 +204,7 @@ __device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
     a = v.x; b = v.y;
 }
 
-// Stop decision of one sweep from the C partials (warp 0 of every CTA computes the same thing):
+// Stop decision of one sweep from the C partials (the sync warp of every CTA computes the same thing):
 // delta = nanmean|new-old| / nanmean(old) with the known-cell constants added (VPint/SD_MRP.py:139).
 // Returns 0 continue, 1 stop, 2 non-finite data (leave the problem to the tiled path).
 __device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned ph_s, int C, const double *KK, double n_cells,
