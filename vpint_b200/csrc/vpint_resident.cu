@@ -579,6 +579,10 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         const double gamma = RATIO ? 1.0 : a.gamma[p];
 
         // ---- stage the owned rows and both halo rows (r = P / f in RATIO form) ----------------
+        // The mask words of the owned rows are parked in the (not yet used) feature area, so that the two passes of
+        // the list build below read shared memory instead of paying a global-memory round trip per row.
+        unsigned *mask_s = ((size_t)n_rows * nwords * sizeof(unsigned) <= (size_t)a.fcap * 32)
+                               ? reinterpret_cast<unsigned *>(sm.fseg) : nullptr;
         for (int row = warp; row < n_rows + 2 * LB; row += kAllWarps) {
             // rows 0 .. n_rows-1: owned rows; then for every block its upper and its lower halo row
             int gy;
@@ -594,6 +598,8 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 dst = ((h & 1) ? sm.halo_dn : sm.halo_up) + (size_t)lb * SP;
             }
             const bool in_grid = (gy >= 0) && (gy < H);
+            if (mask_s && !is_halo)
+                for (int w = lane; w < nwords; w += 32) mask_s[row * nwords + w] = mrow[(size_t)gy * g.mpitch + w];
             const int half = SP / 2, ncell = 2 * half - 4;          // 4 * segments per row
             if (lane < 2) {                                         // the zero pairs (grid border left / right)
                 dst[ncell / 2 + lane] = 0.0; dst[half + lane] = 0.0;
@@ -626,6 +632,8 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
             }
         }
 
+        __syncthreads();                               // mask_s complete (rows were staged by other warps)
+
         // ---- compact row-major list of the segments that hold an unknown cell ------------------
         // A mask word covers 8 segments (nibbles); warps take contiguous row chunks, so the list order
         // (and with it every partial sum) is fixed.
@@ -638,7 +646,8 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         };
         int cnt = 0;
         for (int ly = wr0; ly < wr1; ++ly)
-            for (int w = lane; w < nwords; w += 32) cnt += __popc(nibbles(mrow[(size_t)grid_row(ly) * g.mpitch + w]));
+            for (int w = lane; w < nwords; w += 32)
+                cnt += __popc(nibbles(mask_s ? mask_s[ly * nwords + w] : mrow[(size_t)grid_row(ly) * g.mpitch + w]));
         cnt = warp_sum(cnt);
         if (lane == 0) wcount[warp] = cnt;
         __syncthreads();
@@ -656,7 +665,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
             const bool row_edge = (gy == 0) || (gy == H - 1);
             for (int w0 = 0; w0 < nwords; w0 += 32) {
                 const int w = w0 + lane;
-                const unsigned word = (w < nwords) ? mrow[(size_t)gy * g.mpitch + w] : 0u;
+                const unsigned word = (w < nwords) ? (mask_s ? mask_s[ly * nwords + w] : mrow[(size_t)gy * g.mpitch + w]) : 0u;
                 unsigned nz = nibbles(word);
                 const int pc = __popc(nz);
                 int incl = pc;
@@ -708,9 +717,9 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         const int Kmax = (n > w_first) ? (n - 1 - w_first) / kThreads + 1 : 0;   // warp-uniform
         int kt = kMaxSeg;                                  // smallest unrolled variant >= Kmax
         {
-            const int kts[7] = {0, 1, 2, 3, 4, 6, 8};
+            const int kts[8] = {0, 1, 2, 3, 4, 5, 6, 8};
 #pragma unroll
-            for (int q = 6; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
+            for (int q = 7; q >= 0; --q) if (Kmax <= kts[q]) kt = kts[q];
         }
         // segments on the first / last owned row: what the neighbours must expect from this CTA per sweep
         if (tid < 2) sh.edge_cnt[tid] = 0;
@@ -788,6 +797,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 case 2: VPR_RUN(2); break;
                 case 3: VPR_RUN(3); break;
                 case 4: VPR_RUN(4); break;
+                case 5: VPR_RUN(5); break;
                 case 6: VPR_RUN(6); break;
                 case 8: VPR_RUN(8); break;
                 default: VPR_RUN(kMaxSeg); break;
