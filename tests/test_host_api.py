@@ -205,6 +205,12 @@ def test_pipeline_wait_policy(monkeypatch):
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(16)), raising=False)
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
     assert V._pipeline_blocking_waits(6) is False
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert V._pipeline_blocking_waits(6) is True          # 14 threads want more than half of 16 cores
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
+    assert V._pipeline_blocking_waits(6) is False
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    assert V._pipeline_blocking_waits(6) is True
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
     assert V._pipeline_blocking_waits(6) is True
     monkeypatch.setenv("VPINT_PIPELINE_BLOCKING", "0")

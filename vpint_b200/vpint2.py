@@ -46,9 +46,10 @@ PIPELINE_WORKERS = 6
 
 def _pipeline_blocking_waits(n_workers):
     """Should the pipeline threads sleep in their device waits instead of spinning?  Spinning answers a few
-    microseconds sooner, but only while every waiting thread has a core of its own: with several ranks per node
-    (LOCAL_WORLD_SIZE) the spinning threads of all ranks would fight for the cores the process may run on.
-    VPINT_PIPELINE_BLOCKING=0/1 overrides."""
+    microseconds sooner (one GPU, 16 cores: 87 ms per step against 93 ms), but only while the waiting threads leave
+    half of the cores to everything else that runs (NCCL and torch helper threads, the copies): with several ranks
+    per node (LOCAL_WORLD_SIZE) the spinning threads of all ranks fight for the cores the process may run on
+    (4 ranks x 7 threads on 32 cores: 230 ms spinning, 197 ms sleeping).  VPINT_PIPELINE_BLOCKING=0/1 overrides."""
     env = os.environ.get("VPINT_PIPELINE_BLOCKING")
     if env in ("0", "1"):
         return env == "1"
@@ -57,7 +58,7 @@ def _pipeline_blocking_waits(n_workers):
     except AttributeError:
         cores = os.cpu_count() or 1
     ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return (n_workers + 1) * ranks > cores
+    return 2 * (n_workers + 1) * ranks > cores
 
 
 def _known_value_bias(t_dev, kvb, dev):
