@@ -725,6 +725,34 @@ def test_resident_feature_width_switch_on_one_solver():
         s.close()
 
 
+def test_eo_wrapper_multiband_vpint():
+    """multiband_VPint (VPint/utils/EO_wrapper.py:15-21) = per-band WP_SMRP runs, here as one batched solve."""
+    from vpint_b200.utils.EO_wrapper import multiband_VPint
+    rng = np.random.default_rng(515)
+    shape = (60, 72)
+    B = 4
+    base = np.stack([smooth(rng, shape, 500, 2500) for _ in range(B)], axis=-1)
+    target = np.round(base + rng.normal(0, 20, base.shape))
+    feats = np.round(1.1 * base + rng.normal(0, 10, base.shape))
+    target[discs(rng, shape, 3, 5, 18), :] = np.nan
+    keep = target.copy()
+    got = multiband_VPint(target, feats)
+    assert got.dtype == target.dtype and got.shape == target.shape
+    assert np.array_equal(target, keep, equal_nan=True)            # the caller's array is not touched
+    for b in range(B):
+        ref, _, _ = O.wp_run_2d(target[:, :, b], O.init_pred(target[:, :, b]), feats[:, :, b:b + 1].copy())
+        close(got[:, :, b], ref)
+    fixed = multiband_VPint(target, feats, iterations=9)
+    for b in range(B):
+        ref, _, _ = O.wp_run_2d(target[:, :, b], O.init_pred(target[:, :, b]), feats[:, :, b:b + 1].copy(), iterations=9)
+        close(fixed[:, :, b], ref)
+    pair = multiband_VPint(target, feats, iterations=5, method='cosine_similarity', min_gamma=0.2, max_gamma=1.05)
+    for b in range(B):
+        ref, _, _ = O.wp_run_2d(target[:, :, b], O.init_pred(target[:, :, b]), feats[:, :, b:b + 1].copy(), iterations=5,
+                                method='cosine_similarity', min_gamma=0.2, max_gamma=1.05)
+        close(pair[:, :, b], ref)
+
+
 def test_degenerate_grids(kblock):
     rng = np.random.default_rng(12)
     full = smooth(rng, (20, 20), 10, 20)                       # nothing to interpolate: one sweep, delta 0

@@ -235,3 +235,35 @@ def test_bench_numa_binding_degrades_gracefully():
         assert os.sched_getaffinity(0) == before
     else:                                         # a box with NVML: restore for the tests that follow
         os.sched_setaffinity(0, before)
+
+
+def test_eo_wrapper_apply_cloud_mask_matches_reference_loop():
+    """VPint/utils/EO_wrapper.py:23-37 restated as the reference's pixel loop."""
+    from vpint_b200.utils.EO_wrapper import apply_cloud_mask
+    rng = np.random.default_rng(4)
+    target = rng.uniform(1, 2, (9, 11, 4)).astype(np.float32)
+    mask = rng.uniform(0, 1, (9, 11, 2))
+    mask[3, 5, 0] = np.nan
+
+    def loop(target_img, mask, threshold=None):
+        cloud_img = target_img.copy()
+        for i in range(target_img.shape[0]):
+            for j in range(target_img.shape[1]):
+                hit = np.isnan(mask[i, j, 0]) if threshold is None else (mask[i, j, 0] > threshold)
+                if hit:
+                    cloud_img[i, j, :] = np.nan
+        return cloud_img
+
+    for thr in (None, 0.35, 2.0):
+        got = apply_cloud_mask(target, mask, thr)
+        same(got, loop(target, mask, thr))
+        assert got is not target and not np.isnan(target).any()
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")
+def test_eo_wrapper_multiband_fails_loudly_without_cuda():
+    from vpint_b200.utils.EO_wrapper import multiband_VPint
+    t = np.ones((5, 5, 2))
+    t[1, 1, :] = np.nan
+    with pytest.raises(VPintError, match="no CPU fallback"):
+        multiband_VPint(t, np.ones((5, 5, 2)))
