@@ -372,13 +372,17 @@ class VPint2_interpolator():
             cloudy = np.isnan(img).any(axis=2)
             grown = np.zeros((H, W), dtype=bool)
             if b > 0:
-                pad = np.zeros((H + 2 * b, W + 2 * b), dtype=bool)
-                pad[b:b + H, b:b + W] = cloudy
-                # output (y, x) is covered by source (i, j) iff i-b <= y < i+b and j-b <= x < j+b
+                # output (y, x) is covered by source (i, j) iff i-b <= y < i+b and j-b <= x < j+b: a rectangle, so the
+                # dilation separates into a pass along the rows and a pass along the columns (4b shifts, not 4b^2)
+                pad = np.zeros((H + 2 * b, W), dtype=bool)
+                pad[b:b + H, :] = cloudy
+                tall = np.zeros((H, W), dtype=bool)
                 for dy in range(-b + 1, b + 1):
-                    rows = pad[b + dy:b + dy + H, :]
-                    for dx in range(-b + 1, b + 1):
-                        grown |= rows[:, b + dx:b + dx + W]
+                    tall |= pad[b + dy:b + dy + H, :]
+                pad = np.zeros((H, W + 2 * b), dtype=bool)
+                pad[:, b:b + W] = tall
+                for dx in range(-b + 1, b + 1):
+                    grown |= pad[:, b + dx:b + dx + W]
                 if H < W:
                     grown[:, H:] = False
             new_img[grown, :] = np.nan
