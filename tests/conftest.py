@@ -15,6 +15,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: without one they are skipped instead of erroring.  On a box WITH a device a
+    missing library is not a reason to skip -- the tests then fail loudly (there is no CPU fallback to hide behind)."""
+    reason = None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            reason = "no CUDA device"
+    except Exception:                                   # pragma: no cover
+        reason = "torch not importable"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}

@@ -257,6 +257,30 @@ def case_vpint2_ctor():
     save("vpint2_ctor", **out)
 
 
+def case_metrics():
+    """MRP.r_squared / MAE / RMSE / PSNR and SMRP.mean_absolute_error (VPint/MRP.py:116-233,284-325) on a fixed
+    prediction: pred_grid is set by hand, so the fixture pins the formulas, not a solve."""
+    rng = np.random.default_rng(1010)
+    out = {}
+    for tag, shape in (("2d", (24, 24)), ("3d", (10, 12, 5))):
+        true = smooth(rng, shape, 10, 30) + rng.normal(0, 0.5, shape)
+        grid = true.copy()
+        grid[holes(rng, shape, 0.3)] = np.nan
+        true_nan = true.copy()
+        true_nan[holes(rng, shape, 0.05)] = np.nan           # the metrics replace NaNs of the ground truth by its nanmean
+        m = SD_SMRP(grid.copy(), gamma=0.9) if len(shape) == 2 else SD_STMRP(grid.copy(), auto_timesteps=False)
+        pred = np.where(np.isnan(grid), true + rng.normal(0, 1.0, shape), grid)
+        m.pred_grid = pred.copy()
+        out.update({"grid_" + tag: grid, "true_" + tag: true_nan, "pred_" + tag: pred,
+                    "r2_" + tag: np.float64(m.r_squared(true_nan.copy())), "mae_" + tag: np.float64(m.MAE(true_nan.copy())),
+                    "rmse_" + tag: np.float64(m.RMSE(true_nan.copy())), "psnr_" + tag: np.float64(m.PSNR(true_nan.copy()))})
+        if len(shape) == 2:
+            mae, eg = m.mean_absolute_error(true.copy(), scale_factor=1, gridded=True)
+            out.update({"truefull_2d": true, "smae_2d": np.float64(mae), "smae_grid_2d": eg,
+                        "smae2_2d": np.float64(m.mean_absolute_error(true.copy(), scale_factor=2))})
+    save("metrics", **out)
+
+
 def case_adapt():
     """WP_SMRP.run(auto_adapt=True): the host-side search of VPint/WP_MRP.py:212-239, 429-759 with seeded
     global RNG.  Written to its own file so that the earlier fixtures stay untouched."""
@@ -298,3 +322,4 @@ if __name__ == "__main__":
     case_st3d()
     case_vpint2()
     case_adapt()
+    case_metrics()

@@ -267,3 +267,22 @@ def test_eo_wrapper_multiband_fails_loudly_without_cuda():
     t[1, 1, :] = np.nan
     with pytest.raises(VPintError, match="no CPU fallback"):
         multiband_VPint(t, np.ones((5, 5, 2)))
+
+
+def test_metrics_match_reference(golden):
+    """MRP.r_squared / MAE / RMSE / PSNR / SMRP.mean_absolute_error against values produced by the reference
+    (tests/golden/make_golden.py case_metrics; VPint/MRP.py:116-233,284-325)."""
+    g = golden("metrics")
+    for tag in ("2d", "3d"):
+        m = SD_SMRP(g["grid_" + tag].copy(), gamma=0.9) if tag == "2d" else SD_STMRP(g["grid_" + tag].copy(), auto_timesteps=False)
+        m.pred_grid = g["pred_" + tag].copy()
+        t = g["true_" + tag]
+        assert np.isclose(m.r_squared(t.copy()), g["r2_" + tag], rtol=1e-12, atol=0)
+        assert np.isclose(m.MAE(t.copy()), g["mae_" + tag], rtol=1e-12, atol=0)
+        assert np.isclose(m.RMSE(t.copy()), g["rmse_" + tag], rtol=1e-12, atol=0)
+        assert np.isclose(m.PSNR(t.copy()), g["psnr_" + tag], rtol=1e-12, atol=0)
+    m = SD_SMRP(g["grid_2d"].copy(), gamma=0.9)
+    m.pred_grid = g["pred_2d"].copy()
+    mae, eg = m.mean_absolute_error(g["truefull_2d"].copy(), scale_factor=1, gridded=True)
+    assert np.isclose(mae, g["smae_2d"], rtol=1e-12, atol=0) and np.allclose(eg, g["smae_grid_2d"], rtol=1e-12, atol=0)
+    assert np.isclose(m.mean_absolute_error(g["truefull_2d"].copy(), scale_factor=2), g["smae2_2d"], rtol=1e-12, atol=0)

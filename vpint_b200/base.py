@@ -71,25 +71,54 @@ class MRP:
         grid_vec[mask_vec == 1] = np.nan
         return grid_vec.reshape(shp)
 
-    # -- evaluation helpers on unknown cells (VPint/MRP.py:116-230), vectorised ----
+    # -- evaluation helpers on unknown cells (VPint/MRP.py:116-259) -------------------
+    # Host NumPy like the reference (not on the device path); the formulas are the reference's,
+    # its per-cell loops written as array expressions: NaNs of the ground truth are first replaced by
+    # its nanmean, the errors are taken over the cells that were unknown in original_grid.
     def _eval_pairs(self, true_grid):
+        true = np.asarray(true_grid)
+        true = np.nan_to_num(true, nan=np.nanmean(true))
         sel = np.isnan(self.original_grid)
-        return np.asarray(true_grid)[sel], np.asarray(self.pred_grid)[sel]
-
-    def MAE(self, true_grid):
-        t, p = self._eval_pairs(true_grid)
-        return float(np.mean(np.abs(t - p)))
-
-    def RMSE(self, true_grid):
-        """The reference returns the MEAN SQUARED error under this name (VPint/MRP.py:204)."""
-        t, p = self._eval_pairs(true_grid)
-        return float(np.mean((t - p) ** 2))
+        return true, true[sel], np.asarray(self.pred_grid)[sel]
 
     def r_squared(self, true_grid):
-        t, p = self._eval_pairs(true_grid)
-        ss_res = np.sum((t - p) ** 2)
-        ss_tot = np.sum((t - np.mean(t)) ** 2)
-        return float(1 - ss_res / ss_tot)
+        """1 - SS_res / SS_tot over the unknown cells, SS_tot against the mean of the WHOLE ground truth
+        (VPint/MRP.py:123-157)."""
+        true, t, p = self._eval_pairs(true_grid)
+        m = np.mean(true)
+        res = np.sum((t - p) ** 2)
+        tot = np.sum((t - m) ** 2)
+        return 1 - (res / tot)
+
+    def MAE(self, true):
+        """VPint/MRP.py:160-180 (nanmean of |true - pred| over the unknown cells)."""
+        _, t, p = self._eval_pairs(true)
+        return np.nanmean(np.absolute(t - p))
+
+    def RMSE(self, true):
+        """The reference returns the MEAN SQUARED error under this name (VPint/MRP.py:183-204); kept."""
+        _, t, p = self._eval_pairs(true)
+        return np.mean(np.square(t - p))
+
+    def PSNR(self, true):
+        """VPint/MRP.py:207-233: 20 log10(255 / sqrt(mse + 0.001)) / 100."""
+        from math import log10, sqrt
+        _, t, p = self._eval_pairs(true)
+        mse = np.nanmean((t - p) ** 2) + 0.001
+        if mse == 0:
+            return 1
+        return 20 * log10(255.0 / sqrt(mse)) / 100
+
+    def SSIM(self, true):
+        """VPint/MRP.py:235-259 needs scikit-image's ``compare_ssim`` and returns NaN without it; the same here."""
+        _, t, p = self._eval_pairs(true)
+        try:
+            from skimage.measure import compare_ssim
+            (s, d) = compare_ssim(t, p, full=True)
+        except Exception:
+            print("Error running compare_ssim. For this functionality, please ensure that scikit-image is installed.")
+            s = np.nan
+        return s
 
 
 class SMRP(MRP):
@@ -97,6 +126,22 @@ class SMRP(MRP):
 
     def __init__(self, grid, init_strategy='mean', mask=None):
         super().__init__(grid, init_strategy=init_strategy, mask=mask)
+
+    def mean_absolute_error(self, true_grid, scale_factor=1, gridded=False):
+        """Block-summed MAE over the unknown cells ("old code" of the reference, VPint/MRP.py:284-325; the
+        ground truth is only block-summed along the rows there -- kept)."""
+        height, width = self.pred_grid.shape[0], self.pred_grid.shape[1]
+        nh, nw = int(height / scale_factor), int(width / scale_factor)
+        blk = (nh, int(height / nh), nw, int(width / nw))
+        pred = self.pred_grid.copy().reshape(blk).sum(3).sum(1)
+        orig = self.original_grid.copy().reshape(blk).sum(3).sum(1)
+        # (nh, width): summed over row blocks only; the reference then indexes its first nw columns
+        true = true_grid.copy().reshape((nh, int(height / nh), width, int(nw / nw))).sum(3).sum(1)[:, :nw]
+        sel = np.isnan(orig)
+        error_grid = np.zeros((nh, nw))
+        error_grid[sel] = np.abs(pred - true)[sel]
+        mae = error_grid[sel].sum() / int(sel.sum())
+        return (mae, error_grid) if gridded else mae
 
 
 class STMRP(MRP):

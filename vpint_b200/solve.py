@@ -28,13 +28,15 @@ def _as_float(a):
 def propagate(original, pred, *, planes, features=None, method="exact", clamp=False, min_gamma=0.0,
               max_gamma=math.inf, gamma=None, tau=None, max_iter, auto_terminate, threshold, clip_val=math.inf,
               track_delta=False, storage="float64", k_block=None, device=None,
-              priority=None, resistance=None):
+              priority=None, resistance=None, info=None):
     """Run the propagation loop for ONE grid (2-D) or cube (3-D).
 
     original / pred : numpy (H, W) or (H, W, T); NaN in ``original`` = unknown.
     features        : numpy (H, W, F) when ``planes``.
     priority        : None or dict(beta=..., bias=(H, W) ndarray or None, want_planes=bool): prioritise_identity
-                      (VPint/WP_MRP.py:243-276); the planes come back under ``propagate.last_priority``.
+                      (VPint/WP_MRP.py:243-276); the planes come back as ``info["priority_planes"]``.
+    info            : optional dict that receives by-products of the call (no process-global state: the library
+                      is driven from several host threads).
     resistance      : None or (epsilon, mu) (VPint/WP_MRP.py:327-348).
     Returns (pred_grid float64 ndarray, delta_vec float64 ndarray or None, sweeps).
     """
@@ -58,7 +60,6 @@ def propagate(original, pred, *, planes, features=None, method="exact", clamp=Fa
         raise VPintError("prioritise_identity / resistance belong to WP_SMRP (2-D, weight planes)")
     if resistance is not None and kb not in (0, 1):
         kb = 1          # the resistance sweep rewrites every cell: one sweep per launch
-    propagate.last_priority = None
     solver = Solver(ndim, 1, H, W, T, storage=storage, planes=planes, k_block=kb, device=dev,
                     resistance=resistance is not None)
     try:
@@ -73,8 +74,8 @@ def propagate(original, pred, *, planes, features=None, method="exact", clamp=Fa
                 bias = priority.get("bias")
                 b_dev = None if bias is None else to_device(np.ascontiguousarray(bias, dtype=np.float64), dev).unsqueeze(0)
                 planes_out = solver.priority(priority["beta"], bias=b_dev, want_planes=priority.get("want_planes", False))
-                if planes_out is not None:
-                    propagate.last_priority = planes_out[0].cpu().numpy()
+                if planes_out is not None and info is not None:
+                    info["priority_planes"] = planes_out[0].cpu().numpy()
         else:
             solver.discounts(gamma, tau if ndim == 3 else None)
         solver.run(max_iter, auto_terminate=auto_terminate, threshold=threshold, clip_val=clip_val,
@@ -92,5 +93,3 @@ def propagate(original, pred, *, planes, features=None, method="exact", clamp=Fa
     finally:
         solver.close()
 
-
-propagate.last_priority = None

@@ -230,8 +230,10 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
     single = (target.ndim == 3)
     tgt = target[None] if single else target
     fts = features[None] if single else features
+    # WP_SMRP casts the features with astype(float) (VPint/WP_MRP.py:67-71): integer rasters are fine on either side
     if tgt.dtype not in (np.float32, np.float64):
         tgt = tgt.astype(np.float64)
+    if fts.dtype not in (np.float32, np.float64):
         fts = fts.astype(np.float64)
     N, H, W, B = tgt.shape
     max_iter = opts["iterations"]

@@ -166,17 +166,21 @@ class WP_SMRP(SMRP):
                 bias = SD_SMRP(ind, init_strategy='zero', gamma=(1 - known_value_bias)).run()
             priority = dict(beta=priority_intensity, bias=bias, want_planes=True)
         delta_vec = np.zeros(iterations) if track_delta else None
-        if iterations > 0:
+        if iterations > 0 or priority is not None:
+            # iterations == 0 with prioritise_identity: the reference still builds self.priority_grid before its
+            # (empty) loop (VPint/WP_MRP.py:260), so the weights and the planes are formed and no sweep runs
+            info = {}
             new_grid, deltas, sweeps = propagate(
                 self.original_grid, self.pred_grid, planes=True, features=self.feature_grid, method=method,
                 clamp=(method != 'exact'), min_gamma=self.min_gamma, max_gamma=self.max_gamma,
                 max_iter=iterations, auto_terminate=auto_terminate, threshold=auto_terminate_threshold,
                 clip_val=clip_val, track_delta=track_delta, priority=priority,
-                resistance=(epsilon, mu) if resistance else None)
-            self.pred_grid = new_grid
+                resistance=(epsilon, mu) if resistance else None, info=info)
+            if iterations > 0:
+                self.pred_grid = new_grid
             if priority is not None:
-                self.priority_grid = propagate.last_priority     # debugging access, as in the reference (:260)
-            if track_delta:
+                self.priority_grid = info.get("priority_planes")     # debugging access, as in the reference (:260)
+            if track_delta and iterations > 0:
                 delta_vec[:sweeps] = deltas
                 if auto_terminate:
                     delta_vec = delta_vec[0:sweeps]
