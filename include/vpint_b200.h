@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VPINT_ABI_VERSION 1
+#define VPINT_ABI_VERSION 2
 
 /* status codes */
 #define VPINT_OK               0
@@ -46,6 +46,8 @@ extern "C" {
 /* element types */
 #define VPINT_F64 0
 #define VPINT_F32 1
+#define VPINT_U16 2   /* raw rasters of the fused VPint2 load only (Sentinel-2 bands, VPint/utils/EO_utils.py:66) */
+#define VPINT_U8  3   /* cloud masks only */
 
 /* weight modes */
 #define VPINT_W_SCALAR 0   /* SD_*: per-problem gamma (and tau in 3-D)          */
@@ -165,8 +167,9 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
 int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, double *p_out, void *stream);
 
 /* VPINT_W_SCALAR: HOST arrays [nprob]; tau is ignored for ndim == 2
- * (SD_MRP.py:87, 315-321). */
-int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau);
+ * (SD_MRP.py:87, 315-321).  The copy is ordered on `stream` like every other call (the host arrays may be
+ * reused as soon as the call returns). */
+int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau, void *stream);
 
 /* ---- A4 + A5 the loop --------------------------------------------------
  * Jacobi sweeps with the reference's stopping rule
@@ -211,6 +214,74 @@ int     vpint_solver_known_count(const vpint_solver *s);
 int     vpint_solver_any_dirty(const vpint_solver *s);
 int     vpint_solver_halo_pack(vpint_solver *s, int rows, void *to_up, void *to_down, void *stream);
 int     vpint_solver_halo_unpack(vpint_solver *s, int rows, const void *from_up, const void *from_down, void *stream);
+
+/* Non-blocking form of vpint_solver_run for solves the cluster-resident kernel serves (small 2-D grids, one
+ * feature layer or scalar gamma): run_async enqueues the whole run() -- one kernel launch -- and returns; the host
+ * may enqueue vpint_solver_result* behind it and go on to other solvers / streams.  run_finish waits for it and, in
+ * the rare case the kernel declined (non-finite data), completes the run on the tiled path -- after which results
+ * read earlier must be read again; it returns 1 in *reran (may be NULL) then.  For solves the resident kernel
+ * does not serve run_async only records the parameters and run_finish does all the work (== vpint_solver_run). */
+int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *stream);
+int vpint_solver_run_finish(vpint_solver *s, void *stream, int *reran);
+
+/* ---- fused VPint2 load: constructor + A1 + A2 from the raw rasters ---------------------------------------
+ * Replaces, for a band-interleaved stack (n_img, H, W, B) -- nprob = n_img * B, nprob_inner = B --
+ *   VPint2_interpolator.__init__ (VPint/VPint2.py:13-55): astype(DTYPE), clip_target / clip_features, apply_mask
+ *   (mask > threshold -> NaN on every band, :122-132), buffer_clouds (:135-150, incl. the column bound of :146),
+ *   MRP.init_pred_grid 'mean' (VPint/MRP.py:73-77: np.nanmean in DTYPE, NumPy's pairwise summation bit for bit, ANY
+ *   grid size) and the zero -> 0.01 feature rewrite of WP_SMRP.run (VPint/WP_MRP.py:143-145)
+ * with device kernels that read the rasters once.  All pointers are device memory unless stated otherwise. */
+
+/* cloud[i] = mask[i] > threshold (mask dtype VPINT_F64 / F32 / U16 / U8; n = n_img * H * W). */
+int vpint_cloud_mask(const void *mask, int dtype, double threshold, int64_t n, uint8_t *cloud_out, void *stream);
+
+/* buffer_clouds on the all-band mask.  cloud (in/out, [n_img][H][W]) holds the thresholded mask when have_cloud,
+ * else it is output only.  target (dtype F32 / F64; U16 has no NaN) contributes pixels with a NaN in any band to
+ * the dilated footprint.  scratch: 3 * n_img * H * W bytes. */
+int vpint_buffer_clouds(const void *target, int dtype, uint8_t *cloud, int have_cloud, int n_img, int H, int W, int B,
+                        int buffer_size, int passes, uint8_t *scratch, void *stream);
+
+typedef struct vpint_ingest_params {
+    const void *target, *features;  /* (n_img, H, W, B) contiguous, band fastest; H = the solver's (local) rows   */
+    int32_t raster_dtype;           /* VPINT_U16 / VPINT_F32 / VPINT_F64, both rasters                             */
+    int32_t value_dtype;            /* the interpolator's DTYPE (VPINT_F32 = VPint2's default, or VPINT_F64)       */
+    const uint8_t *cloud;           /* [n_img][H][W], nonzero = unknown on every band; may be NULL                 */
+    int32_t clip_target, clip_features;             /* 0 / 1                                                      */
+    double  target_min, target_max, features_min, features_max;
+    int32_t fill_mode;              /* VPINT_FILL_DEVICE, VPINT_FILL_READY or VPINT_FILL_HOST                     */
+    const double *fill_host;        /* HOST [nprob], VPINT_FILL_HOST only                                          */
+    void   *scratch;                /* VPINT_FILL_DEVICE: vpint_fill_scratch_bytes() bytes                         */
+    void   *out;                    /* known cells of the result are written here (full output); may be NULL      */
+    int32_t out_dtype;              /* VPINT_F32 / VPINT_F64                                                       */
+    int64_t out_stride[4];          /* element strides {image, band, row, column} of out                          */
+} vpint_ingest_params;
+
+#define VPINT_FILL_DEVICE 0   /* np.nanmean per band on the device, inside vpint_solver_ingest_bands (unsharded)     */
+#define VPINT_FILL_READY  1   /* the solver already holds the fill values (vpint_solver_fill_combine)                */
+#define VPINT_FILL_HOST   2   /* fill_host[nprob]                                                                    */
+
+size_t vpint_fill_scratch_bytes(int64_t cells_global, int nprob, int value_dtype);
+/* Row shards (and anyone who wants the mean alone): fill_leaves sums the leaves of NumPy's summation tree that START in
+ * this solver's owned rows into scratch (zeros elsewhere; a leaf runs up to 127 cells past the owned rows, which the
+ * halo rows must cover), the caller all-reduces (SUM) vpint_fill_leaf_count() values of value_dtype at scratch and
+ * nprob uint64 counts at scratch + vpint_fill_count_offset(), and fill_combine adds the leaf sums up in NumPy's
+ * order -- every rank gets the bit-identical np.nanmean of the WHOLE band. */
+int     vpint_solver_fill_leaves(vpint_solver *s, const vpint_ingest_params *p, void *stream);
+int64_t vpint_fill_leaf_count(int64_t cells_global, int nprob);
+size_t  vpint_fill_count_offset(int64_t cells_global, int nprob, int value_dtype);
+int     vpint_solver_fill_combine(vpint_solver *s, int value_dtype, void *scratch, void *stream);
+double *vpint_solver_fill_ptr(vpint_solver *s);                /* device double[nprob] */
+
+/* The load itself: state, unknown-cell mask, feature plane, known-cell sums (what vpint_solver_load +
+ * vpint_solver_weights(exact, F = 1) build), without a host synchronisation. */
+int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, void *stream);
+
+/* The unknown cells of the result only (the known ones are the caller's own input, or were written by
+ * vpint_solver_ingest_bands through vpint_ingest_params.out).  out may be device memory or pinned host memory
+ * mapped into the device (cudaHostAlloc / cudaHostRegister): the stores leave as contiguous runs, so only the
+ * cloud cells cross the host link.  stride: {outer problem, inner problem, row, column}. */
+int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
+                                void *stream);
 
 /* ---- results -----------------------------------------------------------
  * out: device, dtype `dtype`, element strides as in load.  This is

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in syms:
         assert hasattr(lib, name), "missing export: " + name
     assert sorted(N.SIGNATURES) == syms, "ctypes prototypes and header disagree"
-    assert lib.vpint_abi_version() == 1
+    assert lib.vpint_abi_version() == N.ABI_VERSION
 
 
 def test_row_pitch():

@@ -16,7 +16,9 @@ LIB_NAME = "libvpint_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
-F64, F32 = 0, 1
+F64, F32, U16, U8 = 0, 1, 2, 3
+FILL_DEVICE, FILL_READY, FILL_HOST = 0, 1, 2
+ABI_VERSION = 2
 W_SCALAR, W_PLANES = 0, 1
 METHOD_EXACT, METHOD_COSINE, METHOD_EXACT_INVERSE = 0, 1, 2
 LOOP_CHUNKED, LOOP_GRAPH = 0, 1
@@ -46,6 +48,22 @@ class RunParams(C.Structure):
     ]
 
 
+class IngestParams(C.Structure):
+    _fields_ = [
+        ("target", C.c_void_p), ("features", C.c_void_p),
+        ("raster_dtype", C.c_int32), ("value_dtype", C.c_int32),
+        ("cloud", C.c_void_p),
+        ("clip_target", C.c_int32), ("clip_features", C.c_int32),
+        ("target_min", C.c_double), ("target_max", C.c_double), ("features_min", C.c_double), ("features_max", C.c_double),
+        ("fill_mode", C.c_int32),
+        ("fill_host", C.POINTER(C.c_double)),
+        ("scratch", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_dtype", C.c_int32),
+        ("out_stride", C.c_int64 * 4),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/vpint_b200.h declares
 SIGNATURES = {
     "vpint_abi_version": (C.c_int, []),
@@ -60,7 +78,20 @@ SIGNATURES = {
     "vpint_solver_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_double, C.c_void_p]),
     "vpint_solver_priority": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "vpint_solver_set_discounts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "vpint_solver_set_discounts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
+    "vpint_solver_run_async": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),
+    "vpint_solver_run_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "vpint_cloud_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vpint_buffer_clouds": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p]),
+    "vpint_fill_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "vpint_fill_leaf_count": (C.c_int64, [C.c_int64, C.c_int]),
+    "vpint_fill_count_offset": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "vpint_solver_fill_leaves": (C.c_int, [C.c_void_p, C.POINTER(IngestParams), C.c_void_p]),
+    "vpint_solver_fill_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vpint_solver_fill_ptr": (C.c_void_p, [C.c_void_p]),
+    "vpint_solver_ingest_bands": (C.c_int, [C.c_void_p, C.POINTER(IngestParams), C.c_void_p]),
+    "vpint_solver_result_unknown": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "vpint_solver_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),
     "vpint_solver_begin_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),
     "vpint_solver_step_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -104,7 +135,7 @@ def load_library(path=None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.vpint_abi_version() != 1:
+    if lib.vpint_abi_version() != ABI_VERSION:
         raise VPintError("vpint_b200: ABI version mismatch in %s" % p)
     if path is None:
         _lib = lib

@@ -85,6 +85,9 @@ struct vpint_solver {
         off_state, off_counters, off_tileflag, off_tiles, off_tilestart, off_partial, off_sums, ws_bytes;
     char *ws = nullptr;
     bool loaded = false, weights_ready = false, run_begun = false, first_step_pending = false;
+    bool tiles_pending = false;       // fused load: tile list / counters not built yet (only the tiled kernels need them)
+    bool bufB_pending = false;        // fused load: second ping-pong buffer not written yet (ditto)
+    bool async_pending = false;       // vpint_solver_run_async launched the resident kernel; run_finish has not checked it
     bool use_tb = false;
     int halo_up = 0, halo_down = 0;   // halo rows above / below the owned band (row-sharded scenes)
     // cluster-resident solve (vpint_resident.cu): chosen when k_block == 0 and one problem fits on chip
@@ -278,12 +281,47 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     s->ws = static_cast<char *>(workspace);
     s->loaded = s->weights_ready = s->run_begun = false;
     s->planes_valid = s->fplane_valid = false;
-    VP_CUDA(cudaMemset(s->at<int>(s->off_flags), 0, 16 * sizeof(int)), "memset flags");
+    // bind has no stream argument: the memset runs on the legacy default stream and is waited for, so that it is
+    // ordered before whatever the caller enqueues next on any (also non-blocking) stream
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, 16 * sizeof(int), cudaStreamLegacy), "memset flags");
+    VP_CUDA(cudaStreamSynchronize(cudaStreamLegacy), "bind sync");
+    s->tiles_pending = s->bufB_pending = s->async_pending = false;
     if (s->use_tb) {
         if (tb_maps_bytes() > sizeof(s->tb_maps)) return fail(VPINT_ERR_INVALID, "internal: tensor map storage too small");
         VP_CUDA(tb_make_maps(s->g, s->storage, s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]), s->tb_maps),
                 "cuTensorMapEncodeTiled");
     }
+    return VPINT_OK;
+}
+
+// Active-tile list + the host copies of the load counters.  vpint_solver_load does this at once (it needs any_dirty);
+// the fused load leaves it to the first tiled launch, because the cluster-resident kernel needs none of it.
+static int resolve_tiles(vpint_solver *s, cudaStream_t st) {
+    if (!s->tiles_pending) return VPINT_OK;
+    const Geom &g = s->g;
+    if (s->bufB_pending) {
+        const size_t plane = (size_t)g.P * g.S * g.H * g.pitch * s->elem;
+        VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_buf[1]), s->at<void>(s->off_buf[0]), plane, cudaMemcpyDeviceToDevice, st),
+                "second state buffer");
+        s->bufB_pending = false;
+    }
+    VP_CUDA(launch_tiles(g, s->at<uint32_t>(s->off_mask), s->at<int>(s->off_tileflag), s->at<TileRef>(s->off_tiles),
+                         s->at<int>(s->off_tilestart), s->at<int>(s->off_counters), st, &s->launches),
+            "tile list");
+    VP_CUDA(cudaMemcpyAsync(s->h_counters, s->at<int>(s->off_counters), kCntTotal * sizeof(int), cudaMemcpyDeviceToHost, st),
+            "read counters");
+    if (s->blocking_wait) {
+        VP_CUDA(cudaEventRecord(s->ev, st), "event record");
+        VP_CUDA(cudaEventSynchronize(s->ev), "load sync");
+    } else {
+        VP_CUDA(cudaStreamSynchronize(st), "load sync");
+    }
+    s->any_dirty = s->h_counters[kCntDirty];
+    s->tiles_active = s->h_counters[kCntActiveTiles];
+    s->tiles_full = s->tiles_active;
+    s->tiles_trimmed = false;
+    s->tileless = s->h_counters[kCntTileless];
+    s->tiles_pending = false;
     return VPINT_OK;
 }
 
@@ -314,25 +352,12 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
                            s->at<double>(s->off_rowpart), s->at<double>(s->off_known0), s->at<double>(s->off_known),
                            s->at<double>(s->off_extreme), s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
             "prepare");
-    VP_CUDA(launch_tiles(g, s->at<uint32_t>(s->off_mask), s->at<int>(s->off_tileflag), s->at<TileRef>(s->off_tiles),
-                         s->at<int>(s->off_tilestart), s->at<int>(s->off_counters), st, &s->launches),
-            "tile list");
-    VP_CUDA(cudaMemcpyAsync(s->h_counters, s->at<int>(s->off_counters), kCntTotal * sizeof(int), cudaMemcpyDeviceToHost, st),
-            "read counters");
-    if (s->blocking_wait) {
-        VP_CUDA(cudaEventRecord(s->ev, st), "event record");
-        VP_CUDA(cudaEventSynchronize(s->ev), "load sync");
-    } else {
-        VP_CUDA(cudaStreamSynchronize(st), "load sync");
-    }
-    s->any_dirty = s->h_counters[kCntDirty];
-    s->tiles_active = s->h_counters[kCntActiveTiles];
-    s->tiles_full = s->tiles_active;
-    s->tiles_trimmed = false;
-    s->tileless = s->h_counters[kCntTileless];
+    s->tiles_pending = true;
+    s->bufB_pending = false;
+    s->async_pending = false;
     s->loaded = true;
     s->run_begun = false;
-    return VPINT_OK;
+    return resolve_tiles(s, st);
 }
 
 int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int64_t *stride, int F, int method,
@@ -374,20 +399,23 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     return VPINT_OK;
 }
 
-int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau) {
+int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const double *tau, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (s->weight_mode != VPINT_W_SCALAR) return fail(VPINT_ERR_INVALID, "solver was created with weight planes");
     if (!gamma || (s->g.ndim == 3 && !tau)) return fail(VPINT_ERR_INVALID, "vpint_solver_set_discounts: null argument");
     const size_t bytes = (size_t)s->g.P * sizeof(double);
-    VP_CUDA(cudaMemcpy(s->at<double>(s->off_gamma), gamma, bytes, cudaMemcpyHostToDevice), "copy gamma");
-    if (tau) VP_CUDA(cudaMemcpy(s->at<double>(s->off_tau), tau, bytes, cudaMemcpyHostToDevice), "copy tau");
+    // pageable sources are staged before cudaMemcpyAsync returns; the copy itself is ordered on the caller's stream
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_gamma), gamma, bytes, cudaMemcpyHostToDevice, st), "copy gamma");
+    if (tau) VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_tau), tau, bytes, cudaMemcpyHostToDevice, st), "copy tau");
     s->weights_ready = true;
     return VPINT_OK;
 }
 
 static int recompact_tiles(vpint_solver *s, cudaStream_t st, bool trim);
 
-int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+// Start of a run(): parameter checks + per-problem loop state.  Nothing here needs the tile list.
+static int begin_run_light(vpint_solver *s, const vpint_run_params *prm, cudaStream_t st) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!prm) return fail(VPINT_ERR_INVALID, "null run params");
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
@@ -397,19 +425,34 @@ int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *s
         if (!s->has_orig) return fail(VPINT_ERR_INVALID, "resistance needs a solver created with VPINT_FEAT_RESISTANCE");
         if (s->g.ndim != 2 || s->use_tb) return fail(VPINT_ERR_UNSUPPORTED, "resistance runs on the 2-D one-sweep-per-launch path (k_block 0 or 1)");
     }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     s->prm = *prm;
     VP_CUDA(launch_init_state(s->g, s->at<ProbState>(s->off_state), s->at<int>(s->off_counters) + kCntActiveProblems,
                               prm->max_iter, st, &s->launches),
             "init state");
+    s->run_begun = false;
+    s->async_pending = false;
+    return VPINT_OK;
+}
+
+// What the tiled kernels need on top of begin_run_light.
+static int begin_run_tiled(vpint_solver *s, cudaStream_t st) {
+    int rc = resolve_tiles(s, st);
+    if (rc != VPINT_OK) return rc;
     if (s->tiles_trimmed) {
-        const int rc = recompact_tiles(s, st, false);
+        rc = recompact_tiles(s, st, false);
         if (rc != VPINT_OK) return rc;
     }
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_done), 0, (size_t)s->g.P * sizeof(int), st), "memset tickets");
     s->run_begun = true;
     s->first_step_pending = true;
     return VPINT_OK;
+}
+
+int vpint_solver_begin_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = begin_run_light(s, prm, st);
+    if (rc != VPINT_OK) return rc;
+    return begin_run_tiled(s, st);
 }
 
 static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, bool fused = false);
@@ -685,14 +728,15 @@ static int run_graph_loop(vpint_solver *s, void *stream) {
     return VPINT_OK;
 }
 
-int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
-    int rc = vpint_solver_begin_run(s, prm, stream);
+int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = begin_run_light(s, prm, st);
     if (rc != VPINT_OK) return rc;
     if (prm->loop_mode != VPINT_LOOP_CHUNKED && prm->loop_mode != VPINT_LOOP_GRAPH)
         return fail(VPINT_ERR_INVALID, "bad loop_mode");
     if (prm->max_iter == 0) return VPINT_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ratio = (s->weight_mode == VPINT_W_PLANES);
+    // any_dirty is known without a sync: the fused load has no separate start state, vpint_solver_load has read it
     if (s->res_ok && !s->any_dirty && !prm->resistance && !s->no_nc && (!ratio || s->fplane_valid)) {
         // whole run() in one launch: a cluster per problem, state resident in shared memory
         rc = leave_ratio(s, st);                   // a previous tiled run may have left the state in ratio space
@@ -731,10 +775,27 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
                                 sizeof(int), cudaMemcpyDeviceToHost, st),
                 "read active count");
         VP_CUDA(cudaEventRecord(s->ev, st), "event record");
+        s->async_pending = true;
+    }
+    return VPINT_OK;
+}
+
+int vpint_solver_run_finish(vpint_solver *s, void *stream, int *reran) {
+    if (reran) *reran = 0;
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (s->prm.max_iter == 0) return VPINT_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->async_pending) {
+        s->async_pending = false;
         VP_CUDA(cudaEventSynchronize(s->ev), "event sync");
         if (s->h_counters[kCntActiveProblems] <= 0) return VPINT_OK;
         // the kernel declined (non-finite features): continue on the tiled path from the untouched state
     }
+    if (reran) *reran = 1;
+    int rc = begin_run_tiled(s, st);
+    if (rc != VPINT_OK) return rc;
+    const vpint_run_params *prm = &s->prm;
     if (prm->loop_mode == VPINT_LOOP_GRAPH) return run_graph_loop(s, stream);
     int chunk = prm->chunk > 0 ? prm->chunk : 4;
     const int chunk_cap = prm->chunk > 0 ? prm->chunk : 64;
@@ -765,6 +826,178 @@ int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream)
         if (chunk < chunk_cap) chunk = (chunk * 2 < chunk_cap) ? chunk * 2 : chunk_cap;
     }
     return fail(VPINT_ERR_INVALID, "internal error: loop did not terminate within its launch budget");
+}
+
+int vpint_solver_run(vpint_solver *s, const vpint_run_params *prm, void *stream) {
+    const int rc = vpint_solver_run_async(s, prm, stream);
+    if (rc != VPINT_OK) return rc;
+    return vpint_solver_run_finish(s, stream, nullptr);
+}
+
+// ---- fused VPint2 load (vpint_ingest.cu) ---------------------------------------------------------------------
+int vpint_cloud_mask(const void *mask, int dtype, double threshold, int64_t n, uint8_t *cloud_out, void *stream) {
+    if (!mask || !cloud_out || n < 0) return fail(VPINT_ERR_INVALID, "vpint_cloud_mask: bad argument");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32 && dtype != VPINT_U16 && dtype != VPINT_U8)
+        return fail(VPINT_ERR_INVALID, "vpint_cloud_mask: bad dtype");
+    VP_CUDA(launch_cloud_mask(mask, dtype, threshold, n, cloud_out, static_cast<cudaStream_t>(stream)), "cloud mask");
+    return VPINT_OK;
+}
+
+int vpint_buffer_clouds(const void *target, int dtype, uint8_t *cloud, int have_cloud, int n_img, int H, int W, int B,
+                        int buffer_size, int passes, uint8_t *scratch, void *stream) {
+    if (!cloud || !scratch || n_img < 1 || H < 1 || W < 1 || B < 1) return fail(VPINT_ERR_INVALID, "vpint_buffer_clouds: bad argument");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32 && dtype != VPINT_U16) return fail(VPINT_ERR_INVALID, "vpint_buffer_clouds: bad dtype");
+    if (dtype != VPINT_U16 && !target) return fail(VPINT_ERR_INVALID, "vpint_buffer_clouds: null target");
+    VP_CUDA(launch_buffer_clouds(target, dtype, cloud, have_cloud != 0, n_img, H, W, B, buffer_size, passes, scratch,
+                                 static_cast<cudaStream_t>(stream)),
+            "buffer clouds");
+    return VPINT_OK;
+}
+
+size_t vpint_fill_scratch_bytes(int64_t cells_global, int nprob, int value_dtype) {
+    return fill_general_scratch_bytes(cells_global, nprob, value_dtype);
+}
+
+int64_t vpint_fill_leaf_count(int64_t cells_global, int nprob) { return (int64_t)nprob * ((cells_global + 63) / 64); }
+
+size_t vpint_fill_count_offset(int64_t cells_global, int nprob, int value_dtype) {
+    const size_t esz = (value_dtype == VPINT_F64) ? 8 : 4;
+    return ((size_t)vpint_fill_leaf_count(cells_global, nprob) * esz + 255) / 256 * 256;
+}
+
+static int check_ingest(const vpint_solver *s, const vpint_ingest_params *p, const char *who) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!p || !p->target) return fail(VPINT_ERR_INVALID, std::string(who) + ": null argument");
+    if (p->raster_dtype != VPINT_U16 && p->raster_dtype != VPINT_F32 && p->raster_dtype != VPINT_F64)
+        return fail(VPINT_ERR_INVALID, std::string(who) + ": raster dtype must be VPINT_U16, VPINT_F32 or VPINT_F64");
+    if (p->value_dtype != VPINT_F32 && p->value_dtype != VPINT_F64)
+        return fail(VPINT_ERR_INVALID, std::string(who) + ": value dtype must be VPINT_F32 or VPINT_F64");
+    if (s->g.ndim != 2 || s->storage != VPINT_F64 || s->weight_mode != VPINT_W_PLANES)
+        return fail(VPINT_ERR_UNSUPPORTED, std::string(who) + ": needs a 2-D fp64 solver with weight planes");
+    return VPINT_OK;
+}
+
+int vpint_solver_fill_leaves(vpint_solver *s, const vpint_ingest_params *p, void *stream) {
+    int rc = check_ingest(s, p, "vpint_solver_fill_leaves");
+    if (rc != VPINT_OK) return rc;
+    if (!p->scratch) return fail(VPINT_ERR_INVALID, "vpint_solver_fill_leaves: null scratch");
+    const Geom &g = s->g;
+    const int64_t n = (int64_t)g.global_H * g.W;
+    if (n < 128) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_fill_leaves: grids below 128 cells take the mean through vpint_solver_load");
+    const int n_img = g.P / g.Pin;
+    const bool sharded = (g.global_H != g.H || g.own_row0 != 0 || g.own_rows != g.H);
+    if (sharded && n_img != 1) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_fill_leaves: a row shard holds one image");
+    const int64_t cell_offset = (int64_t)g.row_offset * g.W, cells_local = (int64_t)g.H * g.W;
+    const int64_t own0 = (int64_t)(g.row_offset + g.own_row0) * g.W, own1 = own0 + (int64_t)g.own_rows * g.W;
+    if (own1 < n && own1 + 127 > cell_offset + cells_local)
+        return fail(VPINT_ERR_INVALID, "vpint_solver_fill_leaves: the halo rows below the owned band must cover 127 cells");
+    VP_CUDA(launch_fill_leaves(p->target, p->raster_dtype, p->value_dtype, p->cloud, n_img, g.Pin, n, cell_offset, cells_local,
+                               own0, own1, p->clip_target, p->target_min, p->target_max, p->scratch,
+                               static_cast<cudaStream_t>(stream), &s->launches),
+            "fill leaves");
+    return VPINT_OK;
+}
+
+int vpint_solver_fill_combine(vpint_solver *s, int value_dtype, void *scratch, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!scratch) return fail(VPINT_ERR_INVALID, "vpint_solver_fill_combine: null scratch");
+    if (value_dtype != VPINT_F32 && value_dtype != VPINT_F64) return fail(VPINT_ERR_INVALID, "bad value dtype");
+    const Geom &g = s->g;
+    VP_CUDA(launch_fill_combine(value_dtype, g.P, (int64_t)g.global_H * g.W, scratch, s->at<double>(s->off_fill),
+                                static_cast<cudaStream_t>(stream), &s->launches),
+            "fill combine");
+    return VPINT_OK;
+}
+
+double *vpint_solver_fill_ptr(vpint_solver *s) { return (s && s->ws) ? s->at<double>(s->off_fill) : nullptr; }
+
+int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, void *stream) {
+    int rc = check_ingest(s, p, "vpint_solver_ingest_bands");
+    if (rc != VPINT_OK) return rc;
+    if (!p->features) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: null features");
+    if (s->n_planes != 5) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_ingest_bands: solver has no feature plane");
+    if (!ingest_bands_supported(s->g, p->raster_dtype))
+        return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_ingest_bands: rows too long for the staged load");
+    if (p->out && p->out_dtype != VPINT_F32 && p->out_dtype != VPINT_F64) return fail(VPINT_ERR_INVALID, "bad out dtype");
+    if (s->state_ratio) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: a run is in flight");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geom &g = s->g;
+    if (p->fill_mode == VPINT_FILL_DEVICE) {
+        const bool sharded = (g.global_H != g.H || g.own_row0 != 0 || g.own_rows != g.H);
+        if (sharded) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: a row shard takes the mean through fill_leaves / all-reduce / fill_combine");
+        rc = vpint_solver_fill_leaves(s, p, stream);
+        if (rc != VPINT_OK) return rc;
+        rc = vpint_solver_fill_combine(s, p->value_dtype, p->scratch, stream);
+        if (rc != VPINT_OK) return rc;
+    } else if (p->fill_mode == VPINT_FILL_HOST) {
+        if (!p->fill_host) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: null fill_host");
+        VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_fill), p->fill_host, (size_t)g.P * sizeof(double), cudaMemcpyHostToDevice, st),
+                "copy fill");
+    } else if (p->fill_mode != VPINT_FILL_READY) {
+        return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: bad fill_mode");
+    }
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
+    VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme), 0, 2 * sizeof(double), st), "memset range check");
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags) + 3, 0, sizeof(int), st), "memset flag");
+    s->state_ratio = false;
+    s->ratio_verdict = -1;
+    s->planes_valid = false;
+    s->no_nc = false;
+    // the second ping-pong buffer is only read by the tiled kernels: written lazily when the resident kernel will run
+    const bool skip_b = s->res_ok && !s->has_orig;
+    VP_CUDA(launch_ingest_bands(g, p->target, p->features, p->raster_dtype, p->value_dtype, p->cloud, p->clip_target,
+                                p->target_min, p->target_max, p->clip_features, p->features_min, p->features_max,
+                                s->at<double>(s->off_fill), s->at<double>(s->off_buf[0]),
+                                skip_b ? nullptr : s->at<double>(s->off_buf[1]), s->at<uint32_t>(s->off_mask),
+                                s->at<double>(s->off_w[4]), s->at<double>(s->off_rowpart), s->at<double>(s->off_extreme),
+                                s->at<int>(s->off_flags), p->out, p->out_dtype, p->out_stride, st, &s->launches),
+            "ingest bands");
+    if (s->has_orig)
+        VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_orig), s->at<void>(s->off_buf[0]),
+                                (size_t)g.P * g.S * g.H * g.pitch * s->elem, cudaMemcpyDeviceToDevice, st),
+                "copy known values");
+    VP_CUDA(launch_prepare_reduce(g, s->at<double>(s->off_rowpart), s->at<double>(s->off_known0), s->at<double>(s->off_known),
+                                  s->at<ProbState>(s->off_state), s->at<int>(s->off_counters), st, &s->launches),
+            "prepare reduce");
+    s->fplane_valid = true;
+    s->weights_ready = true;
+    s->loaded = true;
+    s->run_begun = false;
+    s->any_dirty = 0;                 // no separate start state: it equals the original on every known cell
+    s->tiles_pending = true;
+    s->bufB_pending = skip_b;
+    s->async_pending = false;
+    return VPINT_OK;
+}
+
+int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
+                                void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (!out || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: null argument");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    if (s->g.ndim != 2 || s->storage != VPINT_F64) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_result_unknown: 2-D fp64 solvers");
+    {
+        const int rc = leave_ratio(s, static_cast<cudaStream_t>(stream));
+        if (rc != VPINT_OK) return rc;
+    }
+    {
+        // pinned host memory is written through its device mapping (same address under unified addressing, but ask)
+        cudaPointerAttributes attr;
+        VP_CUDA(cudaPointerGetAttributes(&attr, out), "cudaPointerGetAttributes");
+        if (attr.type == cudaMemoryTypeHost) {
+            if (!attr.devicePointer) return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: host memory is not mapped into the device");
+            out = attr.devicePointer;
+        } else if (attr.type == cudaMemoryTypeUnregistered) {
+            return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: out must be device memory or pinned (mapped) host memory");
+        }
+    }
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    VP_CUDA(launch_result_unknown(s->g, s->at<ProbState>(s->off_state), bufs, s->at<uint32_t>(s->off_mask), out, dtype,
+                                  stride, niter_out, static_cast<cudaStream_t>(stream), &s->launches),
+            "result unknown");
+    return VPINT_OK;
 }
 
 double *vpint_solver_sums_ptr(vpint_solver *s) { return (s && s->ws) ? s->at<double>(s->off_sums) : nullptr; }

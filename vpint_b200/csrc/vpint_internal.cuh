@@ -183,6 +183,27 @@ cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, vo
                           int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
                           int64_t *launches);
 
+// ---- fused VPint2 load (vpint_ingest.cu) -----------------------------------
+cudaError_t launch_cloud_mask(const void *mask, int dtype, double threshold, int64_t n, uint8_t *cloud, cudaStream_t st);
+cudaError_t launch_buffer_clouds(const void *target, int dtype, uint8_t *cloud, bool have_cloud, int n_img, int H, int W, int B,
+                                 int buffer_size, int passes, uint8_t *scratch, cudaStream_t st);
+size_t fill_general_scratch_bytes(int64_t n, int n_prob, int acc_dtype);
+cudaError_t launch_fill_leaves(const void *target, int t_dtype, int acc_dtype, const uint8_t *cloud, int n_img, int B, int64_t n,
+                               int64_t cell_offset, int64_t cells_local, int64_t own_cell0, int64_t own_cell1, int clip,
+                               double lo, double hi, void *scratch, cudaStream_t st, int64_t *launches);
+cudaError_t launch_fill_combine(int acc_dtype, int n_prob, int64_t n, void *scratch, double *fill_dev, cudaStream_t st,
+                                int64_t *launches);
+bool ingest_bands_supported(const Geom &g, int t_dtype);
+cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *features, int t_dtype, int acc_dtype,
+                                const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
+                                double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
+                                double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
+                                const int64_t *out_stride, cudaStream_t st, int64_t *launches);
+cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,
+                                  int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st, int64_t *launches);
+cudaError_t launch_prepare_reduce(const Geom &g, const double *rowpart, double *known0, double *known, ProbState *state,
+                                  int *counters, cudaStream_t st, int64_t *launches);
+
 // ---- device helpers -------------------------------------------------------
 #if defined(__CUDACC__)
 

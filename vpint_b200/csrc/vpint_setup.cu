@@ -740,6 +740,13 @@ cudaError_t launch_prepare(const Geom &g, const void *original, const void *pred
     return cudaSuccess;
 }
 
+cudaError_t launch_prepare_reduce(const Geom &g, const double *rowpart, double *known0, double *known, ProbState *state,
+                                  int *counters, cudaStream_t st, int64_t *launches) {
+    prepare_reduce_kernel<<<g.P, 256, 0, st>>>(g, rowpart, known0, known, state, counters);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_tiles(const Geom &g, const uint32_t *mask, int *tile_flag, TileRef *tiles, int *tile_start,
                          int *counters, cudaStream_t st, int64_t *launches) {
     const int64_t n_tiles = (int64_t)g.P * g.S * g.tiles_per_prob;

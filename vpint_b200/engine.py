@@ -43,6 +43,58 @@ def _code(t):
     raise VPintError("unsupported tensor dtype %s (float32 / float64 only)" % t.dtype)
 
 
+def _raster_code(t):
+    torch = _torch()
+    code = {torch.float64: N.F64, torch.float32: N.F32, torch.uint16: N.U16, torch.uint8: N.U8}.get(t.dtype)
+    if code is None:
+        raise VPintError("unsupported raster dtype %s (uint16 / float32 / float64; uint8 for masks)" % t.dtype)
+    return code
+
+
+def _clip_pair(clip):
+    """clip_target / clip_features of the VPint2 constructor (VPint/VPint2.py:30-41): a number is an upper bound,
+    anything else is (min, max).  -> (on, lo, hi)."""
+    if clip is None:
+        return 0, 0.0, 0.0
+    if type(clip) == type(2) or type(clip) == type(2.1):
+        return 1, -math.inf, float(clip)
+    return 1, float(clip[0]), float(clip[1])
+
+
+def cloud_mask(mask, threshold, out=None):
+    """``mask > threshold`` as a uint8 CUDA tensor of the same shape (VPint/VPint2.py:122-132).  mask: CUDA tensor,
+    float64 / float32 / uint16 / uint8."""
+    torch = _torch()
+    lib = N.load_library()
+    mask = mask.contiguous()
+    if out is None:
+        out = torch.empty(mask.shape, dtype=torch.uint8, device=mask.device)
+    st = C.c_void_p(torch.cuda.current_stream(mask.device).cuda_stream)
+    N.check(lib, lib.vpint_cloud_mask(C.c_void_p(mask.data_ptr()), _raster_code(mask), float(threshold), int(mask.numel()),
+                                      C.c_void_p(out.data_ptr()), st), "vpint_cloud_mask")
+    return out
+
+
+def buffer_clouds(target, cloud=None, buffer_size=5, passes=1, scratch=None, out=None):
+    """Cloud buffering of the VPint2 constructor on the device (VPint/VPint2.py:135-150, column bound of :146 kept).
+    target: CUDA (N, H, W, B) raster (its NaNs join the footprint); cloud: uint8 CUDA (N, H, W) all-band mask, rewritten
+    in place, or None -- then the footprint is the target's NaNs alone and the mask is written to ``out``.
+    Returns the dilated all-band mask."""
+    torch = _torch()
+    lib = N.load_library()
+    n, H, W, B = target.shape
+    have = cloud is not None
+    if not have:
+        cloud = out if out is not None else torch.empty((n, H, W), dtype=torch.uint8, device=target.device)
+    if scratch is None:
+        scratch = torch.empty(3 * n * H * W, dtype=torch.uint8, device=target.device)
+    st = C.c_void_p(torch.cuda.current_stream(target.device).cuda_stream)
+    N.check(lib, lib.vpint_buffer_clouds(C.c_void_p(target.data_ptr()), _raster_code(target), C.c_void_p(cloud.data_ptr()),
+                                         int(have), int(n), int(H), int(W), int(B), int(buffer_size), int(passes),
+                                         C.c_void_p(scratch.data_ptr()), st), "vpint_buffer_clouds")
+    return cloud
+
+
 def _i64(vals):
     return (C.c_int64 * len(vals))(*[int(v) for v in vals])
 
@@ -84,8 +136,10 @@ class Solver:
         d.storage = _DTYPE_CODE[storage]
         d.weight_mode = N.W_PLANES if planes else N.W_SCALAR
         d.k_block = int(k_block)
+        self._global_H = self.H
         if shard is not None:
             d.global_H, d.row_offset, d.own_row0, d.own_rows = [int(v) for v in shard]
+            self._global_H = int(shard[0]) or self.H
         d.features = (N.FEAT_RESISTANCE if resistance else 0) | (N.FEAT_BLOCKING_WAIT if blocking_wait else 0)
         self._h = C.c_void_p()
         N.check(self.lib, self.lib.vpint_solver_create(C.byref(d), C.byref(self._h)), "vpint_solver_create")
@@ -188,7 +242,7 @@ class Solver:
         if tau is not None:
             t = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (self.nprob,)))
             tp = t.ctypes.data_as(C.POINTER(C.c_double))
-        N.check(self.lib, self.lib.vpint_solver_set_discounts(self._h, gp, tp), "vpint_solver_set_discounts")
+        N.check(self.lib, self.lib.vpint_solver_set_discounts(self._h, gp, tp, self._stream()), "vpint_solver_set_discounts")
         return self
 
     def priority(self, beta, bias=None, want_planes=False):
@@ -236,6 +290,128 @@ class Solver:
         prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk, resistance)
         N.check(self.lib, self.lib.vpint_solver_run(self._h, C.byref(prm), self._stream()), "vpint_solver_run")
         return self
+
+    def run_async(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False,
+                  loop_mode=None, chunk=0, resistance=None):
+        """Non-blocking :meth:`run` where the cluster-resident kernel serves the solve; :meth:`run_finish` completes it."""
+        if loop_mode is None:
+            loop_mode = DEFAULT_LOOP_MODE
+        prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, loop_mode, chunk, resistance)
+        N.check(self.lib, self.lib.vpint_solver_run_async(self._h, C.byref(prm), self._stream()), "vpint_solver_run_async")
+        return self
+
+    def run_finish(self):
+        """Waits for :meth:`run_async`.  True when the run had to be completed on the tiled path (results read
+        before must be read again)."""
+        reran = C.c_int(0)
+        N.check(self.lib, self.lib.vpint_solver_run_finish(self._h, self._stream(), C.byref(reran)), "vpint_solver_run_finish")
+        return bool(reran.value)
+
+    # -- fused VPint2 load ---------------------------------------------------------------------------
+    def fill_scratch(self, value_dtype="float32"):
+        """Scratch tensor for the on-device np.nanmean (leaf sums of NumPy's summation tree + counts)."""
+        cells = self._global_H * self.W
+        nbytes = self.lib.vpint_fill_scratch_bytes(cells, self.nprob, _DTYPE_CODE[value_dtype])
+        return self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+
+    def fill_views(self, scratch, value_dtype="float32"):
+        """(leaf sums, counts) views of ``scratch`` for the all-reduce of a row-sharded mean."""
+        torch = self.torch
+        cells = self._global_H * self.W
+        n = int(self.lib.vpint_fill_leaf_count(cells, self.nprob))
+        off = int(self.lib.vpint_fill_count_offset(cells, self.nprob, _DTYPE_CODE[value_dtype]))
+        esz, dt = (8, torch.float64) if value_dtype == "float64" else (4, torch.float32)
+        return scratch[:n * esz].view(dt), scratch[off:off + 8 * self.nprob].view(torch.int64)
+
+    def _ingest_params(self, target, features, cloud, value_dtype, clip_target, clip_features, fill, fill_ready, out, scratch):
+        p = N.IngestParams()
+        lead = self.nprob // self.nprob_inner
+        shape = (lead, self.H, self.W, self.nprob_inner)
+        for name, t in (("target", target), ("features", features)):
+            if t is None:
+                continue
+            if tuple(t.shape) != shape or not t.is_contiguous():
+                raise VPintError("%s must be a contiguous (N, H, W, B) = %s raster, got %s" % (name, shape, tuple(t.shape)))
+        if features is not None and features.dtype != target.dtype:
+            raise VPintError("target and features must have the same raster dtype")
+        p.target = target.data_ptr()
+        p.features = features.data_ptr() if features is not None else None
+        p.raster_dtype = _raster_code(target)
+        if p.raster_dtype == N.U8:
+            raise VPintError("uint8 rasters are not supported (uint16 / float32 / float64)")
+        p.value_dtype = _DTYPE_CODE[value_dtype]
+        if cloud is not None:
+            if tuple(cloud.shape) != shape[:3] or cloud.dtype != self.torch.uint8 or not cloud.is_contiguous():
+                raise VPintError("cloud must be a contiguous uint8 (N, H, W) tensor")
+            p.cloud = cloud.data_ptr()
+        p.clip_target, p.target_min, p.target_max = _clip_pair(clip_target)
+        p.clip_features, p.features_min, p.features_max = _clip_pair(clip_features)
+        keep = [target, features, cloud]
+        if fill_ready:
+            p.fill_mode = N.FILL_READY
+        elif fill is not None:
+            f = np.ascontiguousarray(np.asarray(fill, dtype=np.float64).reshape(-1))
+            if f.size != self.nprob:
+                raise VPintError("fill needs one value per problem")
+            p.fill_mode = N.FILL_HOST
+            p.fill_host = f.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(f)
+        else:
+            p.fill_mode = N.FILL_DEVICE
+        if scratch is not None:
+            p.scratch = scratch.data_ptr()
+            keep.append(scratch)
+        if out is not None:
+            st = self._strides(out, (self.H, self.W))[:4]
+            p.out = out.data_ptr()
+            p.out_dtype = _code(out)
+            for i in range(4):
+                p.out_stride[i] = int(st[i])
+            keep.append(out)
+        return p, keep
+
+    def ingest_bands(self, target, features, cloud=None, *, value_dtype="float32", clip_target=None, clip_features=None,
+                     fill=None, fill_ready=False, out=None, scratch=None):
+        """Fused load of a band-interleaved stack straight from the raw rasters (uint16 / float32 / float64 CUDA
+        tensors (N, H, W, B)): VPint2_interpolator's constructor steps, the per-band mean init and the feature plane
+        in one pass, no host synchronisation.  ``cloud``: uint8 (N, H, W), nonzero = unknown on every band.
+        ``out``: tensor in any layout :meth:`result` accepts; receives the KNOWN cells of the result."""
+        if fill is None and not fill_ready and scratch is None:
+            scratch = self.fill_scratch(value_dtype)
+        p, keep = self._ingest_params(target, features, cloud, value_dtype, clip_target, clip_features, fill, fill_ready,
+                                      out, scratch)
+        self._keep = keep
+        N.check(self.lib, self.lib.vpint_solver_ingest_bands(self._h, C.byref(p), self._stream()), "vpint_solver_ingest_bands")
+        return self
+
+    def fill_leaves(self, target, cloud, scratch, *, value_dtype="float32", clip_target=None):
+        p, keep = self._ingest_params(target, None, cloud, value_dtype, clip_target, None, None, False, None, scratch)
+        self._keep += keep
+        N.check(self.lib, self.lib.vpint_solver_fill_leaves(self._h, C.byref(p), self._stream()), "vpint_solver_fill_leaves")
+
+    def fill_combine(self, scratch, value_dtype="float32"):
+        N.check(self.lib, self.lib.vpint_solver_fill_combine(self._h, _DTYPE_CODE[value_dtype], C.c_void_p(scratch.data_ptr()),
+                                                            self._stream()), "vpint_solver_fill_combine")
+
+    def fill_tensor(self):
+        """Device float64 [nprob]: the start value of every problem's unknown cells."""
+        ptr = int(self.lib.vpint_solver_fill_ptr(self._h))
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off:off + 8 * self.nprob].view(self.torch.float64)
+
+    def result_unknown(self, out, niter=None):
+        """Writes ONLY the unknown cells of the current state into ``out`` (layouts as :meth:`result`); ``out`` may be a
+        CUDA tensor or a pinned host tensor (written through its device mapping).  Returns sweeps[int32, nprob]."""
+        torch = self.torch
+        st = self._strides(out, (self.H, self.W))[:4]
+        if niter is None:
+            niter = torch.zeros(self.nprob, dtype=torch.int32, device=self.device)
+        if out.device.type == "cpu" and not out.is_pinned():
+            raise VPintError("result_unknown writes through a device mapping: a host `out` must be pinned memory")
+        N.check(self.lib, self.lib.vpint_solver_result_unknown(self._h, C.c_void_p(out.data_ptr()), _code(out), _i64(st),
+                                                                C.c_void_p(niter.data_ptr()), self._stream()),
+                "vpint_solver_result_unknown")
+        return niter
 
     def begin_run(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf, track_delta=False):
         prm = self._params(max_iter, auto_terminate, threshold, clip_val, track_delta, N.LOOP_CHUNKED, 0)

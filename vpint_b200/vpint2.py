@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import solve as _solve
-from .engine import Solver, require_cuda, to_device
+from .engine import Solver, buffer_clouds, cloud_mask, require_cuda, to_device
 from .errors import VPintError
 from .wp import wp_run_options
 
@@ -271,10 +271,200 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
     return (res, sweeps) if return_sweeps else res
 
 
+# Streams (each with its own solver and staging buffers) that take alternate chunks in :func:`solve_raw`.
+RAW_STREAMS = 4
+
+
+def _fused_ok(opts):
+    """Can :func:`solve_raw` serve these run() options?  (exact weights, no priority / bias / resistance / search)"""
+    return (opts["method"] == "exact" and not opts.get("prioritise_identity") and not opts.get("resistance")
+            and not opts.get("auto_adapt") and opts["iterations"] != 0)
+
+
+class _RawSlot:
+    """One stream of the :func:`solve_raw` pipeline: staging buffers, solver and the chunk in flight."""
+
+    def __init__(self, dev, chunk, H, W, B, raster_dtype, mask_dtype, res_shape, res_dtype, need_res, need_cloud, buffer):
+        import torch
+        self.dev = dev
+        self.stream = torch.cuda.Stream(device=dev)
+        self.solvers = {}
+        self.t_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev)
+        self.f_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev)
+        self.m_buf = None if mask_dtype is None else torch.empty((chunk, H, W), dtype=mask_dtype, device=dev)
+        self.cloud = torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) if need_cloud else None
+        self.buf_scratch = torch.empty(3 * chunk * H * W, dtype=torch.uint8, device=dev) if buffer else None
+        self.res = torch.empty(res_shape(chunk), dtype=res_dtype, device=dev) if need_res else None
+        self.niter = torch.zeros(chunk * B, dtype=torch.int32, device=dev)
+        self.fill_scratch = None
+        self.pending = None
+
+    def close(self):
+        for sv in self.solvers.values():
+            sv.close()
+        self.solvers = {}
+
+
+def solve_raw(target, features, mask=None, opts=None, *, mask_threshold=0.2, buffer_mask=False, mask_buffer_size=5,
+              mask_buffer_passes=1, clip_target=None, clip_features=None, dtype=np.float32, out=None, out_layout="bhw",
+              out_dtype=None, result="full", device=None, chunk_patches=None, streams=None, return_sweeps=False):
+    """VPint2 cloud removal of a stack of patches straight from the RAW rasters: the interpolator's constructor
+    (VPint/VPint2.py:13-55), every band's mean init (VPint/MRP.py:73-77) and run() (VPint/VPint2.py:58-119) on the
+    device, chunk by chunk on ``streams`` CUDA streams driven by ONE host thread -- no step blocks the host, so the
+    host->device copy of a chunk, the solve of another and the result of a third overlap.
+
+    target, features : (N, H, W, B) uint16 / float32 / float64, NumPy or torch, host (pinned for asynchronous copies)
+                       or CUDA.  NaN in a float target = unknown.
+    mask             : (N, H, W) cloud mask (any real dtype) -> unknown on every band where ``mask > mask_threshold``.
+    dtype            : the interpolator's DTYPE (np.float32 = VPint2's default): values, clip and mean init live in it.
+    result           : 'full'    -> every cell of the result (float64 (N, B, H, W) for out_layout 'bhw' as run()
+                                    assembles it, ``out_dtype`` (N, H, W, B) for 'hwb' as run_serial() returns it);
+                       'unknown' -> ONLY the cloud cells are written, into ``out`` (required; CUDA or pinned host
+                                    memory, written in place through its device mapping): the known cells are the
+                                    caller's own data and never cross the host link.
+    Returns out (and the sweep counts (N, B) with ``return_sweeps``) as torch tensors."""
+    import torch
+    dev = require_cuda(device)
+    opts = wp_run_options() if opts is None else opts
+    if not _fused_ok(opts):
+        raise VPintError("solve_raw serves run() with exact weights and without prioritise_identity / resistance / "
+                         "auto_adapt; use VPint2_interpolator for those")
+    if result not in ("full", "unknown"):
+        raise VPintError("result must be 'full' or 'unknown'")
+    as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+    target, features = as_t(target), as_t(features)
+    mask = None if mask is None else as_t(mask)
+    if target.dim() != 4 or target.shape != features.shape:
+        raise VPintError("target and features must be (N, H, W, B) stacks of one shape")
+    if target.dtype != features.dtype:
+        features = features.to(target.dtype)
+    N_, H, W, B = target.shape
+    if mask is not None and tuple(mask.shape) != (N_, H, W):
+        raise VPintError("mask must have shape (N, H, W)")
+    if mask is not None and mask.dtype not in (torch.uint8, torch.uint16, torch.float32, torch.float64):
+        mask = mask.to(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.float64)
+    if H * W < 128:
+        raise VPintError("solve_raw needs grids of at least 128 cells (smaller ones: VPint2_interpolator / solve_bands)")
+    value_dtype = "float64" if np.dtype(dtype) == np.float64 else "float32"
+    if target.dtype == torch.float64 and value_dtype == "float32":
+        pass            # astype(float32) happens on the device
+    kb = 0
+    chunk = int(chunk_patches or PIPELINE_CHUNK_PATCHES)
+    K = int(streams or RAW_STREAMS)
+    if out_layout == "bhw":
+        res_shape, res_dtype = (lambda m: (m, B, H, W)), torch.float64
+    else:
+        tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {np.dtype(np.float32): torch.float32}.get(
+            np.dtype(out_dtype if out_dtype is not None else dtype), torch.float64)
+        res_shape, res_dtype = (lambda m: (m, H, W, B)), tdt
+    if out is None:
+        if result == "unknown":
+            raise VPintError("result='unknown' writes into the caller's array: pass out")
+        out = torch.empty(res_shape(N_), dtype=res_dtype, device=dev if target.device.type != "cpu" else "cpu",
+                          pin_memory=(target.device.type == "cpu"))
+    if tuple(out.shape) != res_shape(N_) or out.dtype != res_dtype:
+        raise VPintError("out must have shape %s and dtype %s" % (res_shape(N_), res_dtype))
+    out_on_dev = out.device.type != "cpu"
+    if result == "unknown" and not out_on_dev and not out.is_pinned():
+        raise VPintError("result='unknown' needs a CUDA or pinned host `out`")
+    need_res = (result == "full") and not out_on_dev
+    in_on_dev = target.device.type != "cpu"
+    spans = [(a, min(a + chunk, N_)) for a in range(0, N_, chunk)]
+    K = max(1, min(K, len(spans)))
+    sweeps_host = torch.empty(N_ * B, dtype=torch.int32, pin_memory=True)
+    need_cloud = mask is not None or buffer_mask
+    main = torch.cuda.current_stream(dev)
+    run_kw = dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"], clip_val=opts["clip_val"])
+    as_prob = (lambda t: t) if out_layout == "bhw" else (lambda t: t.permute(0, 3, 1, 2))
+    slots = []
+    try:
+        with torch.cuda.device(dev):
+            for _ in range(K):
+                sl = _RawSlot(dev, chunk, H, W, B, target.dtype, None if (mask is None or mask.device.type != "cpu") else mask.dtype,
+                              res_shape, res_dtype, need_res, need_cloud, buffer_mask)
+                sl.stream.wait_stream(main)
+                slots.append(sl)
+
+            def emit_result(sl, a, b, solver, dst):
+                m = b - a
+                if result == "unknown" or not need_res:
+                    solver.result_unknown(as_prob(dst), niter=sl.niter[:m * B])
+                else:
+                    solver.result_unknown(as_prob(sl.res[:m]), niter=sl.niter[:m * B])
+                    out[a:b].copy_(sl.res[:m], non_blocking=True)
+                sweeps_host[a * B:b * B].copy_(sl.niter[:m * B], non_blocking=True)
+
+            def finish(sl):
+                if sl.pending is None:
+                    return
+                a, b, solver = sl.pending
+                sl.pending = None
+                with torch.cuda.stream(sl.stream):
+                    if solver.run_finish():            # the resident kernel declined: the tiled path finished the run
+                        if result == "full":           # known cells again, then the unknown ones
+                            dst = out[a:b] if not need_res else sl.res[:b - a]
+                            solver.result(out=as_prob(dst))
+                        emit_result(sl, a, b, solver, out[a:b])
+
+            for i, (a, b) in enumerate(spans):
+                sl = slots[i % K]
+                finish(sl)                             # the chunk this slot carried K chunks ago
+                m = b - a
+                with torch.cuda.stream(sl.stream):
+                    if in_on_dev:
+                        t_c, f_c = target[a:b], features[a:b]
+                    else:
+                        sl.t_buf[:m].copy_(target[a:b], non_blocking=True)
+                        sl.f_buf[:m].copy_(features[a:b], non_blocking=True)
+                        t_c, f_c = sl.t_buf[:m], sl.f_buf[:m]
+                    cloud = None
+                    if mask is not None:
+                        if mask.device.type == "cpu":
+                            sl.m_buf[:m].copy_(mask[a:b], non_blocking=True)
+                            m_c = sl.m_buf[:m]
+                        else:
+                            m_c = mask[a:b]
+                        cloud = cloud_mask(m_c, mask_threshold, out=sl.cloud[:m])
+                    if buffer_mask:
+                        cloud = buffer_clouds(t_c, cloud, mask_buffer_size, mask_buffer_passes, scratch=sl.buf_scratch,
+                                              out=sl.cloud[:m])
+                    if m not in sl.solvers:
+                        sl.solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, planes=True, k_block=kb, device=dev,
+                                               blocking_wait=True)
+                        sl.fill_scratch = sl.solvers[m].fill_scratch(value_dtype) if sl.fill_scratch is None else sl.fill_scratch
+                    solver = sl.solvers[m]
+                    scratch = sl.fill_scratch if m == chunk else solver.fill_scratch(value_dtype)
+                    known_dst = None
+                    if result == "full":
+                        known_dst = as_prob(out[a:b] if not need_res else sl.res[:m])
+                    solver.ingest_bands(t_c, f_c, cloud, value_dtype=value_dtype, clip_target=clip_target,
+                                        clip_features=clip_features, out=known_dst, scratch=scratch)
+                    solver.run_async(opts["iterations"], **run_kw)
+                    emit_result(sl, a, b, solver, out[a:b])
+                sl.pending = (a, b, solver)
+            for sl in slots:
+                finish(sl)
+            for sl in slots:
+                sl.stream.synchronize()
+                main.wait_stream(sl.stream)
+    finally:
+        for sl in slots:
+            sl.close()
+    sweeps = sweeps_host.to(torch.int64).view(N_, B)
+    return (out, sweeps) if return_sweeps else out
+
+
 class VPint2_interpolator():
-    """Reference: VPint/VPint2.py:12-150.  Constructor semantics are unchanged
-    (dtype cast, optional axis move, clipping, cloud mask -> NaN on every band,
-    optional cloud buffering); only the per-pixel Python loops are vectorised."""
+    """Reference: VPint/VPint2.py:12-150.  Constructor semantics are unchanged (dtype cast, optional axis move,
+    clipping, cloud mask -> NaN on every band, optional cloud buffering).
+
+    The constructor does not run them on the host, though: it keeps (copies of) the raw rasters, and ``run()`` /
+    ``run_serial()`` hand those to the device, where the same steps are kernels (:func:`solve_raw`: a uint16 scene
+    crosses the host link as uint16, not as two float32 copies).  ``target`` / ``features`` stay available as
+    attributes -- the first access builds them on the host exactly as the reference does, assigning to them switches
+    the object to the host-built arrays for good."""
+
+    _LAZY_DTYPES = (np.dtype(np.uint16), np.dtype(np.float32), np.dtype(np.float64))
 
     def __init__(self, target, features, mask=None, buffer_mask=False, mask_buffer_size=5, mask_buffer_passes=1,
                  bands_first=False, clip_target=None, clip_features=None, dtype=None, **kwargs):
@@ -283,13 +473,35 @@ class VPint2_interpolator():
         assert len(features.shape) == 3
 
         self.DTYPE = dtype if dtype is not None else np.float32
-        target = target.astype(self.DTYPE)
-        features = features.astype(self.DTYPE)
+        if mask is not None:
+            shp = np.moveaxis(target, 0, -1).shape if bands_first else target.shape
+            assert len(mask.shape) == 2
+            assert mask.shape[0] == shp[0]
+            assert mask.shape[1] == shp[1]
+        self._ctor = dict(mask=None if mask is None else np.array(mask, copy=True), buffer_mask=buffer_mask,
+                          mask_buffer_size=mask_buffer_size, mask_buffer_passes=mask_buffer_passes,
+                          clip_target=clip_target, clip_features=clip_features, kwargs=dict(kwargs))
+        self._target = self._features = None
+        lazy = (np.dtype(self.DTYPE) in (np.dtype(np.float32), np.dtype(np.float64))
+                and isinstance(target, np.ndarray) and isinstance(features, np.ndarray)
+                and target.dtype in self._LAZY_DTYPES and features.dtype == target.dtype
+                and set(kwargs) <= {"threshold"})
         if bands_first:
             target = np.moveaxis(target, 0, -1)
             features = np.moveaxis(features, 0, -1)
+        if lazy:
+            self._raw = (np.array(target, copy=True, order="C"), np.array(features, copy=True, order="C"))
+        else:
+            self._raw = None
+            self._build_host(target, features)
 
+    # -- host construction (the reference's own steps, vectorised) -------------------------------------------------
+    def _build_host(self, target, features):
+        c = self._ctor
+        target = target.astype(self.DTYPE)
+        features = features.astype(self.DTYPE)
         # clip_* : int / float = upper bound only, otherwise (min, max)   (VPint/VPint2.py:30-41)
+        clip_target, clip_features = c["clip_target"], c["clip_features"]
         if clip_target is not None:
             if type(clip_target) == type(2) or type(clip_target) == type(2.1):
                 target = np.clip(target, a_min=-np.inf, a_max=clip_target)
@@ -300,19 +512,56 @@ class VPint2_interpolator():
                 features = np.clip(features, a_min=-np.inf, a_max=clip_features)
             else:
                 features = np.clip(features, a_min=clip_features[0], a_max=clip_features[1])
-
-        if mask is not None:
-            assert len(mask.shape) == 2
-            assert mask.shape[0] == target.shape[0]
-            assert mask.shape[1] == target.shape[1]
-            self.target = self.apply_mask(target, mask, **kwargs).astype(self.DTYPE)
+        if c["mask"] is not None:
+            tgt = self.apply_mask(target, c["mask"], **c["kwargs"]).astype(self.DTYPE)
         else:
-            self.target = target.astype(self.DTYPE)
+            tgt = target.astype(self.DTYPE)
+        if c["buffer_mask"]:
+            tgt = self.buffer_clouds(tgt, buffer_size=c["mask_buffer_size"], passes=c["mask_buffer_passes"])
+        self._target = tgt
+        self._features = features.astype(self.DTYPE)
 
-        if buffer_mask:
-            self.target = self.buffer_clouds(self.target, buffer_size=mask_buffer_size, passes=mask_buffer_passes)
+    def _materialise(self):
+        if self._target is None:
+            self._build_host(*self._raw)
 
-        self.features = features.astype(self.DTYPE)
+    @property
+    def target(self):
+        self._materialise()
+        return self._target
+
+    @target.setter
+    def target(self, value):
+        self._materialise()
+        self._raw = None
+        self._target = value
+
+    @property
+    def features(self):
+        self._materialise()
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._materialise()
+        self._raw = None
+        self._features = value
+
+    def _run_raw(self, opts, out_layout):
+        """run() / run_serial() from the raw rasters on the device (None when the options need the host-built arrays)."""
+        if self._raw is None or not _fused_ok(opts) or self._raw[0].shape[0] * self._raw[0].shape[1] < 128:
+            return None
+        c = self._ctor
+        t, f = self._raw
+        m = c["mask"]
+        if m is not None and m.dtype not in (np.uint8, np.uint16, np.float32, np.float64):
+            m = m.astype(np.float64)
+        res = solve_raw(t[None], f[None], None if m is None else m[None], opts,
+                        mask_threshold=c["kwargs"].get("threshold", 0.2), buffer_mask=c["buffer_mask"],
+                        mask_buffer_size=c["mask_buffer_size"], mask_buffer_passes=c["mask_buffer_passes"],
+                        clip_target=c["clip_target"], clip_features=c["clip_features"], dtype=self.DTYPE,
+                        out_layout=out_layout, out_dtype=self.DTYPE, chunk_patches=1, streams=1)
+        return res[0].numpy()
 
     def run(self, **kwargs):
         """All bands in one batched device solve (the reference forks one process per
@@ -321,7 +570,9 @@ class VPint2_interpolator():
         opts = wp_run_options(**kwargs)
         if opts["auto_adapt"]:
             return self._run_bands_with_search(kwargs, forked=True).swapaxes(0, 2).swapaxes(0, 1)
-        pred_bhw = solve_bands(self.target, self.features, opts, out_layout="bhw")
+        pred_bhw = self._run_raw(opts, "bhw")
+        if pred_bhw is None:
+            pred_bhw = solve_bands(self.target, self.features, opts, out_layout="bhw")
         return pred_bhw.swapaxes(0, 2).swapaxes(0, 1)
 
     def _run_bands_with_search(self, kwargs, forked):
@@ -354,6 +605,9 @@ class VPint2_interpolator():
         if opts["auto_adapt"]:
             pred = self._run_bands_with_search(kwargs, forked=False)
             return np.ascontiguousarray(np.moveaxis(pred, 0, -1)).astype(self.DTYPE)
+        res = self._run_raw(opts, "hwb")
+        if res is not None:
+            return res
         return solve_bands(self.target, self.features, opts, out_dtype=self.DTYPE, out_layout="hwb")
 
     def apply_mask(self, target, mask, threshold=0.2):
