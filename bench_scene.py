@@ -2,18 +2,20 @@
 """BASELINE config 4: VPint2 cloud removal of ONE full Sentinel-2-shaped scene (default 10980 x 10980 x 13),
 row-sharded over the ranks with halo exchange + all-reduce of the per-sweep sums (vpint_b200/sharded.py).
 
-  python bench_scene.py --size 10980 --k-block 1                      # one GPU
-  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_scene.py --k-block 4
+  python bench_scene.py --size 10980                                   # one GPU
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_scene.py
 
-Every rank generates only its own rows (+ halos) of the synthetic scene on its device; the per-band init
-value (the reference's float32 nanmean of the whole band, VPint/MRP.py:73-77) is formed from all-reduced
-fp64 sums.  A step = load + weights + Jacobi sweeps to every band's own stopping sweep + result gather.
-Prints one JSON line (rank 0): whole-job Mpx*it/s, sweeps per band, HBM roofline of the stencil kernel.
+`bench.py` calls :func:`scene_record` under its own torchrun and puts the result into its JSON line as `scene`:
+
+  parity : a reduced scene solved row-sharded over the N ranks (N = 1: two shards in lockstep on the one device) AND
+           unsharded on rank 0, compared per pixel (<= 1e-9 relative) and per band (equal stopping sweeps)
+  c4     : the full scene -- every rank generates only its own rows (+ halos) of the synthetic product on its device
+           as uint16 rasters + a cloud mask; a step = the NumPy-exact per-band mean init on the device (leaf sums
+           all-reduced), fused load, Jacobi sweeps to every band's own stopping sweep, result of the owned rows.
 """
 import argparse
 import json
 import os
-import statistics
 import sys
 
 import numpy as np
@@ -22,20 +24,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def scene_rows(lo, hi, Hs, Ws, B, seed, dev, cloud_frac_discs):
-    """Rows [lo, hi) of the synthetic scene: (target, features) float32 (rows, Ws, B), NaN = cloud."""
+def scene_rows(lo, hi, Hs, Ws, B, seed, dev, n_discs):
+    """Rows [lo, hi) of the synthetic scene as a product holds it: (target, features) uint16 (rows, Ws, B) -- cloudy
+    pixels keep a measured value -- and the cloud mask uint8 (rows, Ws), 1 = cloud."""
     import torch
     rng = np.random.default_rng(seed)
     modes = rng.uniform(0, 1, (B, 6, 5))
-    discs = rng.uniform(0, 1, (cloud_frac_discs, 3))
+    discs = rng.uniform(0, 1, (n_discs, 3))
     yy = (torch.arange(lo, hi, device=dev, dtype=torch.float64) / Hs).view(-1, 1)
     xx = (torch.arange(Ws, device=dev, dtype=torch.float64) / Ws).view(1, -1)
     rows = hi - lo
-    target = torch.empty((rows, Ws, B), dtype=torch.float32, device=dev)
-    feats = torch.empty((rows, Ws, B), dtype=torch.float32, device=dev)
+    target = torch.empty((rows, Ws, B), dtype=torch.uint16, device=dev)
+    feats = torch.empty((rows, Ws, B), dtype=torch.uint16, device=dev)
     cloud = torch.zeros((rows, Ws), dtype=torch.bool, device=dev)
     for cy, cx, r in discs:
-        rad = (100.0 + 500.0 * r) / 10980.0
+        rad = (100.0 + 500.0 * r) / 10980.0      # relative to the scene: the cloud fraction does not depend on its size
         cloud |= (yy - cy) ** 2 + (xx - cx) ** 2 < rad * rad
     BLK = 256            # noise is generated per fixed block of rows so that it does not depend on the sharding
     for b in range(B):
@@ -51,32 +54,169 @@ def scene_rows(lo, hi, Hs, Ws, B, seed, dev, cloud_frac_discs):
             a, e = max(lo, blk * BLK), min(hi, (blk + 1) * BLK)
             sl = slice(a - lo, e - lo)
             nb = slice(a - blk * BLK, e - blk * BLK)
-            target[sl, :, b] = torch.round(base[sl] + 20.0 * nz[0, nb]).clamp(1, 65535).to(torch.float32)
-            feats[sl, :, b] = torch.round(1.1 * base[sl] + 10.0 * nz[1, nb]).clamp(1, 65535).to(torch.float32)
+            target[sl, :, b] = torch.round(base[sl] + 20.0 * nz[0, nb]).clamp(1, 65535).to(torch.int32).to(torch.uint16)
+            feats[sl, :, b] = torch.round(1.1 * base[sl] + 10.0 * nz[1, nb]).clamp(1, 65535).to(torch.int32).to(torch.uint16)
         del acc, base
-    target[cloud] = float("nan")
-    return target, feats, cloud
+    return target, feats, cloud.to(torch.uint8)
+
+
+class _LocalComm:
+    """Comm of a single process (nothing to exchange)."""
+    world, rank = 1, 0
+
+    def all_reduce_sum(self, t):
+        pass
+
+
+def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, warmup=0, poll=8):
+    """Generate this shard's rows, solve, return (pred (B, own_rows, W) float64, sweeps, launches, ms per step, cloud cells)."""
+    import torch
+    from vpint_b200.sharded import open_shard_raw, run_sharded, shard_result, stage_shard_raw
+    target, feats, cloud = scene_rows(shard.lo, shard.hi, Hs, Ws, B, seed, dev, discs)
+    solver, eng = open_shard_raw(target, feats, cloud, shard, comm, opts, k_block=kb)
+    try:
+        def step():
+            stage_shard_raw(solver, target, feats, cloud, comm, eng.fill_scratch)
+            launches = run_sharded(eng, shard, comm, opts["iterations"], poll_every=poll)
+            pred, sweeps = shard_result(solver, shard)
+            return pred, sweeps, launches
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if comm.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(max(steps, 1)):
+            pred, sweeps, launches = step()
+        e1.record()
+        if comm.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / max(steps, 1)
+        own = slice(shard.own_row0, shard.own_row0 + shard.own_rows)
+        cloud_cells = float(cloud[own].sum().item())
+        tiles = (solver.active_tiles, solver.total_tiles)
+    finally:
+        solver.close()
+    return pred, sweeps, launches, ms, cloud_cells, tiles
+
+
+def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=13, k_block=1, discs=150, seed=1004):
+    """The `scene` record of bench.py's JSON line (rank 0 returns it, the others None)."""
+    import torch
+    import torch.distributed as dist
+    from vpint_b200.sharded import Comm, RowShard, run_lockstep, open_shard_raw, shard_result
+    from vpint_b200.wp import wp_run_options
+    opts = wp_run_options()
+    kb = max(1, k_block)
+    comm = Comm() if world > 1 else _LocalComm()
+    torch.cuda.empty_cache()
+    rec = {"k_block": kb}
+
+    # ---- parity: sharded == unsharded on a reduced scene --------------------------------------------------------
+    Hp = Wp = parity_size
+    pdiscs = max(4, discs // 6)
+    if world > 1:
+        shard = RowShard(Hp, world, rank, halo=kb)
+        pred, sweeps, _, _, _, _ = _solve_rows(shard, comm, Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb)
+        if rank == 0:
+            parts = [pred]
+            for r in range(1, world):
+                sh = RowShard(Hp, world, r, halo=kb)
+                buf = torch.empty((bands, sh.own_rows, Wp), dtype=torch.float64, device=dev)
+                dist.recv(buf, src=r)
+                parts.append(buf)
+            got = torch.cat(parts, dim=1)
+        else:
+            dist.send(pred.contiguous(), dst=0)
+        how = "row-sharded over %d NCCL ranks vs unsharded on rank 0" % world
+    else:
+        # one device: two shards driven in lockstep (the all-reduce and the halo exchange become tensor copies)
+        shards = [RowShard(Hp, 2, r, halo=kb) for r in range(2)]
+        solvers, engines = [], []
+        try:
+            # the mean init of the whole band: both shards' leaf sums added before either combines
+            from vpint_b200.engine import Solver
+            raws = [scene_rows(sh.lo, sh.hi, Hp, Wp, bands, seed + 1, dev, pdiscs) for sh in shards]
+            scr = []
+            for sh, (t, f, c) in zip(shards, raws):
+                s = Solver(2, bands, sh.local_rows, Wp, nprob_inner=bands, planes=True, k_block=kb, shard=sh.desc(), device=dev)
+                solvers.append(s)
+                sc = s.fill_scratch("float32")
+                s.fill_leaves(t.unsqueeze(0), c.unsqueeze(0), sc)
+                scr.append(sc)
+            views = [s.fill_views(sc) for s, sc in zip(solvers, scr)]
+            tot_l, tot_c = views[0][0] + views[1][0], views[0][1] + views[1][1]
+            from vpint_b200.sharded import SolverEngine
+            for s, sh, sc, (l, c), (t, f, cl) in zip(solvers, shards, scr, views, raws):
+                l.copy_(tot_l); c.copy_(tot_c)
+                s.fill_combine(sc)
+                s.ingest_bands(t.unsqueeze(0), f.unsqueeze(0), cl.unsqueeze(0), fill_ready=True)
+                engines.append(SolverEngine(s, sh, dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
+                                                        clip_val=opts["clip_val"])))
+            run_lockstep(engines, shards, opts["iterations"])
+            res = [shard_result(s, sh) for s, sh in zip(solvers, shards)]
+            got = torch.cat([r[0] for r in res], dim=1)
+            sweeps = res[0][1]
+        finally:
+            for s in solvers:
+                s.close()
+        del raws
+        how = "two row shards in lockstep on the one device vs unsharded"
+    if rank == 0:
+        full = RowShard(Hp, 1, 0, halo=0)
+        ref, ref_sweeps, _, _, _, _ = _solve_rows(full, _LocalComm(), Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb)
+        rel = float(((got - ref).abs() / ref.abs()).max().item())
+        rec["parity"] = {"scene": "%dx%dx%d" % (Hp, Wp, bands), "how": how, "max_rel": rel,
+                         "sweeps_sharded": [int(v) for v in sweeps], "sweeps_unsharded": [int(v) for v in ref_sweeps],
+                         "tolerance": 1e-9}
+        rec["parity_ok"] = bool(rel <= 1e-9 and list(sweeps) == list(ref_sweeps))
+        del got, ref
+    torch.cuda.empty_cache()
+
+    # ---- the full scene ---------------------------------------------------------------------------------------
+    if size > 0:
+        shard = RowShard(size, world, rank, halo=kb if world > 1 else 0)
+        pred, sweeps, launches, ms, cloud_cells, tiles = _solve_rows(shard, comm, size, size, bands, seed, dev, discs, opts, kb,
+                                                                     steps=steps, warmup=1)
+        ok = bool(torch.isfinite(pred).all().item())
+        del pred
+        t = torch.tensor([ms, cloud_cells, 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t[:1].clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t[1:].clone()
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ms, cloud_cells, ok = float(tm.item()), float(ts[0].item()), bool(ts[1].item() == world)
+        if rank == 0:
+            pxit = float(np.sum(sweeps)) * size * size
+            frac = cloud_cells / (float(size) * size)
+            rec["c4"] = {"workload": "C4: VPint2 cloud removal of one %dx%dx%d scene from uint16 rasters + cloud mask, "
+                                     "row-sharded over %d GPU(s), auto-terminate 1e-4; a step = device mean init (NumPy-exact), "
+                                     "fused load, sweeps, result" % (size, size, bands, world),
+                         "ms": ms, "steps": steps, "value": pxit / (ms * 1e-3) / 1e6, "unit": "Mpx*it/s", "scaling": "strong",
+                         "sweeps_per_band": [int(v) for v in sweeps], "launches": int(launches), "cloud_fraction": round(frac, 4),
+                         "rows_rank0": shard.own_rows, "halo": shard.halo, "finite": ok,
+                         "active_tiles_rank0": tiles[0], "total_tiles_rank0": tiles[1],
+                         "unknown_cell_gbps_48B": 48.0 * pxit * frac / (ms * 1e-3) / 1e9}
+    torch.cuda.empty_cache()
+    return rec if rank == 0 else None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=10980)
-    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--parity-size", type=int, default=2048)
     ap.add_argument("--bands", type=int, default=13)
     ap.add_argument("--k-block", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--discs", type=int, default=150)
-    ap.add_argument("--iterations", type=int, default=-1)
-    ap.add_argument("--poll", type=int, default=8)
-    ap.add_argument("--graph", type=int, default=0, help="replay one captured launch group (kernels + NCCL) per launch")
     args = ap.parse_args()
 
     import torch
     import torch.distributed as dist
-    from vpint_b200.sharded import Comm, RowShard, open_shard, run_sharded, shard_result, stage_shard
-    from vpint_b200.wp import wp_run_options
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -84,76 +224,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    Hs, Ws, B = args.size, (args.width or args.size), args.bands
-    kb = max(1, args.k_block)
-    shard = RowShard(Hs, world, rank, halo=kb if world > 1 else 0)
-    target, feats, cloud = scene_rows(shard.lo, shard.hi, Hs, Ws, B, 1004, dev, args.discs)
-    # per-band float32 mean of the known cells of the WHOLE band (owned rows only, summed over ranks in fp64)
-    own = slice(shard.own_row0, shard.own_row0 + shard.own_rows)
-    known = ~cloud[own]
-    sums = torch.stack([target[own, :, b][known].double().sum() for b in range(B)] + [known.sum().double()])
-    if world > 1:
-        dist.all_reduce(sums)
-    fill = (sums[:B] / sums[B]).to(torch.float32).double().cpu().numpy()
-    cloud_cells = cloud[own].sum().double()
-    if world > 1:
-        dist.all_reduce(cloud_cells)
-    opts = wp_run_options(iterations=args.iterations)
-    comm = Comm()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    solver, eng = open_shard(target, feats, shard, fill, opts, k_block=kb)      # workspace + first staging
-
-    def step():
-        stage_shard(solver, target, feats, fill, opts)
-        launches = run_sharded(eng, shard, comm, opts["iterations"], poll_every=args.poll,
-                               use_graph=bool(args.graph))
-        pred, sweeps = shard_result(solver, shard)
-        return pred, sweeps, launches, (solver.active_tiles, solver.total_tiles)
-
-    for _ in range(args.warmup):
-        step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        pred, sweeps, launches, tiles = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ok = bool(torch.isfinite(pred).all().item())
-    solver.close()
-    pxit = float(sweeps.sum()) * Hs * Ws
+    rec = scene_record(world, rank, dev, size=args.size, parity_size=args.parity_size, steps=args.steps, bands=args.bands,
+                       k_block=args.k_block, discs=args.discs)
     if rank == 0:
-        peak = 6542.4
-        try:
-            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        except Exception:
-            pass
-        frac_cloud = float(cloud_cells.item()) / (Hs * Ws)
-        line = {
-            "metric": "vpint2_mpixel_iter_per_s", "value": pxit / (ms * 1e-3) / 1e6, "unit": "Mpx*it/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong", "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "C4: VPint2 cloud removal of one %dx%dx%d scene, row-sharded over %d GPU(s), k_block %d, "
-                                   "auto-terminate 1e-4" % (Hs, Ws, B, world, kb),
-                       "cloud_fraction": round(frac_cloud, 4), "sweeps_per_band": [int(s) for s in sweeps],
-                       "launches": int(launches), "active_tiles_rank0": tiles[0], "total_tiles_rank0": tiles[1],
-                       "rows_rank0": shard.own_rows, "halo": shard.halo, "finite": ok,
-                       "launch_groups": "CUDA graph replay (kernels + NCCL)" if args.graph and world > 0 else "eager"},
-            "algorithmic_gbps_whole_grid": 48.0 * pxit / (ms * 1e-3) / 1e9,
-            "algorithmic_gbps_unknown_cells": 48.0 * pxit * frac_cloud / (ms * 1e-3) / 1e9,
-            "hbm_peak_gbps": peak,
-        }
-        print(json.dumps(line))
+        print(json.dumps(rec))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

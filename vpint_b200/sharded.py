@@ -293,6 +293,47 @@ def stage_shard(solver, t_dev, f_dev, fill, opts):
                    clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
 
 
+def open_shard_raw(target_local, features_local, cloud_local, shard, comm, opts, *, value_dtype="float32", k_block=1,
+                   device=None):
+    """:func:`open_shard` from the RAW rasters of this rank's rows (uint16 / float32 / float64 CUDA tensors
+    (local_rows, W, B) = ``shard.local(full)``) and the all-band cloud mask (uint8 (local_rows, W), nonzero = cloud,
+    or None): no host pass at all -- the per-band mean init is formed on the device, every rank summing the leaves of
+    NumPy's summation tree that start in its rows and all ranks all-reducing the leaf sums (VPint/MRP.py:73-77 bit
+    for bit for the WHOLE band).  Needs >= 1 halo row (W >= 127) on interior sides, which ``halo >= k_block`` gives."""
+    from .engine import Solver, require_cuda
+    dev = require_cuda(device)
+    Hl, W, B = target_local.shape
+    if Hl != shard.local_rows:
+        raise VPintError("target_local has %d rows, the shard expects %d" % (Hl, shard.local_rows))
+    kb = max(1, int(k_block))
+    if shard.world > 1 and shard.halo < kb:
+        raise VPintError("halo (%d) must be at least k_block (%d)" % (shard.halo, kb))
+    solver = Solver(2, B, Hl, W, nprob_inner=B, planes=True, k_block=kb, shard=shard.desc(), device=dev)
+    try:
+        scratch = solver.fill_scratch(value_dtype)
+        stage_shard_raw(solver, target_local, features_local, cloud_local, comm, scratch, value_dtype)
+        eng = SolverEngine(solver, shard, dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
+                                               clip_val=opts["clip_val"]))
+        eng.fill_scratch = scratch
+    except Exception:
+        solver.close()
+        raise
+    return solver, eng
+
+
+def stage_shard_raw(solver, t_dev, f_dev, cloud_dev, comm, scratch, value_dtype="float32"):
+    """(Re)load one rank's rows from the raw rasters: device mean init (leaf sums all-reduced over the ranks), then the
+    fused load (state, unknown-cell mask, feature plane, known-cell sums)."""
+    t4, f4 = t_dev.unsqueeze(0), f_dev.unsqueeze(0)
+    c3 = None if cloud_dev is None else cloud_dev.unsqueeze(0)
+    solver.fill_leaves(t4, c3, scratch, value_dtype=value_dtype)
+    leaves, counts = solver.fill_views(scratch, value_dtype)
+    comm.all_reduce_sum(leaves)
+    comm.all_reduce_sum(counts)
+    solver.fill_combine(scratch, value_dtype)
+    solver.ingest_bands(t4, f4, c3, value_dtype=value_dtype, fill_ready=True)
+
+
 def shard_result(solver, shard):
     """(pred float64 torch tensor (B, own_rows, W) on the device, sweeps int64 ndarray (B,))."""
     out, niter = solver.result()

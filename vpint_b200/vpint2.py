@@ -284,19 +284,20 @@ def _fused_ok(opts):
 class _RawSlot:
     """One stream of the :func:`solve_raw` pipeline: staging buffers, solver and the chunk in flight."""
 
-    def __init__(self, dev, chunk, H, W, B, raster_dtype, mask_dtype, res_shape, res_dtype, need_res, need_cloud, buffer):
+    def __init__(self, dev, chunk, H, W, B, raster_dtype, mask_dtype, res_shape, res_dtype, need_res, need_cloud, buffer,
+                 stage_in=True):
         import torch
         self.dev = dev
         self.stream = torch.cuda.Stream(device=dev)
         self.solvers = {}
-        self.t_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev)
-        self.f_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev)
+        self.t_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
+        self.f_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
         self.m_buf = None if mask_dtype is None else torch.empty((chunk, H, W), dtype=mask_dtype, device=dev)
         self.cloud = torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) if need_cloud else None
         self.buf_scratch = torch.empty(3 * chunk * H * W, dtype=torch.uint8, device=dev) if buffer else None
         self.res = torch.empty(res_shape(chunk), dtype=res_dtype, device=dev) if need_res else None
         self.niter = torch.zeros(chunk * B, dtype=torch.int32, device=dev)
-        self.fill_scratch = None
+        self.fill_scratch = {}
         self.pending = None
 
     def close(self):
@@ -305,107 +306,126 @@ class _RawSlot:
         self.solvers = {}
 
 
-def solve_raw(target, features, mask=None, opts=None, *, mask_threshold=0.2, buffer_mask=False, mask_buffer_size=5,
+class RawPipeline:
+    """The streams, staging buffers and solvers of :func:`solve_raw`, kept across calls: a caller that cleans many
+    stacks of one shape (a tile server, the benchmark) pays for workspace allocation and solver creation once."""
+
+    def __init__(self, device=None, chunk_patches=None, streams=None, k_block=None):
+        self.dev = require_cuda(device)
+        self.k_block = _solve.DEFAULT_K_BLOCK if k_block is None else int(k_block)
+        self.chunk = int(chunk_patches or PIPELINE_CHUNK_PATCHES)
+        self.K = int(streams or RAW_STREAMS)
+        self.slots = []
+        self.key = None
+        self.launches = 0
+
+    def close(self):
+        for sl in self.slots:
+            self.launches += sum(sv.launches for sv in sl.solvers.values())
+            sl.close()
+        self.slots = []
+        self.key = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def total_launches(self):
+        """Kernels launched by the library through this pipeline so far."""
+        return self.launches + sum(sv.launches for sl in self.slots for sv in sl.solvers.values())
+
+    def _slots(self, key, make):
+        if self.key != key:
+            self.close()
+            import torch
+            with torch.cuda.device(self.dev):
+                self.slots = [make() for _ in range(self.K)]
+            self.key = key
+        return self.slots
+
+    def solve(self, target, features, mask=None, opts=None, *, mask_threshold=0.2, buffer_mask=False, mask_buffer_size=5,
               mask_buffer_passes=1, clip_target=None, clip_features=None, dtype=np.float32, out=None, out_layout="bhw",
-              out_dtype=None, result="full", device=None, chunk_patches=None, streams=None, return_sweeps=False):
-    """VPint2 cloud removal of a stack of patches straight from the RAW rasters: the interpolator's constructor
-    (VPint/VPint2.py:13-55), every band's mean init (VPint/MRP.py:73-77) and run() (VPint/VPint2.py:58-119) on the
-    device, chunk by chunk on ``streams`` CUDA streams driven by ONE host thread -- no step blocks the host, so the
-    host->device copy of a chunk, the solve of another and the result of a third overlap.
+              out_dtype=None, result="full", return_sweeps=False):
+        """See :func:`solve_raw`."""
+        import torch
+        dev = self.dev
+        opts = wp_run_options() if opts is None else opts
+        if not _fused_ok(opts):
+            raise VPintError("solve_raw serves run() with exact weights and without prioritise_identity / resistance / "
+                             "auto_adapt; use VPint2_interpolator for those")
+        if result not in ("full", "unknown"):
+            raise VPintError("result must be 'full' or 'unknown'")
+        as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+        target, features = as_t(target), as_t(features)
+        mask = None if mask is None else as_t(mask)
+        if target.dim() != 4 or target.shape != features.shape:
+            raise VPintError("target and features must be (N, H, W, B) stacks of one shape")
+        if target.dtype != features.dtype:
+            features = features.to(target.dtype)
+        N_, H, W, B = target.shape
+        if mask is not None and tuple(mask.shape) != (N_, H, W):
+            raise VPintError("mask must have shape (N, H, W)")
+        if mask is not None and mask.dtype not in (torch.uint8, torch.uint16, torch.float32, torch.float64):
+            mask = mask.to(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.float64)
+        if H * W < 128:
+            raise VPintError("solve_raw needs grids of at least 128 cells (smaller ones: VPint2_interpolator / solve_bands)")
+        value_dtype = "float64" if np.dtype(dtype) == np.float64 else "float32"
+        chunk = self.chunk
+        if out_layout == "bhw":
+            res_shape, res_dtype = (lambda m: (m, B, H, W)), torch.float64
+        else:
+            tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {np.dtype(np.float32): torch.float32}.get(
+                np.dtype(out_dtype if out_dtype is not None else dtype), torch.float64)
+            res_shape, res_dtype = (lambda m: (m, H, W, B)), tdt
+        in_on_dev = target.device.type != "cpu"
+        if out is None:
+            if result == "unknown":
+                raise VPintError("result='unknown' writes into the caller's array: pass out")
+            out = torch.empty(res_shape(N_), dtype=res_dtype, device=dev) if in_on_dev else \
+                torch.empty(res_shape(N_), dtype=res_dtype, pin_memory=True)
+        if tuple(out.shape) != res_shape(N_) or out.dtype != res_dtype:
+            raise VPintError("out must have shape %s and dtype %s" % (res_shape(N_), res_dtype))
+        out_on_dev = out.device.type != "cpu"
+        if result == "unknown" and not out_on_dev and not out.is_pinned():
+            raise VPintError("result='unknown' needs a CUDA or pinned host `out`")
+        need_res = (result == "full") and not out_on_dev
+        spans = [(a, min(a + chunk, N_)) for a in range(0, N_, chunk)]
+        sweeps_host = torch.empty(N_ * B, dtype=torch.int32, pin_memory=True)
+        need_cloud = mask is not None or buffer_mask
+        mask_stage = None if (mask is None or mask.device.type != "cpu") else mask.dtype
+        main = torch.cuda.current_stream(dev)
+        run_kw = dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"], clip_val=opts["clip_val"])
+        as_prob = (lambda t: t) if out_layout == "bhw" else (lambda t: t.permute(0, 3, 1, 2))
+        key = (H, W, B, target.dtype, mask_stage, out_layout, res_dtype, need_res, need_cloud, bool(buffer_mask), in_on_dev)
+        slots = self._slots(key, lambda: _RawSlot(dev, chunk, H, W, B, target.dtype, mask_stage, res_shape, res_dtype,
+                                                  need_res, need_cloud, buffer_mask, stage_in=not in_on_dev))
+        K = max(1, min(self.K, len(spans)))
 
-    target, features : (N, H, W, B) uint16 / float32 / float64, NumPy or torch, host (pinned for asynchronous copies)
-                       or CUDA.  NaN in a float target = unknown.
-    mask             : (N, H, W) cloud mask (any real dtype) -> unknown on every band where ``mask > mask_threshold``.
-    dtype            : the interpolator's DTYPE (np.float32 = VPint2's default): values, clip and mean init live in it.
-    result           : 'full'    -> every cell of the result (float64 (N, B, H, W) for out_layout 'bhw' as run()
-                                    assembles it, ``out_dtype`` (N, H, W, B) for 'hwb' as run_serial() returns it);
-                       'unknown' -> ONLY the cloud cells are written, into ``out`` (required; CUDA or pinned host
-                                    memory, written in place through its device mapping): the known cells are the
-                                    caller's own data and never cross the host link.
-    Returns out (and the sweep counts (N, B) with ``return_sweeps``) as torch tensors."""
-    import torch
-    dev = require_cuda(device)
-    opts = wp_run_options() if opts is None else opts
-    if not _fused_ok(opts):
-        raise VPintError("solve_raw serves run() with exact weights and without prioritise_identity / resistance / "
-                         "auto_adapt; use VPint2_interpolator for those")
-    if result not in ("full", "unknown"):
-        raise VPintError("result must be 'full' or 'unknown'")
-    as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
-    target, features = as_t(target), as_t(features)
-    mask = None if mask is None else as_t(mask)
-    if target.dim() != 4 or target.shape != features.shape:
-        raise VPintError("target and features must be (N, H, W, B) stacks of one shape")
-    if target.dtype != features.dtype:
-        features = features.to(target.dtype)
-    N_, H, W, B = target.shape
-    if mask is not None and tuple(mask.shape) != (N_, H, W):
-        raise VPintError("mask must have shape (N, H, W)")
-    if mask is not None and mask.dtype not in (torch.uint8, torch.uint16, torch.float32, torch.float64):
-        mask = mask.to(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.float64)
-    if H * W < 128:
-        raise VPintError("solve_raw needs grids of at least 128 cells (smaller ones: VPint2_interpolator / solve_bands)")
-    value_dtype = "float64" if np.dtype(dtype) == np.float64 else "float32"
-    if target.dtype == torch.float64 and value_dtype == "float32":
-        pass            # astype(float32) happens on the device
-    kb = 0
-    chunk = int(chunk_patches or PIPELINE_CHUNK_PATCHES)
-    K = int(streams or RAW_STREAMS)
-    if out_layout == "bhw":
-        res_shape, res_dtype = (lambda m: (m, B, H, W)), torch.float64
-    else:
-        tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {np.dtype(np.float32): torch.float32}.get(
-            np.dtype(out_dtype if out_dtype is not None else dtype), torch.float64)
-        res_shape, res_dtype = (lambda m: (m, H, W, B)), tdt
-    if out is None:
-        if result == "unknown":
-            raise VPintError("result='unknown' writes into the caller's array: pass out")
-        out = torch.empty(res_shape(N_), dtype=res_dtype, device=dev if target.device.type != "cpu" else "cpu",
-                          pin_memory=(target.device.type == "cpu"))
-    if tuple(out.shape) != res_shape(N_) or out.dtype != res_dtype:
-        raise VPintError("out must have shape %s and dtype %s" % (res_shape(N_), res_dtype))
-    out_on_dev = out.device.type != "cpu"
-    if result == "unknown" and not out_on_dev and not out.is_pinned():
-        raise VPintError("result='unknown' needs a CUDA or pinned host `out`")
-    need_res = (result == "full") and not out_on_dev
-    in_on_dev = target.device.type != "cpu"
-    spans = [(a, min(a + chunk, N_)) for a in range(0, N_, chunk)]
-    K = max(1, min(K, len(spans)))
-    sweeps_host = torch.empty(N_ * B, dtype=torch.int32, pin_memory=True)
-    need_cloud = mask is not None or buffer_mask
-    main = torch.cuda.current_stream(dev)
-    run_kw = dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"], clip_val=opts["clip_val"])
-    as_prob = (lambda t: t) if out_layout == "bhw" else (lambda t: t.permute(0, 3, 1, 2))
-    slots = []
-    try:
+        def emit_result(sl, a, b, solver):
+            m = b - a
+            if need_res:
+                solver.result_unknown(as_prob(sl.res[:m]), niter=sl.niter[:m * B])
+                out[a:b].copy_(sl.res[:m], non_blocking=True)
+            else:
+                solver.result_unknown(as_prob(out[a:b]), niter=sl.niter[:m * B])
+            sweeps_host[a * B:b * B].copy_(sl.niter[:m * B], non_blocking=True)
+
+        def finish(sl):
+            if sl.pending is None:
+                return
+            a, b, solver = sl.pending
+            sl.pending = None
+            with torch.cuda.stream(sl.stream):
+                if solver.run_finish():            # the resident kernel declined: the tiled path finished the run
+                    if result == "full":           # every cell again (the known ones were written by the load)
+                        solver.result(out=as_prob(sl.res[:b - a] if need_res else out[a:b]))
+                    emit_result(sl, a, b, solver)
+
         with torch.cuda.device(dev):
-            for _ in range(K):
-                sl = _RawSlot(dev, chunk, H, W, B, target.dtype, None if (mask is None or mask.device.type != "cpu") else mask.dtype,
-                              res_shape, res_dtype, need_res, need_cloud, buffer_mask)
+            for sl in slots[:K]:
                 sl.stream.wait_stream(main)
-                slots.append(sl)
-
-            def emit_result(sl, a, b, solver, dst):
-                m = b - a
-                if result == "unknown" or not need_res:
-                    solver.result_unknown(as_prob(dst), niter=sl.niter[:m * B])
-                else:
-                    solver.result_unknown(as_prob(sl.res[:m]), niter=sl.niter[:m * B])
-                    out[a:b].copy_(sl.res[:m], non_blocking=True)
-                sweeps_host[a * B:b * B].copy_(sl.niter[:m * B], non_blocking=True)
-
-            def finish(sl):
-                if sl.pending is None:
-                    return
-                a, b, solver = sl.pending
-                sl.pending = None
-                with torch.cuda.stream(sl.stream):
-                    if solver.run_finish():            # the resident kernel declined: the tiled path finished the run
-                        if result == "full":           # known cells again, then the unknown ones
-                            dst = out[a:b] if not need_res else sl.res[:b - a]
-                            solver.result(out=as_prob(dst))
-                        emit_result(sl, a, b, solver, out[a:b])
-
             for i, (a, b) in enumerate(spans):
                 sl = slots[i % K]
                 finish(sl)                             # the chunk this slot carried K chunks ago
@@ -419,7 +439,7 @@ def solve_raw(target, features, mask=None, opts=None, *, mask_threshold=0.2, buf
                         t_c, f_c = sl.t_buf[:m], sl.f_buf[:m]
                     cloud = None
                     if mask is not None:
-                        if mask.device.type == "cpu":
+                        if mask_stage is not None:
                             sl.m_buf[:m].copy_(mask[a:b], non_blocking=True)
                             m_c = sl.m_buf[:m]
                         else:
@@ -429,29 +449,47 @@ def solve_raw(target, features, mask=None, opts=None, *, mask_threshold=0.2, buf
                         cloud = buffer_clouds(t_c, cloud, mask_buffer_size, mask_buffer_passes, scratch=sl.buf_scratch,
                                               out=sl.cloud[:m])
                     if m not in sl.solvers:
-                        sl.solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, planes=True, k_block=kb, device=dev,
+                        sl.solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, planes=True, k_block=self.k_block, device=dev,
                                                blocking_wait=True)
-                        sl.fill_scratch = sl.solvers[m].fill_scratch(value_dtype) if sl.fill_scratch is None else sl.fill_scratch
+                        sl.fill_scratch[m] = sl.solvers[m].fill_scratch(value_dtype)
                     solver = sl.solvers[m]
-                    scratch = sl.fill_scratch if m == chunk else solver.fill_scratch(value_dtype)
                     known_dst = None
                     if result == "full":
-                        known_dst = as_prob(out[a:b] if not need_res else sl.res[:m])
+                        known_dst = as_prob(sl.res[:m] if need_res else out[a:b])
                     solver.ingest_bands(t_c, f_c, cloud, value_dtype=value_dtype, clip_target=clip_target,
-                                        clip_features=clip_features, out=known_dst, scratch=scratch)
+                                        clip_features=clip_features, out=known_dst, scratch=sl.fill_scratch[m])
                     solver.run_async(opts["iterations"], **run_kw)
-                    emit_result(sl, a, b, solver, out[a:b])
+                    emit_result(sl, a, b, solver)
                 sl.pending = (a, b, solver)
-            for sl in slots:
+            for sl in slots[:K]:
                 finish(sl)
-            for sl in slots:
+            for sl in slots[:K]:
                 sl.stream.synchronize()
                 main.wait_stream(sl.stream)
-    finally:
-        for sl in slots:
-            sl.close()
-    sweeps = sweeps_host.to(torch.int64).view(N_, B)
-    return (out, sweeps) if return_sweeps else out
+        sweeps = sweeps_host.to(torch.int64).view(N_, B)
+        return (out, sweeps) if return_sweeps else out
+
+
+def solve_raw(target, features, mask=None, opts=None, *, device=None, chunk_patches=None, streams=None, k_block=None, **kw):
+    """VPint2 cloud removal of a stack of patches straight from the RAW rasters: the interpolator's constructor
+    (VPint/VPint2.py:13-55), every band's mean init (VPint/MRP.py:73-77) and run() (VPint/VPint2.py:58-119) on the
+    device, chunk by chunk on ``streams`` CUDA streams driven by ONE host thread -- no step blocks the host, so the
+    host->device copy of a chunk, the solve of another and the result of a third overlap.
+
+    target, features : (N, H, W, B) uint16 / float32 / float64, NumPy or torch, host (pinned for asynchronous copies)
+                       or CUDA.  NaN in a float target = unknown.
+    mask             : (N, H, W) cloud mask (any real dtype) -> unknown on every band where ``mask > mask_threshold``.
+    buffer_mask, mask_buffer_size, mask_buffer_passes, clip_target, clip_features : as the VPint2 constructor.
+    dtype            : the interpolator's DTYPE (np.float32 = VPint2's default): values, clip and mean init live in it.
+    result           : 'full'    -> every cell of the result (float64 (N, B, H, W) for out_layout 'bhw' as run()
+                                    assembles it, ``out_dtype`` (N, H, W, B) for 'hwb' as run_serial() returns it);
+                       'unknown' -> ONLY the cloud cells are written, into ``out`` (required; CUDA or pinned host
+                                    memory, written in place through its device mapping): the known cells are the
+                                    caller's own data and never cross the host link.
+    Returns out (and the sweep counts (N, B) with ``return_sweeps``) as torch tensors.  :class:`RawPipeline` is the
+    same thing with its buffers kept across calls."""
+    with RawPipeline(device, chunk_patches, streams, k_block) as pipe:
+        return pipe.solve(target, features, mask, opts, **kw)
 
 
 class VPint2_interpolator():
