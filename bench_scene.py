@@ -103,7 +103,7 @@ def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, war
     return pred, sweeps, launches, ms, cloud_cells, tiles
 
 
-def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=13, k_block=1, discs=150, seed=1004):
+def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=13, k_block=1, discs=60, seed=1004):
     """The `scene` record of bench.py's JSON line (rank 0 returns it, the others None)."""
     import torch
     import torch.distributed as dist
@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--bands", type=int, default=13)
     ap.add_argument("--k-block", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--discs", type=int, default=150)
+    ap.add_argument("--discs", type=int, default=60)
     args = ap.parse_args()
 
     import torch
