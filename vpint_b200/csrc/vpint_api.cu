@@ -91,8 +91,11 @@ struct vpint_solver {
     bool use_tb = false;
     int halo_up = 0, halo_down = 0;   // halo rows above / below the owned band (row-sharded scenes)
     // cluster-resident solve (vpint_resident.cu): chosen when k_block == 0 and one problem fits on chip
-    bool res_ok = false;              // plan valid for this solver's weight form
-    ResidentPlan rplan;
+    bool res_ok = false;              // plans valid for this solver's weight form
+    ResidentPlan rplans[kResidentMaxC + 1];   // per cluster size (problems run on the smallest cluster that holds the rows
+    int res_caps[kResidentMaxC + 1] = {0};    //   their sweeps touch); caps = rows a cluster of C CTAs holds, 0 = no plan
+    int res_cmax = 0;                 // smallest cluster that holds ALL rows of a problem
+    size_t off_cls = 0;               // int[P] class of every problem, int[32]: [0..8] problems per class, [16..24] class queues
     bool planes_valid = false;        // the 4 (5) weight planes hold current weights
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue, [2] sweeps left (graph loop), [3] a feature that is not a float32 value
@@ -181,7 +184,14 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     const bool unsharded = (g.global_H == g.H && g.own_row0 == 0 && g.own_rows == g.H);
     if (d->k_block == 0 && d->ndim == 2 && d->storage == VPINT_F64 && unsharded && !getenv("VPINT_NO_RESIDENT")) {
         const int smem_optin = (233472 - kResidentCtasPerSm * 1024) / kResidentCtasPerSm;   // sm_100a: 228 KB per SM, 1 KB reserved per CTA
-        s->res_ok = resident_plan(g, d->weight_mode == VPINT_W_PLANES, smem_optin, &s->rplan);
+        for (int c = 1; c <= kResidentMaxC && s->res_cmax == 0; ++c) {
+            if (!resident_plan(g, d->weight_mode == VPINT_W_PLANES, smem_optin, c, &s->rplans[c])) continue;
+            s->res_caps[c] = c * s->rplans[c].R;
+            if (s->res_caps[c] >= g.H) s->res_cmax = c;
+        }
+        s->res_ok = s->res_cmax > 0;
+        if (!s->res_ok)
+            for (int c = 0; c <= kResidentMaxC; ++c) s->res_caps[c] = 0;
     }
     if (d->ndim == 2 && d->weight_mode == VPINT_W_PLANES && d->storage == VPINT_F64) s->n_planes = 5;   // + the feature plane
 
@@ -245,7 +255,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_flags = take(16 * sizeof(int));
     s->off_stage = take(reduce_stage_bytes(g));
     s->off_done = take((size_t)g.P * sizeof(int));
-    s->off_order = take((size_t)g.P * sizeof(int));
+    s->off_order = take((size_t)(kResidentMaxC + 1) * g.P * sizeof(int));
+    s->off_cls = take(((size_t)g.P + 32) * sizeof(int));
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
@@ -742,7 +753,8 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
         rc = leave_ratio(s, st);                   // a previous tiled run may have left the state in ratio space
         if (rc != VPINT_OK) return rc;
         int *flags = s->at<int>(s->off_flags);
-        VP_CUDA(cudaMemsetAsync(flags + 1, 0, sizeof(int), st), "memset queue");
+        int *cls_of = s->at<int>(s->off_cls), *cls_count = cls_of + s->g.P, *cls_queue = cls_count + 16;
+        VP_CUDA(cudaMemsetAsync(cls_count, 0, 32 * sizeof(int), st), "memset queues");
         ResidentArgs ra;
         ra.g = s->g;
         ra.state = s->at<ProbState>(s->off_state);
@@ -755,22 +767,38 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
         ra.known = s->at<double>(s->off_known);
         ra.delta_out = prm->delta_out;
         ra.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
-        ra.queue = flags + 1;
-        ra.order = nullptr;
-        if (s->g.P > 2 * 33 && s->g.P <= kResidentOrderMax && !getenv("VPINT_NO_QUEUE_ORDER")) {
-            // longest problems first: big clouds need the most sweeps, so they must not start last
-            VP_CUDA(launch_resident_order(s->g, ra.state, s->at<int>(s->off_order), st, &s->launches), "queue order");
-            ra.order = s->at<int>(s->off_order);
-        }
         ra.bad_flag = ratio ? flags : nullptr;
         ra.f32_flag = ratio ? flags + 3 : nullptr;
         ra.max_iter = prm->max_iter;
         ra.auto_terminate = prm->auto_terminate;
         ra.threshold = prm->threshold;
         ra.clip = prm->clip_val;
-        ra.C = s->rplan.C; ra.R = s->rplan.R; ra.SP = s->rplan.SP; ra.fcap = s->rplan.fcap;
-        ra.BS = s->rplan.BS; ra.LB = s->rplan.LB;
-        VP_CUDA(launch_resident2d(ra, ratio, s->rplan.smem_bytes, 0, st, &s->launches), "resident2d");
+        auto launch_class = [&](int c, const int *order, const int *count) -> cudaError_t {
+            const ResidentPlan &pl = s->rplans[c];
+            ra.queue = cls_queue + c;
+            ra.order = order;
+            ra.count = count;
+            ra.C = pl.C; ra.R = pl.R; ra.SP = pl.SP; ra.fcap = pl.fcap; ra.BS = pl.BS; ra.LB = pl.LB;
+            return launch_resident2d(ra, ratio, pl.smem_bytes, 0, st, &s->launches);
+        };
+        if (s->g.P > 2 * 33 && s->g.P <= kResidentOrderMax && !getenv("VPINT_NO_QUEUE_ORDER")) {
+            // A batch: every problem runs on the smallest cluster that holds the rows its sweeps touch (a class per
+            // cluster size, one launch each, largest first), and inside a class the longest problems go first -- big
+            // clouds need the most sweeps, so they must not start last.
+            int *order = s->at<int>(s->off_order);
+            const int c_top = getenv("VPINT_ONE_CLASS") ? 0 : s->res_cmax;
+            int caps[kResidentMaxC + 1];
+            for (int c = 0; c <= kResidentMaxC; ++c) caps[c] = (c_top && c <= c_top) ? s->res_caps[c] : 0;
+            if (!c_top) caps[s->res_cmax] = s->res_caps[s->res_cmax];
+            VP_CUDA(launch_resident_order(s->g, ra.state, s->at<double>(s->off_rowpart), caps, s->res_cmax, cls_of, order,
+                                          cls_count, st, &s->launches),
+                    "queue order");
+            for (int c = s->res_cmax; c >= 1; --c)
+                if (caps[c] > 0)
+                    VP_CUDA(launch_class(c, order + (size_t)c * s->g.P, cls_count + c), "resident2d");
+        } else {
+            VP_CUDA(launch_class(s->res_cmax, nullptr, nullptr), "resident2d");
+        }
         VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
                                 sizeof(int), cudaMemcpyDeviceToHost, st),
                 "read active count");

@@ -101,6 +101,8 @@ struct DecideArgs {
 constexpr int kResidentThreads = 512;   // 15 worker warps + the sync warp
 constexpr int kResidentCtasPerSm = 1;  // measured: 2 x 256 threads (clusters of 8) and 1 x 1024 threads are both slower than 1 x 512
 constexpr int kResidentMaxSeg = 9;    // 4-cell segments per worker thread (new values kept in registers); 480 x 9 >= 64 rows x 64 segments
+constexpr int kResidentMaxRows = 512; // grid rows of a problem the resident kernel takes (row map in static shared memory)
+constexpr int kResidentMaxC = 8;      // portable cluster size
 
 struct ResidentPlan {
     int C, R, SP, fcap;     // cluster size, rows per CTA, shared-memory row pitch, on-chip feature capacity
@@ -120,6 +122,7 @@ struct ResidentArgs {
     int *n_active;
     int *queue;              // zeroed before the launch
     const int *order;        // queue position -> problem, largest clouds first; null = index order
+    const int *count;        // problems in the queue (device; the launch of one class); null = all g.P problems
     const int *bad_flag;     // nonzero: decline (non-finite features); null = none
     const int *f32_flag;     // zero: every feature is exactly a float32 value; null = unknown (keep fp64 on chip)
     int max_iter, auto_terminate;
@@ -127,11 +130,12 @@ struct ResidentArgs {
     int C, R, SP, fcap, BS, LB;
 };
 
-bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out);
+bool resident_plan(const Geom &g, bool ratio, int smem_limit, int C, ResidentPlan *out);
 cudaError_t launch_resident2d(const ResidentArgs &a, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
                               int64_t *launches);
 constexpr int kResidentOrderMax = 32768;   // problems per solver up to which the queue is ordered (rank by counting)
-cudaError_t launch_resident_order(const Geom &g, const ProbState *state, int *order, cudaStream_t st, int64_t *launches);
+cudaError_t launch_resident_order(const Geom &g, const ProbState *state, const double *rowpart, const int *caps, int c_max,
+                                  int *cls_of, int *order, int *cls_count, cudaStream_t st, int64_t *launches);
 cudaError_t launch_fplane(const Geom &g, const void *feat, int dtype, const int64_t *stride, double *fplane, int *bad_flag,
                           double *extreme, cudaStream_t st, int64_t *launches);
 cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int storage, void *const *planes,

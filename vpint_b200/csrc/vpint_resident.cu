@@ -56,7 +56,7 @@ constexpr int kThreads = kLaunchThreads - 32;   // worker threads: they own the 
 constexpr int kWarps = kThreads / 32;           // cross-CTA bookkeeping of a sweep (the "sync warp")
 static_assert(kWarps <= 16, "the partial-sum tree below covers 16 warps");
 constexpr int kMaxSeg = kResidentMaxSeg;   // segments per thread (4 new values each, in registers)
-constexpr int kMaxC = 8;                   // portable cluster size
+constexpr int kMaxC = kResidentMaxC;       // portable cluster size
 
 constexpr int kBlockRows = 16;             // rows per round-robin block (clusters of more than one CTA)
 constexpr int kMaxBlocks = 8;              // blocks per CTA
@@ -177,13 +177,14 @@ struct SweepCtx {
     int shift_up, shift_dn;           // local block index of block b-1 / b+1 in the neighbour CTA, relative to mine
     int part_lb, part_rows;           // local index / row count of this CTA's partial block (H % BS rows), or -1
     const double *zero4;              // four zeros in shared memory (features of segments that must not count)
+    const unsigned short *rowmap;     // compact row -> grid row (only the rows a sweep can touch are on chip)
     double gamma, clip;
     // local row of the last row of block lb
     __device__ __forceinline__ int bot_row(int lb) const { return lb * BS + ((lb == part_lb) ? part_rows : BS) - 1; }
-    // grid row of local row ly: blocks are dealt round robin
+    // grid row of local row ly: blocks of COMPACT rows are dealt round robin
     __device__ __forceinline__ int grid_row(int ly) const {
         const int lb = ly / BS;
-        return (lb * C + crank) * BS + (ly - lb * BS);
+        return (int)rowmap[(lb * C + crank) * BS + (ly - lb * BS)];
     }
 };
 
@@ -528,6 +529,8 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
     __shared__ __align__(16) SyncShared sh;
     __shared__ int wcount[kAllWarps];
     __shared__ int next_problem;
+    __shared__ unsigned short rowmap[kResidentMaxRows];    // compact row -> grid row of the current problem
+    __shared__ unsigned char rowflag[kResidentMaxRows + 2];
 
     if (a.bad_flag && *a.bad_flag) return;             // grid-uniform: leave everything to the tiled path
     cg::cluster_group cluster = cg::this_cluster();
@@ -550,14 +553,6 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
     }
     unsigned ph_h = 0, ph_s = 0;                       // phase parities of bar_h[2] / bar_s[3], carried across problems
 
-    // round-robin blocks: local block lb is grid block lb * C + crank; the local rows that exist are contiguous
-    const int NB = (H + BS - 1) / BS;
-    int n_rows = 0;
-    for (int lb = 0; lb < LB; ++lb) {
-        const int gb = lb * C + crank;
-        if (gb < NB) n_rows += min(BS, H - gb * BS);
-    }
-    auto grid_row = [&](int ly) { const int lb = ly / BS; return (lb * C + crank) * BS + (ly - lb * BS); };
     const size_t plane_elems = (size_t)H * g.pitch;
     const int nwords = (W + 31) >> 5;
     const double n_cells = g.n_cells;
@@ -568,7 +563,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         cluster_barrier();
         const int qi = *next_remote;
         cluster_barrier();                             // everyone has read before rank 0 overwrites or exits
-        if (qi >= g.P) break;
+        if (qi >= (a.count ? *a.count : g.P)) break;
         const int p = a.order ? a.order[qi] : qi;
         const ProbState st = a.state[p];
         if (st.status != 0) continue;                  // nothing to run (cluster-uniform)
@@ -577,6 +572,49 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         const double *fp = RATIO ? a.fplane + (size_t)p * plane_elems : nullptr;
         const uint32_t *mrow = a.mask + (size_t)p * H * g.mpitch;
         const double gamma = RATIO ? 1.0 : a.gamma[p];
+
+        // ---- the rows a sweep can touch: rows with an unknown cell and their two neighbours -----------------
+        // Only those go on chip, in grid order (the COMPACT rows).  A row with an unknown cell always has both its
+        // neighbours next to it in the compact order, so "row above / below" stays an index +-1; rows at the seam of
+        // two groups hold no unknown cell and are only ever read.  Hc compact rows are dealt to the CTAs in blocks
+        // of BS rows, round robin: local block lb is compact block lb * C + crank.
+        for (int y = tid; y < H + 2; y += kLaunchThreads) {
+            bool any = false;
+            if (y >= 1 && y <= H) {
+                const uint32_t *mr = mrow + (size_t)(y - 1) * g.mpitch;
+                for (int w = 0; w < nwords && !any; ++w) any = mr[w] != 0u;
+            }
+            rowflag[y] = any ? 1 : 0;                    // rowflag[y + 1]: grid row y holds an unknown cell
+        }
+        __syncthreads();
+        int Hc = 0;
+        {
+            // ordered compaction of the needed rows: warps take 32 rows each, in turn
+            int base_c = 0;
+            for (int y0 = 0; y0 < H; y0 += kLaunchThreads) {
+                const int y = y0 + tid;
+                const bool need = (y < H) && (rowflag[y] | rowflag[y + 1] | rowflag[y + 2]);
+                const unsigned vote = __ballot_sync(0xffffffffu, need);
+                if (lane == 0) wcount[warp] = __popc(vote);
+                __syncthreads();
+                int before = base_c, total = 0;
+                for (int w = 0; w < kAllWarps; ++w) {
+                    if (w < warp) before += wcount[w];
+                    total += wcount[w];
+                }
+                if (need) rowmap[before + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)y;
+                base_c += total;
+                __syncthreads();
+            }
+            Hc = base_c;
+        }
+        const int NB = (Hc + BS - 1) / BS;
+        int n_rows = 0;
+        for (int lb = 0; lb < LB; ++lb) {
+            const int gb = lb * C + crank;
+            if (gb < NB) n_rows += min(BS, Hc - gb * BS);
+        }
+        auto grid_row = [&](int ly) { const int lb = ly / BS; return (int)rowmap[(lb * C + crank) * BS + (ly - lb * BS)]; };
 
         // ---- stage the owned rows and both halo rows (r = P / f in RATIO form) ----------------
         // The mask words of the owned rows are parked in the (not yet used) feature area, so that the two passes of
@@ -593,8 +631,9 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
                 dst = sm.plane + (size_t)row * SP;
             } else {
                 const int h = row - n_rows, lb = h >> 1, gb = lb * C + crank;
-                const int rows_in = (gb < NB) ? min(BS, H - gb * BS) : 0;
-                gy = (gb < NB) ? ((h & 1) ? gb * BS + rows_in : gb * BS - 1) : -1;
+                const int rows_in = (gb < NB) ? min(BS, Hc - gb * BS) : 0;
+                const int cy = (gb < NB) ? ((h & 1) ? gb * BS + rows_in : gb * BS - 1) : -1;     // compact row
+                gy = (cy >= 0 && cy < Hc) ? (int)rowmap[cy] : -1;
                 dst = ((h & 1) ? sm.halo_dn : sm.halo_up) + (size_t)lb * SP;
             }
             const bool in_grid = (gy >= 0) && (gy < H);
@@ -659,7 +698,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         for (int ly = wr0; ly < wr1; ++ly) {
             const int gy = grid_row(ly);
             const int lb = ly / BS, gb = lb * C + crank;
-            const bool top = (ly == lb * BS), bot = (ly == lb * BS + min(BS, H - gb * BS) - 1);
+            const bool top = (ly == lb * BS), bot = (ly == lb * BS + min(BS, Hc - gb * BS) - 1);
             const unsigned row_flags = (top ? kSegTop : 0u) | (bot ? kSegBot : 0u) | ((top && gb > 0) ? kSegSendUp : 0u) |
                                        ((bot && gb < NB - 1) ? kSegSendDn : 0u) | ((unsigned)lb << 25);
             const bool row_edge = (gy == 0) || (gy == H - 1);
@@ -757,8 +796,9 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         ctx.shift_up = (crank == 0) ? -1 : 0;       // block b-1 lives in CTA c-1 under the same local index, or one less after the wrap
         ctx.shift_dn = (crank == C - 1) ? 1 : 0;
         ctx.part_lb = -1; ctx.part_rows = BS;      // the partial block, if any, is the grid's last one
-        if ((H % BS) != 0 && ((NB - 1) % C) == crank) { ctx.part_lb = (NB - 1) / C; ctx.part_rows = H % BS; }
+        if ((Hc % BS) != 0 && ((NB - 1) % C) == crank) { ctx.part_lb = (NB - 1) / C; ctx.part_rows = Hc % BS; }
         ctx.zero4 = sh.zero4;
+        ctx.rowmap = rowmap;
         ctx.SP = SP; ctx.half = SP / 2; ctx.fcap = fcap; ctx.pitch = g.pitch; ctx.tid = tid;
         ctx.n = n; ctx.H = H; ctx.W = W;
         ctx.gamma = gamma; ctx.clip = a.clip;
@@ -840,67 +880,126 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
 
 }  // namespace
 
-// Smallest portable cluster that holds one problem on chip; returns false if none does.
-// order[rank] = p with the problems ranked by descending unknown-cell count (ties by index): every thread counts
-// the problems that come before its own.  P <= kResidentOrderMax keeps the quadratic scan in the microseconds.
-__global__ void __launch_bounds__(256) resident_order_kernel(int P, const ProbState *__restrict__ state, int *__restrict__ order) {
+// order[c * P + rank] = p for the problems of class c, ranked by descending unknown-cell count (ties by index): every
+// thread counts the problems of its class that come before its own.  P <= kResidentOrderMax keeps the quadratic scan
+// in the microseconds.  cls_of == null: one class (0).
+__global__ void __launch_bounds__(256) resident_order_kernel(int P, const ProbState *__restrict__ state,
+                                                             const int *__restrict__ cls_of, int *__restrict__ order,
+                                                             int *__restrict__ cls_count) {
     __shared__ int keys[1024];
+    __shared__ int kcls[1024];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int mine = (p < P) ? state[p].n_unknown : 0;
+    const int mycls = (p < P && cls_of) ? cls_of[p] : 0;
     int rank = 0;
     for (int q0 = 0; q0 < P; q0 += 1024) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) keys[i] = (q0 + i < P) ? state[q0 + i].n_unknown : -1;
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            keys[i] = (q0 + i < P) ? state[q0 + i].n_unknown : -1;
+            kcls[i] = (q0 + i < P && cls_of) ? cls_of[q0 + i] : 0;
+        }
         __syncthreads();
         const int m = min(1024, P - q0);
         for (int i = 0; i < m; ++i) {
             const int k = keys[i];
-            rank += (k > mine || (k == mine && q0 + i < p)) ? 1 : 0;
+            rank += (kcls[i] == mycls && (k > mine || (k == mine && q0 + i < p))) ? 1 : 0;
         }
     }
-    if (p < P) order[rank] = p;
+    if (p < P) {
+        order[(size_t)mycls * P + rank] = p;
+        if (cls_count) atomicAdd(&cls_count[mycls], 1);
+    }
 }
 
-cudaError_t launch_resident_order(const Geom &g, const ProbState *state, int *order, cudaStream_t st, int64_t *launches) {
-    resident_order_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, state, order);
+// Class of every problem = the smallest cluster whose CTAs hold its COMPACT rows (rows with an unknown cell and their
+// neighbours; the kernel derives the same set from the bit mask).  rowpart[.][7] = unknown cells of a row (load).
+struct ResidentCaps {
+    int cap[kResidentMaxC + 1];        // compact rows a cluster of C CTAs holds; 0 = no plan
+};
+
+__global__ void __launch_bounds__(256) resident_class_kernel(Geom g, const double *__restrict__ rowpart, ResidentCaps caps,
+                                                             int c_max, int *__restrict__ cls_of) {
+    __shared__ unsigned char flag[kResidentMaxRows + 2];
+    __shared__ int part[8];
+    const int p = blockIdx.x, H = g.H;
+    for (int y = threadIdx.x; y < H + 2; y += blockDim.x)
+        flag[y] = (y >= 1 && y <= H && rowpart[((size_t)p * H + (y - 1)) * 8 + 7] > 0.0) ? 1 : 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int y = threadIdx.x; y < H; y += blockDim.x) cnt += (flag[y] | flag[y + 1] | flag[y + 2]) ? 1 : 0;
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int hc = 0;
+        for (int w = 0; w < 8; ++w) hc += part[w];
+        int c = c_max;
+        for (int q = c_max; q >= 1; --q)
+            if (caps.cap[q] >= hc) c = q;
+        cls_of[p] = c;
+    }
+}
+
+cudaError_t launch_resident_order(const Geom &g, const ProbState *state, const double *rowpart, const int *caps, int c_max,
+                                  int *cls_of, int *order, int *cls_count, cudaStream_t st, int64_t *launches) {
+    ResidentCaps rc;
+    for (int c = 0; c <= kResidentMaxC; ++c) rc.cap[c] = caps[c];
+    resident_class_kernel<<<g.P, 256, 0, st>>>(g, rowpart, rc, c_max, cls_of);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    resident_order_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, state, cls_of, order, cls_count);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     return cudaSuccess;
 }
 
-bool resident_plan(const Geom &g, bool ratio, int smem_limit, ResidentPlan *out) {
+// Plan for a cluster of C CTAs: as many (compact) rows per CTA as shared memory, the 16-bit plane offsets and the
+// register budget allow.  C == 1 holds its rows as one block (no halo exchange), larger clusters deal blocks of
+// kBlockRows rows round robin.  Returns false if not even one block fits.
+bool resident_plan(const Geom &g, bool ratio, int smem_limit, int C, ResidentPlan *out) {
     if (g.ndim != 2 || g.H < 1 || g.L < 1 || (g.H < 2 && g.L < 2)) return false;   // 1x1: neighbour count 0
+    if (g.H > kResidentMaxRows || C < 1 || C > kMaxC) return false;
     const int W = g.L;
     const int segs_per_row = (W + 3) / 4;
     const int SP = 4 * segs_per_row + 4;        // split-row layout: two halves of (segs_per_row + 1) pairs each
     if (g.pitch < 4 * segs_per_row) return false;
-    const int static_bytes = 2048;              // SyncShared, wcount, next_problem (+ slack)
-    for (int C = 1; C <= kMaxC; C *= 2) {
-        // one block per CTA when the cluster is a single CTA, round-robin blocks of kBlockRows rows otherwise
-        const int BS = (C == 1) ? g.H : kBlockRows;
-        const int NB = (g.H + BS - 1) / BS;
-        if (NB < C) continue;                                                   // every CTA must own at least one block
-        const int LB = (NB + C - 1) / C;
-        if (LB > kMaxBlocks) continue;
+    const int static_bytes = 3584;              // SyncShared, wcount, next_problem, rowmap, rowflag (+ slack)
+    auto fits = [&](int BS, int LB, int *fcap_out, size_t *bytes_out) {
         const int R = LB * BS;
-        if ((int64_t)R * segs_per_row > (int64_t)kThreads * kMaxSeg) continue;  // register budget for the new values
-        if ((int64_t)R * SP > 65535) continue;                                  // 16-bit shared-memory offsets
+        if ((int64_t)R * segs_per_row > (int64_t)kThreads * kMaxSeg) return false;  // register budget for the new values
+        if ((int64_t)R * SP > 65535) return false;                                  // 16-bit shared-memory offsets
         const int64_t fixed = ((int64_t)R * SP + 4 * (int64_t)LB * SP) * 8 + (int64_t)R * segs_per_row * 4;
         const int64_t room = (int64_t)smem_limit - static_bytes - fixed;
-        if (room < 0) continue;
+        if (room < 0) return false;
         int fcap = 0;
         if (ratio) {
             const int64_t all = (int64_t)R * segs_per_row;
             fcap = (int)((room / 32 < all) ? room / 32 : all);
-            if (fcap < 1) continue;
-            if (fcap * 4 < all && C < kMaxC) continue;                           // want >= 25 % of the features on chip
+            if (fcap < 1) return false;
+            if (fcap * 4 < all) return false;                                       // want >= 25 % of the features on chip
         }
-        out->C = C; out->R = R; out->SP = SP; out->fcap = fcap; out->BS = BS; out->LB = LB;
-        out->smem_bytes = (size_t)(fixed + (int64_t)fcap * 32);
+        *fcap_out = fcap;
+        *bytes_out = (size_t)(fixed + (int64_t)fcap * 32);
         return true;
+    };
+    int BS = 0, LB = 0, fcap = 0;
+    size_t bytes = 0;
+    if (C == 1) {
+        for (int R = g.H; R >= 1; --R)
+            if (fits(R, 1, &fcap, &bytes)) { BS = R; LB = 1; break; }
+    } else {
+        for (int lb = kMaxBlocks; lb >= 1; --lb)
+            if (fits(kBlockRows, lb, &fcap, &bytes)) { BS = kBlockRows; LB = lb; break; }
+        // no more blocks than the whole grid needs
+        const int need = ((g.H + kBlockRows - 1) / kBlockRows + C - 1) / C;
+        if (LB > need && need >= 1 && fits(kBlockRows, need, &fcap, &bytes)) LB = need;
     }
-    return false;
+    if (LB < 1) return false;
+    out->C = C; out->R = LB * BS; out->SP = SP; out->fcap = fcap; out->BS = BS; out->LB = LB;
+    out->smem_bytes = bytes;
+    return true;
 }
 
 cudaError_t launch_resident2d(const ResidentArgs &a_in, bool ratio, size_t smem_bytes, int max_clusters, cudaStream_t st,
