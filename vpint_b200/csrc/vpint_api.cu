@@ -96,6 +96,8 @@ struct vpint_solver {
     int res_caps[kResidentMaxC + 1] = {0};    //   their sweeps touch); caps = rows a cluster of C CTAs holds, 0 = no plan
     int res_cmax = 0;                 // smallest cluster that holds ALL rows of a problem
     size_t off_cls = 0;               // int[P] class of every problem, int[32]: [0..8] problems per class, [16..24] class queues
+    cudaStream_t cls_stream[kResidentMaxC + 1] = {nullptr};   // the launches of the classes run side by side: forked from the
+    cudaEvent_t cls_fork = nullptr, cls_join[kResidentMaxC + 1] = {nullptr};   //   caller's stream and joined back into it
     bool planes_valid = false;        // the 4 (5) weight planes hold current weights
     bool fplane_valid = false;        // w[4] holds the single-layer feature plane (RATIO form)
     size_t off_flags = 0;             // int[16]: [0] non-finite feature seen, [1] problem queue, [2] sweeps left (graph loop), [3] a feature that is not a float32 value
@@ -271,6 +273,11 @@ void vpint_solver_destroy(vpint_solver *s) {
     if (!s) return;
     pinned_release(s->h_counters);
     if (s->ev) cudaEventDestroy(s->ev);
+    if (s->cls_fork) cudaEventDestroy(s->cls_fork);
+    for (int c = 0; c <= kResidentMaxC; ++c) {
+        if (s->cls_join[c]) cudaEventDestroy(s->cls_join[c]);
+        if (s->cls_stream[c]) cudaStreamDestroy(s->cls_stream[c]);
+    }
     delete s;
 }
 
@@ -773,13 +780,13 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
         ra.auto_terminate = prm->auto_terminate;
         ra.threshold = prm->threshold;
         ra.clip = prm->clip_val;
-        auto launch_class = [&](int c, const int *order, const int *count) -> cudaError_t {
+        auto launch_class = [&](int c, const int *order, const int *count, cudaStream_t on) -> cudaError_t {
             const ResidentPlan &pl = s->rplans[c];
             ra.queue = cls_queue + c;
             ra.order = order;
             ra.count = count;
             ra.C = pl.C; ra.R = pl.R; ra.SP = pl.SP; ra.fcap = pl.fcap; ra.BS = pl.BS; ra.LB = pl.LB;
-            return launch_resident2d(ra, ratio, pl.smem_bytes, 0, st, &s->launches);
+            return launch_resident2d(ra, ratio, pl.smem_bytes, 0, on, &s->launches);
         };
         if (s->g.P > 2 * 33 && s->g.P <= kResidentOrderMax && !getenv("VPINT_NO_QUEUE_ORDER")) {
             // A batch: every problem runs on the smallest cluster that holds the rows its sweeps touch (a class per
@@ -793,11 +800,30 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
             VP_CUDA(launch_resident_order(s->g, ra.state, s->at<double>(s->off_rowpart), caps, s->res_cmax, cls_of, order,
                                           cls_count, st, &s->launches),
                     "queue order");
-            for (int c = s->res_cmax; c >= 1; --c)
-                if (caps[c] > 0)
-                    VP_CUDA(launch_class(c, order + (size_t)c * s->g.P, cls_count + c), "resident2d");
+            // the largest class on the caller's stream, the others forked beside it (their clusters take the SMs the
+            // first leaves free -- a cluster of 4 cannot use the last 2 SMs of a GPC, a cluster of 2 or 3 can -- and fill
+            // the machine while the long problems of another class drain)
+            const bool fork = !getenv("VPINT_CLASS_SERIAL");
+            if (fork && !s->cls_fork) {
+                VP_CUDA(cudaEventCreateWithFlags(&s->cls_fork, cudaEventDisableTiming), "cudaEventCreate");
+                for (int c = 1; c < s->res_cmax; ++c) {
+                    if (caps[c] <= 0) continue;
+                    VP_CUDA(cudaStreamCreateWithFlags(&s->cls_stream[c], cudaStreamNonBlocking), "cudaStreamCreate");
+                    VP_CUDA(cudaEventCreateWithFlags(&s->cls_join[c], cudaEventDisableTiming), "cudaEventCreate");
+                }
+            }
+            if (fork) VP_CUDA(cudaEventRecord(s->cls_fork, st), "event record");
+            for (int c = s->res_cmax; c >= 1; --c) {
+                if (caps[c] <= 0) continue;
+                cudaStream_t on = (fork && s->cls_stream[c]) ? s->cls_stream[c] : st;
+                if (on != st) VP_CUDA(cudaStreamWaitEvent(on, s->cls_fork, 0), "stream wait");
+                VP_CUDA(launch_class(c, order + (size_t)c * s->g.P, cls_count + c, on), "resident2d");
+                if (on != st) VP_CUDA(cudaEventRecord(s->cls_join[c], on), "event record");
+            }
+            for (int c = 1; c < s->res_cmax; ++c)
+                if (fork && s->cls_stream[c] && caps[c] > 0) VP_CUDA(cudaStreamWaitEvent(st, s->cls_join[c], 0), "stream wait");
         } else {
-            VP_CUDA(launch_class(s->res_cmax, nullptr, nullptr), "resident2d");
+            VP_CUDA(launch_class(s->res_cmax, nullptr, nullptr, st), "resident2d");
         }
         VP_CUDA(cudaMemcpyAsync(s->h_counters + kCntActiveProblems, s->at<int>(s->off_counters) + kCntActiveProblems,
                                 sizeof(int), cudaMemcpyDeviceToHost, st),
