@@ -1,9 +1,5 @@
 #!/bin/bash
 # quick C3 comparison: prints device / kernel / e2e ms for a set of env / flag variants
-run() {
-  name="$1"; shift
-  env "$@" > /dev/null 2>&1 || true
-}
 one() {
   label="$1"; shift
   out=gpurun_out/q_$label.json
@@ -18,9 +14,7 @@ except Exception as e:
 PY
 }
 B="python bench.py --no-scene --no-variants --no-cpu-baseline"
-one fork16 $B
-one fork32 $B --chunk-patches 32
-one fork64 $B --chunk-patches 64
-one fork32s6 $B --chunk-patches 32 --streams 6
-VPINT_CLASS_SERIAL=1 one serial32 $B --chunk-patches 32
-VPINT_ONE_CLASS=1 one onecls16 $B
+one prio16 $B
+one prio32 $B --chunk-patches 32
+one prio32s6 $B --chunk-patches 32 --streams 6
+one prio64s3 $B --chunk-patches 64 --streams 3

@@ -800,15 +800,19 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
             VP_CUDA(launch_resident_order(s->g, ra.state, s->at<double>(s->off_rowpart), caps, s->res_cmax, cls_of, order,
                                           cls_count, st, &s->launches),
                     "queue order");
-            // the largest class on the caller's stream, the others forked beside it (their clusters take the SMs the
-            // first leaves free -- a cluster of 4 cannot use the last 2 SMs of a GPC, a cluster of 2 or 3 can -- and fill
-            // the machine while the long problems of another class drain)
+            // Every class is launched on a stream of its own, forked from the caller's stream and joined back into it:
+            // the classes run side by side (a cluster of 4 cannot use the last 2 SMs of a GPC, a cluster of 2 or 3 can;
+            // the long problems of one class drain while another fills the machine).  The class streams have the LOWEST
+            // priority, so that whatever else the caller has in flight on higher-priority streams -- the load / result
+            // kernels of other chunks of a pipeline -- gets the next SM a persistent cluster leaves.
             const bool fork = !getenv("VPINT_CLASS_SERIAL");
             if (fork && !s->cls_fork) {
+                int lo = 0, hi = 0;
+                VP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range");
                 VP_CUDA(cudaEventCreateWithFlags(&s->cls_fork, cudaEventDisableTiming), "cudaEventCreate");
-                for (int c = 1; c < s->res_cmax; ++c) {
+                for (int c = 1; c <= s->res_cmax; ++c) {
                     if (caps[c] <= 0) continue;
-                    VP_CUDA(cudaStreamCreateWithFlags(&s->cls_stream[c], cudaStreamNonBlocking), "cudaStreamCreate");
+                    VP_CUDA(cudaStreamCreateWithPriority(&s->cls_stream[c], cudaStreamNonBlocking, lo), "cudaStreamCreate");
                     VP_CUDA(cudaEventCreateWithFlags(&s->cls_join[c], cudaEventDisableTiming), "cudaEventCreate");
                 }
             }
@@ -820,7 +824,7 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
                 VP_CUDA(launch_class(c, order + (size_t)c * s->g.P, cls_count + c, on), "resident2d");
                 if (on != st) VP_CUDA(cudaEventRecord(s->cls_join[c], on), "event record");
             }
-            for (int c = 1; c < s->res_cmax; ++c)
+            for (int c = 1; c <= s->res_cmax; ++c)
                 if (fork && s->cls_stream[c] && caps[c] > 0) VP_CUDA(cudaStreamWaitEvent(st, s->cls_join[c], 0), "stream wait");
         } else {
             VP_CUDA(launch_class(s->res_cmax, nullptr, nullptr, st), "resident2d");
