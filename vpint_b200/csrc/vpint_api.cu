@@ -812,7 +812,12 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
                 VP_CUDA(cudaEventCreateWithFlags(&s->cls_fork, cudaEventDisableTiming), "cudaEventCreate");
                 for (int c = 1; c <= s->res_cmax; ++c) {
                     if (caps[c] <= 0) continue;
-                    VP_CUDA(cudaStreamCreateWithPriority(&s->cls_stream[c], cudaStreamNonBlocking, lo), "cudaStreamCreate");
+                    // among the classes the larger clusters go first (they hold the largest clouds = the longest runs, and
+                    // a cluster of 4 needs 4 free SMs of one GPC at once), but all stay below the default priority
+                    int pr = lo - (c - 1);
+                    if (pr < hi + 1) pr = hi + 1;
+                    if (pr > lo) pr = lo;
+                    VP_CUDA(cudaStreamCreateWithPriority(&s->cls_stream[c], cudaStreamNonBlocking, pr), "cudaStreamCreate");
                     VP_CUDA(cudaEventCreateWithFlags(&s->cls_join[c], cudaEventDisableTiming), "cudaEventCreate");
                 }
             }

@@ -290,7 +290,7 @@ class _RawSlot:
         self.dev = dev
         # high priority: the copies, load and result kernels of this chunk should take the next free SM ahead of the
         # (low-priority, persistent) solve kernels of the chunks in flight on the other streams
-        self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.stream = torch.cuda.Stream(device=dev, priority=-8)     # mapped to the highest the device has
         self.solvers = {}
         self.t_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
         self.f_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
