@@ -283,6 +283,24 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
 int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
                                 void *stream);
 
+/* Low-latency form of the row-sharded loop (k_block 1): the stop decision lags one sweep, so the all-reduce of sweep
+ * t's sums travels while sweep t + 1 computes, and halo rows go straight into the neighbour's memory.
+ *   step_begin                 : sweep t + local sums (as above)
+ *   (caller copies vpint_solver_sums_ptr() aside and all-reduces the copy on a side stream)
+ *   step_commit_lagged(prev)   : prev = the reduced sums of sweep t - 1 (device, [nprob][4]; NULL in the first launch of
+ *                                a run): problems whose delta(t - 1) <= threshold stop WITHOUT committing sweep t (commit-
+ *                                then-break with the exact stopping sweep, VPint/SD_MRP.py:143-147); the others commit it
+ *   halo_push / halo_pull      : the `rows` boundary rows of the current state are stored into the neighbours' receive
+ *                                slots ([nprob][rows][pitch] doubles in THEIR memory, mapped into this process: CUDA IPC /
+ *                                symmetric memory over NVLink) and the sequence number `seq` is published in their flag;
+ *                                pull waits for flag >= seq and copies the received rows into the halo rows.  Receive
+ *                                slots are double buffered by the caller (a sender is at most one exchange ahead). */
+int vpint_solver_step_commit_lagged(vpint_solver *s, const double *sums_prev, void *stream);
+int vpint_solver_halo_push(vpint_solver *s, int rows, void *peer_up, int32_t *flag_up, void *peer_down, int32_t *flag_down,
+                           int seq, void *stream);
+int vpint_solver_halo_pull(vpint_solver *s, int rows, const void *from_up, const int32_t *flag_up, const void *from_down,
+                           const int32_t *flag_down, int seq, void *stream);
+
 /* ---- results -----------------------------------------------------------
  * out: device, dtype `dtype`, element strides as in load.  This is
  * self.pred_grid after run().  niter_out: device int32[nprob] sweeps executed

@@ -407,6 +407,39 @@ def test_row_sharded_scene_lockstep(world, k):
     close(np.moveaxis(got, 0, -1), ref)
 
 
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("iterations", [-1, 7, 1])
+def test_row_sharded_scene_lockstep_lagged(world, iterations):
+    """The low-latency protocol of the row-sharded loop on one device: stop decision lagging one sweep, halo rows
+    pushed into the neighbour's receive slots with a flag (the kernels that run across GPUs over NVLink)."""
+    from vpint_b200.sharded import RowShard, open_shard, run_lockstep_lagged, shard_result
+    from vpint_b200.vpint2 import _band_fill_values
+    from vpint_b200.wp import wp_run_options
+    rng = np.random.default_rng(405 + world)
+    vp = make_patch(rng, 150, 90, 3)
+    opts = wp_run_options(iterations=iterations)
+    ref, ref_sweeps = O.vpint2_run(vp.target, vp.features, iterations=iterations)
+    fill = _band_fill_values(vp.target)
+    shards = [RowShard(150, world, r, halo=1) for r in range(world)]
+    opened = [open_shard(s.local(vp.target), s.local(vp.features), s, fill, opts, k_block=1) for s in shards]
+    try:
+        for _ in range(2):                                  # a second run() on the same engines (sequence numbers go on)
+            for (sv, e), s in zip(opened, shards):
+                from vpint_b200.sharded import stage_shard
+                import torch
+                stage_shard(sv, torch.from_numpy(np.ascontiguousarray(s.local(vp.target))).cuda(),
+                            torch.from_numpy(np.ascontiguousarray(s.local(vp.features))).cuda(), fill, opts)
+            run_lockstep_lagged([e for _, e in opened], shards, opts["iterations"])
+            parts = [shard_result(sv, s) for (sv, _), s in zip(opened, shards)]
+            got = np.concatenate([p.cpu().numpy() for p, _ in parts], axis=1)
+            for _, sweeps in parts:
+                assert list(sweeps) == list(ref_sweeps)
+            close(np.moveaxis(got, 0, -1), ref)
+    finally:
+        for sv, _ in opened:
+            sv.close()
+
+
 # ---- 5. A1 on the device and the pipelined host path -----------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape", [(256, 256), (100, 100), (37, 91), (2, 3), (1, 130), (300, 301)])

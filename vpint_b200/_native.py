@@ -107,6 +107,9 @@ SIGNATURES = {
     "vpint_solver_any_dirty": (C.c_int, [C.c_void_p]),
     "vpint_solver_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpint_solver_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpint_solver_step_commit_lagged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpint_solver_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vpint_solver_halo_pull": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vpint_solver_result": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "vpint_solver_active_tiles": (C.c_int64, [C.c_void_p]),
     "vpint_solver_total_tiles": (C.c_int64, [C.c_void_p]),

@@ -1112,6 +1112,56 @@ int vpint_solver_halo_unpack(vpint_solver *s, int rows, const void *from_up, con
     return halo_impl(s, rows, const_cast<void *>(from_up), const_cast<void *>(from_down), false, stream);
 }
 
+int vpint_solver_step_commit_lagged(vpint_solver *s, const double *sums_prev, void *stream) {
+    if (!s || !s->run_begun) return fail(VPINT_ERR_INVALID, "vpint_solver_begin_run has not been called");
+    if (s->g.KB != 1) return fail(VPINT_ERR_UNSUPPORTED, "the lagged stop decision needs one sweep per launch (k_block 1)");
+    if (s->prm.delta_out || s->prm.resistance) return fail(VPINT_ERR_UNSUPPORTED, "the lagged stop decision does not record deltas / run resistance sweeps");
+    if (s->any_dirty) return fail(VPINT_ERR_INVALID, "the lagged stop decision needs a start state that equals the original on known cells");
+    DecideArgs d;
+    d.g = s->g;
+    d.state = s->at<ProbState>(s->off_state);
+    d.sums = nullptr;
+    d.known0 = s->at<double>(s->off_known0);
+    d.known = s->at<double>(s->off_known);
+    d.delta_out = nullptr;
+    d.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
+    d.max_iter = s->prm.max_iter;
+    d.auto_terminate = s->prm.auto_terminate;
+    d.threshold = s->prm.threshold;
+    d.all_cells = 0;
+    VP_CUDA(launch_lagged_commit(d, sums_prev, static_cast<cudaStream_t>(stream), &s->launches), "lagged commit");
+    s->first_step_pending = false;
+    return VPINT_OK;
+}
+
+int vpint_solver_halo_push(vpint_solver *s, int rows, void *peer_up, int32_t *flag_up, void *peer_down, int32_t *flag_down,
+                           int seq, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (s->storage != VPINT_F64) return fail(VPINT_ERR_UNSUPPORTED, "peer halo exchange: fp64 state only");
+    if (rows < 1 || rows > s->g.own_rows || (peer_up && !flag_up) || (peer_down && !flag_down))
+        return fail(VPINT_ERR_INVALID, "vpint_solver_halo_push: bad argument");
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    VP_CUDA(launch_halo_push(s->g, s->at<ProbState>(s->off_state), bufs, peer_up, peer_down, flag_up, flag_down, rows, seq,
+                             s->at<int>(s->off_flags) + 4, static_cast<cudaStream_t>(stream), &s->launches),
+            "halo push");
+    return VPINT_OK;
+}
+
+int vpint_solver_halo_pull(vpint_solver *s, int rows, const void *from_up, const int32_t *flag_up, const void *from_down,
+                           const int32_t *flag_down, int seq, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
+    if (s->storage != VPINT_F64) return fail(VPINT_ERR_UNSUPPORTED, "peer halo exchange: fp64 state only");
+    if (rows < 1 || (from_up && (rows > s->halo_up || !flag_up)) || (from_down && (rows > s->halo_down || !flag_down)))
+        return fail(VPINT_ERR_INVALID, "vpint_solver_halo_pull: bad argument");
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    VP_CUDA(launch_halo_pull(s->g, s->at<ProbState>(s->off_state), bufs, from_up, from_down, flag_up, flag_down, rows, seq,
+                             static_cast<cudaStream_t>(stream), &s->launches),
+            "halo pull");
+    return VPINT_OK;
+}
+
 int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");

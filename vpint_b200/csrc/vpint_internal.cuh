@@ -183,6 +183,11 @@ cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, v
                                  const uint32_t *mask, cudaStream_t st, int64_t *launches);
 cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state, void *const *buf, void *msg,
                              int first_row, int rows, bool pack, cudaStream_t st, int64_t *launches);
+cudaError_t launch_lagged_commit(const DecideArgs &a, const double *sums_prev, cudaStream_t st, int64_t *launches);
+cudaError_t launch_halo_push(const Geom &g, const ProbState *state, void *const *buf, void *dst_up, void *dst_down,
+                             int *flag_up, int *flag_down, int rows, int seq, int *tickets, cudaStream_t st, int64_t *launches);
+cudaError_t launch_halo_pull(const Geom &g, const ProbState *state, void *const *buf, const void *src_up, const void *src_down,
+                             const int *flag_up, const int *flag_down, int rows, int seq, cudaStream_t st, int64_t *launches);
 cudaError_t launch_result(const Geom &g, int storage, const ProbState *state, void *const *buf, void *out,
                           int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st,
                           int64_t *launches);

@@ -659,6 +659,93 @@ __global__ void __launch_bounds__(256) halo_rows_kernel(Geom g, const ProbState 
     }
 }
 
+// ---- row-sharded scenes, low-latency protocol ----------------------------------------------------------------
+// Stop decision with a lag of one sweep (the trick of the cluster-resident kernel): launch t computes sweep t and its
+// local sums; while their all-reduce travels, launch t + 1 already computes sweep t + 1.  This kernel runs after the
+// stencil of launch t + 1: it first takes the decision on sweep t from the reduced sums (stop = sweep t + 1 is simply
+// not committed -- commit-then-break, VPint/SD_MRP.py:143-147, with the exact stopping sweep and no rollback), and
+// otherwise commits sweep t + 1 (flips the ping-pong buffer).  One sweep per launch only.
+__global__ void lagged_commit_kernel(Geom g, ProbState *state, const double *__restrict__ sums_prev,
+                                     const double *__restrict__ known0, const double *__restrict__ known, int *n_active,
+                                     int max_iter, int auto_terminate, double threshold) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.P) return;
+    ProbState st = state[p];
+    if (st.status != 0 || st.k_run == 0) return;
+    if (sums_prev) {
+        const double *S = sums_prev + (size_t)p * kSumSlots;
+        const double *K = (st.fresh ? known0 : known) + (size_t)p * kSumSlots;
+        const double s_abs = S[0] + K[0], s_old = S[1] + K[1];
+        const double n_abs = g.n_cells - (S[2] + K[2]), n_old = g.n_cells - (S[3] + K[3]);
+        const double delta = (s_abs / n_abs) / (s_old / n_old);
+        st.fresh = 0;
+        if (auto_terminate && delta <= threshold) {
+            st.status = 1; st.k_run = 0;
+            state[p] = st;
+            atomicSub(n_active, 1);
+            return;
+        }
+    }
+    st.iters_done += 1;
+    st.cur ^= 1;
+    if (st.iters_done >= max_iter) {
+        st.status = 1; st.k_run = 0; st.fresh = 0;
+        atomicSub(n_active, 1);
+    }
+    state[p] = st;
+}
+
+// Halo rows straight into the neighbour's memory (peer-mapped over NVLink) instead of pack -> NCCL send/recv -> unpack:
+// every block copies one boundary row of one problem's CURRENT state into the neighbour's receive slot; the block that
+// finishes last publishes the sequence number of this exchange in the neighbour's flag (system-scope release).
+// blockIdx.y: 0 = rows for the upper neighbour (my first owned rows), 1 = rows for the lower neighbour.
+__global__ void __launch_bounds__(256) halo_push_kernel(Geom g, const ProbState *__restrict__ state, const double *buf0,
+                                                        const double *buf1, double *dst_up, double *dst_down, int *flag_up,
+                                                        int *flag_down, int rows, int seq, int *tickets) {
+    const int side = blockIdx.y;
+    double *dst = side ? dst_down : dst_up;
+    int *flag = side ? flag_down : flag_up;
+    if (!dst) return;
+    const int p = blockIdx.x / rows, r = blockIdx.x - p * rows;
+    const int first = side ? g.own_row0 + g.own_rows - rows : g.own_row0;
+    const double *src = (state[p].cur ? buf1 : buf0) + ((size_t)p * g.H + first + r) * g.pitch;
+    double *out = dst + ((size_t)p * rows + r) * g.pitch;
+    for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) out[e] = src[e];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&tickets[side], 1);
+        if (done == (int)gridDim.x - 1) {
+            tickets[side] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+        }
+    }
+}
+
+// Receiver: wait until the neighbour has published exchange `seq`, then copy its rows into the halo rows next to the
+// owned band.  blockIdx.y: 0 = from the upper neighbour (rows above the band), 1 = from the lower neighbour.
+__global__ void __launch_bounds__(256) halo_pull_kernel(Geom g, const ProbState *__restrict__ state, double *buf0, double *buf1,
+                                                        const double *src_up, const double *src_down, const int *flag_up,
+                                                        const int *flag_down, int rows, int seq) {
+    const int side = blockIdx.y;
+    const double *src = side ? src_down : src_up;
+    const int *flag = side ? flag_down : flag_up;
+    if (!src) return;
+    if (threadIdx.x == 0) {
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v < seq);
+    }
+    __syncthreads();
+    const int p = blockIdx.x / rows, r = blockIdx.x - p * rows;
+    const int first = side ? g.own_row0 + g.own_rows : g.own_row0 - rows;
+    double *dstrow = (state[p].cur ? buf1 : buf0) + ((size_t)p * g.H + first + r) * g.pitch;
+    const double *in = src + ((size_t)p * rows + r) * g.pitch;
+    for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dstrow[e] = __ldcv(in + e);
+}
+
 }  // namespace
 
 #define VP_LAUNCH_CHECK()                         \
@@ -844,6 +931,33 @@ cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state,
         if (pack) halo_rows_kernel<float, true><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
         else halo_rows_kernel<float, false><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
     }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_lagged_commit(const DecideArgs &a, const double *sums_prev, cudaStream_t st, int64_t *launches) {
+    lagged_commit_kernel<<<(a.g.P + 127) / 128, 128, 0, st>>>(a.g, a.state, sums_prev, a.known0, a.known, a.n_active,
+                                                             a.max_iter, a.auto_terminate, a.threshold);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_halo_push(const Geom &g, const ProbState *state, void *const *buf, void *dst_up, void *dst_down,
+                             int *flag_up, int *flag_down, int rows, int seq, int *tickets, cudaStream_t st, int64_t *launches) {
+    if (!dst_up && !dst_down) return cudaSuccess;
+    halo_push_kernel<<<dim3((unsigned)((int64_t)g.P * rows), 2), 256, 0, st>>>(
+        g, state, (const double *)buf[0], (const double *)buf[1], (double *)dst_up, (double *)dst_down, flag_up, flag_down, rows,
+        seq, tickets);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_halo_pull(const Geom &g, const ProbState *state, void *const *buf, const void *src_up, const void *src_down,
+                             const int *flag_up, const int *flag_down, int rows, int seq, cudaStream_t st, int64_t *launches) {
+    if (!src_up && !src_down) return cudaSuccess;
+    halo_pull_kernel<<<dim3((unsigned)((int64_t)g.P * rows), 2), 256, 0, st>>>(
+        g, state, (double *)buf[0], (double *)buf[1], (const double *)src_up, (const double *)src_down, flag_up, flag_down, rows,
+        seq);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -430,6 +430,24 @@ class Solver:
     def step_end(self):
         N.check(self.lib, self.lib.vpint_solver_step_end(self._h, self._stream()), "vpint_solver_step_end")
 
+    def step_commit_lagged(self, sums_prev):
+        """Lagged stop decision (sums of the PREVIOUS sweep, all-reduced, or None in the first launch of a run) + commit
+        of the sweep the last step_begin computed."""
+        N.check(self.lib, self.lib.vpint_solver_step_commit_lagged(
+            self._h, C.c_void_p(sums_prev.data_ptr()) if sums_prev is not None else None, self._stream()),
+            "vpint_solver_step_commit_lagged")
+
+    def halo_push(self, rows, peer_up, flag_up, peer_down, flag_down, seq):
+        """Boundary rows of the current state into the neighbours' receive slots (raw device pointers as ints, 0 = none)."""
+        N.check(self.lib, self.lib.vpint_solver_halo_push(
+            self._h, int(rows), C.c_void_p(peer_up or None), C.c_void_p(flag_up or None), C.c_void_p(peer_down or None),
+            C.c_void_p(flag_down or None), int(seq), self._stream()), "vpint_solver_halo_push")
+
+    def halo_pull(self, rows, from_up, flag_up, from_down, flag_down, seq):
+        N.check(self.lib, self.lib.vpint_solver_halo_pull(
+            self._h, int(rows), C.c_void_p(from_up or None), C.c_void_p(flag_up or None), C.c_void_p(from_down or None),
+            C.c_void_p(flag_down or None), int(seq), self._stream()), "vpint_solver_halo_pull")
+
     def result(self, out=None, dtype=None):
         """Current state of every problem gathered into ``out`` (same layouts as
         :meth:`load` accepts).  Returns (out, sweeps[int32, nprob])."""
@@ -500,6 +518,12 @@ class Solver:
         slices = self.nprob * (self.T if self.ndim == 3 else 1)
         n = slices * self.H * pitch
         return self.workspace[off:off + n * esz].view(dt).view(slices, self.H, pitch)
+
+    def active_tensor(self):
+        """Device int32[1]: problems still running (a view of workspace memory)."""
+        ptr = int(self.lib.vpint_solver_active_ptr(self._h))
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off:off + 4].view(self.torch.int32)
 
     def active_count(self):
         ptr = int(self.lib.vpint_solver_active_ptr(self._h))

@@ -96,6 +96,74 @@ class Comm:
                 req.wait()
 
 
+def run_sharded_lagged(engine, shard, comm, max_iter, poll_every=8):
+    """:func:`run_sharded` with the reductions off the critical path (CUDA engines, one sweep per launch).
+
+    Launch t:   sweep t on the local rows + local sums          (main stream)
+                copy of the sums -> all-reduce                  (side stream: travels while the next sweep computes)
+                decision on sweep t - 1 from ITS reduced sums, then commit of sweep t -- a problem that stops at t - 1
+                simply does not commit sweep t (commit-then-break, exact stopping sweep, nothing to roll back)
+                halo rows of the new state to both neighbours   (peer stores + flag over NVLink when the engine has
+                                                                 mapped its neighbours' memory, else pack / NCCL / unpack)
+    Every rank takes the same decisions from the same reduced sums, so all ranks issue the same launches."""
+    import torch
+    if engine.comm is None:
+        engine.comm = comm
+    if shard.world > 1 and hasattr(comm, "dist") and not getattr(engine, "peer_tried", False):
+        engine.setup_peer(comm)
+    comm.all_reduce_sum(engine.known())
+    engine.begin(max_iter)
+    if max_iter <= 0:
+        return 0
+    dev = engine.s.device
+    main = torch.cuda.current_stream(dev)
+    side = engine.side_stream()
+    lag = engine.lag_buffers()
+    ev_sums = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_red = [torch.cuda.Event(), torch.cuda.Event()]
+    # "problems still running" after every launch, read back without draining the queue: the host stays DEPTH launches
+    # ahead of the device and stops as soon as the count of launch L - DEPTH is zero.  The count is the same on every
+    # rank at every launch (same decisions), so all ranks stop after the same launch.
+    DEPTH = max(1, min(int(poll_every), 4))
+    ring = torch.zeros(DEPTH + 1, dtype=torch.int32).pin_memory()
+    ring_ev = [torch.cuda.Event() for _ in range(DEPTH + 1)]
+    active_dev = engine.s.active_tensor()
+    launches = 0
+    budget = 2 * int(max_iter) + 4 + DEPTH
+    prev = None
+    while launches < budget:
+        q = launches & 1
+        engine.step_begin()
+        lag[q].copy_(engine.sums().view(-1), non_blocking=True)
+        ev_sums[q].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_sums[q])
+            comm.all_reduce_sum(lag[q])
+            ev_red[q].record(side)
+        if prev is not None:
+            main.wait_event(ev_red[q ^ 1])
+        engine.s.step_commit_lagged(prev)
+        r = launches % (DEPTH + 1)
+        ring[r:r + 1].copy_(active_dev, non_blocking=True)
+        ring_ev[r].record(main)
+        if shard.world > 1:
+            engine.halo_exchange()
+        prev = lag[q]
+        launches += 1
+        if launches > DEPTH:
+            o = (launches - 1 - DEPTH) % (DEPTH + 1)
+            ring_ev[o].synchronize()
+            if int(ring[o]) <= 0:
+                break
+    else:
+        raise VPintError("internal error: sharded loop did not terminate within its launch budget")
+    main.wait_stream(side)
+    torch.cuda.current_stream(dev).synchronize()
+    if engine.active() > 0:
+        raise VPintError("internal error: sharded loop stopped with problems still running")
+    return launches
+
+
 def run_sharded(engine, shard, comm, max_iter, poll_every=8, use_graph=None):
     """Drive one run() of a row-sharded batch to the reference's stopping sweeps.
 
@@ -115,6 +183,9 @@ def run_sharded(engine, shard, comm, max_iter, poll_every=8, use_graph=None):
     dozen enqueues (at 8 GPUs a launch group is only ~0.2 ms of stencil work).
     Returns the number of launches issued.
     """
+    import os
+    if getattr(engine, "lagged_capable", False) and os.environ.get("VPINT_SHARD_LAGGED", "1") != "0" and not use_graph:
+        return run_sharded_lagged(engine, shard, comm, max_iter, poll_every=poll_every)
     comm.all_reduce_sum(engine.known())
     engine.begin(max_iter)
     if max_iter <= 0:
@@ -191,12 +262,62 @@ def run_lockstep(engines, shards, max_iter, poll_every=8):
     raise VPintError("internal error: sharded loop did not terminate within its launch budget")
 
 
+def run_lockstep_lagged(engines, shards, max_iter):
+    """:func:`run_sharded_lagged` with every shard in THIS process (one device, one stream): the all-reduce becomes a
+    tensor sum, the neighbours' receive slots are ordinary device buffers of the other engines -- the lagged stop
+    decision and the push / flag / pull kernels run exactly as they do across GPUs.  For single-GPU checks."""
+    import torch
+    n = len(engines)
+    dev = engines[0].s.device
+    total = engines[0].known().clone()
+    for e in engines[1:]:
+        total += e.known()
+    bufs = []
+    for e in engines:
+        e.known().copy_(total)
+        e.begin(max_iter)
+        pitch = e.s.state_tensor(0).shape[-1]
+        msg = e.s.nprob * e.rows * pitch * 8          # the same for every shard: equal problem count and row pitch
+        bufs.append(torch.zeros(4 * msg + 256, dtype=torch.uint8, device=dev))
+    ptrs = [int(b.data_ptr()) for b in bufs]
+    for e, b in zip(engines, bufs):
+        e.peer = dict(buf=b, hdl=None, msg=msg, ptrs=ptrs, seq=0)
+    if max_iter <= 0:
+        return 0
+    lag = [[torch.zeros(e.s.sums_tensor().numel(), dtype=torch.float64, device=dev) for _ in range(2)] for e in engines]
+    launches, prev = 0, False
+    budget = 2 * int(max_iter) + 4
+    while launches < budget:
+        q = launches & 1
+        for e in engines:
+            e.step_begin()
+        tot = engines[0].sums().view(-1).clone()
+        for e in engines[1:]:
+            tot += e.sums().view(-1)
+        for i, e in enumerate(engines):
+            e.s.step_commit_lagged(lag[i][q ^ 1] if prev else None)
+            lag[i][q].copy_(tot)
+        if n > 1:
+            seqs = []
+            for e in engines:                       # every push is enqueued before any pull (one stream: no deadlock)
+                seqs.append(e.halo_exchange(push_only=True))
+            for e, sq in zip(engines, seqs):
+                e.halo_exchange(pull_only=sq)
+        prev = True
+        launches += 1
+        if max(e.active() for e in engines) <= 0:
+            return launches
+    raise VPintError("internal error: sharded loop did not terminate within its launch budget")
+
+
 class SolverEngine:
     """Engine protocol over the CUDA :class:`~vpint_b200.engine.Solver` (NCCL path)."""
 
     def __init__(self, solver, shard, run_kwargs):
         self.s = solver
         self.shard = shard
+        self.comm = None
+        self.peer = None
         self.kw = dict(run_kwargs)
         torch = solver.torch
         k = solver.k_block
@@ -210,6 +331,84 @@ class SolverEngine:
         self.recv_down = mk() if shard.down is not None else None
 
     graph_capable = True
+
+    @property
+    def lagged_capable(self):
+        return self.rows == 1 and self.s.storage == "float64" and "track_delta" not in self.kw
+
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = self.s.torch.cuda.Stream(device=self.s.device)
+        return self._side
+
+    def lag_buffers(self):
+        """Two copies of the per-sweep sums (all-reduced on the side stream while the next sweep runs)."""
+        if getattr(self, "_lag", None) is None:
+            torch = self.s.torch
+            n = self.s.sums_tensor().numel()
+            self._lag = [torch.zeros(n, dtype=torch.float64, device=self.s.device) for _ in range(2)]
+        return self._lag
+
+    def setup_peer(self, comm):
+        """Map the neighbours' receive slots into this process (torch symmetric memory: CUDA virtual-memory handles
+        exchanged through the process group's store), so that halo rows travel as plain stores over NVLink.  Returns
+        False -- on every rank alike -- when that is not available; the NCCL send / recv path then stays in use."""
+        import os
+        self.peer = None
+        self.peer_tried = True
+        if self.shard.world <= 1 or os.environ.get("VPINT_PEER_HALO", "1") == "0":
+            return False
+        torch = self.s.torch
+        ok = 1
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            pitch = self.s.state_tensor(0).shape[-1]
+            msg = self.s.nprob * self.rows * pitch * 8
+            buf = symm_mem.empty(4 * msg + 256, dtype=torch.uint8, device=self.s.device)
+            hdl = symm_mem.rendezvous(buf, comm.group if comm.group is not None else dist.group.WORLD)
+            buf.zero_()
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self.peer = dict(buf=buf, hdl=hdl, msg=msg, ptrs=ptrs, seq=0)
+        except Exception as exc:                      # noqa: BLE001 -- any failure means "not available here"
+            self.peer_error = "%s: %s" % (type(exc).__name__, exc)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.s.device)
+        comm.dist.all_reduce(flag, op=comm.dist.ReduceOp.MIN, group=comm.group)
+        torch.cuda.synchronize(self.s.device)
+        if int(flag.item()) == 0:
+            self.peer = None
+            return False
+        comm.dist.barrier(group=comm.group)            # every rank has zeroed its flags before anyone pushes
+        return True
+
+    def halo_exchange(self, push_only=False, pull_only=None):
+        peer = getattr(self, "peer", None)
+        if peer is None:
+            su, sd = self.halo_send()
+            ru, rd = self.halo_recv()
+            self.comm.exchange(self.shard, su, sd, ru, rd)
+            self.halo_apply()
+            return None
+        if pull_only is None:
+            peer["seq"] += 1
+        seq, msg, ptrs = (peer["seq"] if pull_only is None else pull_only), peer["msg"], peer["ptrs"]
+        slot = seq & 1
+        sh = self.shard
+        flags = 4 * msg
+        mine = ptrs[sh.rank]
+        # my first owned rows -> the upper neighbour's "from below" slot; my last owned rows -> the lower one's "from above"
+        up_dst = ptrs[sh.up] + (2 * slot + 1) * msg if sh.up is not None else 0
+        up_flag = ptrs[sh.up] + flags + 128 if sh.up is not None else 0
+        dn_dst = ptrs[sh.down] + (2 * slot + 0) * msg if sh.down is not None else 0
+        dn_flag = ptrs[sh.down] + flags if sh.down is not None else 0
+        if pull_only is None:
+            self.s.halo_push(self.rows, up_dst, up_flag, dn_dst, dn_flag, seq)
+        if push_only:
+            return seq
+        self.s.halo_pull(self.rows, mine + (2 * slot + 0) * msg if sh.up is not None else 0, mine + flags if sh.up is not None else 0,
+                         mine + (2 * slot + 1) * msg if sh.down is not None else 0,
+                         mine + flags + 128 if sh.down is not None else 0, seq)
 
     def capture(self, fn):
         """Capture ``fn`` (one launch group) into a CUDA graph on a side stream (per run: replaying a graph
@@ -315,6 +514,9 @@ def open_shard_raw(target_local, features_local, cloud_local, shard, comm, opts,
         eng = SolverEngine(solver, shard, dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
                                                clip_val=opts["clip_val"]))
         eng.fill_scratch = scratch
+        eng.comm = comm
+        if shard.world > 1 and hasattr(comm, "dist"):
+            eng.setup_peer(comm)
     except Exception:
         solver.close()
         raise
