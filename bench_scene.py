@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def scene_rows(lo, hi, Hs, Ws, B, seed, dev, n_discs):
+def scene_rows(lo, hi, Hs, Ws, B, seed, dev, n_discs, rad_scale=1.0):
     """Rows [lo, hi) of the synthetic scene as a product holds it: (target, features) uint16 (rows, Ws, B) -- cloudy
     pixels keep a measured value -- and the cloud mask uint8 (rows, Ws), 1 = cloud."""
     import torch
@@ -38,7 +38,7 @@ def scene_rows(lo, hi, Hs, Ws, B, seed, dev, n_discs):
     feats = torch.empty((rows, Ws, B), dtype=torch.uint16, device=dev)
     cloud = torch.zeros((rows, Ws), dtype=torch.bool, device=dev)
     for cy, cx, r in discs:
-        rad = (100.0 + 500.0 * r) / 10980.0      # relative to the scene: the cloud fraction does not depend on its size
+        rad = rad_scale * (100.0 + 500.0 * r) / 10980.0      # relative to the scene: the cloud fraction does not depend on its size
         cloud |= (yy - cy) ** 2 + (xx - cx) ** 2 < rad * rad
     BLK = 256            # noise is generated per fixed block of rows so that it does not depend on the sharding
     for b in range(B):
@@ -68,11 +68,11 @@ class _LocalComm:
         pass
 
 
-def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, warmup=0, poll=8):
+def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, warmup=0, poll=8, rad_scale=1.0):
     """Generate this shard's rows, solve, return (pred (B, own_rows, W) float64, sweeps, launches, ms per step, cloud cells)."""
     import torch
     from vpint_b200.sharded import open_shard_raw, run_sharded, shard_result, stage_shard_raw
-    target, feats, cloud = scene_rows(shard.lo, shard.hi, Hs, Ws, B, seed, dev, discs)
+    target, feats, cloud = scene_rows(shard.lo, shard.hi, Hs, Ws, B, seed, dev, discs, rad_scale)
     solver, eng = open_shard_raw(target, feats, cloud, shard, comm, opts, k_block=kb)
     try:
         def step():
@@ -97,7 +97,8 @@ def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, war
         ms = e0.elapsed_time(e1) / max(steps, 1)
         own = slice(shard.own_row0, shard.own_row0 + shard.own_rows)
         cloud_cells = float(cloud[own].sum().item())
-        tiles = (solver.active_tiles, solver.total_tiles)
+        tiles = (solver.active_tiles, solver.total_tiles, "peer stores + flag (symmetric memory)" if eng.peer is not None else
+                 ("NCCL send/recv" if comm.world > 1 else "none"), getattr(eng, "peer_error", None))
     finally:
         solver.close()
     return pred, sweeps, launches, ms, cloud_cells, tiles
@@ -107,7 +108,7 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
     """The `scene` record of bench.py's JSON line (rank 0 returns it, the others None)."""
     import torch
     import torch.distributed as dist
-    from vpint_b200.sharded import Comm, RowShard, run_lockstep, open_shard_raw, shard_result
+    from vpint_b200.sharded import Comm, RowShard, run_lockstep_lagged, open_shard_raw, shard_result
     from vpint_b200.wp import wp_run_options
     opts = wp_run_options()
     kb = max(1, k_block)
@@ -117,10 +118,10 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
 
     # ---- parity: sharded == unsharded on a reduced scene --------------------------------------------------------
     Hp = Wp = parity_size
-    pdiscs = max(4, discs // 6)
+    pdiscs, pscale = 14, 3.0          # fewer, larger clouds than the full scene: tens of sweeps per band
     if world > 1:
         shard = RowShard(Hp, world, rank, halo=kb)
-        pred, sweeps, _, _, _, _ = _solve_rows(shard, comm, Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb)
+        pred, sweeps, _, _, _, ptiles = _solve_rows(shard, comm, Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb, rad_scale=pscale)
         if rank == 0:
             parts = [pred]
             for r in range(1, world):
@@ -131,7 +132,7 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
             got = torch.cat(parts, dim=1)
         else:
             dist.send(pred.contiguous(), dst=0)
-        how = "row-sharded over %d NCCL ranks vs unsharded on rank 0" % world
+        how = "row-sharded over %d ranks (halo rows: %s) vs unsharded on rank 0" % (world, ptiles[2])
     else:
         # one device: two shards driven in lockstep (the all-reduce and the halo exchange become tensor copies)
         shards = [RowShard(Hp, 2, r, halo=kb) for r in range(2)]
@@ -139,7 +140,7 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
         try:
             # the mean init of the whole band: both shards' leaf sums added before either combines
             from vpint_b200.engine import Solver
-            raws = [scene_rows(sh.lo, sh.hi, Hp, Wp, bands, seed + 1, dev, pdiscs) for sh in shards]
+            raws = [scene_rows(sh.lo, sh.hi, Hp, Wp, bands, seed + 1, dev, pdiscs, pscale) for sh in shards]
             scr = []
             for sh, (t, f, c) in zip(shards, raws):
                 s = Solver(2, bands, sh.local_rows, Wp, nprob_inner=bands, planes=True, k_block=kb, shard=sh.desc(), device=dev)
@@ -156,7 +157,7 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
                 s.ingest_bands(t.unsqueeze(0), f.unsqueeze(0), cl.unsqueeze(0), fill_ready=True)
                 engines.append(SolverEngine(s, sh, dict(auto_terminate=opts["auto_terminate"], threshold=opts["threshold"],
                                                         clip_val=opts["clip_val"])))
-            run_lockstep(engines, shards, opts["iterations"])
+            run_lockstep_lagged(engines, shards, opts["iterations"])
             res = [shard_result(s, sh) for s, sh in zip(solvers, shards)]
             got = torch.cat([r[0] for r in res], dim=1)
             sweeps = res[0][1]
@@ -164,10 +165,10 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
             for s in solvers:
                 s.close()
         del raws
-        how = "two row shards in lockstep on the one device vs unsharded"
+        how = "two row shards in lockstep on the one device (lagged stop decision, halo rows pushed with a flag) vs unsharded"
     if rank == 0:
         full = RowShard(Hp, 1, 0, halo=0)
-        ref, ref_sweeps, _, _, _, _ = _solve_rows(full, _LocalComm(), Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb)
+        ref, ref_sweeps, _, _, _, _ = _solve_rows(full, _LocalComm(), Hp, Wp, bands, seed + 1, dev, pdiscs, opts, kb, rad_scale=pscale)
         rel = float(((got - ref).abs() / ref.abs()).max().item())
         rec["parity"] = {"scene": "%dx%dx%d" % (Hp, Wp, bands), "how": how, "max_rel": rel,
                          "sweeps_sharded": [int(v) for v in sweeps], "sweeps_unsharded": [int(v) for v in ref_sweeps],
@@ -199,7 +200,9 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
                          "ms": ms, "steps": steps, "value": pxit / (ms * 1e-3) / 1e6, "unit": "Mpx*it/s", "scaling": "strong",
                          "sweeps_per_band": [int(v) for v in sweeps], "launches": int(launches), "cloud_fraction": round(frac, 4),
                          "rows_rank0": shard.own_rows, "halo": shard.halo, "finite": ok,
-                         "active_tiles_rank0": tiles[0], "total_tiles_rank0": tiles[1],
+                         "active_tiles_rank0": tiles[0], "total_tiles_rank0": tiles[1], "halo_rows": tiles[2],
+                         "halo_fallback_reason": tiles[3],
+                         "protocol": "stop decision lags one sweep (all-reduce overlaps the next sweep)" if os.environ.get("VPINT_SHARD_LAGGED", "1") != "0" else "all-reduce and decision every sweep",
                          "unknown_cell_gbps_48B": 48.0 * pxit * frac / (ms * 1e-3) / 1e9}
     torch.cuda.empty_cache()
     return rec if rank == 0 else None

@@ -252,7 +252,8 @@ typedef struct vpint_ingest_params {
     const double *fill_host;        /* HOST [nprob], VPINT_FILL_HOST only                                          */
     void   *scratch;                /* VPINT_FILL_DEVICE: vpint_fill_scratch_bytes() bytes                         */
     void   *out;                    /* known cells of the result are written here (full output); may be NULL      */
-    int32_t out_dtype;              /* VPINT_F32 / VPINT_F64                                                       */
+    int32_t out_dtype;              /* VPINT_F32 / VPINT_F64 / VPINT_U16 (write-back of a product: clip to [0, 65535],
+                                       truncate, NaN -> 0)                                                        */
     int64_t out_stride[4];          /* element strides {image, band, row, column} of out                          */
 } vpint_ingest_params;
 
@@ -279,7 +280,8 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
 /* The unknown cells of the result only (the known ones are the caller's own input, or were written by
  * vpint_solver_ingest_bands through vpint_ingest_params.out).  out may be device memory or pinned host memory
  * mapped into the device (cudaHostAlloc / cudaHostRegister): the stores leave as contiguous runs, so only the
- * cloud cells cross the host link.  stride: {outer problem, inner problem, row, column}. */
+ * cloud cells cross the host link.  dtype VPINT_F64 / VPINT_F32 / VPINT_U16.  stride: {outer problem, inner problem,
+ * row, column}. */
 int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
                                 void *stream);
 

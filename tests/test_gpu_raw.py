@@ -117,6 +117,23 @@ def test_raw_unknown_only_result_in_place():
         solve_raw(t, f, m, out=torch.empty((6, 5, 64, 64), dtype=torch.float64), result="unknown")   # pageable host memory
 
 
+def test_raw_uint16_write_back():
+    """out_dtype uint16 (N4 write-back): the float64 result clipped to [0, 65535] and truncated like astype(uint16);
+    full result and cloud-cells-only in place."""
+    import torch
+    rng = np.random.default_rng(2010)
+    t, f, m = raw_stack(rng, 3, 64, 96, 4)
+    ref, _ = host_reference(t, f, m, threshold=10)
+    want = np.clip(np.moveaxis(ref, 1, -1), 0, 65535).astype(np.uint16)
+    out = solve_raw(t, f, m, mask_threshold=10, out_layout="hwb", out_dtype=np.uint16)
+    assert out.dtype == torch.uint16 and np.array_equal(out.numpy(), want)
+    cloud = np.broadcast_to((m > 10)[..., None], t.shape)
+    assert np.array_equal(out.numpy()[~cloud], t[~cloud]), "known cells come back exactly"
+    img = torch.from_numpy(t.copy()).pin_memory()                # the caller's own product: only its cloud cells change
+    solve_raw(t, f, m, mask_threshold=10, out=img, out_layout="hwb", out_dtype=np.uint16, result="unknown")
+    assert np.array_equal(img.numpy(), want)
+
+
 @pytest.mark.parametrize("raster", [np.float32, np.float64])
 def test_raw_float_rasters_nan_clip_and_buffer(raster):
     """float rasters with their own NaNs (per band), clip_target / clip_features, cloud buffering (incl. two passes and

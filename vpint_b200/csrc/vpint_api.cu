@@ -981,7 +981,8 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
     if (s->n_planes != 5) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_ingest_bands: solver has no feature plane");
     if (!ingest_bands_supported(s->g, p->raster_dtype))
         return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_ingest_bands: rows too long for the staged load");
-    if (p->out && p->out_dtype != VPINT_F32 && p->out_dtype != VPINT_F64) return fail(VPINT_ERR_INVALID, "bad out dtype");
+    if (p->out && p->out_dtype != VPINT_F32 && p->out_dtype != VPINT_F64 && p->out_dtype != VPINT_U16)
+        return fail(VPINT_ERR_INVALID, "bad out dtype");
     if (s->state_ratio) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: a run is in flight");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Geom &g = s->g;
@@ -1039,7 +1040,7 @@ int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
     if (!out || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: null argument");
-    if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    if (dtype != VPINT_F64 && dtype != VPINT_F32 && dtype != VPINT_U16) return fail(VPINT_ERR_INVALID, "bad dtype");
     if (s->g.ndim != 2 || s->storage != VPINT_F64) return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_result_unknown: 2-D fp64 solvers");
     {
         const int rc = leave_ratio(s, static_cast<cudaStream_t>(stream));

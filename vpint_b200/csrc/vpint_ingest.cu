@@ -38,6 +38,22 @@ __device__ __forceinline__ TAcc conv_in(TIn raw, int clip, double lo, double hi)
     return v;
 }
 
+// Result element in the caller's dtype.  uint16 is the write-back of a Sentinel-2 product (N4): what
+// np.clip(pred, 0, 65535).astype(np.uint16) gives (truncation toward zero, NaN -> 0).
+template <typename TOut>
+__device__ __forceinline__ TOut to_out(double v) { return (TOut)v; }
+template <>
+__device__ __forceinline__ uint16_t to_out<uint16_t>(double v) {
+    if (!(v > 0.0)) return 0;
+    return (uint16_t)(v >= 65535.0 ? 65535.0 : v);
+}
+
+__device__ __forceinline__ void store_out(void *out, int code, int64_t idx, double v) {
+    if (code == VPINT_F32) reinterpret_cast<float *>(out)[idx] = (float)v;
+    else if (code == VPINT_U16) reinterpret_cast<uint16_t *>(out)[idx] = to_out<uint16_t>(v);
+    else reinterpret_cast<double *>(out)[idx] = v;
+}
+
 template <typename TM>
 __global__ void __launch_bounds__(256) cloud_mask_kernel(const TM *__restrict__ mask, double threshold, int64_t n,
                                                          uint8_t *__restrict__ cloud) {
@@ -283,7 +299,7 @@ struct IngestArgs {
     uint32_t *mask;
     int *flags;
     void *out;
-    int out_f32;
+    int out_code;            // VPINT_F64 / VPINT_F32 / VPINT_U16
     Strides osd;
     int TW;
 };
@@ -321,10 +337,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
             for (int i = lane; i < tw * B; i += 32) {
                 const int x = i / B;
                 const TAcc v = conv_in<TAcc>(my[i], a.clip_t, a.t_lo, a.t_hi);
-                if (!((v != v) || myc[x])) {
-                    if (a.out_f32) reinterpret_cast<float *>(a.out)[obase + i] = (float)v;
-                    else reinterpret_cast<double *>(a.out)[obase + i] = (double)v;
-                }
+                if (!((v != v) || myc[x])) store_out(a.out, a.out_code, obase + i, (double)v);
             }
         }
         for (int b = 0; b < B; ++b) {
@@ -348,10 +361,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
                         else {
                             sum_o += o;
                             if (isinf(o)) counts += 1 << 16;
-                            if (a.out && !out_interleaved) {
-                                if (a.out_f32) reinterpret_cast<float *>(a.out)[obase + (int64_t)(x0 + e) * a.osd.sX] = (float)o;
-                                else reinterpret_cast<double *>(a.out)[obase + (int64_t)(x0 + e) * a.osd.sX] = o;
-                            }
+                            if (a.out && !out_interleaved) store_out(a.out, a.out_code, obase + (int64_t)(x0 + e) * a.osd.sX, o);
                         }
                     }
                 }
@@ -432,7 +442,7 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
             const unsigned word = mr[x0 >> 5];
             if (word == 0) continue;
             const int x = x0 + lane;
-            if ((word >> lane) & 1u) dst[(int64_t)x * sd.sX] = (TOut)src[x];
+            if ((word >> lane) & 1u) dst[(int64_t)x * sd.sX] = to_out<TOut>(src[x]);
         }
         return;
     }
@@ -454,7 +464,7 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
             const unsigned word = mask[((size_t)p * g.H + y) * g.mpitch + (x >> 5)];
             if ((word >> (x & 31)) & 1u) {
                 const double *src = (state[p].cur ? buf1 : buf0) + (size_t)p * plane + (size_t)y * g.pitch;
-                dst[i] = (TOut)src[x];
+                dst[i] = to_out<TOut>(src[x]);
             }
         }
     }
@@ -608,7 +618,7 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     a.clip_t = clip_t; a.clip_f = clip_f; a.t_lo = t_lo; a.t_hi = t_hi; a.f_lo = f_lo; a.f_hi = f_hi;
     a.fill = fill; a.bufA = bufA; a.bufB = bufB; a.fplane = fplane; a.rowpart = rowpart; a.extreme = extreme;
     a.mask = mask; a.flags = flags;
-    a.out = out; a.out_f32 = (out_dtype == VPINT_F32) ? 1 : 0;
+    a.out = out; a.out_code = out_dtype;
     a.osd = out ? Strides{out_stride[0], out_stride[1], out_stride[2], out_stride[3]} : Strides{0, 0, 0, 0};
     const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
     a.TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
@@ -643,6 +653,9 @@ cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *c
     if (dtype == VPINT_F64)
         result_unknown_kernel<double><<<grid, kUnkWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1],
                                                                        mask, (double *)out, sd, interleaved, niter_out);
+    else if (dtype == VPINT_U16)
+        result_unknown_kernel<uint16_t><<<grid, kUnkWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1],
+                                                                         mask, (uint16_t *)out, sd, interleaved, niter_out);
     else
         result_unknown_kernel<float><<<grid, kUnkWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1],
                                                                       mask, (float *)out, sd, interleaved, niter_out);

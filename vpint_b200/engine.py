@@ -51,6 +51,14 @@ def _raster_code(t):
     return code
 
 
+def _out_code(t):
+    """dtype code of a result tensor: float64 / float32, or uint16 for the write-back of a product."""
+    torch = _torch()
+    if t.dtype == torch.uint16:
+        return N.U16
+    return _code(t)
+
+
 def _clip_pair(clip):
     """clip_target / clip_features of the VPint2 constructor (VPint/VPint2.py:30-41): a number is an upper bound,
     anything else is (min, max).  -> (on, lo, hi)."""
@@ -364,7 +372,7 @@ class Solver:
         if out is not None:
             st = self._strides(out, (self.H, self.W))[:4]
             p.out = out.data_ptr()
-            p.out_dtype = _code(out)
+            p.out_dtype = _out_code(out)
             for i in range(4):
                 p.out_stride[i] = int(st[i])
             keep.append(out)
@@ -408,7 +416,7 @@ class Solver:
             niter = torch.zeros(self.nprob, dtype=torch.int32, device=self.device)
         if out.device.type == "cpu" and not out.is_pinned():
             raise VPintError("result_unknown writes through a device mapping: a host `out` must be pinned memory")
-        N.check(self.lib, self.lib.vpint_solver_result_unknown(self._h, C.c_void_p(out.data_ptr()), _code(out), _i64(st),
+        N.check(self.lib, self.lib.vpint_solver_result_unknown(self._h, C.c_void_p(out.data_ptr()), _out_code(out), _i64(st),
                                                                 C.c_void_p(niter.data_ptr()), self._stream()),
                 "vpint_solver_result_unknown")
         return niter

@@ -378,7 +378,8 @@ class RawPipeline:
         if out_layout == "bhw":
             res_shape, res_dtype = (lambda m: (m, B, H, W)), torch.float64
         else:
-            tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {np.dtype(np.float32): torch.float32}.get(
+            tdt = out_dtype if isinstance(out_dtype, torch.dtype) else {
+                np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16}.get(
                 np.dtype(out_dtype if out_dtype is not None else dtype), torch.float64)
             res_shape, res_dtype = (lambda m: (m, H, W, B)), tdt
         in_on_dev = target.device.type != "cpu"
@@ -485,6 +486,8 @@ def solve_raw(target, features, mask=None, opts=None, *, device=None, chunk_patc
     dtype            : the interpolator's DTYPE (np.float32 = VPint2's default): values, clip and mean init live in it.
     result           : 'full'    -> every cell of the result (float64 (N, B, H, W) for out_layout 'bhw' as run()
                                     assembles it, ``out_dtype`` (N, H, W, B) for 'hwb' as run_serial() returns it);
+                                    ``out_dtype=np.uint16`` ('hwb' only) is the write-back of a product: the result
+                                    clipped to [0, 65535] and truncated like ``astype(np.uint16)``;
                        'unknown' -> ONLY the cloud cells are written, into ``out`` (required; CUDA or pinned host
                                     memory, written in place through its device mapping): the known cells are the
                                     caller's own data and never cross the host link.
