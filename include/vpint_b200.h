@@ -166,6 +166,12 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
  * NULL) receives the planes (self.priority_grid). */
 int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, double *p_out, void *stream);
 
+/* Batched trials of a parameter search (WP_SMRP.auto_adapt, VPint/WP_MRP.py:429-759: the same grid solved with many
+ * candidate (beta, epsilon, mu)): HOST arrays [nprob], NULL = not per problem.  beta replaces the scalar of the next
+ * vpint_solver_priority call, epsilon / mu (together) the scalars of vpint_run_params in resistance runs.  Stays in
+ * force until called again (all NULL switches it off). */
+int vpint_solver_set_trial_params(vpint_solver *s, const double *beta, const double *epsilon, const double *mu, void *stream);
+
 /* VPINT_W_SCALAR: HOST arrays [nprob]; tau is ignored for ndim == 2
  * (SD_MRP.py:87, 315-321).  The copy is ordered on `stream` like every other call (the host arrays may be
  * reused as soon as the call returns). */

@@ -79,6 +79,8 @@ SIGNATURES = {
                                         C.c_int, C.c_double, C.c_double, C.c_void_p]),
     "vpint_solver_priority": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpint_solver_set_discounts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
+    "vpint_solver_set_trial_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                 C.c_void_p]),
     "vpint_solver_run_async": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p]),
     "vpint_solver_run_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "vpint_cloud_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]),

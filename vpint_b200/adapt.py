@@ -105,6 +105,10 @@ def auto_adapt(interp, params, search_epochs, subsample_proportion, search_strat
         return out
 
     if search_strategy == 'random':
+        # The candidates of this strategy do not depend on one another and a trial draws nothing from the RNG, so all
+        # of them are drawn first -- same calls, same order as the reference's epoch loop -- and run as ONE batched
+        # solve (problem = candidate); the pick below walks the errors in epoch order like the reference.
+        drawn = []
         for ep in range(search_epochs):
             if ep == 0:
                 vals = defaults(0)
@@ -117,7 +121,14 @@ def auto_adapt(interp, params, search_epochs, subsample_proportion, search_strat
                         vals[k] = min(max(0, np.random.uniform(low=0, high=0.3)), 1)
                     if k == 'mu':
                         vals[k] = np.random.uniform(low=bounds[k][0], high=bounds[k][1])
-            mae = trial(vals)
+            drawn.append(vals)
+        if params and ('beta' in params or 'epsilon' in params):
+            from .batch import wp_trials
+            cand = [dict(v, mu=v['mu'] if 'mu' in v else default_mu()) if 'epsilon' in v else dict(v) for v in drawn]
+            maes = wp_trials(sub_grid, interp.feature_grid, original, cand, max_sub_iter=max_sub_iter)
+        else:
+            maes = [trial(v) for v in drawn]
+        for vals, mae in zip(drawn, maes):
             if mae < best_loss:
                 best_vals, best_loss = vals, mae
 

@@ -95,6 +95,8 @@ struct vpint_solver {
     ResidentPlan rplans[kResidentMaxC + 1];   // per cluster size (problems run on the smallest cluster that holds the rows
     int res_caps[kResidentMaxC + 1] = {0};    //   their sweeps touch); caps = rows a cluster of C CTAs holds, 0 = no plan
     int res_cmax = 0;                 // smallest cluster that holds ALL rows of a problem
+    size_t off_trial = 0;             // double[3][P]: per-problem beta, epsilon, mu of batched search trials
+    bool trial_beta = false, trial_res = false;
     size_t off_cls = 0;               // int[P] class of every problem, int[32]: [0..8] problems per class, [16..24] class queues
     cudaStream_t cls_stream[kResidentMaxC + 1] = {nullptr};   // the launches of the classes run side by side: forked from the
     cudaEvent_t cls_fork = nullptr, cls_join[kResidentMaxC + 1] = {nullptr};   //   caller's stream and joined back into it
@@ -259,6 +261,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_done = take((size_t)g.P * sizeof(int));
     s->off_order = take((size_t)(kResidentMaxC + 1) * g.P * sizeof(int));
     s->off_cls = take(((size_t)g.P + 32) * sizeof(int));
+    s->off_trial = take(3 * (size_t)g.P * sizeof(double));
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
@@ -430,6 +433,22 @@ int vpint_solver_set_discounts(vpint_solver *s, const double *gamma, const doubl
     return VPINT_OK;
 }
 
+int vpint_solver_set_trial_params(vpint_solver *s, const double *beta, const double *epsilon, const double *mu, void *stream) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if ((epsilon == nullptr) != (mu == nullptr)) return fail(VPINT_ERR_INVALID, "epsilon and mu come together");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)s->g.P * sizeof(double);
+    double *base = s->at<double>(s->off_trial);
+    if (beta) VP_CUDA(cudaMemcpyAsync(base, beta, bytes, cudaMemcpyHostToDevice, st), "copy beta");
+    if (epsilon) {
+        VP_CUDA(cudaMemcpyAsync(base + s->g.P, epsilon, bytes, cudaMemcpyHostToDevice, st), "copy epsilon");
+        VP_CUDA(cudaMemcpyAsync(base + 2 * (size_t)s->g.P, mu, bytes, cudaMemcpyHostToDevice, st), "copy mu");
+    }
+    s->trial_beta = beta != nullptr;
+    s->trial_res = epsilon != nullptr;
+    return VPINT_OK;
+}
+
 static int recompact_tiles(vpint_solver *s, cudaStream_t st, bool trim);
 
 // Start of a run(): parameter checks + per-problem loop state.  Nothing here needs the tile list.
@@ -549,7 +568,9 @@ int vpint_solver_priority(vpint_solver *s, double beta, const double *bias, doub
     if (rc != VPINT_OK) return rc;
     void *planes[5];
     for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
-    VP_CUDA(launch_priority(s->g, s->storage, planes, beta, bias, p_out, st, &s->launches), "priority");
+    VP_CUDA(launch_priority(s->g, s->storage, planes, beta, s->trial_beta ? s->at<double>(s->off_trial) : nullptr, bias, p_out,
+                            st, &s->launches),
+            "priority");
     s->fplane_valid = false;          // the ratio form no longer describes these weights
     s->no_nc = true;
     return VPINT_OK;
@@ -604,6 +625,8 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
     a.resist = s->prm.resistance ? 1 : 0;
     a.eps = s->prm.epsilon;
     a.mu = s->prm.mu;
+    a.eps_arr = s->trial_res ? s->at<double>(s->off_trial) + s->g.P : nullptr;
+    a.mu_arr = s->trial_res ? s->at<double>(s->off_trial) + 2 * (size_t)s->g.P : nullptr;
     a.orig = s->has_orig ? s->at<void>(s->off_orig) : nullptr;
     a.fused = fused ? 1 : 0;
     a.done = s->at<int>(s->off_done);

@@ -69,6 +69,7 @@ struct StepArgs {
     int no_nc;               // 1: weights already carry the priority normalisation, no division by the neighbour count
     int resist;              // 1: resistance sweep over ALL cells (vpint_step_k1.cu, jacobi2d_resist_kernel)
     double eps, mu;
+    const double *eps_arr, *mu_arr;   // [P] per-problem epsilon / mu (batched trials of a parameter search) or null
     const void *orig;        // [P][H][pitch] known values (resistance)
     // fused finish (vpint_solver_run on an unsharded solver): the last tile block of a problem reduces the
     // per-tile partials and takes the stop decision, so a launch group is ONE kernel
@@ -167,8 +168,8 @@ cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const i
                                    const ProbState *state, double *sums, double *stage, bool all_tiles,
                                    cudaStream_t st, int64_t *launches);
 cudaError_t launch_step2d_resist(const StepArgs &a, int storage, int weight_mode, cudaStream_t st, int64_t *launches);
-cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *bias,
-                            double *p_out, cudaStream_t st, int64_t *launches);
+cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *beta_arr,
+                            const double *bias, double *p_out, cudaStream_t st, int64_t *launches);
 cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, int max_iter, cudaStream_t st,
                               int64_t *launches);
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);

@@ -229,8 +229,9 @@ __global__ void __launch_bounds__(256) jacobi2d_resist_kernel(const StepArgs a) 
                 }
                 const double dy = nv - ov;
                 double t = nv;
-                if (nv <= a.mu) t = ov + dy;                   // WP_MRP.py:340-344
-                if (t > a.mu) t = (ov + dy) - a.eps * ov;      // WP_MRP.py:346-348
+                const double mu = a.mu_arr ? a.mu_arr[p] : a.mu, eps = a.eps_arr ? a.eps_arr[p] : a.eps;   // per problem: batched trials
+                if (nv <= mu) t = ov + dy;                     // WP_MRP.py:340-344
+                if (t > mu) t = (ov + dy) - eps * ov;          // WP_MRP.py:346-348
                 out[row + x] = acc.commit(t, ov);
             }
         }

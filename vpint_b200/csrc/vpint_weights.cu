@@ -294,9 +294,11 @@ __global__ void __launch_bounds__(256) planes_from_fplane_kernel(int H, int W, i
 template <typename TSt>
 __global__ void __launch_bounds__(256) priority_kernel(int H, int W, int pitch, int row_offset, int global_H,
                                                        TSt *__restrict__ w0, TSt *__restrict__ w1,
-                                                       TSt *__restrict__ w2, TSt *__restrict__ w3, double beta,
+                                                       TSt *__restrict__ w2, TSt *__restrict__ w3, double beta_all,
+                                                       const double *__restrict__ beta_arr,
                                                        const double *__restrict__ bias, double *__restrict__ p_out) {
     const int p = blockIdx.x / H, y = blockIdx.x - p * H;
+    const double beta = beta_arr ? beta_arr[p] : beta_all;      // per problem: batched trials of a parameter search
     const size_t row = ((size_t)p * H + y) * pitch;
     const int yg = y + row_offset;
     TSt *wp[4] = {w0, w1, w2, w3};
@@ -426,17 +428,17 @@ cudaError_t launch_planes_from_fplane(const Geom &g, const double *fplane, int s
     return cudaSuccess;
 }
 
-cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *bias,
-                            double *p_out, cudaStream_t st, int64_t *launches) {
+cudaError_t launch_priority(const Geom &g, int storage, void *const *planes, double beta, const double *beta_arr,
+                            const double *bias, double *p_out, cudaStream_t st, int64_t *launches) {
     const unsigned grid = (unsigned)((int64_t)g.P * g.H);
     if (storage == VPINT_F64)
         priority_kernel<double><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, (double *)planes[0],
                                                       (double *)planes[1], (double *)planes[2], (double *)planes[3],
-                                                      beta, bias, p_out);
+                                                      beta, beta_arr, bias, p_out);
     else
         priority_kernel<float><<<grid, 256, 0, st>>>(g.H, g.W, g.pitch, g.row_offset, g.global_H, (float *)planes[0],
                                                      (float *)planes[1], (float *)planes[2], (float *)planes[3], beta,
-                                                     bias, p_out);
+                                                     beta_arr, bias, p_out);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -253,6 +253,18 @@ class Solver:
         N.check(self.lib, self.lib.vpint_solver_set_discounts(self._h, gp, tp, self._stream()), "vpint_solver_set_discounts")
         return self
 
+    def trial_params(self, beta=None, epsilon=None, mu=None):
+        """Per-problem beta and / or (epsilon, mu) for batched trials of a parameter search (arrays of nprob values)."""
+        def arr(v):
+            if v is None:
+                return None, None
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.nprob,)))
+            return a, a.ctypes.data_as(C.POINTER(C.c_double))
+        (b, bp), (e, ep), (m, mp) = arr(beta), arr(epsilon), arr(mu)
+        N.check(self.lib, self.lib.vpint_solver_set_trial_params(self._h, bp, ep, mp, self._stream()),
+                "vpint_solver_set_trial_params")
+        return self
+
     def priority(self, beta, bias=None, want_planes=False):
         """prioritise_identity: fold the priority planes into the weights (after :meth:`weights`).
         ``bias``: CUDA float64 tensor (nprob, H, W) of the known_value_bias sub-solve, or None.

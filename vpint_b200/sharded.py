@@ -131,7 +131,12 @@ def run_sharded_lagged(engine, shard, comm, max_iter, poll_every=8):
     launches = 0
     budget = 2 * int(max_iter) + 4 + DEPTH
     prev = None
+    import os
+    import time
+    trace = os.environ.get("VPINT_SHARD_TRACE") == "1"
+    t_host, t_wait, t0_all = 0.0, 0.0, time.perf_counter()
     while launches < budget:
+        t0 = time.perf_counter()
         q = launches & 1
         engine.step_begin()
         lag[q].copy_(engine.sums().view(-1), non_blocking=True)
@@ -150,15 +155,23 @@ def run_sharded_lagged(engine, shard, comm, max_iter, poll_every=8):
             engine.halo_exchange()
         prev = lag[q]
         launches += 1
+        t1 = time.perf_counter()
+        t_host += t1 - t0
         if launches > DEPTH:
             o = (launches - 1 - DEPTH) % (DEPTH + 1)
             ring_ev[o].synchronize()
+            t_wait += time.perf_counter() - t1
             if int(ring[o]) <= 0:
                 break
     else:
         raise VPintError("internal error: sharded loop did not terminate within its launch budget")
     main.wait_stream(side)
     torch.cuda.current_stream(dev).synchronize()
+    if trace and shard.rank == 0:
+        wall = time.perf_counter() - t0_all
+        print("[vpint shard trace] %d launches, wall %.2f ms (%.1f us / launch), host enqueue %.1f us / launch, host waiting on "
+              "the device %.1f us / launch" % (launches, 1e3 * wall, 1e6 * wall / launches, 1e6 * t_host / launches,
+                                                1e6 * t_wait / launches), flush=True)
     if engine.active() > 0:
         raise VPintError("internal error: sharded loop stopped with problems still running")
     return launches
