@@ -309,6 +309,18 @@ int vpint_solver_halo_push(vpint_solver *s, int rows, void *peer_up, int32_t *fl
 int vpint_solver_halo_pull(vpint_solver *s, int rows, const void *from_up, const int32_t *flag_up, const void *from_down,
                            const int32_t *flag_down, int seq, void *stream);
 
+/* The same loop entirely inside the library, without a collective library in it: every rank owns a PEER BLOCK of
+ * vpint_solver_peer_bytes() bytes (zero-filled symmetric / IPC memory that every rank has mapped; peer_base[r] = rank
+ * r's block as seen from this process, ranks in row order).  Per launch: sweep + local sums, ONE kernel that waits for
+ * the previous sweep's sums of all ranks, adds them up in rank order (every rank the same order -> the same decision),
+ * decides, commits and publishes this sweep's sums in every rank's block, ONE kernel that pushes / pulls the halo rows.
+ * The host stays a few launches ahead and reads "problems still running" from mapped pinned memory; all ranks stop
+ * after the same launch.  Call after vpint_solver_load / ingest on every rank, with the known-cell sums
+ * (vpint_solver_known_ptr) already all-reduced.  launches_out (may be NULL): launch groups issued. */
+size_t vpint_solver_peer_bytes(const vpint_solver *s, int world);
+int    vpint_solver_peer_bind(vpint_solver *s, int world, int rank, void *const *peer_base);
+int    vpint_solver_run_sharded(vpint_solver *s, const vpint_run_params *prm, void *stream, int64_t *launches_out);
+
 /* ---- results -----------------------------------------------------------
  * out: device, dtype `dtype`, element strides as in load.  This is
  * self.pred_grid after run().  niter_out: device int32[nprob] sweeps executed

@@ -440,6 +440,34 @@ def test_row_sharded_scene_lockstep_lagged(world, iterations):
             sv.close()
 
 
+def test_in_library_sharded_loop_single_rank():
+    """vpint_solver_run_sharded with a world of one (the peer block is an ordinary device buffer): the peer commit
+    kernel, the launch record in mapped pinned memory and the host's run-ahead polling, against the ordinary run()."""
+    import torch
+    from vpint_b200.wp import wp_run_options
+    rng = np.random.default_rng(407)
+    vp = make_patch(rng, 120, 200, 4)
+    ref, ref_sweeps = O.vpint2_run(vp.target, vp.features)
+    for iterations in (-1, 9, 1):
+        rr, rs = O.vpint2_run(vp.target, vp.features, iterations=iterations) if iterations != -1 else (ref, ref_sweeps)
+        opts = wp_run_options(iterations=iterations)
+        s = Solver(2, 4, 120, 200, nprob_inner=4, planes=True, k_block=1)
+        try:
+            t = torch.from_numpy(vp.target[None]).cuda()
+            f = torch.from_numpy(vp.features[None]).cuda()
+            block = torch.zeros(s.peer_bytes(1), dtype=torch.uint8, device="cuda")
+            s.peer_bind(1, 0, [block.data_ptr()])
+            for _ in range(2):                                   # twice: the launch counter runs on across runs
+                s.ingest_bands(t, f, None, value_dtype="float32")
+                n = s.run_sharded(opts["iterations"], auto_terminate=opts["auto_terminate"], threshold=opts["threshold"])
+                out, sweeps = s.result()
+                assert list(sweeps.cpu().numpy()) == list(rs)
+                close(np.moveaxis(out.cpu().numpy(), 0, -1), rr)
+                assert n >= max(rs)
+        finally:
+            s.close()
+
+
 # ---- 5. A1 on the device and the pipelined host path -----------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape", [(256, 256), (100, 100), (37, 91), (2, 3), (1, 130), (300, 301)])

@@ -112,6 +112,9 @@ SIGNATURES = {
     "vpint_solver_step_commit_lagged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpint_solver_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vpint_solver_halo_pull": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vpint_solver_peer_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "vpint_solver_peer_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vpint_solver_run_sharded": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.c_void_p, C.POINTER(C.c_int64)]),
     "vpint_solver_result": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "vpint_solver_active_tiles": (C.c_int64, [C.c_void_p]),
     "vpint_solver_total_tiles": (C.c_int64, [C.c_void_p]),

@@ -95,6 +95,12 @@ struct vpint_solver {
     ResidentPlan rplans[kResidentMaxC + 1];   // per cluster size (problems run on the smallest cluster that holds the rows
     int res_caps[kResidentMaxC + 1] = {0};    //   their sweeps touch); caps = rows a cluster of C CTAs holds, 0 = no plan
     int res_cmax = 0;                 // smallest cluster that holds ALL rows of a problem
+    // row shards over peer-mapped memory (vpint_solver_peer_bind / vpint_solver_run_sharded)
+    bool peer_bound = false;
+    PeerCtx peer;
+    size_t off_peerctr = 0;           // int[2]: lifetime launch counter of the sharded loop, first-launch-of-a-run flag
+    unsigned long long *h_ring = nullptr, *d_ring = nullptr;   // mapped pinned ring: (launch << 32) | problems still running
+    int peer_t = 0;                   // host mirror of the launch counter
     size_t off_trial = 0;             // double[3][P]: per-problem beta, epsilon, mu of batched search trials
     bool trial_beta = false, trial_res = false;
     size_t off_cls = 0;               // int[P] class of every problem, int[32]: [0..8] problems per class, [16..24] class queues
@@ -262,6 +268,7 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_order = take((size_t)(kResidentMaxC + 1) * g.P * sizeof(int));
     s->off_cls = take(((size_t)g.P + 32) * sizeof(int));
     s->off_trial = take(3 * (size_t)g.P * sizeof(double));
+    s->off_peerctr = take(4 * sizeof(int));
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
@@ -276,6 +283,7 @@ void vpint_solver_destroy(vpint_solver *s) {
     if (!s) return;
     pinned_release(s->h_counters);
     if (s->ev) cudaEventDestroy(s->ev);
+    if (s->h_ring) cudaFreeHost(s->h_ring);
     if (s->cls_fork) cudaEventDestroy(s->cls_fork);
     for (int c = 0; c <= kResidentMaxC; ++c) {
         if (s->cls_join[c]) cudaEventDestroy(s->cls_join[c]);
@@ -1183,6 +1191,118 @@ int vpint_solver_halo_pull(vpint_solver *s, int rows, const void *from_up, const
     VP_CUDA(launch_halo_pull(s->g, s->at<ProbState>(s->off_state), bufs, from_up, from_down, flag_up, flag_down, rows, seq,
                              static_cast<cudaStream_t>(stream), &s->launches),
             "halo pull");
+    return VPINT_OK;
+}
+
+// ---- row shards over peer-mapped memory: the whole loop in the library --------------------------------------------
+static size_t peer_layout(const vpint_solver *s, int world, int rows, size_t *msg, size_t *off_gather, size_t *off_sflag) {
+    const Geom &g = s->g;
+    const size_t m = (size_t)g.P * rows * g.pitch * sizeof(double);
+    const size_t og = align_up(4 * m + 256, 256);
+    const size_t os = align_up(og + 2 * (size_t)world * g.P * kSumSlots * sizeof(double), 256);
+    if (msg) *msg = m;
+    if (off_gather) *off_gather = og;
+    if (off_sflag) *off_sflag = os;
+    return os + (size_t)world * 128;
+}
+
+size_t vpint_solver_peer_bytes(const vpint_solver *s, int world) {
+    if (!s || world < 1 || world > kPeerMaxWorld) return 0;
+    return peer_layout(s, world, s->g.KB, nullptr, nullptr, nullptr);
+}
+
+int vpint_solver_peer_bind(vpint_solver *s, int world, int rank, void *const *peer_base) {
+    if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
+    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || !peer_base)
+        return fail(VPINT_ERR_INVALID, "vpint_solver_peer_bind: bad argument (up to 16 ranks)");
+    if (s->g.KB != 1 || s->storage != VPINT_F64 || s->g.ndim != 2)
+        return fail(VPINT_ERR_UNSUPPORTED, "the peer-memory loop runs 2-D fp64 solvers with one sweep per launch (k_block 1)");
+    PeerCtx &pc = s->peer;
+    pc.world = world; pc.rank = rank;
+    for (int r = 0; r < kPeerMaxWorld; ++r) pc.base[r] = (r < world) ? static_cast<char *>(peer_base[r]) : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!pc.base[r]) return fail(VPINT_ERR_INVALID, "vpint_solver_peer_bind: null peer block");
+    peer_layout(s, world, s->g.KB, &pc.msg_bytes, &pc.off_gather, &pc.off_sflag);
+    const Geom &g = s->g;
+    const bool top = (g.row_offset + g.own_row0 == 0), bottom = (g.row_offset + g.own_row0 + g.own_rows == g.global_H);
+    pc.up = top ? -1 : rank - 1;
+    pc.down = bottom ? -1 : rank + 1;
+    if (pc.up < -1 || pc.down >= world) return fail(VPINT_ERR_INVALID, "vpint_solver_peer_bind: rank order must follow the row order");
+    if (!s->h_ring) {
+        VP_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s->h_ring), 64 * sizeof(unsigned long long), cudaHostAllocMapped),
+                "cudaHostAlloc");
+        memset(s->h_ring, 0, 64 * sizeof(unsigned long long));
+        VP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d_ring), s->h_ring, 0), "cudaHostGetDevicePointer");
+    }
+    VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_peerctr), 0, 4 * sizeof(int), cudaStreamLegacy), "memset launch counter");
+    VP_CUDA(cudaStreamSynchronize(cudaStreamLegacy), "peer bind sync");
+    s->peer_t = 0;
+    s->peer_bound = true;
+    return VPINT_OK;
+}
+
+int vpint_solver_run_sharded(vpint_solver *s, const vpint_run_params *prm, void *stream, int64_t *launches_out) {
+    if (launches_out) *launches_out = 0;
+    if (!s || !s->peer_bound) return fail(VPINT_ERR_INVALID, "vpint_solver_peer_bind has not been called");
+    if (!prm) return fail(VPINT_ERR_INVALID, "null run params");
+    if (prm->delta_out || prm->resistance) return fail(VPINT_ERR_UNSUPPORTED, "the peer-memory loop does not record deltas / run resistance sweeps");
+    int rc = vpint_solver_begin_run(s, prm, stream);
+    if (rc != VPINT_OK) return rc;
+    if (s->any_dirty) return fail(VPINT_ERR_INVALID, "a row-sharded run needs a start state that equals the original on known cells");
+    if (prm->max_iter == 0) return VPINT_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int *ctr = s->at<int>(s->off_peerctr);
+    const int one = 1;
+    VP_CUDA(cudaMemcpyAsync(ctr + 1, &one, sizeof(int), cudaMemcpyHostToDevice, st), "first-launch flag");
+    DecideArgs d;
+    d.g = s->g;
+    d.state = s->at<ProbState>(s->off_state);
+    d.sums = nullptr;
+    d.known0 = s->at<double>(s->off_known0);
+    d.known = s->at<double>(s->off_known);
+    d.delta_out = nullptr;
+    d.n_active = s->at<int>(s->off_counters) + kCntActiveProblems;
+    d.max_iter = prm->max_iter;
+    d.auto_terminate = prm->auto_terminate;
+    d.threshold = prm->threshold;
+    d.all_cells = 0;
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    const int kDepth = 4;                          // launches the host stays ahead of the device
+    const int64_t budget = 2 * (int64_t)prm->max_iter + 8;
+    int64_t n = 0;
+    bool done = false;
+    while (n < budget && !done) {
+        rc = step_begin_impl(s, stream, nullptr, false);          // sweep + local per-sweep sums
+        if (rc != VPINT_OK) return rc;
+        VP_CUDA(launch_peer_commit(d, s->at<double>(s->off_sums), s->peer, ctr, s->d_ring, st, &s->launches), "peer commit");
+        VP_CUDA(launch_peer_halo(s->g, d.state, bufs, s->peer, s->g.KB, ctr, s->at<int>(s->off_flags) + 4, st, &s->launches),
+                "peer halo");
+        s->first_step_pending = false;
+        ++n;
+        ++s->peer_t;
+        if (n > kDepth) {
+            // the count the launch peer_t - kDepth left behind (every rank reads the same value: same decisions)
+            const unsigned want = (unsigned)(s->peer_t - kDepth);
+            volatile unsigned long long *slot = s->h_ring + ((want - 1u) & 63u);
+            unsigned long long v;
+            int spins = 0;
+            while ((unsigned)((v = *slot) >> 32) != want) {
+                if (++spins > 64) {
+                    spins = 0;
+                    if (cudaStreamQuery(st) == cudaSuccess && (unsigned)((v = *slot) >> 32) != want)
+                        return fail(VPINT_ERR_INVALID, "internal error: sharded loop lost its launch record");
+                }
+            }
+            if ((unsigned)(v & 0xffffffffu) == 0u) done = true;
+        }
+    }
+    VP_CUDA(cudaStreamSynchronize(st), "sharded run sync");
+    if (launches_out) *launches_out = n;
+    if (!done) {
+        int left = 0;
+        VP_CUDA(cudaMemcpy(&left, d.n_active, sizeof(int), cudaMemcpyDeviceToHost), "read active count");
+        if (left > 0) return fail(VPINT_ERR_INVALID, "internal error: sharded loop did not terminate within its launch budget");
+    }
     return VPINT_OK;
 }
 

@@ -214,6 +214,24 @@ cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *c
 cudaError_t launch_prepare_reduce(const Geom &g, const double *rowpart, double *known0, double *known, ProbState *state,
                                   int *counters, cudaStream_t st, int64_t *launches);
 
+// ---- row shards over peer-mapped memory (vpint_setup.cu) -----------------------
+// Layout of every rank's peer block (symmetric memory; vpint_solver_peer_bytes):
+//   [0, 4 msg)                       halo receive slots: [2 exchanges by parity][from above, from below][P][rows][pitch] fp64
+//   [4 msg, +256)                    halo flags: int at +0 (from above), int at +128 (from below)
+//   then [2 slots by parity][world][P * 4] doubles   per-sweep sums of every rank ("gather")
+//   then [world] ints, 128 bytes apart               sequence number of the last sums rank r pushed
+constexpr int kPeerMaxWorld = 16;
+struct PeerCtx {
+    int world, rank;
+    char *base[kPeerMaxWorld];        // every rank's peer block, mapped into this process
+    size_t off_gather, off_sflag, msg_bytes;
+    int up, down;                     // row neighbours (-1 = none)
+};
+cudaError_t launch_peer_commit(const DecideArgs &a, const double *my_sums, const PeerCtx &pc, int *ctr,
+                               unsigned long long *host_ring, cudaStream_t st, int64_t *launches);
+cudaError_t launch_peer_halo(const Geom &g, const ProbState *state, void *const *buf, const PeerCtx &pc, int rows, const int *ctr,
+                             int *tickets, cudaStream_t st, int64_t *launches);
+
 // ---- device helpers -------------------------------------------------------
 #if defined(__CUDACC__)
 

@@ -746,6 +746,135 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(Geom g, const ProbState 
     for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dstrow[e] = __ldcv(in + e);
 }
 
+// The whole reduction + stop decision + commit of one launch of a row-sharded run, without a collective library: every
+// rank stores its per-sweep sums into every rank's peer block (plain stores over NVLink + one flag per source rank), and
+// adds the `world` contributions up in rank order -- the same order on every rank, so all ranks take the same decision.
+// Launch t (lifetime counter ctr[0]):  wait for the sums of launch t - 1 from every rank; decide on sweep t - 1 (a stop
+// = sweep t is not committed, see lagged_commit_kernel); commit sweep t; publish the sums of sweep t; count the launch;
+// report "problems still running" to the host through mapped pinned memory (tagged with the launch number, so that the
+// host polls without events or copies).  One block.
+__global__ void __launch_bounds__(256) peer_commit_kernel(Geom g, ProbState *state, const double *__restrict__ my_sums,
+                                                          const double *__restrict__ known0, const double *__restrict__ known,
+                                                          int *n_active, int max_iter, int auto_terminate, double threshold,
+                                                          PeerCtx pc, int *ctr, unsigned long long *host_ring) {
+    const int t = ctr[0], first = ctr[1];
+    const int tid = threadIdx.x;
+    const size_t slot_elems = (size_t)pc.world * g.P * kSumSlots;
+    char *mine = pc.base[pc.rank];
+    if (!first && tid < pc.world) {
+        const int *flag = reinterpret_cast<const int *>(mine + pc.off_sflag + (size_t)tid * 128);
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v < t);
+    }
+    __syncthreads();
+    const double *prev = reinterpret_cast<const double *>(mine + pc.off_gather) + (size_t)((t - 1) & 1) * slot_elems;
+    for (int p = tid; p < g.P; p += blockDim.x) {
+        ProbState st = state[p];
+        if (st.status != 0 || st.k_run == 0) continue;
+        bool stop = false;
+        if (!first) {
+            double S[kSumSlots] = {0.0, 0.0, 0.0, 0.0};
+            for (int r = 0; r < pc.world; ++r) {
+                const double *q = prev + ((size_t)r * g.P + p) * kSumSlots;
+#pragma unroll
+                for (int i = 0; i < kSumSlots; ++i) S[i] += __ldcv(q + i);
+            }
+            const double *K = (st.fresh ? known0 : known) + (size_t)p * kSumSlots;
+            const double s_abs = S[0] + K[0], s_old = S[1] + K[1];
+            const double n_abs = g.n_cells - (S[2] + K[2]), n_old = g.n_cells - (S[3] + K[3]);
+            const double delta = (s_abs / n_abs) / (s_old / n_old);
+            st.fresh = 0;
+            stop = auto_terminate && delta <= threshold;
+        }
+        if (stop) {
+            st.status = 1; st.k_run = 0;
+            atomicSub(n_active, 1);
+        } else {
+            st.iters_done += 1;
+            st.cur ^= 1;
+            if (st.iters_done >= max_iter) {
+                st.status = 1; st.k_run = 0; st.fresh = 0;
+                atomicSub(n_active, 1);
+            }
+        }
+        state[p] = st;
+    }
+    // publish the sums of sweep t
+    const int n_mine = g.P * kSumSlots;
+    for (int idx = tid; idx < pc.world * n_mine; idx += blockDim.x) {
+        const int r = idx / n_mine, e = idx - r * n_mine;
+        double *dst = reinterpret_cast<double *>(pc.base[r] + pc.off_gather) + (size_t)(t & 1) * slot_elems + (size_t)pc.rank * n_mine;
+        dst[e] = my_sums[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pc.world) {
+        int *flag = reinterpret_cast<int *>(pc.base[tid] + pc.off_sflag + (size_t)pc.rank * 128);
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(t + 1) : "memory");
+    }
+    if (tid == 0) {
+        ctr[0] = t + 1;
+        ctr[1] = 0;
+        const int left = *reinterpret_cast<volatile int *>(n_active);
+        *reinterpret_cast<volatile unsigned long long *>(host_ring + ((unsigned)t & 63u)) =
+            ((unsigned long long)(unsigned)(t + 1) << 32) | (unsigned)(left < 0 ? 0 : left);
+    }
+}
+
+// Halo rows of the new state to both row neighbours and the neighbours' rows into the halo rows, one launch (push
+// blocks as halo_push_kernel, pull blocks as halo_pull_kernel); the exchange number is the launch counter
+// peer_commit_kernel has just advanced.  Pull blocks wait for stores of ANOTHER GPU only, and come after all push
+// blocks in dispatch order, so they cannot starve the pushes the neighbour is waiting for.
+__global__ void __launch_bounds__(256) peer_halo_kernel(Geom g, const ProbState *__restrict__ state, double *buf0, double *buf1,
+                                                        PeerCtx pc, int rows, const int *__restrict__ ctr, int *tickets) {
+    const int seq = ctr[0];
+    const int slot = seq & 1;
+    const int n = g.P * rows;
+    // blocks [0, 2n) push, blocks [2n, 4n) pull: every push block is dispatched before any (spinning) pull block
+    const bool pull = (int)blockIdx.x >= 2 * n;
+    const int side = ((int)blockIdx.x / n) & 1;       // 0: the upper neighbour, 1: the lower neighbour
+    const int b = (int)blockIdx.x % n;
+    const int nb = side ? pc.down : pc.up;
+    if (nb < 0) return;
+    const int p = b / rows, r = b - p * rows;
+    const size_t msg = pc.msg_bytes, row_off = ((size_t)p * rows + r) * g.pitch;
+    double *cur = state[p].cur ? buf1 : buf0;
+    if (!pull) {
+        // my first owned rows -> the upper neighbour's "from below" slot; my last owned rows -> the lower one's "from above"
+        double *dst = reinterpret_cast<double *>(pc.base[nb] + (size_t)(2 * slot + (side ? 0 : 1)) * msg) + row_off;
+        int *flag = reinterpret_cast<int *>(pc.base[nb] + 4 * msg + (side ? 0 : 128));
+        const int first = side ? g.own_row0 + g.own_rows - rows : g.own_row0;
+        const double *src = cur + ((size_t)p * g.H + first + r) * g.pitch;
+        for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dst[e] = src[e];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int done = atomicAdd(&tickets[side], 1);
+            if (done == n - 1) {
+                tickets[side] = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+            }
+        }
+    } else {
+        char *mine = pc.base[pc.rank];
+        const double *in = reinterpret_cast<const double *>(mine + (size_t)(2 * slot + side) * msg) + row_off;
+        const int *flag = reinterpret_cast<const int *>(mine + 4 * msg + (side ? 128 : 0));
+        if (threadIdx.x == 0) {
+            int v;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            } while (v < seq);
+        }
+        __syncthreads();
+        const int first = side ? g.own_row0 + g.own_rows : g.own_row0 - rows;
+        double *dstrow = cur + ((size_t)p * g.H + first + r) * g.pitch;
+        for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dstrow[e] = __ldcv(in + e);
+    }
+}
+
 }  // namespace
 
 #define VP_LAUNCH_CHECK()                         \
@@ -958,6 +1087,23 @@ cudaError_t launch_halo_pull(const Geom &g, const ProbState *state, void *const 
     halo_pull_kernel<<<dim3((unsigned)((int64_t)g.P * rows), 2), 256, 0, st>>>(
         g, state, (double *)buf[0], (double *)buf[1], (const double *)src_up, (const double *)src_down, flag_up, flag_down, rows,
         seq);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_peer_commit(const DecideArgs &a, const double *my_sums, const PeerCtx &pc, int *ctr,
+                               unsigned long long *host_ring, cudaStream_t st, int64_t *launches) {
+    peer_commit_kernel<<<1, 256, 0, st>>>(a.g, a.state, my_sums, a.known0, a.known, a.n_active, a.max_iter, a.auto_terminate,
+                                          a.threshold, pc, ctr, host_ring);
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_peer_halo(const Geom &g, const ProbState *state, void *const *buf, const PeerCtx &pc, int rows, const int *ctr,
+                             int *tickets, cudaStream_t st, int64_t *launches) {
+    if (pc.up < 0 && pc.down < 0) return cudaSuccess;
+    peer_halo_kernel<<<(unsigned)(4 * (int64_t)g.P * rows), 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], pc, rows,
+                                                                         ctr, tickets);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -468,6 +468,23 @@ class Solver:
             self._h, int(rows), C.c_void_p(from_up or None), C.c_void_p(flag_up or None), C.c_void_p(from_down or None),
             C.c_void_p(flag_down or None), int(seq), self._stream()), "vpint_solver_halo_pull")
 
+    def peer_bytes(self, world):
+        return int(self.lib.vpint_solver_peer_bytes(self._h, int(world)))
+
+    def peer_bind(self, world, rank, base_ptrs):
+        """base_ptrs: every rank's peer block (device pointers valid in THIS process), in rank = row order."""
+        arr = (C.c_void_p * int(world))(*[C.c_void_p(int(p)) for p in base_ptrs])
+        N.check(self.lib, self.lib.vpint_solver_peer_bind(self._h, int(world), int(rank), arr), "vpint_solver_peer_bind")
+
+    def run_sharded(self, max_iter, auto_terminate=True, threshold=1e-4, clip_val=math.inf):
+        """The row-sharded loop inside the library (after :meth:`peer_bind`; known-cell sums already all-reduced).
+        Blocks until every problem has stopped on every rank; returns the launch groups issued."""
+        prm = self._params(max_iter, auto_terminate, threshold, clip_val, False, N.LOOP_CHUNKED, 0)
+        n = C.c_int64(0)
+        N.check(self.lib, self.lib.vpint_solver_run_sharded(self._h, C.byref(prm), self._stream(), C.byref(n)),
+                "vpint_solver_run_sharded")
+        return int(n.value)
+
     def result(self, out=None, dtype=None):
         """Current state of every problem gathered into ``out`` (same layouts as
         :meth:`load` accepts).  Returns (out, sweeps[int32, nprob])."""

@@ -111,6 +111,12 @@ def run_sharded_lagged(engine, shard, comm, max_iter, poll_every=8):
         engine.comm = comm
     if shard.world > 1 and hasattr(comm, "dist") and not getattr(engine, "peer_tried", False):
         engine.setup_peer(comm)
+    if engine.peer is not None and engine.peer.get("bound"):
+        # the whole loop inside the library: no collective library and no Python between the launches
+        comm.all_reduce_sum(engine.known())
+        if engine.s.any_dirty:
+            raise VPintError("a row-sharded run needs a start state that equals the original on known cells")
+        return engine.s.run_sharded(max_iter, **engine.kw)
     comm.all_reduce_sum(engine.known())
     engine.begin(max_iter)
     if max_iter <= 0:
@@ -378,11 +384,12 @@ class SolverEngine:
             import torch.distributed._symmetric_memory as symm_mem
             pitch = self.s.state_tensor(0).shape[-1]
             msg = self.s.nprob * self.rows * pitch * 8
-            buf = symm_mem.empty(4 * msg + 256, dtype=torch.uint8, device=self.s.device)
+            nbytes = self.s.peer_bytes(self.shard.world)      # halo slots + flags (the layout used below), then the sums
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.s.device)
             hdl = symm_mem.rendezvous(buf, comm.group if comm.group is not None else dist.group.WORLD)
             buf.zero_()
             ptrs = [int(p) for p in hdl.buffer_ptrs]
-            self.peer = dict(buf=buf, hdl=hdl, msg=msg, ptrs=ptrs, seq=0)
+            self.peer = dict(buf=buf, hdl=hdl, msg=msg, ptrs=ptrs, seq=0, bound=False)
         except Exception as exc:                      # noqa: BLE001 -- any failure means "not available here"
             self.peer_error = "%s: %s" % (type(exc).__name__, exc)
             ok = 0
@@ -393,6 +400,9 @@ class SolverEngine:
             self.peer = None
             return False
         comm.dist.barrier(group=comm.group)            # every rank has zeroed its flags before anyone pushes
+        if os.environ.get("VPINT_SHARD_CLOOP", "1") != "0" and self.rows == 1:
+            self.s.peer_bind(self.shard.world, self.shard.rank, self.peer["ptrs"])
+            self.peer["bound"] = True
         return True
 
     def halo_exchange(self, push_only=False, pull_only=None):
