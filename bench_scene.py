@@ -60,6 +60,27 @@ def scene_rows(lo, hi, Hs, Ws, B, seed, dev, n_discs, rad_scale=1.0):
     return target, feats, cloud.to(torch.uint8)
 
 
+def scene_cloud_rows(Hs, Ws, seed, B, n_discs, rad_scale=1.0):
+    """Cloudy pixels per row of the synthetic scene (what a caller reads off the cloud mask before it deals the rows
+    out): the discs of :func:`scene_rows`, rasterised row by row on the host -- only their row extents are needed."""
+    rng = np.random.default_rng(seed)
+    rng.uniform(0, 1, (B, 6, 5))
+    discs = rng.uniform(0, 1, (n_discs, 3))
+    y = np.arange(Hs) / Hs
+    x = np.arange(Ws) / Ws
+    counts = np.zeros(Hs, dtype=np.int64)
+    for y0 in range(0, Hs, 512):
+        yy = y[y0:y0 + 512, None]
+        cloud = np.zeros((yy.shape[0], Ws), dtype=bool)
+        for cy, cx, r in discs:
+            rad = rad_scale * (100.0 + 500.0 * r) / 10980.0
+            if abs(cy - y[y0]) > rad + 512.0 / Hs and abs(cy - y[min(y0 + 511, Hs - 1)]) > rad + 512.0 / Hs:
+                continue
+            cloud |= (yy - cy) ** 2 + (x[None, :] - cx) ** 2 < rad * rad
+        counts[y0:y0 + 512] = cloud.sum(axis=1)
+    return counts
+
+
 class _LocalComm:
     """Comm of a single process (nothing to exchange)."""
     world, rank = 1, 0
@@ -75,10 +96,16 @@ def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, war
     target, feats, cloud = scene_rows(shard.lo, shard.hi, Hs, Ws, B, seed, dev, discs, rad_scale)
     solver, eng = open_shard_raw(target, feats, cloud, shard, comm, opts, k_block=kb)
     try:
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
         def step():
+            marks[0].record()
             stage_shard_raw(solver, target, feats, cloud, comm, eng.fill_scratch)
+            marks[1].record()
             launches = run_sharded(eng, shard, comm, opts["iterations"], poll_every=poll)
+            marks[2].record()
             pred, sweeps = shard_result(solver, shard)
+            marks[3].record()
             return pred, sweeps, launches
         for _ in range(warmup):
             step()
@@ -97,8 +124,10 @@ def _solve_rows(shard, comm, Hs, Ws, B, seed, dev, discs, opts, kb, steps=1, war
         ms = e0.elapsed_time(e1) / max(steps, 1)
         own = slice(shard.own_row0, shard.own_row0 + shard.own_rows)
         cloud_cells = float(cloud[own].sum().item())
+        phases = {"mean_init_and_load": marks[0].elapsed_time(marks[1]), "sweeps": marks[1].elapsed_time(marks[2]),
+                  "result": marks[2].elapsed_time(marks[3])}
         tiles = (solver.active_tiles, solver.total_tiles, "peer stores + flag (symmetric memory)" if eng.peer is not None else
-                 ("NCCL send/recv" if comm.world > 1 else "none"), getattr(eng, "peer_error", None))
+                 ("NCCL send/recv" if comm.world > 1 else "none"), getattr(eng, "peer_error", None), phases)
     finally:
         solver.close()
     return pred, sweeps, launches, ms, cloud_cells, tiles
@@ -179,9 +208,16 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
 
     # ---- the full scene ---------------------------------------------------------------------------------------
     if size > 0:
-        shard = RowShard(size, world, rank, halo=kb if world > 1 else 0)
+        bounds = None
+        if world > 1 and os.environ.get("VPINT_EQUAL_ROWS", "0") != "1":
+            # rows dealt by WORK: the unknown cells of a row (read off the cloud mask) + a little for its set-up cost
+            from vpint_b200.sharded import balanced_bounds
+            counts = scene_cloud_rows(size, size, seed, bands, discs)
+            bounds = balanced_bounds(counts + 0.02 * size, world, min_rows=max(kb, 16))
+        shard = RowShard(size, world, rank, halo=kb if world > 1 else 0, bounds=bounds)
         pred, sweeps, launches, ms, cloud_cells, tiles = _solve_rows(shard, comm, size, size, bands, seed, dev, discs, opts, kb,
                                                                      steps=steps, warmup=1)
+        phases = {k: round(v, 3) for k, v in tiles[4].items()}
         ok = bool(torch.isfinite(pred).all().item())
         del pred
         t = torch.tensor([ms, cloud_cells, 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
@@ -200,6 +236,8 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
                          "ms": ms, "steps": steps, "value": pxit / (ms * 1e-3) / 1e6, "unit": "Mpx*it/s", "scaling": "strong",
                          "sweeps_per_band": [int(v) for v in sweeps], "launches": int(launches), "cloud_fraction": round(frac, 4),
                          "rows_rank0": shard.own_rows, "halo": shard.halo, "finite": ok,
+                         "row_partition": "by work (unknown cells per row)" if bounds is not None else "equal rows",
+                         "row_bounds": bounds, "phases_ms_rank0": phases,
                          "active_tiles_rank0": tiles[0], "total_tiles_rank0": tiles[1], "halo_rows": tiles[2],
                          "halo_fallback_reason": tiles[3],
                          "protocol": "stop decision lags one sweep (all-reduce overlaps the next sweep)" if os.environ.get("VPINT_SHARD_LAGGED", "1") != "0" else "all-reduce and decision every sweep",

@@ -30,15 +30,23 @@ class RowShard:
     band inside the local slice; ``row_offset`` (= ``lo``) global row of local row 0.
     """
 
-    def __init__(self, H, world, rank, halo):
+    def __init__(self, H, world, rank, halo, bounds=None):
+        """``bounds``: world + 1 ascending row indices (0 ... H) = a partition by WORK instead of by rows, see
+        :func:`balanced_bounds`; every rank must pass the same list."""
         if world < 1 or not (0 <= rank < world):
             raise VPintError("bad rank / world size")
         if H < world:
             raise VPintError("fewer rows than ranks")
         base, rem = divmod(int(H), int(world))
         self.H, self.world, self.rank, self.halo = int(H), int(world), int(rank), int(halo)
-        self.r0 = rank * base + min(rank, rem)
-        self.r1 = self.r0 + base + (1 if rank < rem else 0)
+        if bounds is not None:
+            bounds = [int(b) for b in bounds]
+            if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != H or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+                raise VPintError("bounds must be world + 1 strictly ascending row indices from 0 to H")
+            self.r0, self.r1 = bounds[rank], bounds[rank + 1]
+        else:
+            self.r0 = rank * base + min(rank, rem)
+            self.r1 = self.r0 + base + (1 if rank < rem else 0)
         self.lo = max(0, self.r0 - halo)
         self.hi = min(self.H, self.r1 + halo)
         self.own_row0 = self.r0 - self.lo
@@ -60,6 +68,30 @@ class RowShard:
 
     def owned(self, local):
         return local[self.own_row0:self.own_row0 + self.own_rows]
+
+
+def balanced_bounds(row_weights, world, min_rows=1):
+    """Row boundaries (world + 1 indices) that give every rank about the same WORK instead of the same number of rows.
+
+    A sweep touches the unknown cells only and the ranks of a row-sharded run move in lockstep (halo exchange every
+    sweep), so the rank with the most unknown cells sets the pace: with equal row bands one cloud bank can leave a
+    rank with 1.2 - 1.5x the average work.  ``row_weights``: per-row cost, e.g. the unknown cells of a row (from the
+    cloud mask) plus a small constant for the per-row set-up cost."""
+    w = np.asarray(row_weights, dtype=np.float64)
+    H = w.shape[0]
+    if H < world * min_rows:
+        raise VPintError("fewer rows than ranks")
+    cw = np.cumsum(w)
+    if not cw[-1] > 0:
+        cw = np.arange(1, H + 1, dtype=np.float64)
+    bounds = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(cw, cw[-1] * r / world)) + 1
+        b = max(b, bounds[-1] + min_rows)
+        b = min(b, H - (world - r) * min_rows)
+        bounds.append(b)
+    bounds.append(H)
+    return bounds
 
 
 class Comm:
