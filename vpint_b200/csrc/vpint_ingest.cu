@@ -8,7 +8,7 @@
 //
 //   cloud_mask_kernel      mask > threshold                                   (VPint2.py:122-132)
 //   footprint / dilate_*   cloud buffering as a separable dilation            (VPint2.py:135-150, :146 quirk kept)
-//   fill_leaf_kernel, fill_combine_kernel
+//   fill_leaf_kernel, fill_subtree_kernel, fill_top_kernel
 //                          np.nanmean of every band in the interpolator's dtype, NumPy's pairwise summation
 //                          tree reproduced bit for bit for ANY grid size (MRP.py:73-77); row shards compute the
 //                          leaves they own and all-reduce the leaf sums
@@ -235,42 +235,48 @@ __device__ TAcc subtree_sum(const TAcc *__restrict__ leaf_sum, int64_t a0, int64
     return ret;
 }
 
-// One block per band problem.  The tree is cut at depth D (2^D subtrees, each far above leaf size): thread t sums
-// subtree t sequentially, then thread 0 combines the 2^D sums along the top of the tree.  fill = dtype(double(sum) /
-// count), as np.nanmean forms it for a float32 grid (float64 division, result cast back).
+// The tree is cut at depth D (2^D subtrees, each far above leaf size).  fill_subtree_kernel: one thread per subtree
+// sums its leaves sequentially in recursion order.  fill_top_kernel: one block per band problem adds the 2^D subtree
+// sums level by level -- above depth D every range still splits, so that part of the tree is a complete binary tree
+// and node i of a level is node 2i + node 2i+1 of the level below -- and forms
+// fill = dtype(double(sum) / count), as np.nanmean does for a float32 grid (float64 division, result cast back).
+constexpr int kFillMaxDepth = 14;
+
 template <typename TAcc>
-__global__ void __launch_bounds__(256) fill_combine_kernel(const TAcc *__restrict__ leaf_sum,
-                                                           const unsigned long long *__restrict__ count, int64_t n,
-                                                           int64_t n_chunks, int D, double *__restrict__ fill) {
-    __shared__ TAcc part[1024];
+__global__ void __launch_bounds__(128) fill_subtree_kernel(const TAcc *__restrict__ leaf_sum, int64_t n, int64_t n_chunks, int D,
+                                                           TAcc *__restrict__ part) {
     const int p = blockIdx.x;
-    const TAcc *ls = leaf_sum + (size_t)p * n_chunks;
-    const int n_sub = 1 << D;
-    for (int t = threadIdx.x; t < n_sub; t += blockDim.x) {
-        int64_t a = 0, len = n;
-        for (int d = D - 1; d >= 0; --d) {
-            int64_t h = len / 2;
-            h -= h % 8;
-            if ((t >> d) & 1) { a += h; len -= h; }
-            else len = h;
-        }
-        part[t] = subtree_sum<TAcc>(ls, a, len);
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    if (t >= (1 << D)) return;
+    int64_t a = 0, len = n;
+    for (int d = D - 1; d >= 0; --d) {
+        int64_t h = len / 2;
+        h -= h % 8;
+        if ((t >> d) & 1) { a += h; len -= h; }
+        else len = h;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // post-order over the complete binary tree of depth D: parts are in left-to-right order
-        TAcc st_acc[16];
-        int st_state[16];
-        int sp = 0, next = 0;                              // sp = depth of the node on top of the stack
-        st_state[0] = 0;
-        TAcc ret = (TAcc)0;
-        while (sp >= 0) {
-            if (sp == D) { ret = part[next++]; --sp; continue; }
-            if (st_state[sp] == 0) { st_state[sp] = 1; ++sp; st_state[sp] = 0; }
-            else if (st_state[sp] == 1) { st_acc[sp] = ret; st_state[sp] = 2; ++sp; st_state[sp] = 0; }
-            else { ret = st_acc[sp] + ret; --sp; }
+    part[((size_t)p << D) + t] = subtree_sum<TAcc>(leaf_sum + (size_t)p * n_chunks, a, len);
+}
+
+template <typename TAcc>
+__global__ void __launch_bounds__(1024) fill_top_kernel(TAcc *__restrict__ part, const unsigned long long *__restrict__ count,
+                                                        int D, double *__restrict__ fill) {
+    const int p = blockIdx.x;
+    TAcc *v = part + ((size_t)p << D);
+    for (int lvl = D - 1; lvl >= 0; --lvl) {
+        const int nodes = 1 << lvl;
+        // node i <- node 2i + node 2i+1: read both children before anyone overwrites them
+        for (int i0 = 0; i0 < nodes; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            TAcc sum = (TAcc)0;
+            if (i < nodes) sum = v[2 * i] + v[2 * i + 1];
+            __syncthreads();
+            if (i < nodes) v[i] = sum;
+            __syncthreads();
         }
-        const TAcc total = (TAcc)0 + ret;                                // add.reduce starts from the identity
+    }
+    if (threadIdx.x == 0) {
+        const TAcc total = (TAcc)0 + v[0];                               // add.reduce starts from the identity
         fill[p] = (double)(TAcc)((double)total / (double)count[p]);
     }
 }
@@ -539,10 +545,13 @@ cudaError_t launch_buffer_clouds(const void *target, int dtype, uint8_t *cloud, 
     return cudaSuccess;
 }
 
+// scratch: [leaf sums: n_prob x n_chunks][known-cell counts: n_prob x uint64][subtree sums: n_prob x 2^kFillMaxDepth]
 size_t fill_general_scratch_bytes(int64_t n, int n_prob, int acc_dtype) {
     const int64_t n_chunks = (n + 63) / 64;
     const size_t esz = (acc_dtype == VPINT_F64) ? 8 : 4;
-    return (size_t)n_prob * n_chunks * esz + 256 + (size_t)n_prob * sizeof(unsigned long long) + 256;
+    const size_t leaf_bytes = ((size_t)n_prob * n_chunks * esz + 255) / 256 * 256;
+    const size_t count_bytes = ((size_t)n_prob * sizeof(unsigned long long) + 255) / 256 * 256;
+    return leaf_bytes + count_bytes + ((size_t)n_prob << kFillMaxDepth) * esz + 256;
 }
 
 // Leaf sums of the leaves this shard owns (zeros elsewhere) + known-cell counts.  leaf_sum / count live in `scratch`.
@@ -590,12 +599,20 @@ cudaError_t launch_fill_combine(int acc_dtype, int n_prob, int64_t n, void *scra
     const size_t esz = (acc_dtype == VPINT_F64) ? 8 : 4;
     const size_t leaf_bytes = ((size_t)n_prob * n_chunks * esz + 255) / 256 * 256;
     const unsigned long long *count = reinterpret_cast<const unsigned long long *>(static_cast<char *>(scratch) + leaf_bytes);
+    const size_t count_bytes = ((size_t)n_prob * sizeof(unsigned long long) + 255) / 256 * 256;
+    void *part = static_cast<char *>(scratch) + leaf_bytes + count_bytes;
     int D = 0;
-    while (D < 10 && (n >> (D + 1)) >= 4096) ++D;          // subtrees of >= 4096 cells: far above leaf size
-    if (acc_dtype == VPINT_F64)
-        fill_combine_kernel<double><<<n_prob, 256, 0, st>>>((const double *)scratch, count, n, n_chunks, D, fill_dev);
-    else
-        fill_combine_kernel<float><<<n_prob, 256, 0, st>>>((const float *)scratch, count, n, n_chunks, D, fill_dev);
+    while (D < kFillMaxDepth && (n >> (D + 1)) >= 2048) ++D;        // subtrees of >= 2048 cells: far above leaf size
+    const dim3 grid((unsigned)n_prob, (unsigned)(((1 << D) + 127) / 128));
+    if (acc_dtype == VPINT_F64) {
+        fill_subtree_kernel<double><<<grid, 128, 0, st>>>((const double *)scratch, n, n_chunks, D, (double *)part);
+        VP_LAUNCH_CHECK();
+        fill_top_kernel<double><<<n_prob, 1024, 0, st>>>((double *)part, count, D, fill_dev);
+    } else {
+        fill_subtree_kernel<float><<<grid, 128, 0, st>>>((const float *)scratch, n, n_chunks, D, (float *)part);
+        VP_LAUNCH_CHECK();
+        fill_top_kernel<float><<<n_prob, 1024, 0, st>>>((float *)part, count, D, fill_dev);
+    }
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
