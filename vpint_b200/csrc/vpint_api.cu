@@ -101,6 +101,7 @@ struct vpint_solver {
     size_t off_peerctr = 0;           // int[2]: lifetime launch counter of the sharded loop, first-launch-of-a-run flag
     unsigned long long *h_ring = nullptr, *d_ring = nullptr;   // mapped pinned ring: (launch << 32) | problems still running
     int peer_t = 0;                   // host mirror of the launch counter
+    size_t off_rowchunk = 0;          // fused load of long rows: per-chunk partials of the known-cell row sums
     size_t off_trial = 0;             // double[3][P]: per-problem beta, epsilon, mu of batched search trials
     bool trial_beta = false, trial_res = false;
     size_t off_cls = 0;               // int[P] class of every problem, int[32]: [0..8] problems per class, [16..24] class queues
@@ -269,6 +270,10 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_cls = take(((size_t)g.P + 32) * sizeof(int));
     s->off_trial = take(3 * (size_t)g.P * sizeof(double));
     s->off_peerctr = take(4 * sizeof(int));
+    {
+        const int xc = (g.ndim == 2) ? ingest_row_chunks(g) : 1;
+        s->off_rowchunk = (xc > 1) ? take((size_t)g.P * g.H * xc * 3 * sizeof(double)) : 0;
+    }
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
     s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
@@ -1046,7 +1051,8 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
                                 s->at<double>(s->off_fill), s->at<double>(s->off_buf[0]),
                                 skip_b ? nullptr : s->at<double>(s->off_buf[1]), s->at<uint32_t>(s->off_mask),
                                 s->at<double>(s->off_w[4]), s->at<double>(s->off_rowpart), s->at<double>(s->off_extreme),
-                                s->at<int>(s->off_flags), p->out, p->out_dtype, p->out_stride, st, &s->launches),
+                                s->at<int>(s->off_flags), p->out, p->out_dtype, p->out_stride,
+                                s->off_rowchunk ? s->at<double>(s->off_rowchunk) : nullptr, st, &s->launches),
             "ingest bands");
     if (s->has_orig)
         VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_orig), s->at<void>(s->off_buf[0]),

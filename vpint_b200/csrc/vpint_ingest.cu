@@ -308,7 +308,23 @@ struct IngestArgs {
     int out_code;            // VPINT_F64 / VPINT_F32 / VPINT_U16
     Strides osd;
     int TW;
+    int XC;                  // column chunks per row (one warp each)
+    double *rowchunk;        // [P][H][XC][3] chunk partials when XC > 1
 };
+
+// rowpart of a row = its chunk partials added in chunk order (fixed order: the known-cell sums are reproducible).
+__global__ void __launch_bounds__(256) ingest_rowsum_kernel(int64_t n_rows_all, int XC, const double *__restrict__ rowchunk,
+                                                            double *__restrict__ rowpart) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows_all) return;
+    double s = 0.0, ninf = 0.0, nunk = 0.0;
+    for (int c = 0; c < XC; ++c) {
+        const double *rc = rowchunk + ((size_t)i * XC + c) * 3;
+        s += rc[0]; ninf += rc[1]; nunk += rc[2];
+    }
+    double *rp = rowpart + (size_t)i * 8;
+    rp[0] = 0.0; rp[1] = s; rp[2] = 0.0; rp[3] = 0.0; rp[4] = s; rp[5] = ninf; rp[6] = 0.0; rp[7] = nunk;
+}
 
 template <typename TIn, typename TAcc>
 __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const IngestArgs a) {
@@ -316,10 +332,16 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
     __shared__ double racc[kIngestWarps][kIngestMaxBands][2];           // per band: sum of known values, packed counts
     const Geom &g = a.g;
     const int B = g.Pin, W = g.L, TW = a.TW, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r = (int64_t)blockIdx.x * kIngestWarps + warp;
+    // a warp takes one of XC column chunks of one row (long rows of a scene are split so that there are enough warps)
+    const int64_t wid = (int64_t)blockIdx.x * kIngestWarps + warp;
     const int64_t n_rows = (int64_t)(g.P / B) * g.H;
-    if (r >= n_rows) return;
+    const int XC = a.XC;
+    if (wid >= n_rows * XC) return;
+    const int64_t r = wid / XC;
+    const int xc = (int)(wid - r * XC);
     const int po = (int)(r / g.H), y = (int)(r - (int64_t)po * g.H);
+    const int tiles = (g.pitch + TW - 1) / TW, per = (tiles + XC - 1) / XC;
+    const int x_begin = xc * per * TW, x_end = min(g.pitch, (xc + 1) * per * TW);
     TIn *my = reinterpret_cast<TIn *>(ing_raw) + (size_t)warp * TW * B;
     uint8_t *myc = ing_raw + (size_t)kIngestWarps * TW * B * sizeof(TIn) + (size_t)warp * TW;
     const int64_t row_elems = (int64_t)W * B;
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
     bool wild = false, bad = false, fwild = false, wide = false;
     for (int b = lane; b < B; b += 32) { racc[warp][b][0] = 0.0; racc[warp][b][1] = 0.0; }
     // the row goes through shared memory in tiles of TW pixels (one tile for the 256-pixel patches)
-    for (int x0 = 0; x0 < g.pitch; x0 += TW) {
+    for (int x0 = x_begin; x0 < x_end; x0 += TW) {
         const int tw = max(0, min(TW, W - x0));                          // pixels of this tile inside the grid
         const int te = min(TW, g.pitch - x0);                            // plane elements of this tile (incl. padding)
         __syncwarp();
@@ -406,9 +428,14 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
     for (int b = lane; b < B; b += 32) {
         const double sum_o = racc[warp][b][0];
         const long long counts = (long long)racc[warp][b][1];
-        double *rp = a.rowpart + ((size_t)(po * B + b) * g.H + y) * 8;
-        rp[0] = 0.0; rp[1] = sum_o; rp[2] = 0.0; rp[3] = 0.0;
-        rp[4] = sum_o; rp[5] = (double)(counts >> 16); rp[6] = 0.0; rp[7] = (double)(counts & 0xffff);
+        if (XC == 1) {
+            double *rp = a.rowpart + ((size_t)(po * B + b) * g.H + y) * 8;
+            rp[0] = 0.0; rp[1] = sum_o; rp[2] = 0.0; rp[3] = 0.0;
+            rp[4] = sum_o; rp[5] = (double)(counts >> 16); rp[6] = 0.0; rp[7] = (double)(counts & 0xffff);
+        } else {                                                        // chunk partials, added up in order by ingest_rowsum_kernel
+            double *rc = a.rowchunk + (((size_t)(po * B + b) * g.H + y) * XC + xc) * 3;
+            rc[0] = sum_o; rc[1] = (double)(counts >> 16); rc[2] = (double)(counts & 0xffff);
+        }
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(a.flags, 1);
     if (__any_sync(0xffffffffu, wide) && lane == 0) atomicExch(a.flags + 3, 1);
@@ -617,6 +644,17 @@ cudaError_t launch_fill_combine(int acc_dtype, int n_prob, int64_t n, void *scra
     return cudaSuccess;
 }
 
+// Column chunks per row: enough warps to fill the machine (a scene shard has ~10^3 long rows), one chunk for patches.
+int ingest_row_chunks(const Geom &g) {
+    const int TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
+    const int tiles = (g.pitch + TW - 1) / TW;
+    const int64_t n_rows = (int64_t)(g.P / g.Pin) * g.H;
+    int64_t want = (16384 + n_rows - 1) / n_rows;
+    if (want > tiles) want = tiles;
+    if (want > 16) want = 16;
+    return want < 1 ? 1 : (int)want;
+}
+
 bool ingest_bands_supported(const Geom &g, int t_dtype) {
     const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
     const int TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
@@ -628,7 +666,7 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, cudaStream_t st, int64_t *launches) {
+                                const int64_t *out_stride, double *rowchunk, cudaStream_t st, int64_t *launches) {
     IngestArgs a;
     a.g = g;
     a.target = target; a.features = features; a.cloud = cloud;
@@ -641,7 +679,10 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     a.TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
     const size_t smem = (size_t)kIngestWarps * a.TW * g.Pin * tsz + (size_t)kIngestWarps * a.TW;
     const int64_t n_rows = (int64_t)(g.P / g.Pin) * g.H;
-    const unsigned grid = (unsigned)((n_rows + kIngestWarps - 1) / kIngestWarps);
+    a.XC = ingest_row_chunks(g);
+    a.rowchunk = rowchunk;
+    if (a.XC > 1 && !rowchunk) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((n_rows * a.XC + kIngestWarps - 1) / kIngestWarps);
     cudaError_t e;
 #define VP_ING(TIN, TACC)                                                                                                \
     do {                                                                                                                 \
@@ -658,6 +699,11 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     else return cudaErrorInvalidValue;
 #undef VP_ING
     VP_LAUNCH_CHECK();
+    if (a.XC > 1) {
+        const int64_t n_all = (int64_t)g.P * g.H;
+        ingest_rowsum_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(n_all, a.XC, rowchunk, rowpart);
+        VP_LAUNCH_CHECK();
+    }
     return cudaSuccess;
 }
 

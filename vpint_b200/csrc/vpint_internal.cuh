@@ -208,7 +208,8 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, cudaStream_t st, int64_t *launches);
+                                const int64_t *out_stride, double *rowchunk, cudaStream_t st, int64_t *launches);
+int ingest_row_chunks(const Geom &g);
 cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,
                                   int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st, int64_t *launches);
 cudaError_t launch_prepare_reduce(const Geom &g, const double *rowpart, double *known0, double *known, ProbState *state,

@@ -5,6 +5,8 @@
 //   Per tile: {sum |new-old|, sum old, NaN counts} over unknown owned cells (VPint/SD_MRP.py:139).
 // These kernels serve k_block == 1 and the 3-D path; the temporally blocked 2-D kernel lives in
 // vpint_step_tb.cu.
+#include <cstdlib>
+
 #include "vpint_internal.cuh"
 
 namespace vpint {
@@ -173,6 +175,116 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_ratio_kernel(const StepArgs a
                 out[row + x + 1] = n1;
             }
         }
+    }
+    Acc<double> acc;
+    acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
+    write_partial(acc, a, p);
+}
+
+// The same sweep with a sliding window (the default; VPINT_RATIO_V1=1 selects the kernel above): a warp walks its 8 rows
+// top to bottom and keeps the rows above / at / below in registers, so every state row is loaded once per strip (10
+// row loads instead of 24), the left / right neighbours come from the adjacent lanes by shuffle (two edge loads per
+// row instead of 64), rows are skipped on WARP-uniform tests of the 64-bit mask words (no divergence), and tiles that
+// do not touch the grid border take a branch without neighbour counts.  Thread <-> cell mapping, arithmetic and
+// summation order are those of the kernel above: results are bit-identical.
+template <bool INTERIOR>
+__device__ __forceinline__ void ratio_strip(const StepArgs &a, const Geom &g, const double *__restrict__ in,
+                                            double *__restrict__ out, const double *__restrict__ fpl,
+                                            const uint64_t *__restrict__ m64, int mp64, int xw, int lane, int yb, int y_lim,
+                                            double &s_abs, double &s_old, int &c_abs, int &c_old) {
+    const int x = xw + 2 * lane;
+    // mask words of rows yb-1 .. yb+8 (this warp's 64 columns): lane i holds row yb-1+i
+    uint64_t mword = 0;
+    {
+        const int y = yb - 1 + lane;
+        if (lane < 10 && y >= g.own_row0 && y < y_lim) mword = m64[(size_t)y * mp64];
+    }
+    auto row_bits = [&](int r) { return __shfl_sync(0xffffffffu, mword, r + 1); };   // r = -1 .. 8
+    const bool lane_first = (lane == 0), lane_last = (lane == 31);
+    const bool has_left = xw > 0, has_right = xw + 64 < g.L;
+    double u0 = 0.0, u1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    uint64_t b_prev = 0, b_cur = row_bits(0), b_next = row_bits(1);
+    auto load_row = [&](int y, double &v0, double &v1) {
+        // rows outside the GLOBAL grid read as 0 (VPint/WP_MRP.py:291-308); halo rows of a shard are ordinary rows
+        const int yg = y + g.row_offset;
+        if (yg >= 0 && yg < g.global_H && y >= 0 && y < g.H) load2(in + (size_t)y * g.pitch + x, v0, v1);
+        else { v0 = 0.0; v1 = 0.0; }
+    };
+    if (b_cur) load_row(yb - 1, u0, u1);
+    if (b_cur | b_next) load_row(yb, c0, c1);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int y = yb + r;
+        if (y >= y_lim) break;                                 // warp-uniform
+        const uint64_t b_nn = (r + 2 <= 8) ? row_bits(r + 2) : 0ull;
+        // the row below is needed by this row, and as the centre / upper row of the next two
+        if (b_cur | b_next | b_nn) load_row(y + 1, d0, d1);
+        if (b_cur) {                                           // warp-uniform: some cell of this row strip is unknown
+            const size_t row = (size_t)y * g.pitch;
+            const unsigned mb = (unsigned)(b_cur >> (2 * lane)) & 3u;
+            double f0, f1;
+            load2(fpl + row + x, f0, f1);
+            double lf = __shfl_up_sync(0xffffffffu, c1, 1), rt = __shfl_down_sync(0xffffffffu, c0, 1);
+            if (lane_first) lf = has_left ? in[row + x - 1] : 0.0;
+            if (lane_last) rt = has_right ? in[row + x + 2] : 0.0;
+            double n0 = ((u0 + c1) + d0) + lf;
+            double n1 = ((u1 + rt) + d1) + c0;
+            if (INTERIOR) {
+                n0 *= 0.25; n1 *= 0.25;
+            } else {
+                const int yg = y + g.row_offset;
+                const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+                const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+                const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
+                n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
+                n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+            }
+            double v0 = f0 * n0, v1 = f1 * n1;
+            if (v0 > a.clip) { v0 = a.clip; n0 = a.clip / f0; }
+            if (v1 > a.clip) { v1 = a.clip; n1 = a.clip / f1; }
+            if (mb & 1u) {
+                const double o = f0 * c0, d = fabs(v0 - o);
+                if (d != d) ++c_abs; else s_abs += d;
+                if (o != o) ++c_old; else s_old += o;
+                out[row + x] = n0;
+            }
+            if (mb & 2u) {
+                const double o = f1 * c1, d = fabs(v1 - o);
+                if (d != d) ++c_abs; else s_abs += d;
+                if (o != o) ++c_old; else s_old += o;
+                out[row + x + 1] = n1;
+            }
+        }
+        u0 = c0; u1 = c1; c0 = d0; c1 = d1;
+        b_prev = b_cur; b_cur = b_next; b_next = b_nn;
+    }
+    (void)b_prev;
+}
+
+__global__ void __launch_bounds__(256) jacobi2d_k1_ratio2_kernel(const StepArgs a) {
+    const TileRef tile = a.tiles[blockIdx.x];
+    const int p = tile.p;
+    const ProbState st = a.state[p];
+    if (st.k_run == 0) return;
+    const Geom &g = a.g;
+    const size_t plane = (size_t)g.H * g.pitch;
+    const double *__restrict__ in = reinterpret_cast<const double *>(a.buf[st.cur]) + (size_t)p * plane;
+    double *__restrict__ out = reinterpret_cast<double *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const double *__restrict__ fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xw = tile.x0 + (warp & 1) * 64;
+    const int yb = tile.y0 + (warp >> 1) * 8;
+    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
+    double s_abs = 0.0, s_old = 0.0;
+    int c_abs = 0, c_old = 0;
+    if (xw < g.L && yb < y_lim) {
+        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
+        const int mp64 = g.mpitch >> 1;
+        // no cell of the tile on the border of the GLOBAL grid: every neighbour count is 4
+        const bool interior = (tile.y0 + g.row_offset > 0) && (tile.y0 + kTileH2 + g.row_offset < g.global_H) && (tile.x0 > 0) &&
+                              (tile.x0 + kTileW2 < g.L);
+        if (interior) ratio_strip<true>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
+        else ratio_strip<false>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
     }
     Acc<double> acc;
     acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
@@ -364,7 +476,9 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
 
 cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches) {
     if (n_tiles <= 0) return cudaSuccess;
-    jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    static const bool v1 = getenv("VPINT_RATIO_V1") != nullptr;
+    if (v1) jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    else jacobi2d_k1_ratio2_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
