@@ -101,6 +101,7 @@ struct vpint_solver {
     size_t off_peerctr = 0;           // int[2]: lifetime launch counter of the sharded loop, first-launch-of-a-run flag
     unsigned long long *h_ring = nullptr, *d_ring = nullptr;   // mapped pinned ring: (launch << 32) | problems still running
     int peer_t = 0;                   // host mirror of the launch counter
+    size_t off_partial8 = 0;          // per-warp partials of the ratio stencil (step API / sharded runs: no block barrier)
     size_t off_rowchunk = 0;          // fused load of long rows: per-chunk partials of the known-cell row sums
     size_t off_trial = 0;             // double[3][P]: per-problem beta, epsilon, mu of batched search trials
     bool trial_beta = false, trial_res = false;
@@ -262,6 +263,8 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
     s->off_tiles = take((size_t)s->tiles_total * sizeof(TileRef));
     s->off_tilestart = take((size_t)(g.P * g.S + 1) * sizeof(int));
     s->off_partial = take((size_t)s->tiles_total * g.KB * kSumSlots * sizeof(double));
+    if (g.ndim == 2 && g.KB == 1 && d->storage == VPINT_F64 && d->weight_mode == VPINT_W_PLANES && !getenv("VPINT_NO_WARP_PARTIALS"))
+        s->off_partial8 = take((size_t)s->tiles_total * 8 * kSumSlots * sizeof(double));
     s->off_sums = take((size_t)g.P * g.KB * kSumSlots * sizeof(double));
     s->off_flags = take(16 * sizeof(int));
     s->off_stage = take(reduce_stage_bytes(g));
@@ -633,6 +636,9 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
     a.gamma = s->at<double>(s->off_gamma);
     a.tau = s->at<double>(s->off_tau);
     a.partial = s->at<double>(s->off_partial);
+    // the ratio stencil of a launch whose sums are reduced by a separate kernel writes per-warp partials (no barrier)
+    static const bool ratio_v4 = !getenv("VPINT_RATIO_KERNEL") || atoi(getenv("VPINT_RATIO_KERNEL")) == 4;   // triage switch
+    a.partial8 = (use_ratio && !fused && s->off_partial8 && ratio_v4) ? s->at<double>(s->off_partial8) : nullptr;
     a.clip = s->prm.clip_val;
     a.no_nc = s->no_nc ? 1 : 0;
     a.resist = s->prm.resistance ? 1 : 0;
@@ -672,7 +678,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
         cudaEventDestroy(e1);
     }
     if (fused) return VPINT_OK;          // the last tile block of every problem has reduced and decided
-    VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), s->at<int>(s->off_tilestart),
+    VP_CUDA(launch_reduce_partials(s->g, s->at<double>(s->off_partial), a.partial8, s->at<int>(s->off_tilestart),
                                    s->at<ProbState>(s->off_state), s->at<double>(s->off_sums), s->at<double>(s->off_stage),
                                    s->prm.resistance != 0, st, &s->launches),
             "reduce partials");

@@ -65,6 +65,8 @@ struct StepArgs {
     const double *gamma;     // [P] scalar mode
     const double *tau;       // [P] scalar mode, 3-D
     double *partial;         // [tile][KB][kSumSlots]
+    double *partial8;        // [tile][8 warps][kSumSlots]: per-WARP partials of the ratio kernel when the caller reduces in
+                             // a separate launch (no block barrier in the stencil kernel); null = block partials
     double clip;
     int no_nc;               // 1: weights already carry the priority normalisation, no division by the neighbour count
     int resist;              // 1: resistance sweep over ALL cells (vpint_step_k1.cu, jacobi2d_resist_kernel)
@@ -164,7 +166,7 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
 cudaError_t launch_step3d(const StepArgs &a, int storage, int weight_mode, int64_t n_tiles, cudaStream_t st,
                           int64_t *launches);
 size_t reduce_stage_bytes(const Geom &g);
-cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
+cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const double *partial8, const int *tile_start,
                                    const ProbState *state, double *sums, double *stage, bool all_tiles,
                                    cudaStream_t st, int64_t *launches);
 cudaError_t launch_step2d_resist(const StepArgs &a, int storage, int weight_mode, cudaStream_t st, int64_t *launches);

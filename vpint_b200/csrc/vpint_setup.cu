@@ -464,8 +464,21 @@ __global__ void init_state_kernel(Geom g, ProbState *state, int *n_active, int m
     state[p] = st;
 }
 
+// Sum slot i of tile t (sweep j).  With per-warp partials the tile's value is formed first, the 8 warps added in order
+// -- exactly what the block reduction of a stencil kernel does -- so both forms give the same bits.
+__device__ __forceinline__ double tile_partial(const double *__restrict__ partial, const double *__restrict__ partial8, int KB,
+                                               int t, int j, int i) {
+    if (!partial8) return partial[((size_t)t * KB + j) * kSumSlots + i];
+    const double *q = partial8 + (size_t)t * 8 * kSumSlots + i;
+    double acc = q[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) acc += q[w * kSumSlots];
+    return acc;
+}
+
 // Block per problem: fixed-order sum of the per-tile partials of the sweeps this launch executed.
 __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const double *__restrict__ partial,
+                                                              const double *__restrict__ partial8,
                                                               const int *__restrict__ tile_start,
                                                               const ProbState *__restrict__ state,
                                                               double *__restrict__ sums, int all_tiles) {
@@ -484,9 +497,8 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const doub
         double acc[kSumSlots] = {0, 0, 0, 0};
         if (j < kr) {
             for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-                const double *q = partial + ((size_t)t * g.KB + j) * kSumSlots;
 #pragma unroll
-                for (int i = 0; i < kSumSlots; ++i) acc[i] += q[i];
+                for (int i = 0; i < kSumSlots; ++i) acc[i] += tile_partial(partial, partial8, g.KB, t, j, i);
             }
         }
         block_sum<kSumSlots>(acc, scratch);
@@ -502,6 +514,7 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Geom g, const doub
 constexpr int kReduceChunks = 64;
 
 __global__ void __launch_bounds__(128) reduce_partials_stage1_kernel(Geom g, const double *__restrict__ partial,
+                                                                     const double *__restrict__ partial8,
                                                                      const int *__restrict__ tile_start,
                                                                      const ProbState *__restrict__ state,
                                                                      double *__restrict__ stage, int all_tiles) {
@@ -517,9 +530,8 @@ __global__ void __launch_bounds__(128) reduce_partials_stage1_kernel(Geom g, con
         double acc[kSumSlots] = {0, 0, 0, 0};
         if (j < kr) {
             for (int t = a0 + threadIdx.x; t < a1; t += blockDim.x) {
-                const double *q = partial + ((size_t)t * g.KB + j) * kSumSlots;
 #pragma unroll
-                for (int i = 0; i < kSumSlots; ++i) acc[i] += q[i];
+                for (int i = 0; i < kSumSlots; ++i) acc[i] += tile_partial(partial, partial8, g.KB, t, j, i);
             }
         }
         block_sum<kSumSlots>(acc, scratch);
@@ -993,18 +1005,19 @@ cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, in
 
 size_t reduce_stage_bytes(const Geom &g) { return (size_t)g.P * kReduceChunks * g.KB * kSumSlots * sizeof(double); }
 
-cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const int *tile_start,
+cudaError_t launch_reduce_partials(const Geom &g, const double *partial, const double *partial8, const int *tile_start,
                                    const ProbState *state, double *sums, double *stage, bool all_tiles,
                                    cudaStream_t st, int64_t *launches) {
     // one block per problem is enough unless a problem has tens of thousands of tiles
     if (stage && (int64_t)g.S * g.tiles_per_prob >= 8192) {
-        reduce_partials_stage1_kernel<<<g.P * kReduceChunks, 128, 0, st>>>(g, partial, tile_start, state, stage, all_tiles ? 1 : 0);
+        reduce_partials_stage1_kernel<<<g.P * kReduceChunks, 128, 0, st>>>(g, partial, partial8, tile_start, state, stage,
+                                                                           all_tiles ? 1 : 0);
         VP_LAUNCH_CHECK();
         reduce_partials_stage2_kernel<<<g.P, 64, 0, st>>>(g, stage, sums);
         VP_LAUNCH_CHECK();
         return cudaSuccess;
     }
-    reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, tile_start, state, sums, all_tiles ? 1 : 0);
+    reduce_partials_kernel<<<g.P, 128, 0, st>>>(g, partial, partial8, tile_start, state, sums, all_tiles ? 1 : 0);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -375,6 +375,130 @@ __global__ void __launch_bounds__(256, 2) jacobi2d_k1_ratio3_kernel(const StepAr
     write_partial(acc, a, p);
 }
 
+// Fourth form (the default): the prefetching of the third in two half-strips of 4 rows (6 state rows + 4 feature rows
+// requested before any arithmetic; ~80 registers, 3 blocks per SM), and -- when the caller reduces the sums in a
+// separate launch (step API, row-sharded runs) -- no block barrier at all: every warp writes its own partial sums and
+// the reduction kernel adds the 8 warps of a tile in order (the same bits as the block reduction).
+template <bool INTERIOR>
+__device__ __forceinline__ void ratio_half_strip(const StepArgs &a, const Geom &g, const double *__restrict__ in,
+                                                 double *__restrict__ out, const double *__restrict__ fpl, int xw, int lane,
+                                                 int y0, unsigned any, unsigned mine, double &s_abs, double &s_old, int &c_abs,
+                                                 int &c_old) {
+    // any / mine: bits of the 4 rows y0 .. y0+3 (row r: bit r of any, bits 2r, 2r+1 of mine)
+    const int x = xw + 2 * lane;
+    const unsigned need = (any << 2) | (any << 1) | any;      // state row i = grid row y0 - 1 + i
+    double v0[6], v1[6], f0[4], f1[4], edge[4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int y = y0 - 1 + i, yg = y + g.row_offset;
+        v0[i] = 0.0; v1[i] = 0.0;
+        if (((need >> i) & 1u) && yg >= 0 && yg < g.global_H && y >= 0 && y < g.H) load2(in + (size_t)y * g.pitch + x, v0[i], v1[i]);
+    }
+    const bool has_left = xw > 0, has_right = xw + 64 < g.L;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        f0[r] = 1.0; f1[r] = 1.0; edge[r] = 0.0;
+        if ((any >> r) & 1u) {
+            const size_t row = (size_t)(y0 + r) * g.pitch;
+            load2(fpl + row + x, f0[r], f1[r]);
+            if (lane == 0 && has_left) edge[r] = in[row + x - 1];
+            if (lane == 31 && has_right) edge[r] = in[row + x + 2];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!((any >> r) & 1u)) continue;                       // warp-uniform
+        const int y = y0 + r;
+        const size_t row = (size_t)y * g.pitch;
+        const unsigned mb = (mine >> (2 * r)) & 3u;
+        const double u0 = v0[r], u1 = v1[r], c0 = v0[r + 1], c1 = v1[r + 1], d0 = v0[r + 2], d1 = v1[r + 2];
+        double lf = __shfl_up_sync(0xffffffffu, c1, 1), rt = __shfl_down_sync(0xffffffffu, c0, 1);
+        if (lane == 0) lf = edge[r];
+        if (lane == 31) rt = edge[r];
+        double n0 = ((u0 + c1) + d0) + lf;
+        double n1 = ((u1 + rt) + d1) + c0;
+        if (INTERIOR) {
+            n0 *= 0.25; n1 *= 0.25;
+        } else {
+            const int yg = y + g.row_offset;
+            const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
+            const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
+            const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
+            n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
+            n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
+        }
+        double w0 = f0[r] * n0, w1 = f1[r] * n1;
+        if (w0 > a.clip) { w0 = a.clip; n0 = a.clip / f0[r]; }
+        if (w1 > a.clip) { w1 = a.clip; n1 = a.clip / f1[r]; }
+        if (mb & 1u) {
+            const double o = f0[r] * c0, d = fabs(w0 - o);
+            if (d != d) ++c_abs; else s_abs += d;
+            if (o != o) ++c_old; else s_old += o;
+            out[row + x] = n0;
+        }
+        if (mb & 2u) {
+            const double o = f1[r] * c1, d = fabs(w1 - o);
+            if (d != d) ++c_abs; else s_abs += d;
+            if (o != o) ++c_old; else s_old += o;
+            out[row + x + 1] = n1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) jacobi2d_k1_ratio4_kernel(const StepArgs a) {
+    const TileRef tile = a.tiles[blockIdx.x];
+    const int p = tile.p;
+    const ProbState st = a.state[p];
+    if (st.k_run == 0) return;
+    const Geom &g = a.g;
+    const size_t plane = (size_t)g.H * g.pitch;
+    const double *__restrict__ in = reinterpret_cast<const double *>(a.buf[st.cur]) + (size_t)p * plane;
+    double *__restrict__ out = reinterpret_cast<double *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
+    const double *__restrict__ fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xw = tile.x0 + (warp & 1) * 64;
+    const int yb = tile.y0 + (warp >> 1) * 8;
+    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
+    double s_abs = 0.0, s_old = 0.0;
+    int c_abs = 0, c_old = 0;
+    if (xw < g.L && yb < y_lim) {
+        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
+        const int mp64 = g.mpitch >> 1;
+        uint64_t mword = 0;
+        if (lane < 8 && yb + lane < y_lim) mword = m64[(size_t)(yb + lane) * mp64];
+        unsigned any = 0, mine = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint64_t w = __shfl_sync(0xffffffffu, mword, r);
+            any |= (w != 0ull) ? (1u << r) : 0u;
+            mine |= ((unsigned)(w >> (2 * lane)) & 3u) << (2 * r);
+        }
+        // no cell of the tile on the border of the GLOBAL grid: every neighbour count is 4
+        const bool interior = (tile.y0 + g.row_offset > 0) && (tile.y0 + kTileH2 + g.row_offset < g.global_H) && (tile.x0 > 0) &&
+                              (tile.x0 + kTileW2 < g.L);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const unsigned any_h = (any >> (4 * h)) & 15u, mine_h = (mine >> (8 * h)) & 255u;
+            if (any_h == 0) continue;
+            if (interior) ratio_half_strip<true>(a, g, in, out, fpl, xw, lane, yb + 4 * h, any_h, mine_h, s_abs, s_old, c_abs, c_old);
+            else ratio_half_strip<false>(a, g, in, out, fpl, xw, lane, yb + 4 * h, any_h, mine_h, s_abs, s_old, c_abs, c_old);
+        }
+    }
+    if (a.partial8) {
+        // per-warp partial sums, no block barrier: the reduction kernel adds the 8 warps of a tile in order
+        const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
+        const int q2 = warp_sum(c_abs), q3 = warp_sum(c_old);
+        if (lane == 0) {
+            double *dst = a.partial8 + ((size_t)blockIdx.x * 8 + warp) * kSumSlots;
+            dst[0] = q0; dst[1] = q1; dst[2] = (double)q2; dst[3] = (double)q3;
+        }
+        return;
+    }
+    Acc<double> acc;
+    acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
+    write_partial(acc, a, p);
+}
+
 __global__ void __launch_bounds__(256) jacobi2d_k1_ratio2_kernel(const StepArgs a) {
     const TileRef tile = a.tiles[blockIdx.x];
     const int p = tile.p;
@@ -590,8 +714,9 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
 
 cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches) {
     if (n_tiles <= 0) return cudaSuccess;
-    static const int ver = getenv("VPINT_RATIO_KERNEL") ? atoi(getenv("VPINT_RATIO_KERNEL")) : 1;
-    if (ver == 2) jacobi2d_k1_ratio2_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    static const int ver = getenv("VPINT_RATIO_KERNEL") ? atoi(getenv("VPINT_RATIO_KERNEL")) : 4;
+    if (ver == 4) jacobi2d_k1_ratio4_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    else if (ver == 2) jacobi2d_k1_ratio2_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
     else if (ver == 3) jacobi2d_k1_ratio3_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
     else jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
     VP_LAUNCH_CHECK();
