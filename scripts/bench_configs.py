@@ -88,6 +88,16 @@ def main():
             ms, sw = timed_solver(make)
             res.append({"config": "C2 WP_SMRP 1024x1024 F=3 %.0f%% cloud, k_block %d, %s" % (100 * cloud.mean(), kb, "auto-terminate" if it < 0 else "run(200)"),
                         "ms": ms, "sweeps": int(sw[0]), "mpx_it_per_s": 1024 * 1024 * int(sw[0]) / ms / 1e3})
+    # C2 through the drop-in class (host arrays in, host array out, default path: 4 sweeps per launch for F > 1)
+    from vpint_b200 import WP_SMRP
+    WP_SMRP(tgt.copy(), feat.copy()).run()
+    walls = []
+    for _ in range(3):
+        m = WP_SMRP(tgt.copy(), feat.copy())
+        t0 = time.perf_counter()
+        m.run()
+        walls.append(1e3 * (time.perf_counter() - t0))
+    res.append({"config": "C2 WP_SMRP(...).run() through the class API, wall clock incl. H2D / D2H", "ms": min(walls)})
     # C5: SD_STMRP 2048x2048x64, 30 % missing (disc clouds per time slice), generated on the device
     Hc, Wc, Tc = 2048, 2048, 64
     g = torch.Generator(device=dev); g.manual_seed(1005)
