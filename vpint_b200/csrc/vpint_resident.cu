@@ -151,18 +151,15 @@ struct SmemLayout {
     double *fseg;        // [2][fcap][2] features of the first fcap listed segments: cells 0,1 then cells 2,3 (RATIO);
                          // as float pairs (twice the capacity in the same bytes) when every feature is a float32 value
     unsigned *list;      // [n_seg] segment entries, row-major
-    double *part;        // [kPartSlots][C][kWarps][2] partial {sum|new-old|, sum old} of every worker warp of every CTA of
-                         // the cluster, pushed by the warps themselves (st.async); same offset in every CTA
 };
 
-__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, int LB, int fcap, int list_cap) {
+__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int R, int SP, int LB, int fcap) {
     SmemLayout s;
     s.plane = reinterpret_cast<double *>(raw);
     s.halo_up = s.plane + (size_t)R * SP;
     s.halo_dn = s.halo_up + 2 * LB * SP;
     s.fseg = s.halo_dn + 2 * LB * SP;
     s.list = reinterpret_cast<unsigned *>(s.fseg + (size_t)fcap * 4);
-    s.part = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s.list) + (((size_t)list_cap * 4 + 15) & ~(size_t)15));
     return s;
 }
 
@@ -174,7 +171,6 @@ struct SweepCtx {
     const double *fp;                 // global feature plane of this problem (segments beyond fcap)
     // neighbour CTAs (shared::cluster addresses): their halo row buffers [2][SP] and their halo barriers [2]
     uint32_t up_halo, dn_halo, up_bar[2], dn_bar[2];
-    uint32_t part_base, bar_s_base;   // shared::cta addresses of part[] / bar_s[] (the same in every CTA of the cluster)
     bool has_up, has_dn;
     int SP, half, fcap, pitch, tid, n, H, W;   // half = SP / 2 (split-row layout)
     int C, crank, BS, LB;             // cluster size / rank, rows per block, blocks per CTA
@@ -193,11 +189,12 @@ struct SweepCtx {
 };
 
 // Per-CTA synchronisation state (static shared memory).
-constexpr int kPartSlots = 4;          // sweeps whose partial sums can be in flight (see sync_sweeps)
 struct SyncShared {
+    double part[3][kMaxC][2];          // partial {sum|new-old|, sum old} of every CTA of the cluster (16-byte entries)
     double zero4[4];                   // features of segments that must not count (16-byte aligned)
+    double red[2][kWarps][2];          // warp partials by sweep parity (read by the sync warp while the workers go on)
     uint64_t bar_h[2];                 // per sweep parity: this CTA's own stores (one arrival per warp) + neighbours' halo bytes
-    uint64_t bar_s[kPartSlots];        // per sweep mod 4: the partial sums of every worker warp of every CTA (C * 15 * 16 bytes)
+    uint64_t bar_s[3];                 // per sweep mod 3: the C partial sums (C * 16 bytes)
     int verdict[2];                    // stop decision of the previous sweep by sweep parity, written by the sync warp
     int halo_exp[2];                   // bytes per sweep from the upper / lower neighbour
     int edge_cnt[2];                   // segments on the first / last owned row
@@ -211,16 +208,11 @@ __device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
 // Stop decision of one sweep from the C partials (the sync warp of every CTA computes the same thing):
 // delta = nanmean|new-old| / nanmean(old) with the known-cell constants added (VPint/SD_MRP.py:139).
 // Returns 0 continue, 1 stop, 2 non-finite data (leave the problem to the tiled path).
-__device__ __forceinline__ int decide_sweep(SyncShared &sh, const double *part, int slot, unsigned ph_s, int C, const double *KK,
-                                            double n_cells, const ResidentArgs &a, int p, int sweep, bool writer) {
+__device__ __forceinline__ int decide_sweep(SyncShared &sh, int slot, unsigned ph_s, int C, const double *KK, double n_cells,
+                                            const ResidentArgs &a, int p, int sweep, bool writer) {
     mbar_wait(&sh.bar_s[slot], (ph_s >> slot) & 1u);
-    // C * 15 warp partials, the same values in the same order in every CTA: lane-strided sums, then a butterfly (both
-    // operands of every addition are the same pair in both lanes, so all lanes -- and all CTAs -- end with the same bits)
-    const int lane = threadIdx.x & 31, n = C * kWarps;
-    const double *ps = part + (size_t)slot * C * kWarps * 2;
     double S0 = 0.0, S1 = 0.0;
-    for (int e = lane; e < n; e += 32) { S0 += ps[2 * e]; S1 += ps[2 * e + 1]; }
-    S0 = warp_sum(S0); S1 = warp_sum(S1);
+    for (int q = 0; q < C; ++q) { S0 += sh.part[slot][q][0]; S1 += sh.part[slot][q][1]; }
     if (!(fabs(S0) <= 1.7976931348623157e308 && fabs(S1) <= 1.7976931348623157e308)) return 2;
     const double sa = S0 + KK[0], so = S1 + KK[1];
     const double na = n_cells - KK[2], no = n_cells - KK[3];
@@ -413,13 +405,8 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
         }
         VPR_TR(2);
         {
-            // the warp's partial sums go straight to every CTA of the cluster (lane q -> CTA q): the sync warps only
-            // have to add them up, and the transfer overlaps the wait at the block barrier
             const double q0 = warp_sum(s_abs), q1 = warp_sum(s_old);
-            const int slot = t & (kPartSlots - 1);
-            if (lane < c.C)
-                st_async2(map_rank(c.part_base + (uint32_t)((((slot * c.C) + c.crank) * kWarps + warp) * 16), lane), q0, q1,
-                          map_rank(c.bar_s_base + (uint32_t)(slot * 8), lane));
+            if (lane == 0) { sh.red[par][warp][0] = q0; sh.red[par][warp][1] = q1; }
         }
         VPR_TR(3);
         role_barrier();                            // (3) every read of the old state is done; red[] / verdict complete
@@ -481,51 +468,55 @@ __device__ __forceinline__ void worker_sweeps(const SweepCtx &c, SyncShared &sh,
     bailed_out = (verdict == 2);
 }
 
-// Sync warp: steps (4), (3), (5) of every sweep.  The partial sums of sweep t are pushed by the worker warps of every CTA
-// before they reach the block barrier of sweep t; the sync warp announces the bytes it expects (5) and adds them up while
-// the workers compute sweep t + 1 (4).  Four slots: a warp of the fastest CTA pushes sweep t + 4 only after every CTA has
-// passed the barrier of sweep t + 1, i.e. after every sync warp has finished reading sweep t.
-__device__ __forceinline__ void sync_sweeps(int tid, SyncShared &sh, const double *part, const ResidentArgs &a, int p, int C,
-                                            int crank, bool fresh, const double *k0, const double *k1, double n_cells,
-                                            unsigned &ph_s, int &it_out, bool &bailed_out) {
+// Sync warp: steps (4), (3), (5) of every sweep.
+__device__ __forceinline__ void sync_sweeps(int tid, SyncShared &sh, const ResidentArgs &a, int p, int C, int crank, bool fresh,
+                                            const double *k0, const double *k1, double n_cells, unsigned &ph_s, int &it_out,
+                                            bool &bailed_out) {
     const int lane = tid & 31;
     const int T = a.max_iter;
-    const unsigned bytes = (unsigned)(C * kWarps * 16);
+    const uint32_t my_part = smem_u32(&sh.part[0][0][0]);
+    const uint32_t my_bar_s = smem_u32(&sh.bar_s[0]);
     const bool writer = (crank == 0 && lane == 0);
     struct { int tid; } c = {tid};                 // for VPR_TR
     (void)c;
     int t = 0, verdict = 0;
     for (; t < T; ++t) {
-        const int par = t & 1, slot = t & (kPartSlots - 1);
+        const int par = t & 1, slot = t % 3;
         VPR_TR(0);
-        if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], bytes);       // (5) the partials of sweep t, whenever they land
         if (t > 0) {                               // (4) runs beside the workers' (2)
-            const int v = decide_sweep(sh, part, (t - 1) & (kPartSlots - 1), ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
+            const int v = decide_sweep(sh, (t - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, t - 1, writer);
             if (lane == 0) sh.verdict[par] = v;
         }
         VPR_TR(4);
         role_barrier();
         if (t > 0) {
-            ph_s ^= 1u << ((t - 1) & (kPartSlots - 1));
+            ph_s ^= 1u << ((t - 1) % 3);
             fresh = false;
             verdict = sh.verdict[par];
-            if (verdict != 0) {
-                // sweep t is not committed, but its partials are on their way (the workers pushed them before the
-                // barrier): take delivery, so that the slot's barrier is clean for the next problem
-                mbar_wait(&sh.bar_s[slot], (ph_s >> slot) & 1u);
-                ph_s ^= 1u << slot;
-                break;
-            }
+            if (verdict != 0) break;
         }
         VPR_TR(5);
+        // (5) fixed-order sum of the warp partials, one 16-byte push per CTA
+        double v0 = (lane < kWarps) ? sh.red[par][lane][0] : 0.0, v1 = (lane < kWarps) ? sh.red[par][lane][1] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            v0 += __shfl_down_sync(0xffffffffu, v0, o);
+            v1 += __shfl_down_sync(0xffffffffu, v1, o);
+        }
+        v0 = __shfl_sync(0xffffffffu, v0, 0);
+        v1 = __shfl_sync(0xffffffffu, v1, 0);
+        if (lane < C)
+            st_async2(map_rank(my_part + (uint32_t)(((slot * kMaxC) + crank) * 16), lane), v0, v1,
+                      map_rank(my_bar_s + (uint32_t)(slot * 8), lane));
+        if (lane == 0) mbar_arrive_tx(&sh.bar_s[slot], (unsigned)(C * 16));
         VPR_TR(6);
     }
     if (verdict == 0) {                            // ran to max_iter: close the last sweep
         const int par = T & 1;
-        const int v = decide_sweep(sh, part, (T - 1) & (kPartSlots - 1), ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
+        const int v = decide_sweep(sh, (T - 1) % 3, ph_s, C, fresh ? k0 : k1, n_cells, a, p, T - 1, writer);
         if (lane == 0) sh.verdict[par] = v;
         role_barrier();
-        ph_s ^= 1u << ((T - 1) & (kPartSlots - 1));
+        ph_s ^= 1u << ((T - 1) % 3);
         verdict = (sh.verdict[par] == 2) ? 2 : 0;
     }
     it_out = t;
@@ -552,15 +543,15 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
     const int W = g.L, H = g.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BS = a.BS, LB = a.LB;
-    const SmemLayout sm = carve(smem_raw, R, SP, LB, a.fcap, R * ((W + 3) / 4));
+    const SmemLayout sm = carve(smem_raw, R, SP, LB, a.fcap);
     int *next_remote = cluster.map_shared_rank(&next_problem, 0);
     if (tid < 4) sh.zero4[tid] = 0.0;
     if (tid == 0) {
         mbar_init(&sh.bar_h[0], kWarps); mbar_init(&sh.bar_h[1], kWarps);   // one arrival per warp
-        for (int q = 0; q < kPartSlots; ++q) mbar_init(&sh.bar_s[q], 1);
+        mbar_init(&sh.bar_s[0], 1); mbar_init(&sh.bar_s[1], 1); mbar_init(&sh.bar_s[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    unsigned ph_h = 0, ph_s = 0;                       // phase parities of bar_h[2] / bar_s[4], carried across problems
+    unsigned ph_h = 0, ph_s = 0;                       // phase parities of bar_h[2] / bar_s[3], carried across problems
 
     const size_t plane_elems = (size_t)H * g.pitch;
     const int nwords = (W + 31) >> 5;
@@ -802,7 +793,6 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
             ctx.dn_bar[q] = ctx.has_dn ? map_rank(smem_u32(&sh.bar_h[q]), cd) : 0u;
         }
         ctx.C = C; ctx.crank = crank; ctx.BS = BS; ctx.LB = LB;
-        ctx.part_base = smem_u32(sm.part); ctx.bar_s_base = smem_u32(&sh.bar_s[0]);
         ctx.shift_up = (crank == 0) ? -1 : 0;       // block b-1 lives in CTA c-1 under the same local index, or one less after the wrap
         ctx.shift_dn = (crank == C - 1) ? 1 : 0;
         ctx.part_lb = -1; ctx.part_rows = BS;      // the partial block, if any, is the grid's last one
@@ -836,7 +826,7 @@ __global__ void __launch_bounds__(kLaunchThreads, kResidentCtasPerSm) resident2d
         }                                                                                              \
     } while (0)
         if (warp == kWarps) {
-            sync_sweeps(tid, sh, sm.part, a, p, C, crank, fresh, k0, k1, n_cells, ph_s, it, bailed);
+            sync_sweeps(tid, sh, a, p, C, crank, fresh, k0, k1, n_cells, ph_s, it, bailed);
         } else {
 #ifdef VPR_ONLY_KT                                  // build-time triage: one variant only, for per-variant ptxas -v / SASS
             VPR_RUN(VPR_ONLY_KT);
@@ -980,9 +970,8 @@ bool resident_plan(const Geom &g, bool ratio, int smem_limit, int C, ResidentPla
         const int R = LB * BS;
         if ((int64_t)R * segs_per_row > (int64_t)kThreads * kMaxSeg) return false;  // register budget for the new values
         if ((int64_t)R * SP > 65535) return false;                                  // 16-bit shared-memory offsets
-        const int64_t fixed = ((int64_t)R * SP + 4 * (int64_t)LB * SP) * 8 + (((int64_t)R * segs_per_row * 4 + 15) / 16) * 16 +
-                              (int64_t)kPartSlots * C * kWarps * 16;
-        const int64_t room = ((int64_t)smem_limit - static_bytes - fixed) / 32 * 32;
+        const int64_t fixed = ((int64_t)R * SP + 4 * (int64_t)LB * SP) * 8 + (int64_t)R * segs_per_row * 4;
+        const int64_t room = (int64_t)smem_limit - static_bytes - fixed;
         if (room < 0) return false;
         int fcap = 0;
         if (ratio) {
