@@ -354,6 +354,28 @@ def test_fp32_storage_mode():
     close(res, ref, rtol=RTOL32)
 
 
+def test_fp32_storage_mode_auto_terminate_on_benchmark_patches():
+    """north_star's fp32 mode on the C3 recipe (256 x 256 x 13 uint16-valued patches, disc clouds), run to the
+    reference's own stopping rule: float32 state between the sweeps, fp64 arithmetic and fp64 stopping sums -- the
+    same number of sweeps per band as the fp64 reference and values within 1e-4."""
+    from vpint_b200.vpint2 import solve_bands
+    from vpint_b200.wp import wp_run_options
+    import bench
+    t, f, m = bench.make_patches_numpy(2, 515)
+    total = equal = 0
+    for i in range(2):
+        vp = VPint2_interpolator(t[i], f[i], mask=m[i], threshold=10)
+        out, sweeps = solve_bands(vp.target, vp.features, wp_run_options(), storage="float32", k_block=1, return_sweeps=True)
+        ref, ref_sweeps = O.vpint2_run(vp.target, vp.features)
+        close(np.moveaxis(out, 0, -1), ref, rtol=RTOL32)
+        total += len(ref_sweeps)
+        equal += int(np.sum(np.asarray(sweeps) == np.asarray(ref_sweeps)))
+        assert np.max(np.abs(np.asarray(sweeps) - np.asarray(ref_sweeps))) <= 1, (list(sweeps), list(ref_sweeps))
+    # rounding the state to float32 moves delta by ~1e-7 relative: a band stops one sweep apart only if its delta
+    # passes the threshold that closely
+    assert equal >= total - 1, (equal, total)
+
+
 def test_batched_trials_and_stride0_inputs():
     rng = np.random.default_rng(8)
     grid = smooth(rng, (50, 50), 10, 30)
