@@ -169,6 +169,7 @@ class Solver:
             self.lib.vpint_solver_destroy(self._h)
             self._h = None
         self.workspace = None
+        self._shard_result_buf = None
         self._keep = []
 
     def __del__(self):  # pragma: no cover

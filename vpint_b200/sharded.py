@@ -592,9 +592,14 @@ def stage_shard_raw(solver, t_dev, f_dev, cloud_dev, comm, scratch, value_dtype=
 
 
 def shard_result(solver, shard):
-    """(pred float64 torch tensor (B, own_rows, W) on the device, sweeps int64 ndarray (B,))."""
-    out, niter = solver.result()
-    pred = out[:, shard.own_row0:shard.own_row0 + shard.own_rows, :].clone()
+    """(pred float64 torch tensor (B, own_rows, W) on the device, sweeps int64 ndarray (B,)).  ``pred`` is a view of a
+    buffer that belongs to the solver (allocated once, rewritten by the next call): clone it to keep it."""
+    buf = getattr(solver, "_shard_result_buf", None)
+    if buf is None:
+        buf = solver.torch.empty((solver.nprob, solver.H, solver.W), dtype=solver.torch.float64, device=solver.device)
+        solver._shard_result_buf = buf
+    out, niter = solver.result(out=buf)
+    pred = out[:, shard.own_row0:shard.own_row0 + shard.own_rows, :]
     return pred, niter.cpu().numpy().astype(np.int64)
 
 
