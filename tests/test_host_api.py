@@ -286,3 +286,53 @@ def test_metrics_match_reference(golden):
     mae, eg = m.mean_absolute_error(g["truefull_2d"].copy(), scale_factor=1, gridded=True)
     assert np.isclose(mae, g["smae_2d"], rtol=1e-12, atol=0) and np.allclose(eg, g["smae_grid_2d"], rtol=1e-12, atol=0)
     assert np.isclose(m.mean_absolute_error(g["truefull_2d"].copy(), scale_factor=2), g["smae2_2d"], rtol=1e-12, atol=0)
+
+
+def test_balanced_row_bounds():
+    """Row shards dealt by work: boundaries on the cumulative per-row weight, every rank at least min_rows rows."""
+    from vpint_b200.sharded import RowShard, balanced_bounds
+    rng = np.random.default_rng(5)
+    w = np.zeros(1000)
+    w[100:300] = 50.0                                  # one cloud bank
+    w[800:820] = 200.0
+    w += 1.0
+    for world in (1, 2, 3, 8):
+        b = balanced_bounds(w, world, min_rows=4)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == world + 1 and all(x1 - x0 >= 4 for x0, x1 in zip(b, b[1:]))
+        work = [w[b[i]:b[i + 1]].sum() for i in range(world)]
+        assert max(work) <= 1.25 * (w.sum() / world) + w.max()
+        shards = [RowShard(1000, world, r, halo=1, bounds=b) for r in range(world)]
+        assert [s.r0 for s in shards] == b[:-1] and shards[-1].r1 == 1000
+        assert all(s.own_rows == b[r + 1] - b[r] for r, s in enumerate(shards))
+    assert balanced_bounds(np.zeros(10), 3) == [0, 4, 7, 10] or len(balanced_bounds(np.zeros(10), 3)) == 4
+    with pytest.raises(VPintError):
+        RowShard(10, 2, 0, 1, bounds=[0, 5, 9])
+    with pytest.raises(VPintError):
+        balanced_bounds(np.ones(3), 4)
+
+
+def test_interpolator_keeps_raw_rasters_and_materialises_on_demand(golden):
+    """The lazy constructor: uint16 / float rasters are kept as they came; .target / .features are built on the host
+    with the reference's steps only when somebody reads them (fixture: tests/golden/vpint2.npz)."""
+    g = golden("vpint2")
+    vp = VPint2_interpolator(g["target"], g["features"], mask=g["mask"], threshold=10)
+    assert vp._raw is not None and vp._target is None
+    assert vp._raw[0].dtype == g["target"].dtype and vp._raw[0] is not g["target"]      # a copy, not a reference
+    t = vp.target
+    same(t, g["stored_target"])
+    assert vp._target is t and vp.features.dtype == np.float32
+    vp.features = vp.features * 2
+    assert vp._raw is None, "assigning switches to the host-built arrays"
+    # inputs the device constructor does not take are built on the host at once
+    vp2 = VPint2_interpolator(g["target"].astype(np.int32), g["features"].astype(np.int32), mask=g["mask"], threshold=10)
+    assert vp2._raw is None
+    same(vp2.target, g["stored_target"])
+
+
+def test_solve_raw_fails_loudly_without_a_device():
+    if HAS_CUDA:
+        pytest.skip("needs a box without CUDA")
+    from vpint_b200.vpint2 import solve_raw
+    t = np.ones((1, 16, 16, 2), dtype=np.uint16)
+    with pytest.raises(VPintError):
+        solve_raw(t, t, None)

@@ -637,7 +637,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
     a.tau = s->at<double>(s->off_tau);
     a.partial = s->at<double>(s->off_partial);
     // the ratio stencil of a launch whose sums are reduced by a separate kernel writes per-warp partials (no barrier)
-    static const bool ratio_v4 = !getenv("VPINT_RATIO_KERNEL") || atoi(getenv("VPINT_RATIO_KERNEL")) == 4;   // triage switch
+    static const bool ratio_v4 = !getenv("VPINT_RATIO_KERNEL") || atoi(getenv("VPINT_RATIO_KERNEL")) != 1;   // triage switch
     a.partial8 = (use_ratio && !fused && s->off_partial8 && ratio_v4) ? s->at<double>(s->off_partial8) : nullptr;
     a.clip = s->prm.clip_val;
     a.no_nc = s->no_nc ? 1 : 0;

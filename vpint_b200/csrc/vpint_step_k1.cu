@@ -181,204 +181,16 @@ __global__ void __launch_bounds__(256) jacobi2d_k1_ratio_kernel(const StepArgs a
     write_partial(acc, a, p);
 }
 
-// The same sweep with a sliding window (the default; VPINT_RATIO_V1=1 selects the kernel above): a warp walks its 8 rows
-// top to bottom and keeps the rows above / at / below in registers, so every state row is loaded once per strip (10
-// row loads instead of 24), the left / right neighbours come from the adjacent lanes by shuffle (two edge loads per
-// row instead of 64), rows are skipped on WARP-uniform tests of the 64-bit mask words (no divergence), and tiles that
-// do not touch the grid border take a branch without neighbour counts.  Thread <-> cell mapping, arithmetic and
-// summation order are those of the kernel above: results are bit-identical.
-template <bool INTERIOR>
-__device__ __forceinline__ void ratio_strip(const StepArgs &a, const Geom &g, const double *__restrict__ in,
-                                            double *__restrict__ out, const double *__restrict__ fpl,
-                                            const uint64_t *__restrict__ m64, int mp64, int xw, int lane, int yb, int y_lim,
-                                            double &s_abs, double &s_old, int &c_abs, int &c_old) {
-    const int x = xw + 2 * lane;
-    // mask words of rows yb-1 .. yb+8 (this warp's 64 columns): lane i holds row yb-1+i
-    uint64_t mword = 0;
-    {
-        const int y = yb - 1 + lane;
-        if (lane < 10 && y >= g.own_row0 && y < y_lim) mword = m64[(size_t)y * mp64];
-    }
-    auto row_bits = [&](int r) { return __shfl_sync(0xffffffffu, mword, r + 1); };   // r = -1 .. 8
-    const bool lane_first = (lane == 0), lane_last = (lane == 31);
-    const bool has_left = xw > 0, has_right = xw + 64 < g.L;
-    double u0 = 0.0, u1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    uint64_t b_prev = 0, b_cur = row_bits(0), b_next = row_bits(1);
-    auto load_row = [&](int y, double &v0, double &v1) {
-        // rows outside the GLOBAL grid read as 0 (VPint/WP_MRP.py:291-308); halo rows of a shard are ordinary rows
-        const int yg = y + g.row_offset;
-        if (yg >= 0 && yg < g.global_H && y >= 0 && y < g.H) load2(in + (size_t)y * g.pitch + x, v0, v1);
-        else { v0 = 0.0; v1 = 0.0; }
-    };
-    if (b_cur) load_row(yb - 1, u0, u1);
-    if (b_cur | b_next) load_row(yb, c0, c1);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int y = yb + r;
-        if (y >= y_lim) break;                                 // warp-uniform
-        const uint64_t b_nn = (r + 2 <= 8) ? row_bits(r + 2) : 0ull;
-        // the row below is needed by this row, and as the centre / upper row of the next two
-        if (b_cur | b_next | b_nn) load_row(y + 1, d0, d1);
-        if (b_cur) {                                           // warp-uniform: some cell of this row strip is unknown
-            const size_t row = (size_t)y * g.pitch;
-            const unsigned mb = (unsigned)(b_cur >> (2 * lane)) & 3u;
-            double f0, f1;
-            load2(fpl + row + x, f0, f1);
-            double lf = __shfl_up_sync(0xffffffffu, c1, 1), rt = __shfl_down_sync(0xffffffffu, c0, 1);
-            if (lane_first) lf = has_left ? in[row + x - 1] : 0.0;
-            if (lane_last) rt = has_right ? in[row + x + 2] : 0.0;
-            double n0 = ((u0 + c1) + d0) + lf;
-            double n1 = ((u1 + rt) + d1) + c0;
-            if (INTERIOR) {
-                n0 *= 0.25; n1 *= 0.25;
-            } else {
-                const int yg = y + g.row_offset;
-                const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
-                const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
-                const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
-                n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
-                n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
-            }
-            double v0 = f0 * n0, v1 = f1 * n1;
-            if (v0 > a.clip) { v0 = a.clip; n0 = a.clip / f0; }
-            if (v1 > a.clip) { v1 = a.clip; n1 = a.clip / f1; }
-            if (mb & 1u) {
-                const double o = f0 * c0, d = fabs(v0 - o);
-                if (d != d) ++c_abs; else s_abs += d;
-                if (o != o) ++c_old; else s_old += o;
-                out[row + x] = n0;
-            }
-            if (mb & 2u) {
-                const double o = f1 * c1, d = fabs(v1 - o);
-                if (d != d) ++c_abs; else s_abs += d;
-                if (o != o) ++c_old; else s_old += o;
-                out[row + x + 1] = n1;
-            }
-        }
-        u0 = c0; u1 = c1; c0 = d0; c1 = d1;
-        b_prev = b_cur; b_cur = b_next; b_next = b_nn;
-    }
-    (void)b_prev;
-}
-
-// Third form: all ten state rows and the eight feature rows of a strip are requested up front (warp-uniform tests
-// decide which), so a warp has up to 18 loads in flight before it computes anything; then the rows are pure register
-// arithmetic + shuffles.  Same mapping / arithmetic / summation order again.
-template <bool INTERIOR>
-__device__ __forceinline__ void ratio_strip_prefetch(const StepArgs &a, const Geom &g, const double *__restrict__ in,
-                                                     double *__restrict__ out, const double *__restrict__ fpl,
-                                                     const uint64_t *__restrict__ m64, int mp64, int xw, int lane, int yb,
-                                                     int y_lim, double &s_abs, double &s_old, int &c_abs, int &c_old) {
-    const int x = xw + 2 * lane;
-    uint64_t mword = 0;
-    {
-        const int y = yb + lane;
-        if (lane < 8 && y < y_lim) mword = m64[(size_t)y * mp64];
-    }
-    // per row of the strip: does the warp's 64-column span hold an unknown cell (bit r of `any`), and this lane's two
-    // mask bits (packed two per row in `mine`)
-    unsigned any = 0, mine = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint64_t w = __shfl_sync(0xffffffffu, mword, r);
-        any |= (w != 0ull) ? (1u << r) : 0u;
-        mine |= ((unsigned)(w >> (2 * lane)) & 3u) << (2 * r);
-    }
-    if (any == 0) return;
-    // state row i = grid row yb - 1 + i is needed if strip row i - 2, i - 1 or i computes (as its d / c / u row)
-    const unsigned need = (any << 2) | (any << 1) | any;
-    double v0[10], v1[10], f0[8], f1[8], edge[8];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const int y = yb - 1 + i, yg = y + g.row_offset;
-        v0[i] = 0.0; v1[i] = 0.0;
-        if (((need >> i) & 1u) && yg >= 0 && yg < g.global_H && y >= 0 && y < g.H) load2(in + (size_t)y * g.pitch + x, v0[i], v1[i]);
-    }
-    const bool has_left = xw > 0, has_right = xw + 64 < g.L;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        f0[r] = 1.0; f1[r] = 1.0; edge[r] = 0.0;
-        if ((any >> r) & 1u) {
-            const size_t row = (size_t)(yb + r) * g.pitch;
-            load2(fpl + row + x, f0[r], f1[r]);
-            // the cell left of the warp's span (lane 0) / right of it (lane 31)
-            if (lane == 0 && has_left) edge[r] = in[row + x - 1];
-            if (lane == 31 && has_right) edge[r] = in[row + x + 2];
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        if (!((any >> r) & 1u)) continue;                       // warp-uniform
-        const int y = yb + r;
-        const size_t row = (size_t)y * g.pitch;
-        const unsigned mb = (mine >> (2 * r)) & 3u;
-        const double u0 = v0[r], u1 = v1[r], c0 = v0[r + 1], c1 = v1[r + 1], d0 = v0[r + 2], d1 = v1[r + 2];
-        double lf = __shfl_up_sync(0xffffffffu, c1, 1), rt = __shfl_down_sync(0xffffffffu, c0, 1);
-        if (lane == 0) lf = edge[r];
-        if (lane == 31) rt = edge[r];
-        double n0 = ((u0 + c1) + d0) + lf;
-        double n1 = ((u1 + rt) + d1) + c0;
-        if (INTERIOR) {
-            n0 *= 0.25; n1 *= 0.25;
-        } else {
-            const int yg = y + g.row_offset;
-            const int ncy = 4 - (yg == 0 ? 1 : 0) - (yg == g.global_H - 1 ? 1 : 0);
-            const int nc0 = ncy - (x == 0 ? 1 : 0) - (x == g.L - 1 ? 1 : 0);
-            const int nc1 = ncy - (x + 1 == g.L - 1 ? 1 : 0);
-            n0 = (nc0 == 4) ? n0 * 0.25 : n0 / (double)nc0;
-            n1 = (nc1 == 4) ? n1 * 0.25 : n1 / (double)nc1;
-        }
-        double w0 = f0[r] * n0, w1 = f1[r] * n1;
-        if (w0 > a.clip) { w0 = a.clip; n0 = a.clip / f0[r]; }
-        if (w1 > a.clip) { w1 = a.clip; n1 = a.clip / f1[r]; }
-        if (mb & 1u) {
-            const double o = f0[r] * c0, d = fabs(w0 - o);
-            if (d != d) ++c_abs; else s_abs += d;
-            if (o != o) ++c_old; else s_old += o;
-            out[row + x] = n0;
-        }
-        if (mb & 2u) {
-            const double o = f1[r] * c1, d = fabs(w1 - o);
-            if (d != d) ++c_abs; else s_abs += d;
-            if (o != o) ++c_old; else s_old += o;
-            out[row + x + 1] = n1;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) jacobi2d_k1_ratio3_kernel(const StepArgs a) {
-    const TileRef tile = a.tiles[blockIdx.x];
-    const int p = tile.p;
-    const ProbState st = a.state[p];
-    if (st.k_run == 0) return;
-    const Geom &g = a.g;
-    const size_t plane = (size_t)g.H * g.pitch;
-    const double *__restrict__ in = reinterpret_cast<const double *>(a.buf[st.cur]) + (size_t)p * plane;
-    double *__restrict__ out = reinterpret_cast<double *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
-    const double *__restrict__ fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xw = tile.x0 + (warp & 1) * 64;
-    const int yb = tile.y0 + (warp >> 1) * 8;
-    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
-    double s_abs = 0.0, s_old = 0.0;
-    int c_abs = 0, c_old = 0;
-    if (xw < g.L && yb < y_lim) {
-        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
-        const int mp64 = g.mpitch >> 1;
-        const bool interior = (tile.y0 + g.row_offset > 0) && (tile.y0 + kTileH2 + g.row_offset < g.global_H) && (tile.x0 > 0) &&
-                              (tile.x0 + kTileW2 < g.L);
-        if (interior) ratio_strip_prefetch<true>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
-        else ratio_strip_prefetch<false>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
-    }
-    Acc<double> acc;
-    acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
-    write_partial(acc, a, p);
-}
-
-// Fourth form (the default): the prefetching of the third in two half-strips of 4 rows (6 state rows + 4 feature rows
-// requested before any arithmetic; ~80 registers, 3 blocks per SM), and -- when the caller reduces the sums in a
-// separate launch (step API, row-sharded runs) -- no block barrier at all: every warp writes its own partial sums and
-// the reduction kernel adds the 8 warps of a tile in order (the same bits as the block reduction).
+// The default form of the same sweep (VPINT_RATIO_KERNEL=1 selects the kernel above).  A warp takes its 8 rows as two
+// half-strips of 4: the 6 state rows and 4 feature rows of a half-strip are requested before any arithmetic (warp-uniform
+// tests of the 64-bit mask words decide which: no divergence, ~10 loads in flight per warp), the left / right
+// neighbours come from the adjacent lanes by shuffle (two edge loads per row instead of 64), tiles that do not touch
+// the grid border skip the neighbour counts, and -- when the caller reduces the sums in a separate launch (step API,
+// row-sharded runs) -- there is no block barrier at all: every warp writes its own partial sums and the reduction
+// kernel adds the 8 warps of a tile in order.  Thread <-> cell mapping, arithmetic and summation order are those of the
+// kernel above: results are bit-identical; half the warp instructions (ncu: 273 M -> 140 M per launch).
+// Measured and dropped: a plain sliding window over the 8 rows (fewest loads, but too few in flight: 0.51 against
+// 0.42 ms per sweep) and all 10 + 8 rows prefetched at once (128 registers, 2 blocks per SM, barrier stalls: 0.51).
 template <bool INTERIOR>
 __device__ __forceinline__ void ratio_half_strip(const StepArgs &a, const Geom &g, const double *__restrict__ in,
                                                  double *__restrict__ out, const double *__restrict__ fpl, int xw, int lane,
@@ -493,36 +305,6 @@ __global__ void __launch_bounds__(256, 3) jacobi2d_k1_ratio4_kernel(const StepAr
             dst[0] = q0; dst[1] = q1; dst[2] = (double)q2; dst[3] = (double)q3;
         }
         return;
-    }
-    Acc<double> acc;
-    acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
-    write_partial(acc, a, p);
-}
-
-__global__ void __launch_bounds__(256) jacobi2d_k1_ratio2_kernel(const StepArgs a) {
-    const TileRef tile = a.tiles[blockIdx.x];
-    const int p = tile.p;
-    const ProbState st = a.state[p];
-    if (st.k_run == 0) return;
-    const Geom &g = a.g;
-    const size_t plane = (size_t)g.H * g.pitch;
-    const double *__restrict__ in = reinterpret_cast<const double *>(a.buf[st.cur]) + (size_t)p * plane;
-    double *__restrict__ out = reinterpret_cast<double *>(a.buf[st.cur ^ 1]) + (size_t)p * plane;
-    const double *__restrict__ fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xw = tile.x0 + (warp & 1) * 64;
-    const int yb = tile.y0 + (warp >> 1) * 8;
-    const int y_lim = min(tile.y0 + kTileH2, g.own_row0 + g.own_rows);
-    double s_abs = 0.0, s_old = 0.0;
-    int c_abs = 0, c_old = 0;
-    if (xw < g.L && yb < y_lim) {
-        const uint64_t *m64 = reinterpret_cast<const uint64_t *>(a.mask + (size_t)p * g.H * g.mpitch) + (xw >> 6);
-        const int mp64 = g.mpitch >> 1;
-        // no cell of the tile on the border of the GLOBAL grid: every neighbour count is 4
-        const bool interior = (tile.y0 + g.row_offset > 0) && (tile.y0 + kTileH2 + g.row_offset < g.global_H) && (tile.x0 > 0) &&
-                              (tile.x0 + kTileW2 < g.L);
-        if (interior) ratio_strip<true>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
-        else ratio_strip<false>(a, g, in, out, fpl, m64, mp64, xw, lane, yb, y_lim, s_abs, s_old, c_abs, c_old);
     }
     Acc<double> acc;
     acc.s_abs = s_abs; acc.s_old = s_old; acc.c_abs = c_abs; acc.c_old = c_old;
@@ -715,10 +497,8 @@ cudaError_t launch_step2d(const StepArgs &a, int storage, int weight_mode, int64
 cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches) {
     if (n_tiles <= 0) return cudaSuccess;
     static const int ver = getenv("VPINT_RATIO_KERNEL") ? atoi(getenv("VPINT_RATIO_KERNEL")) : 4;
-    if (ver == 4) jacobi2d_k1_ratio4_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
-    else if (ver == 2) jacobi2d_k1_ratio2_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
-    else if (ver == 3) jacobi2d_k1_ratio3_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
-    else jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    if (ver == 1) jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
+    else jacobi2d_k1_ratio4_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }

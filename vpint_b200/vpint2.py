@@ -698,6 +698,9 @@ def run_patches(interpolators, serial=False, **kwargs):
     opts = wp_run_options(**kwargs)
     if opts["auto_adapt"]:          # per-band searches: no batching across patches
         return [vp.run_serial(**kwargs) if serial else vp.run(**kwargs) for vp in interpolators]
+    res = _run_patches_raw(interpolators, opts, serial)
+    if res is not None:
+        return res
     shape, dt = interpolators[0].target.shape, interpolators[0].target.dtype
     for vp in interpolators:
         if vp.target.shape != shape or vp.target.dtype != dt:
@@ -708,4 +711,44 @@ def run_patches(interpolators, serial=False, **kwargs):
         res = solve_bands(tgt, fts, opts, out_dtype=interpolators[0].DTYPE, out_layout="hwb")
         return [res[i] for i in range(len(interpolators))]
     res = solve_bands(tgt, fts, opts, out_layout="bhw")
+    return [res[i].swapaxes(0, 2).swapaxes(0, 1) for i in range(len(interpolators))]
+
+
+def _same(a, b):
+    if isinstance(a, (tuple, list)) or isinstance(b, (tuple, list)):
+        return isinstance(a, (tuple, list)) and isinstance(b, (tuple, list)) and list(a) == list(b)
+    return a == b
+
+
+def _run_patches_raw(interpolators, opts, serial):
+    """run_patches straight from the raw rasters when every interpolator still holds them and was built with the same
+    constructor options (None otherwise: the caller then goes through the host-built arrays)."""
+    first = interpolators[0]
+    if _solve.DEFAULT_K_BLOCK != 0 or not _fused_ok(opts):
+        return None
+    for vp in interpolators:
+        if getattr(vp, "_raw", None) is None or vp._raw[0].shape != first._raw[0].shape or vp._raw[0].dtype != first._raw[0].dtype:
+            return None
+        if np.dtype(vp.DTYPE) != np.dtype(first.DTYPE) or (vp._ctor["mask"] is None) != (first._ctor["mask"] is None):
+            return None
+        for k in ("buffer_mask", "mask_buffer_size", "mask_buffer_passes", "clip_target", "clip_features", "kwargs"):
+            if not _same(vp._ctor[k], first._ctor[k]):
+                return None
+    H, W, _ = first._raw[0].shape
+    if H * W < 128:
+        return None
+    c = first._ctor
+    tgt = np.stack([vp._raw[0] for vp in interpolators])
+    fts = np.stack([vp._raw[1] for vp in interpolators])
+    mask = None
+    if c["mask"] is not None:
+        mask = np.stack([vp._ctor["mask"] for vp in interpolators])
+        if mask.dtype not in (np.uint8, np.uint16, np.float32, np.float64):
+            mask = mask.astype(np.float64)
+    res = solve_raw(tgt, fts, mask, opts, mask_threshold=c["kwargs"].get("threshold", 0.2), buffer_mask=c["buffer_mask"],
+                    mask_buffer_size=c["mask_buffer_size"], mask_buffer_passes=c["mask_buffer_passes"],
+                    clip_target=c["clip_target"], clip_features=c["clip_features"], dtype=first.DTYPE,
+                    out_layout="hwb" if serial else "bhw", out_dtype=first.DTYPE).numpy()
+    if serial:
+        return [res[i] for i in range(len(interpolators))]
     return [res[i].swapaxes(0, 2).swapaxes(0, 1) for i in range(len(interpolators))]
