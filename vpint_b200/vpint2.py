@@ -292,9 +292,15 @@ class _RawSlot:
         # (low-priority, persistent) solve kernels of the chunks in flight on the other streams
         self.stream = torch.cuda.Stream(device=dev, priority=-8)     # mapped to the highest the device has
         self.solvers = {}
-        self.t_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
-        self.f_buf = torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None
-        self.m_buf = None if mask_dtype is None else torch.empty((chunk, H, W), dtype=mask_dtype, device=dev)
+        # two sets of input staging buffers: the rasters of this stream's NEXT chunk are copied in (on a copy stream of
+        # its own) while the current chunk computes, so the host link never makes a chunk wait
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=-8) if stage_in else None
+        self.t_bufs = [torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None for _ in range(2)]
+        self.f_bufs = [torch.empty((chunk, H, W, B), dtype=raster_dtype, device=dev) if stage_in else None for _ in range(2)]
+        self.m_bufs = [None if mask_dtype is None else torch.empty((chunk, H, W), dtype=mask_dtype, device=dev) for _ in range(2)]
+        self.copied = [None, None]          # event: staging set j holds its chunk
+        self.consumed = [None, None]        # event: the load of the chunk that used staging set j has read it
+        self.uses = 0
         self.cloud = torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) if need_cloud else None
         self.buf_scratch = torch.empty(3 * chunk * H * W, dtype=torch.uint8, device=dev) if buffer else None
         self.res = torch.empty(res_shape(chunk), dtype=res_dtype, device=dev) if need_res else None
@@ -429,24 +435,42 @@ class RawPipeline:
         with torch.cuda.device(dev):
             for sl in slots[:K]:
                 sl.stream.wait_stream(main)
+                if sl.copy_stream is not None:
+                    sl.copy_stream.wait_stream(main)
             for i, (a, b) in enumerate(spans):
                 sl = slots[i % K]
                 finish(sl)                             # the chunk this slot carried K chunks ago
                 m = b - a
+                j = sl.uses & 1
+                sl.uses += 1
+
+                def stage(span, jj, on):
+                    """Enqueue the host -> device copies of chunk `span` into staging set jj on stream `on`."""
+                    a2, b2 = span
+                    m2 = b2 - a2
+                    with torch.cuda.stream(on):
+                        if sl.consumed[jj] is not None:
+                            on.wait_event(sl.consumed[jj])
+                        sl.t_bufs[jj][:m2].copy_(target[a2:b2], non_blocking=True)
+                        sl.f_bufs[jj][:m2].copy_(features[a2:b2], non_blocking=True)
+                        if mask_stage is not None:
+                            sl.m_bufs[jj][:m2].copy_(mask[a2:b2], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(on)
+                    sl.copied[jj] = ev
+
+                if not in_on_dev and sl.copied[j] is None:
+                    stage((a, b), j, sl.stream)                # the first chunk of this stream: nothing was prefetched
                 with torch.cuda.stream(sl.stream):
                     if in_on_dev:
                         t_c, f_c = target[a:b], features[a:b]
                     else:
-                        sl.t_buf[:m].copy_(target[a:b], non_blocking=True)
-                        sl.f_buf[:m].copy_(features[a:b], non_blocking=True)
-                        t_c, f_c = sl.t_buf[:m], sl.f_buf[:m]
+                        sl.stream.wait_event(sl.copied[j])
+                        sl.copied[j] = None
+                        t_c, f_c = sl.t_bufs[j][:m], sl.f_bufs[j][:m]
                     cloud = None
                     if mask is not None:
-                        if mask_stage is not None:
-                            sl.m_buf[:m].copy_(mask[a:b], non_blocking=True)
-                            m_c = sl.m_buf[:m]
-                        else:
-                            m_c = mask[a:b]
+                        m_c = sl.m_bufs[j][:m] if mask_stage is not None else mask[a:b]
                         cloud = cloud_mask(m_c, mask_threshold, out=sl.cloud[:m])
                     if buffer_mask:
                         cloud = buffer_clouds(t_c, cloud, mask_buffer_size, mask_buffer_passes, scratch=sl.buf_scratch,
@@ -461,14 +485,22 @@ class RawPipeline:
                         known_dst = as_prob(sl.res[:m] if need_res else out[a:b])
                     solver.ingest_bands(t_c, f_c, cloud, value_dtype=value_dtype, clip_target=clip_target,
                                         clip_features=clip_features, out=known_dst, scratch=sl.fill_scratch[m])
+                    if not in_on_dev:
+                        sl.consumed[j] = torch.cuda.Event()
+                        sl.consumed[j].record(sl.stream)       # the staged rasters have been read (buffer_clouds reads them too)
                     solver.run_async(opts["iterations"], **run_kw)
                     emit_result(sl, a, b, solver)
                 sl.pending = (a, b, solver)
+                if not in_on_dev and i + K < len(spans):
+                    stage(spans[i + K], j ^ 1, sl.copy_stream)     # this stream's next chunk, while this one computes
             for sl in slots[:K]:
                 finish(sl)
             for sl in slots[:K]:
                 sl.stream.synchronize()
                 main.wait_stream(sl.stream)
+                sl.copied = [None, None]
+                sl.consumed = [None, None]
+                sl.uses = 0
         sweeps = sweeps_host.to(torch.int64).view(N_, B)
         return (out, sweeps) if return_sweeps else out
 
