@@ -7,14 +7,11 @@ one() {
   python - "$label" $out <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[2]))
+    d = json.loads([l for l in open(sys.argv[2]) if l.startswith("{")][-1])
     print("%-28s dev %.2f ms  kernel %.2f ms  e2e %.2f ms (min %.2f) ok=%s" % (sys.argv[1], d["ms_per_step"], d["roofline"]["kernel_ms"], d["e2e"]["ms_per_step"], d["e2e"]["ms_per_step_min"], d["e2e"]["result_check"]))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
 B="python bench.py --no-scene --no-variants --no-cpu-baseline"
-one prio16 $B
-one prio32 $B --chunk-patches 32
-one prio32s6 $B --chunk-patches 32 --streams 6
-one prio64s3 $B --chunk-patches 64 --streams 3
+for nb in 16 32 64 128 100000; do VPINT_RESULT_BLOCKS=$nb one rb$nb $B; done

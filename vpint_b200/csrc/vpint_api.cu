@@ -1089,6 +1089,7 @@ int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int
         const int rc = leave_ratio(s, static_cast<cudaStream_t>(stream));
         if (rc != VPINT_OK) return rc;
     }
+    int max_blocks = 0;
     {
         // pinned host memory is written through its device mapping (same address under unified addressing, but ask)
         cudaPointerAttributes attr;
@@ -1096,13 +1097,16 @@ int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int
         if (attr.type == cudaMemoryTypeHost) {
             if (!attr.devicePointer) return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: host memory is not mapped into the device");
             out = attr.devicePointer;
+            // bound by the host link, not by SMs: a few blocks keep enough stores in flight and leave the SMs to the
+            // solve kernels of the other streams
+            max_blocks = getenv("VPINT_RESULT_BLOCKS") ? atoi(getenv("VPINT_RESULT_BLOCKS")) : 32;
         } else if (attr.type == cudaMemoryTypeUnregistered) {
             return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: out must be device memory or pinned (mapped) host memory");
         }
     }
     void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
     VP_CUDA(launch_result_unknown(s->g, s->at<ProbState>(s->off_state), bufs, s->at<uint32_t>(s->off_mask), out, dtype,
-                                  stride, niter_out, static_cast<cudaStream_t>(stream), &s->launches),
+                                  stride, niter_out, max_blocks, static_cast<cudaStream_t>(stream), &s->launches),
             "result unknown");
     return VPINT_OK;
 }

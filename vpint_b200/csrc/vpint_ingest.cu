@@ -456,14 +456,15 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
                                                                         const uint32_t *__restrict__ mask, TOut *__restrict__ out,
                                                                         Strides sd, int interleaved, int32_t *niter_out) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * kUnkWarps + (threadIdx.x >> 5);
     const int B = interleaved ? g.Pin : 1;
     const int64_t n_rows = (int64_t)(g.P / B) * g.H;
-    if (r >= n_rows) return;
+    // grid-stride over the rows: the launcher caps the grid when `out` is host memory (the kernel is then bound by the
+    // host link, and a small grid keeps it from taking SMs the solve kernels of other streams could use)
+    for (int64_t r = (int64_t)blockIdx.x * kUnkWarps + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * kUnkWarps) {
     const int po = (int)(r / g.H), y = (int)(r - (int64_t)po * g.H);
     if (niter_out && y == 0)
         for (int b = lane; b < B; b += 32) niter_out[po * B + b] = state[po * B + b].iters_done;
-    if (y < g.own_row0 || y >= g.own_row0 + g.own_rows) return;
+    if (y < g.own_row0 || y >= g.own_row0 + g.own_rows) continue;
     const size_t plane = (size_t)g.H * g.pitch;
     if (!interleaved) {
         const int p = po;
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
             const int x = x0 + lane;
             if ((word >> lane) & 1u) dst[(int64_t)x * sd.sX] = to_out<TOut>(src[x]);
         }
-        return;
+        continue;
     }
     // any unknown cell in this row, in any band?
     unsigned any = 0;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
         const int b = k / words, w = k - b * words;
         any |= mask[((size_t)(po * B + b) * g.H + y) * g.mpitch + w];
     }
-    if (!__any_sync(0xffffffffu, any != 0)) return;
+    if (!__any_sync(0xffffffffu, any != 0)) continue;
     TOut *dst = out + (int64_t)po * sd.sO + (int64_t)y * sd.sY;
     const int total = g.L * B;
     for (int i0 = 0; i0 < total; i0 += 32) {
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(kUnkWarps * 32) result_unknown_kernel(Geom g, 
                 dst[i] = to_out<TOut>(src[x]);
             }
         }
+    }
     }
 }
 
@@ -708,11 +710,13 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
 }
 
 cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,
-                                  int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st, int64_t *launches) {
+                                  int dtype, const int64_t *stride, int32_t *niter_out, int max_blocks, cudaStream_t st,
+                                  int64_t *launches) {
     const Strides sd{stride[0], stride[1], stride[2], stride[3]};
     const int interleaved = (g.Pin >= 2 && sd.sI == 1 && sd.sX == g.Pin) ? 1 : 0;
     const int64_t n_rows = (int64_t)(interleaved ? g.P / g.Pin : g.P) * g.H;
-    const unsigned grid = (unsigned)((n_rows + kUnkWarps - 1) / kUnkWarps);
+    unsigned grid = (unsigned)((n_rows + kUnkWarps - 1) / kUnkWarps);
+    if (max_blocks > 0 && grid > (unsigned)max_blocks) grid = (unsigned)max_blocks;
     if (dtype == VPINT_F64)
         result_unknown_kernel<double><<<grid, kUnkWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1],
                                                                        mask, (double *)out, sd, interleaved, niter_out);

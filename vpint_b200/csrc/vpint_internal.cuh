@@ -213,7 +213,8 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const int64_t *out_stride, double *rowchunk, cudaStream_t st, int64_t *launches);
 int ingest_row_chunks(const Geom &g);
 cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,
-                                  int dtype, const int64_t *stride, int32_t *niter_out, cudaStream_t st, int64_t *launches);
+                                  int dtype, const int64_t *stride, int32_t *niter_out, int max_blocks, cudaStream_t st,
+                                  int64_t *launches);
 cudaError_t launch_prepare_reduce(const Geom &g, const double *rowpart, double *known0, double *known, ProbState *state,
                                   int *counters, cudaStream_t st, int64_t *launches);
 
