@@ -14,4 +14,5 @@ except Exception as e:
 PY
 }
 B="python bench.py --no-scene --no-variants --no-cpu-baseline"
-for nb in 16 32 64 128 100000; do VPINT_RESULT_BLOCKS=$nb one rb$nb $B; done
+one ramp $B
+VPINT_PIPELINE_RAMP=0 one noramp $B

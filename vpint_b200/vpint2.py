@@ -400,7 +400,17 @@ class RawPipeline:
         if result == "unknown" and not out_on_dev and not out.is_pinned():
             raise VPintError("result='unknown' needs a CUDA or pinned host `out`")
         need_res = (result == "full") and not out_on_dev
-        spans = [(a, min(a + chunk, N_)) for a in range(0, N_, chunk)]
+        # Chunks of `chunk` patches -- after a ramp: with the rasters on the host the first chunk of every stream waits
+        # for its copies (one copy engine serves all streams), so the first two rounds use quarter / half chunks and the
+        # SMs get work a few milliseconds sooner.
+        sizes = []
+        if not in_on_dev and chunk >= 4 and N_ >= 8 * chunk and os.environ.get("VPINT_PIPELINE_RAMP", "1") != "0":
+            sizes = [chunk // 4] * self.K + [chunk // 2] * self.K
+        spans, a0 = [], 0
+        for m0 in sizes:
+            spans.append((a0, a0 + m0))
+            a0 += m0
+        spans += [(a, min(a + chunk, N_)) for a in range(a0, N_, chunk)]
         sweeps_host = torch.empty(N_ * B, dtype=torch.int32, pin_memory=True)
         need_cloud = mask is not None or buffer_mask
         mask_stage = None if (mask is None or mask.device.type != "cpu") else mask.dtype
