@@ -125,6 +125,7 @@ struct vpint_solver {
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
     bool state_ratio = false;         // buffers are in ratio space right now
+    bool ratio_fresh = false;         // ... written so by the fused load, no sweep yet: plane slot 0 holds the exact start state
     int ratio_verdict = -1;           // -1 not evaluated since load/weights, 0 declined (extreme data), 1 allowed
     double *h_extreme = nullptr;      // pinned copy of the two range-check counters
     int64_t tiles_active = 0;
@@ -382,6 +383,7 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
     VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme), 0, sizeof(double), st), "memset range check");
     s->state_ratio = false;
+    s->ratio_fresh = false;
     s->ratio_verdict = -1;
     VP_CUDA(launch_prepare(g, original, pred0, s->at<double>(s->off_fill), dtype, stride, s->storage,
                            s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]),
@@ -408,7 +410,12 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void *planes[5];
     for (int i = 0; i < 5; ++i) planes[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
-    if (s->state_ratio) return fail(VPINT_ERR_INVALID, "vpint_solver_weights: call vpint_solver_load first (a run is in flight)");
+    {
+        // the state may still be in ratio space (a tiled run of a single-layer solve): bring it back with the OLD
+        // feature plane before the planes are rewritten
+        const int rc = leave_ratio(s, st);
+        if (rc != VPINT_OK) return rc;
+    }
     s->planes_valid = s->fplane_valid = false;
     s->no_nc = false;
     s->ratio_verdict = -1;
@@ -532,6 +539,15 @@ static int recompact_tiles(vpint_solver *s, cudaStream_t st, bool trim) {
 // ---- ratio form of the tiled path -----------------------------------------------------------------------
 static int leave_ratio(vpint_solver *s, cudaStream_t st) {
     if (!s->state_ratio) return VPINT_OK;
+    if (s->ratio_fresh) {
+        // nothing has run since the fused load wrote the ratio form: the saved plane IS the start state, bit for bit
+        const size_t plane = (size_t)s->g.P * s->g.S * s->g.H * s->g.pitch * s->elem;
+        VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_buf[0]), s->at<void>(s->off_w[0]), plane, cudaMemcpyDeviceToDevice, st), "restore state");
+        VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_buf[1]), s->at<void>(s->off_w[0]), plane, cudaMemcpyDeviceToDevice, st), "restore state");
+        s->state_ratio = false;
+        s->ratio_fresh = false;
+        return VPINT_OK;
+    }
     void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
     VP_CUDA(launch_from_ratio(s->g, s->at<ProbState>(s->off_state), bufs, s->at<double>(s->off_w[4]),
                               s->at<double>(s->off_w[0]), s->at<uint32_t>(s->off_mask), st, &s->launches),
@@ -658,6 +674,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
     a.max_iter = s->prm.max_iter;
     a.auto_terminate = s->prm.auto_terminate;
     a.threshold = s->prm.threshold;
+    s->ratio_fresh = false;              // (leave_ratio above has already used it if the ratio form is not taken)
     if (a.resist) {
         VP_CUDA(launch_step2d_resist(a, s->storage, s->weight_mode, st, &s->launches), "step2d_resist");
     } else if (use_ratio) {
@@ -1025,7 +1042,6 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
         return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_ingest_bands: rows too long for the staged load");
     if (p->out && p->out_dtype != VPINT_F32 && p->out_dtype != VPINT_F64 && p->out_dtype != VPINT_U16)
         return fail(VPINT_ERR_INVALID, "bad out dtype");
-    if (s->state_ratio) return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: a run is in flight");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Geom &g = s->g;
     if (p->fill_mode == VPINT_FILL_DEVICE) {
@@ -1047,19 +1063,28 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags) + 3, 0, sizeof(int), st), "memset flag");
     s->state_ratio = false;
+    s->ratio_fresh = false;
     s->ratio_verdict = -1;
     s->planes_valid = false;
     s->no_nc = false;
     // the second ping-pong buffer is only read by the tiled kernels: written lazily when the resident kernel will run
     const bool skip_b = s->res_ok && !s->has_orig;
+    // a solve the tiled ratio stencil will run (one sweep per launch, no resident plan): state written in ratio space now
+    const bool direct = !s->res_ok && !s->has_orig && !s->use_tb && s->g.KB == 1 && ingest_direct_supported(g, p->raster_dtype) &&
+                        !getenv("VPINT_NO_RATIO_DIRECT") && !getenv("VPINT_NO_RATIO_TILES");
     VP_CUDA(launch_ingest_bands(g, p->target, p->features, p->raster_dtype, p->value_dtype, p->cloud, p->clip_target,
                                 p->target_min, p->target_max, p->clip_features, p->features_min, p->features_max,
                                 s->at<double>(s->off_fill), s->at<double>(s->off_buf[0]),
                                 skip_b ? nullptr : s->at<double>(s->off_buf[1]), s->at<uint32_t>(s->off_mask),
                                 s->at<double>(s->off_w[4]), s->at<double>(s->off_rowpart), s->at<double>(s->off_extreme),
                                 s->at<int>(s->off_flags), p->out, p->out_dtype, p->out_stride,
-                                s->off_rowchunk ? s->at<double>(s->off_rowchunk) : nullptr, st, &s->launches),
+                                s->off_rowchunk ? s->at<double>(s->off_rowchunk) : nullptr,
+                                direct ? s->at<double>(s->off_w[0]) : nullptr, st, &s->launches),
             "ingest bands");
+    if (direct) {
+        s->state_ratio = true;
+        s->ratio_fresh = true;
+    }
     if (s->has_orig)
         VP_CUDA(cudaMemcpyAsync(s->at<void>(s->off_orig), s->at<void>(s->off_buf[0]),
                                 (size_t)g.P * g.S * g.H * g.pitch * s->elem, cudaMemcpyDeviceToDevice, st),
@@ -1327,11 +1352,19 @@ int vpint_solver_result(vpint_solver *s, void *out, int dtype, const int64_t *st
     if (!s->loaded) return fail(VPINT_ERR_INVALID, "vpint_solver_load has not been called");
     if (!out || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_result: null argument");
     if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
+    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+    if (s->state_ratio && !s->ratio_fresh && s->g.ndim == 2) {
+        // gather straight out of ratio space (unknown cells f * r, known cells their saved value); the state stays there
+        VP_CUDA(launch_result_ratio(s->g, s->at<ProbState>(s->off_state), bufs, s->at<double>(s->off_w[4]),
+                                    s->at<double>(s->off_w[0]), s->at<uint32_t>(s->off_mask), out, dtype, stride, niter_out,
+                                    static_cast<cudaStream_t>(stream), &s->launches),
+                "result (ratio)");
+        return VPINT_OK;
+    }
     {
         const int rc = leave_ratio(s, static_cast<cudaStream_t>(stream));
         if (rc != VPINT_OK) return rc;
     }
-    void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
     VP_CUDA(launch_result(s->g, s->storage, s->at<ProbState>(s->off_state), bufs, out, dtype, stride, niter_out,
                           static_cast<cudaStream_t>(stream), &s->launches),
             "result");

@@ -310,6 +310,7 @@ struct IngestArgs {
     int TW;
     int XC;                  // column chunks per row (one warp each)
     double *rowchunk;        // [P][H][XC][3] chunk partials when XC > 1
+    double *save;            // ratio-direct load: [P][H][pitch] the start state in value space (bufA / bufB then hold value / f)
 };
 
 // rowpart of a row = its chunk partials added in chunk order (fixed order: the known-cell sums are reproducible).
@@ -326,7 +327,10 @@ __global__ void __launch_bounds__(256) ingest_rowsum_kernel(int64_t n_rows_all, 
     rp[0] = 0.0; rp[1] = s; rp[2] = 0.0; rp[3] = 0.0; rp[4] = s; rp[5] = ninf; rp[6] = 0.0; rp[7] = nunk;
 }
 
-template <typename TIn, typename TAcc>
+// DIRECT: the tiled ratio stencil will run this solve (a scene, one feature layer), so the state is written in ratio space
+// at once -- bufA = bufB = value / feature, `save` = value -- instead of a separate pass over both buffers before the first
+// sweep (to_ratio_kernel).  Target and feature tiles are then staged side by side.
+template <typename TIn, typename TAcc, bool DIRECT>
 __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const IngestArgs a) {
     extern __shared__ __align__(16) unsigned char ing_raw[];
     __shared__ double racc[kIngestWarps][kIngestMaxBands][2];           // per band: sum of known values, packed counts
@@ -343,7 +347,8 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
     const int tiles = (g.pitch + TW - 1) / TW, per = (tiles + XC - 1) / XC;
     const int x_begin = xc * per * TW, x_end = min(g.pitch, (xc + 1) * per * TW);
     TIn *my = reinterpret_cast<TIn *>(ing_raw) + (size_t)warp * TW * B;
-    uint8_t *myc = ing_raw + (size_t)kIngestWarps * TW * B * sizeof(TIn) + (size_t)warp * TW;
+    TIn *myf = DIRECT ? reinterpret_cast<TIn *>(ing_raw) + (size_t)(kIngestWarps + warp) * TW * B : my;   // features beside the target
+    uint8_t *myc = ing_raw + (size_t)(DIRECT ? 2 : 1) * kIngestWarps * TW * B * sizeof(TIn) + (size_t)warp * TW;
     const int64_t row_elems = (int64_t)W * B;
     const TIn *trow = reinterpret_cast<const TIn *>(a.target) + ((int64_t)po * g.H + y) * row_elems;
     const TIn *frow = reinterpret_cast<const TIn *>(a.features) + ((int64_t)po * g.H + y) * row_elems;
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
         const int te = min(TW, g.pitch - x0);                            // plane elements of this tile (incl. padding)
         __syncwarp();
         if (tw > 0) warp_stage(my, trow + (int64_t)x0 * B, tw * B, lane);
+        if (DIRECT && tw > 0) warp_stage(myf, frow + (int64_t)x0 * B, tw * B, lane);
         for (int x = lane; x < tw; x += 32) myc[x] = a.cloud ? a.cloud[((int64_t)po * g.H + y) * W + x0 + x] : 0;
         __syncwarp();
         // known cells of the result, band-interleaved output: the staged tile has the output's own order
@@ -378,12 +384,19 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
             int counts = 0;                                             // #inf << 16 | #unknown
             for (int e = lane; e < te; e += 32) {
                 bool unknown = false;
-                double va = 0.0;
+                double va = 0.0, fe = 1.0;
                 if (e < tw) {
                     const double o = (double)conv_in<TAcc>(my[e * B + b], a.clip_t, a.t_lo, a.t_hi);
                     unknown = (o != o) || myc[e];
                     va = unknown ? fillv : o;
                     if (!(fabs(va) < 1e150)) wild = true;
+                    if (DIRECT) {
+                        fe = (double)conv_in<TAcc>(myf[e * B + b], a.clip_f, a.f_lo, a.f_hi);
+                        if (fe == 0.0) fe = 0.01;                 // VPint/WP_MRP.py:143-145
+                        if (!(fabs(fe) <= 1.7976931348623157e308)) bad = true;
+                        if (!(fabs(fe) < 1e150) || !(fabs(fe) > 1e-150)) fwild = true;
+                        if ((double)(float)fe != fe) wide = true;
+                    }
                     if (owned) {
                         if (unknown) counts += 1;
                         else {
@@ -393,8 +406,16 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
                         }
                     }
                 }
-                a.bufA[row + e] = va;
-                if (a.bufB) a.bufB[row + e] = va;
+                if (DIRECT) {
+                    const double ra = va / fe;                  // to_ratio_kernel's quotient, formed here
+                    a.bufA[row + e] = ra;
+                    a.bufB[row + e] = ra;
+                    a.save[row + e] = va;
+                    a.fplane[row + e] = fe;
+                } else {
+                    a.bufA[row + e] = va;
+                    if (a.bufB) a.bufB[row + e] = va;
+                }
                 const unsigned word = __ballot_sync(0xffffffffu, unknown);
                 if (lane == 0) a.mask[mrow + (e >> 5)] = word;
             }
@@ -406,6 +427,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
             }
         }
         __syncwarp();
+        if (DIRECT) continue;                                   // the feature plane was written with the state
         // features of the same tile reuse the staging area
         if (tw > 0) warp_stage(my, frow + (int64_t)x0 * B, tw * B, lane);
         __syncwarp();
@@ -657,6 +679,12 @@ int ingest_row_chunks(const Geom &g) {
     return want < 1 ? 1 : (int)want;
 }
 
+bool ingest_direct_supported(const Geom &g, int t_dtype) {
+    const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
+    const int TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
+    return 2 * (size_t)kIngestWarps * TW * g.Pin * tsz + (size_t)kIngestWarps * TW <= 200 * 1024;
+}
+
 bool ingest_bands_supported(const Geom &g, int t_dtype) {
     const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
     const int TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
@@ -668,8 +696,9 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, double *rowchunk, cudaStream_t st, int64_t *launches) {
+                                const int64_t *out_stride, double *rowchunk, double *save, cudaStream_t st, int64_t *launches) {
     IngestArgs a;
+    a.save = save;
     a.g = g;
     a.target = target; a.features = features; a.cloud = cloud;
     a.clip_t = clip_t; a.clip_f = clip_f; a.t_lo = t_lo; a.t_hi = t_hi; a.f_lo = f_lo; a.f_hi = f_hi;
@@ -679,18 +708,24 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     a.osd = out ? Strides{out_stride[0], out_stride[1], out_stride[2], out_stride[3]} : Strides{0, 0, 0, 0};
     const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
     a.TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
-    const size_t smem = (size_t)kIngestWarps * a.TW * g.Pin * tsz + (size_t)kIngestWarps * a.TW;
+    const bool direct = save != nullptr;
+    const size_t smem = (size_t)(direct ? 2 : 1) * kIngestWarps * a.TW * g.Pin * tsz + (size_t)kIngestWarps * a.TW;
     const int64_t n_rows = (int64_t)(g.P / g.Pin) * g.H;
     a.XC = ingest_row_chunks(g);
     a.rowchunk = rowchunk;
     if (a.XC > 1 && !rowchunk) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)((n_rows * a.XC + kIngestWarps - 1) / kIngestWarps);
     cudaError_t e;
-#define VP_ING(TIN, TACC)                                                                                                \
-    do {                                                                                                                 \
-        e = cudaFuncSetAttribute(ingest_bands_kernel<TIN, TACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                                  \
-        ingest_bands_kernel<TIN, TACC><<<grid, kIngestWarps * 32, smem, st>>>(a);                                        \
+#define VP_ING1(TIN, TACC, DIR)                                                                                               \
+    do {                                                                                                                      \
+        e = cudaFuncSetAttribute(ingest_bands_kernel<TIN, TACC, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                       \
+        ingest_bands_kernel<TIN, TACC, DIR><<<grid, kIngestWarps * 32, smem, st>>>(a);                                        \
+    } while (0)
+#define VP_ING(TIN, TACC)                    \
+    do {                                     \
+        if (direct) VP_ING1(TIN, TACC, true); \
+        else VP_ING1(TIN, TACC, false);      \
     } while (0)
     if (t_dtype == VPINT_U16 && acc_dtype == VPINT_F32) VP_ING(uint16_t, float);
     else if (t_dtype == VPINT_U16 && acc_dtype == VPINT_F64) VP_ING(uint16_t, double);
@@ -700,6 +735,7 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     else if (t_dtype == VPINT_F64 && acc_dtype == VPINT_F32) VP_ING(double, float);
     else return cudaErrorInvalidValue;
 #undef VP_ING
+#undef VP_ING1
     VP_LAUNCH_CHECK();
     if (a.XC > 1) {
         const int64_t n_all = (int64_t)g.P * g.H;

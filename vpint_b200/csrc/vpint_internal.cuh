@@ -186,6 +186,9 @@ cudaError_t launch_restore_known(const Geom &g, int storage, ProbState *state, v
                                  const uint32_t *mask, cudaStream_t st, int64_t *launches);
 cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state, void *const *buf, void *msg,
                              int first_row, int rows, bool pack, cudaStream_t st, int64_t *launches);
+cudaError_t launch_result_ratio(const Geom &g, const ProbState *state, void *const *buf, const double *f, const double *save,
+                                const uint32_t *mask, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
+                                cudaStream_t st, int64_t *launches);
 cudaError_t launch_lagged_commit(const DecideArgs &a, const double *sums_prev, cudaStream_t st, int64_t *launches);
 cudaError_t launch_halo_push(const Geom &g, const ProbState *state, void *const *buf, void *dst_up, void *dst_down,
                              int *flag_up, int *flag_down, int rows, int seq, int *tickets, cudaStream_t st, int64_t *launches);
@@ -210,8 +213,9 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, double *rowchunk, cudaStream_t st, int64_t *launches);
+                                const int64_t *out_stride, double *rowchunk, double *save, cudaStream_t st, int64_t *launches);
 int ingest_row_chunks(const Geom &g);
+bool ingest_direct_supported(const Geom &g, int t_dtype);
 cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,
                                   int dtype, const int64_t *stride, int32_t *niter_out, int max_blocks, cudaStream_t st,
                                   int64_t *launches);

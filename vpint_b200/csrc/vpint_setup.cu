@@ -656,6 +656,37 @@ __global__ void __launch_bounds__(kResultWarps * 32) result_kernel(Geom g, const
     if (niter_out && y == 0 && lane == 0 && p % g.S == 0) niter_out[p / g.S] = st.iters_done;
 }
 
+// The same gather while the state is in ratio space (tiled ratio path): unknown cells P = f * r of the current buffer,
+// known cells their saved original value -- what from_ratio_kernel would write, without the extra pass over both state
+// buffers; the solver stays in ratio space.
+template <typename TOut>
+__global__ void __launch_bounds__(kResultWarps * 32) result_ratio_kernel(Geom g, const ProbState *__restrict__ state,
+                                                                         const double *__restrict__ buf0,
+                                                                         const double *__restrict__ buf1,
+                                                                         const double *__restrict__ f,
+                                                                         const double *__restrict__ save,
+                                                                         const uint32_t *__restrict__ mask, TOut *__restrict__ out,
+                                                                         Strides sd, int32_t *niter_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kResultWarps + (threadIdx.x >> 5);
+    if (r >= (int64_t)g.P * g.H) return;
+    const int p = (int)(r / g.H), y = (int)(r - (int64_t)p * g.H);
+    const ProbState st = state[p];
+    const size_t row = ((size_t)p * g.H + y) * g.pitch;
+    const double *cur = (st.cur ? buf1 : buf0) + row;
+    const uint32_t *mr = mask + ((size_t)p * g.H + y) * g.mpitch;
+    TOut *dst = out + cell_offset(g, sd, p, y, 0);
+    for (int e0 = 0; e0 < g.L; e0 += 32) {
+        const int e = e0 + lane;
+        const unsigned word = mr[e0 >> 5];
+        if (e < g.L) {
+            const double v = ((word >> lane) & 1u) ? f[row + e] * cur[e] : save[row + e];
+            dst[(int64_t)e * sd.sX] = (TOut)v;
+        }
+    }
+    if (niter_out && y == 0 && lane == 0) niter_out[p] = st.iters_done;
+}
+
 // Row-sharded scenes: copy `rows` owned boundary rows of every problem's CURRENT buffer into a
 // contiguous [P][rows][pitch] message (pack), or a received message into the halo rows next to the owned
 // band (unpack).  `first_row` is the local row the block of rows starts at.
@@ -1073,6 +1104,21 @@ cudaError_t launch_halo_rows(const Geom &g, int storage, const ProbState *state,
         if (pack) halo_rows_kernel<float, true><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
         else halo_rows_kernel<float, false><<<grid, 256, 0, st>>>(g, state, (float *)buf[0], (float *)buf[1], (float *)msg, first_row, rows);
     }
+    VP_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_result_ratio(const Geom &g, const ProbState *state, void *const *buf, const double *f, const double *save,
+                                const uint32_t *mask, void *out, int dtype, const int64_t *stride, int32_t *niter_out,
+                                cudaStream_t st, int64_t *launches) {
+    const Strides sd{stride[0], stride[1], stride[2], stride[3], 0};
+    const unsigned grid = (unsigned)(((int64_t)g.P * g.H + kResultWarps - 1) / kResultWarps);
+    if (dtype == VPINT_F64)
+        result_ratio_kernel<double><<<grid, kResultWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1], f,
+                                                                       save, mask, (double *)out, sd, niter_out);
+    else
+        result_ratio_kernel<float><<<grid, kResultWarps * 32, 0, st>>>(g, state, (const double *)buf[0], (const double *)buf[1], f,
+                                                                      save, mask, (float *)out, sd, niter_out);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
