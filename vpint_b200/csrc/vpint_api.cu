@@ -399,6 +399,8 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     return resolve_tiles(s, st);
 }
 
+static int leave_ratio(vpint_solver *s, cudaStream_t st);
+
 int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int64_t *stride, int F, int method,
                          int clamp, double min_gamma, double max_gamma, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
