@@ -13,6 +13,7 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-B="python bench.py --no-scene --no-variants --no-cpu-baseline"
-one ramp $B
-VPINT_PIPELINE_RAMP=0 one noramp $B
+B="python bench.py --no-scene --no-variants --no-cpu-baseline --e2e-steps 5"
+one classes_234 $B
+VPINT_CLASS_MASK=4 one classes_24 $B
+VPINT_CLASS_MASK=8 one classes_34 $B

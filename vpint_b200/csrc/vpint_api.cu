@@ -858,6 +858,11 @@ int vpint_solver_run_async(vpint_solver *s, const vpint_run_params *prm, void *s
             int caps[kResidentMaxC + 1];
             for (int c = 0; c <= kResidentMaxC; ++c) caps[c] = (c_top && c <= c_top) ? s->res_caps[c] : 0;
             if (!c_top) caps[s->res_cmax] = s->res_caps[s->res_cmax];
+            if (const char *m = getenv("VPINT_CLASS_MASK")) {        // triage: bit c set = cluster size c may be used
+                const int mask = atoi(m);
+                for (int c = 1; c < s->res_cmax; ++c)
+                    if (!((mask >> c) & 1)) caps[c] = 0;
+            }
             VP_CUDA(launch_resident_order(s->g, ra.state, s->at<double>(s->off_rowpart), caps, s->res_cmax, cls_of, order,
                                           cls_count, st, &s->launches),
                     "queue order");
@@ -1126,7 +1131,7 @@ int vpint_solver_result_unknown(vpint_solver *s, void *out, int dtype, const int
             out = attr.devicePointer;
             // bound by the host link, not by SMs: a few blocks keep enough stores in flight and leave the SMs to the
             // solve kernels of the other streams
-            max_blocks = getenv("VPINT_RESULT_BLOCKS") ? atoi(getenv("VPINT_RESULT_BLOCKS")) : 32;
+            max_blocks = getenv("VPINT_RESULT_BLOCKS") ? atoi(getenv("VPINT_RESULT_BLOCKS")) : 64;
         } else if (attr.type == cudaMemoryTypeUnregistered) {
             return fail(VPINT_ERR_INVALID, "vpint_solver_result_unknown: out must be device memory or pinned (mapped) host memory");
         }
