@@ -7,7 +7,7 @@ import vpint_b200.vpint2 as V
 from vpint_b200.wp import wp_run_options
 dev = torch.device("cuda", 0)
 n = 512
-target, feats = make_patches_torch(n, 1003, dev)
+target, feats = make_patches_torch(n, 1003, dev)[:2]
 t_host = torch.empty(target.shape, dtype=torch.float32).pin_memory(); t_host.copy_(target)
 f_host = torch.empty(feats.shape, dtype=torch.float32).pin_memory(); f_host.copy_(feats)
 out_host = torch.empty((n, B, H, W), dtype=torch.float64).pin_memory()

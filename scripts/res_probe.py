@@ -9,7 +9,7 @@ from vpint_b200.vpint2 import _band_fill_values
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 dev = torch.device("cuda", 0)
-target, feats = make_patches_torch(n, 1003, dev)
+target, feats = make_patches_torch(n, 1003, dev)[:2]
 fill = _band_fill_values(target.cpu().numpy()).reshape(-1)
 s = Solver(2, n * B, H, W, nprob_inner=B, planes=True, k_block=0, device=dev)
 def ev(): return torch.cuda.Event(enable_timing=True)
