@@ -1346,6 +1346,14 @@ int vpint_solver_run_sharded(vpint_solver *s, const vpint_run_params *prm, void 
     }
     VP_CUDA(cudaStreamSynchronize(st), "sharded run sync");
     if (launches_out) *launches_out = n;
+    {
+        int timed_out = 0;
+        VP_CUDA(cudaMemcpy(&timed_out, ctr + 2, sizeof(int), cudaMemcpyDeviceToHost), "read time-out flag");
+        if (timed_out) {
+            VP_CUDA(cudaMemset(ctr + 2, 0, sizeof(int)), "clear time-out flag");
+            return fail(VPINT_ERR_CUDA, "vpint_solver_run_sharded: a rank did not publish its sums / halo rows within 10 s (peer died?)");
+        }
+    }
     if (!done) {
         int left = 0;
         VP_CUDA(cudaMemcpy(&left, d.n_active, sizeof(int), cudaMemcpyDeviceToHost), "read active count");

@@ -702,6 +702,23 @@ __global__ void __launch_bounds__(256) halo_rows_kernel(Geom g, const ProbState 
     }
 }
 
+// Wait until *flag >= want (system-scope acquire), for at most ~10 s: a rank that died must not hang its neighbours'
+// kernels for ever.  Returns false on a time-out (the caller records it; the results of the run are void then).
+__device__ __forceinline__ bool wait_flag(const int *flag, int want) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= want) return true;
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) return false;
+        }
+    }
+}
+
 // ---- row-sharded scenes, low-latency protocol ----------------------------------------------------------------
 // Stop decision with a lag of one sweep (the trick of the cluster-resident kernel): launch t computes sweep t and its
 // local sums; while their all-reduce travels, launch t + 1 already computes sweep t + 1.  This kernel runs after the
@@ -775,12 +792,7 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(Geom g, const ProbState 
     const double *src = side ? src_down : src_up;
     const int *flag = side ? flag_down : flag_up;
     if (!src) return;
-    if (threadIdx.x == 0) {
-        int v;
-        do {
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        } while (v < seq);
-    }
+    if (threadIdx.x == 0) wait_flag(flag, seq);      // bounded: a dead neighbour must not hang this GPU
     __syncthreads();
     const int p = blockIdx.x / rows, r = blockIdx.x - p * rows;
     const int first = side ? g.own_row0 + g.own_rows : g.own_row0 - rows;
@@ -806,10 +818,7 @@ __global__ void __launch_bounds__(256) peer_commit_kernel(Geom g, ProbState *sta
     char *mine = pc.base[pc.rank];
     if (!first && tid < pc.world) {
         const int *flag = reinterpret_cast<const int *>(mine + pc.off_sflag + (size_t)tid * 128);
-        int v;
-        do {
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        } while (v < t);
+        if (!wait_flag(flag, t)) ctr[2] = 1;          // a rank never published its sums: recorded, reported by the host
     }
     __syncthreads();
     const double *prev = reinterpret_cast<const double *>(mine + pc.off_gather) + (size_t)((t - 1) & 1) * slot_elems;
@@ -905,12 +914,7 @@ __global__ void __launch_bounds__(256) peer_halo_kernel(Geom g, const ProbState 
         char *mine = pc.base[pc.rank];
         const double *in = reinterpret_cast<const double *>(mine + (size_t)(2 * slot + side) * msg) + row_off;
         const int *flag = reinterpret_cast<const int *>(mine + 4 * msg + (side ? 128 : 0));
-        if (threadIdx.x == 0) {
-            int v;
-            do {
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            } while (v < seq);
-        }
+        if (threadIdx.x == 0 && !wait_flag(flag, seq)) const_cast<int *>(ctr)[2] = 1;
         __syncthreads();
         const int first = side ? g.own_row0 + g.own_rows : g.own_row0 - rows;
         double *dstrow = cur + ((size_t)p * g.H + first + r) * g.pitch;
