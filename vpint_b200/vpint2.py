@@ -442,72 +442,84 @@ class RawPipeline:
                         solver.result(out=as_prob(sl.res[:b - a] if need_res else out[a:b]))
                     emit_result(sl, a, b, solver)
 
-        with torch.cuda.device(dev):
-            for sl in slots[:K]:
-                sl.stream.wait_stream(main)
-                if sl.copy_stream is not None:
-                    sl.copy_stream.wait_stream(main)
-            for i, (a, b) in enumerate(spans):
-                sl = slots[i % K]
-                finish(sl)                             # the chunk this slot carried K chunks ago
-                m = b - a
-                j = sl.uses & 1
-                sl.uses += 1
+        try:
+            with torch.cuda.device(dev):
+                for sl in slots[:K]:
+                    sl.stream.wait_stream(main)
+                    if sl.copy_stream is not None:
+                        sl.copy_stream.wait_stream(main)
+                for i, (a, b) in enumerate(spans):
+                    sl = slots[i % K]
+                    finish(sl)                             # the chunk this slot carried K chunks ago
+                    m = b - a
+                    j = sl.uses & 1
+                    sl.uses += 1
 
-                def stage(span, jj, on):
-                    """Enqueue the host -> device copies of chunk `span` into staging set jj on stream `on`."""
-                    a2, b2 = span
-                    m2 = b2 - a2
-                    with torch.cuda.stream(on):
-                        if sl.consumed[jj] is not None:
-                            on.wait_event(sl.consumed[jj])
-                        sl.t_bufs[jj][:m2].copy_(target[a2:b2], non_blocking=True)
-                        sl.f_bufs[jj][:m2].copy_(features[a2:b2], non_blocking=True)
-                        if mask_stage is not None:
-                            sl.m_bufs[jj][:m2].copy_(mask[a2:b2], non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(on)
-                    sl.copied[jj] = ev
+                    def stage(span, jj, on):
+                        """Enqueue the host -> device copies of chunk `span` into staging set jj on stream `on`."""
+                        a2, b2 = span
+                        m2 = b2 - a2
+                        with torch.cuda.stream(on):
+                            if sl.consumed[jj] is not None:
+                                on.wait_event(sl.consumed[jj])
+                            sl.t_bufs[jj][:m2].copy_(target[a2:b2], non_blocking=True)
+                            sl.f_bufs[jj][:m2].copy_(features[a2:b2], non_blocking=True)
+                            if mask_stage is not None:
+                                sl.m_bufs[jj][:m2].copy_(mask[a2:b2], non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record(on)
+                        sl.copied[jj] = ev
 
-                if not in_on_dev and sl.copied[j] is None:
-                    stage((a, b), j, sl.stream)                # the first chunk of this stream: nothing was prefetched
-                with torch.cuda.stream(sl.stream):
-                    if in_on_dev:
-                        t_c, f_c = target[a:b], features[a:b]
-                    else:
-                        sl.stream.wait_event(sl.copied[j])
-                        sl.copied[j] = None
-                        t_c, f_c = sl.t_bufs[j][:m], sl.f_bufs[j][:m]
-                    cloud = None
-                    if mask is not None:
-                        m_c = sl.m_bufs[j][:m] if mask_stage is not None else mask[a:b]
-                        cloud = cloud_mask(m_c, mask_threshold, out=sl.cloud[:m])
-                    if buffer_mask:
-                        cloud = buffer_clouds(t_c, cloud, mask_buffer_size, mask_buffer_passes, scratch=sl.buf_scratch,
-                                              out=sl.cloud[:m])
-                    if m not in sl.solvers:
-                        sl.solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, planes=True, k_block=self.k_block, device=dev,
-                                               blocking_wait=True)
-                        sl.fill_scratch[m] = sl.solvers[m].fill_scratch(value_dtype)
-                    solver = sl.solvers[m]
-                    known_dst = None
-                    if result == "full":
-                        known_dst = as_prob(sl.res[:m] if need_res else out[a:b])
-                    solver.ingest_bands(t_c, f_c, cloud, value_dtype=value_dtype, clip_target=clip_target,
-                                        clip_features=clip_features, out=known_dst, scratch=sl.fill_scratch[m])
-                    if not in_on_dev:
-                        sl.consumed[j] = torch.cuda.Event()
-                        sl.consumed[j].record(sl.stream)       # the staged rasters have been read (buffer_clouds reads them too)
-                    solver.run_async(opts["iterations"], **run_kw)
-                    emit_result(sl, a, b, solver)
-                sl.pending = (a, b, solver)
-                if not in_on_dev and i + K < len(spans):
-                    stage(spans[i + K], j ^ 1, sl.copy_stream)     # this stream's next chunk, while this one computes
+                    if not in_on_dev and sl.copied[j] is None:
+                        stage((a, b), j, sl.stream)                # the first chunk of this stream: nothing was prefetched
+                    with torch.cuda.stream(sl.stream):
+                        if in_on_dev:
+                            t_c, f_c = target[a:b], features[a:b]
+                        else:
+                            sl.stream.wait_event(sl.copied[j])
+                            sl.copied[j] = None
+                            t_c, f_c = sl.t_bufs[j][:m], sl.f_bufs[j][:m]
+                        cloud = None
+                        if mask is not None:
+                            m_c = sl.m_bufs[j][:m] if mask_stage is not None else mask[a:b]
+                            cloud = cloud_mask(m_c, mask_threshold, out=sl.cloud[:m])
+                        if buffer_mask:
+                            cloud = buffer_clouds(t_c, cloud, mask_buffer_size, mask_buffer_passes, scratch=sl.buf_scratch,
+                                                  out=sl.cloud[:m])
+                        if m not in sl.solvers:
+                            sl.solvers[m] = Solver(2, m * B, H, W, nprob_inner=B, planes=True, k_block=self.k_block, device=dev,
+                                                   blocking_wait=True)
+                            sl.fill_scratch[m] = sl.solvers[m].fill_scratch(value_dtype)
+                        solver = sl.solvers[m]
+                        known_dst = None
+                        if result == "full":
+                            known_dst = as_prob(sl.res[:m] if need_res else out[a:b])
+                        solver.ingest_bands(t_c, f_c, cloud, value_dtype=value_dtype, clip_target=clip_target,
+                                            clip_features=clip_features, out=known_dst, scratch=sl.fill_scratch[m])
+                        if not in_on_dev:
+                            sl.consumed[j] = torch.cuda.Event()
+                            sl.consumed[j].record(sl.stream)       # the staged rasters have been read (buffer_clouds reads them too)
+                        solver.run_async(opts["iterations"], **run_kw)
+                        emit_result(sl, a, b, solver)
+                    sl.pending = (a, b, solver)
+                    if not in_on_dev and i + K < len(spans):
+                        stage(spans[i + K], j ^ 1, sl.copy_stream)     # this stream's next chunk, while this one computes
+                for sl in slots[:K]:
+                    finish(sl)
+                for sl in slots[:K]:
+                    sl.stream.synchronize()
+                    main.wait_stream(sl.stream)
+        finally:
+            # whatever happened, the next call starts from a clean pipeline (an error leaves chunks in flight: drain them)
             for sl in slots[:K]:
-                finish(sl)
-            for sl in slots[:K]:
-                sl.stream.synchronize()
-                main.wait_stream(sl.stream)
+                if sl.pending is not None:
+                    try:
+                        sl.stream.synchronize()
+                        if sl.copy_stream is not None:
+                            sl.copy_stream.synchronize()
+                    except Exception:       # noqa: BLE001 -- a sticky CUDA error: nothing more to drain
+                        pass
+                    sl.pending = None
                 sl.copied = [None, None]
                 sl.consumed = [None, None]
                 sl.uses = 0
