@@ -298,11 +298,34 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def prefer_gpu_memory_node(pci):
+    """Host memory allocated from now on (the pinned buffers) prefers the NUMA node the GPU hangs off, even when the
+    CPUs this process may run on sit elsewhere: set_mempolicy(MPOL_PREFERRED).  Returns a note for the bench line."""
+    import ctypes
+    import glob
+    nodes = sorted(int(d.rsplit("node", 1)[1]) for d in glob.glob("/sys/devices/system/node/node[0-9]*"))
+    if len(nodes) < 2 or not pci:
+        return "%d NUMA node(s) visible" % len(nodes)
+    dom, rest = pci.split(":", 1)
+    with open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)) as fh:
+        node = int(fh.read().strip())
+    if node < 0:
+        return "%d NUMA nodes, GPU node unknown" % len(nodes)
+    mask = ctypes.c_ulong(1 << node)
+    libc = ctypes.CDLL(None, use_errno=True)
+    rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(65))      # x86-64 set_mempolicy, MPOL_PREFERRED
+    if rc != 0:
+        return "%d NUMA nodes, GPU on node %d, set_mempolicy refused (errno %d)" % (len(nodes), node, ctypes.get_errno())
+    return "%d NUMA nodes, host buffers prefer node %d (the GPU's)" % (len(nodes), node)
+
+
 def bind_to_gpu_node(index, pci=None, local_ranks=1, local_rank=0):
     """Pin this process (and the threads it starts later) to CPUs NVML reports as local to GPU `index`, so that the
     pinned host buffers of the e2e leg are allocated on the GPU's NUMA node (PCIe traffic across the socket link runs
     at half speed).  When several ranks share the same CPU set (one NUMA node for all GPUs of the box), every rank
-    takes its own slice of it instead of all ranks piling onto the same cores."""
+    takes its own slice of it instead of all ranks piling onto the same cores.  Where the box shows several NUMA
+    nodes, the memory policy is pointed at the GPU's node as well (prefer_gpu_memory_node)."""
+    note = "unbound"
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -318,10 +341,14 @@ def bind_to_gpu_node(index, pci=None, local_ranks=1, local_rank=0):
                 cpus = set(ordered[local_rank * per:(local_rank + 1) * per])
                 note += ", slice of %d for this rank" % len(cpus)
             os.sched_setaffinity(0, cpus)
-            return note
     except Exception as exc:                      # NVML missing or affinity not permitted: run unbound
-        return "unbound (%s)" % type(exc).__name__
-    return "unbound"
+        note = "unbound (%s)" % type(exc).__name__
+    if os.environ.get("VPINT_BENCH_NO_MEMPOLICY") != "1":
+        try:
+            note += "; " + prefer_gpu_memory_node(pci)
+        except Exception as exc:
+            note += "; memory policy untouched (%s)" % type(exc).__name__
+    return note
 
 
 def run_gpu(args):

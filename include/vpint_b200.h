@@ -134,7 +134,10 @@ int    vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes);
  *   fill     : HOST array [nprob]; only read when pred0 == NULL.  With pred0 == NULL and
  *              fill == NULL the init_strategy='mean' value is computed on the device:
  *              np.nanmean of each problem's grid in ITS dtype, bit-identical to NumPy's
- *              pairwise summation (grids up to 131072 cells; larger grids need fill).
+ *              pairwise summation (grids up to 131072 cells in one kernel; for larger grids call
+ *              vpint_solver_fill_leaves + vpint_solver_fill_combine on the band-interleaved raster
+ *              first -- the next load with pred0 == NULL and fill == NULL uses those values -- or
+ *              pass fill).
  *   stride   : 5 element strides {outer problem, inner problem, row, column, t}
  *              of original/pred0 (t ignored for ndim == 2).  This is how the
  *              band-interleaved (N, H, W, B) VPint2 arrays are read in place:

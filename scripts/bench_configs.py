@@ -42,12 +42,52 @@ def timed_solver(make, reps=3):
     return best, sweeps
 
 
+def c5(torch, Solver, dev, res):
+    # C5: SD_STMRP 2048x2048x64, 30 % missing (disc clouds per time slice), generated on the device
+    Hc, Wc, Tc = 2048, 2048, 64
+    g = torch.Generator(device=dev); g.manual_seed(1005)
+    yy = (torch.arange(Hc, device=dev, dtype=torch.float64) / Hc).view(-1, 1, 1)
+    xx = (torch.arange(Wc, device=dev, dtype=torch.float64) / Wc).view(1, -1, 1)
+    tt = (torch.arange(Tc, device=dev, dtype=torch.float64) / Tc).view(1, 1, -1)
+    cube = 20.0 + 5.0 * torch.sin(2 * np.pi * (0.7 * yy + 0.1)) * torch.cos(2 * np.pi * (1.3 * xx + 0.4)) * (1.0 + 0.2 * torch.sin(2 * np.pi * tt))
+    cube = cube + 0.3 * torch.randn((Hc, Wc, Tc), generator=g, device=dev, dtype=torch.float64)
+    miss = torch.zeros((Hc, Wc, Tc), dtype=torch.bool, device=dev)
+    discs = torch.rand((Tc, 8, 3), generator=g, device=dev, dtype=torch.float64)
+    for t in range(Tc):
+        m2 = torch.zeros((Hc, Wc), dtype=torch.bool, device=dev)
+        for k in range(8):
+            cy, cx, r = discs[t, k]
+            rad = 0.05 + 0.12 * r
+            m2 |= (yy[:, :, 0] - cy) ** 2 + (xx[:, :, 0] - cx) ** 2 < rad * rad
+        miss[:, :, t] = m2
+    mean = float(cube[~miss].mean().item())
+    cube[miss] = float("nan")
+    c_dev = cube.unsqueeze(0)
+    frac = float(miss.double().mean().item())
+    for it in (-1, 50):
+        def make(it=it):
+            s = Solver(3, 1, Hc, Wc, Tc, planes=False, device=dev)
+            s.load(c_dev, fill=[mean])
+            s.discounts(0.9, 0.9)
+            return s, (lambda s: s.run(10000 if it < 0 else it, auto_terminate=it < 0))
+        ms, sw = timed_solver(make, reps=2)
+        res.append({"config": "C5 SD_STMRP 2048x2048x64 %.0f%% missing, %s" % (100 * frac, "auto-terminate" if it < 0 else "run(50)"),
+                    "ms": ms, "sweeps": int(sw[0]), "mcell_it_per_s": Hc * Wc * Tc * int(sw[0]) / ms / 1e3,
+                    "algorithmic_gbps_unknown_cells": 16.0 * Hc * Wc * Tc * frac * int(sw[0]) / ms / 1e6})
+
+
 def main():
     import torch
     from vpint_b200.engine import Solver
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(1001)
     res = []
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""     # "c5": the 3-D cube alone (ncu captures)
+    if only == "c5":
+        c5(torch, Solver, dev, res)
+        for r in res:
+            print(json.dumps(r))
+        return
     # C1: SD_SMRP 100x100, 20 % hidden, gamma 0.9
     grid = smooth(rng, (100, 100), 15, 25) + rng.normal(0, 1, (100, 100))
     grid[rng.uniform(size=grid.shape) < 0.2] = np.nan
@@ -98,37 +138,7 @@ def main():
         m.run()
         walls.append(1e3 * (time.perf_counter() - t0))
     res.append({"config": "C2 WP_SMRP(...).run() through the class API, wall clock incl. H2D / D2H", "ms": min(walls)})
-    # C5: SD_STMRP 2048x2048x64, 30 % missing (disc clouds per time slice), generated on the device
-    Hc, Wc, Tc = 2048, 2048, 64
-    g = torch.Generator(device=dev); g.manual_seed(1005)
-    yy = (torch.arange(Hc, device=dev, dtype=torch.float64) / Hc).view(-1, 1, 1)
-    xx = (torch.arange(Wc, device=dev, dtype=torch.float64) / Wc).view(1, -1, 1)
-    tt = (torch.arange(Tc, device=dev, dtype=torch.float64) / Tc).view(1, 1, -1)
-    cube = 20.0 + 5.0 * torch.sin(2 * np.pi * (0.7 * yy + 0.1)) * torch.cos(2 * np.pi * (1.3 * xx + 0.4)) * (1.0 + 0.2 * torch.sin(2 * np.pi * tt))
-    cube = cube + 0.3 * torch.randn((Hc, Wc, Tc), generator=g, device=dev, dtype=torch.float64)
-    miss = torch.zeros((Hc, Wc, Tc), dtype=torch.bool, device=dev)
-    discs = torch.rand((Tc, 8, 3), generator=g, device=dev, dtype=torch.float64)
-    for t in range(Tc):
-        m2 = torch.zeros((Hc, Wc), dtype=torch.bool, device=dev)
-        for k in range(8):
-            cy, cx, r = discs[t, k]
-            rad = 0.05 + 0.12 * r
-            m2 |= (yy[:, :, 0] - cy) ** 2 + (xx[:, :, 0] - cx) ** 2 < rad * rad
-        miss[:, :, t] = m2
-    mean = float(cube[~miss].mean().item())
-    cube[miss] = float("nan")
-    c_dev = cube.unsqueeze(0)
-    frac = float(miss.double().mean().item())
-    for it in (-1, 50):
-        def make(it=it):
-            s = Solver(3, 1, Hc, Wc, Tc, planes=False, device=dev)
-            s.load(c_dev, fill=[mean])
-            s.discounts(0.9, 0.9)
-            return s, (lambda s: s.run(10000 if it < 0 else it, auto_terminate=it < 0))
-        ms, sw = timed_solver(make, reps=2)
-        res.append({"config": "C5 SD_STMRP 2048x2048x64 %.0f%% missing, %s" % (100 * frac, "auto-terminate" if it < 0 else "run(50)"),
-                    "ms": ms, "sweeps": int(sw[0]), "mcell_it_per_s": Hc * Wc * Tc * int(sw[0]) / ms / 1e3,
-                    "algorithmic_gbps_unknown_cells": 16.0 * Hc * Wc * Tc * frac * int(sw[0]) / ms / 1e6})
+    c5(torch, Solver, dev, res)
     for r in res:
         print(json.dumps(r))
 

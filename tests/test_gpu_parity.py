@@ -550,6 +550,42 @@ def test_device_mean_init_band_interleaved_stack(dtype):
             assert np.array_equal(got[i, b][~np.isnan(band)], band[~np.isnan(band)].astype(np.float64))
 
 
+@pytest.mark.parametrize("dtype,storage", [(np.float32, "float64"), (np.float64, "float64"), (np.float32, "float32")])
+def test_large_grid_float_stack_takes_its_mean_on_the_device(dtype, storage, monkeypatch):
+    """Float stacks above the single-kernel limit (131 072 cells): the leaf / subtree kernels give the bit-identical
+    np.nanmean per band, no host pass (VPint/MRP.py:73-77), then the ordinary load; the class entry point agrees."""
+    import torch
+    from vpint_b200 import vpint2 as V
+    rng = np.random.default_rng(4242)
+    N, H, W, B = 2, 397, 411, 3                         # 163 167 cells, not a multiple of 8
+    stack = np.round(rng.uniform(0, 9000, (N, H, W, B))).astype(dtype)
+    for i in range(N):
+        stack[i, rng.uniform(size=(H, W)) < 0.15 + 0.2 * i, :] = np.nan
+    monkeypatch.setattr(V, "_band_fill_values", lambda *a, **k: pytest.fail("host mean taken"))
+    s = Solver(2, N * B, H, W, nprob_inner=B, planes=False, storage=storage)
+    try:
+        t = torch.from_numpy(stack).cuda()
+        V._device_band_means(s, t)
+        s.load(t.permute(0, 3, 1, 2), fill=None)
+        out, _ = s.result(dtype=torch.float64)
+        got = out.cpu().numpy().reshape(N, B, H, W)
+    finally:
+        s.close()
+    for i in range(N):
+        for b in range(B):
+            band = stack[i, :, :, b]
+            want = np.nanmean(band.copy())
+            filled = got[i, b][np.isnan(band)]
+            want = np.float64(np.float32(want)) if storage == "float32" else np.float64(want)
+            assert filled.size > 0 and (filled == want).all(), (i, b, filled[0], want)
+    if storage == "float64":
+        feats = np.round(rng.uniform(100, 9000, (N, H, W, B))).astype(dtype)
+        from vpint_b200.wp import wp_run_options
+        res = V.solve_bands(stack, feats, wp_run_options(iterations=12, auto_terminate=False), out_layout="hwb")
+        ref, _ = O.vpint2_run(stack[1], feats[1], iterations=12, auto_terminate=False)
+        close(np.asarray(res)[1], ref)
+
+
 def test_pipelined_host_stack_equals_single_solve():
     import torch
     from vpint_b200.vpint2 import _solve_bands_torch

@@ -125,6 +125,7 @@ struct vpint_solver {
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
     bool state_ratio = false;         // buffers are in ratio space right now
+    bool fill_ready = false;          // vpint_solver_fill_combine left the start values at off_fill; the next load may use them
     bool ratio_fresh = false;         // ... written so by the fused load, no sweep yet: plane slot 0 holds the exact start state
     int ratio_verdict = -1;           // -1 not evaluated since load/weights, 0 declined (extreme data), 1 allowed
     double *h_extreme = nullptr;      // pinned copy of the two range-check counters
@@ -367,9 +368,11 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
                       const int64_t *stride, void *stream) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!original || !stride) return fail(VPINT_ERR_INVALID, "vpint_solver_load: null argument");
-    const bool device_fill = (!pred0 && !fill);
+    const bool fill_kept = (!pred0 && !fill && s->fill_ready);      // fill_leaves + fill_combine ran before this load
+    s->fill_ready = false;
+    const bool device_fill = (!pred0 && !fill && !fill_kept);
     if (device_fill && !fill_mean_supported(s->g))
-        return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_load: grid too large for the on-device mean init; pass fill");
+        return fail(VPINT_ERR_UNSUPPORTED, "vpint_solver_load: grid too large for the single-kernel mean init; run vpint_solver_fill_leaves + vpint_solver_fill_combine first, or pass fill");
     if (device_fill && (s->g.global_H != s->g.H))
         return fail(VPINT_ERR_INVALID, "vpint_solver_load: a row shard cannot take the mean of the whole grid; pass fill");
     if (dtype != VPINT_F64 && dtype != VPINT_F32) return fail(VPINT_ERR_INVALID, "bad dtype");
@@ -377,7 +380,7 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     const Geom &g = s->g;
     if (device_fill)
         VP_CUDA(launch_fill_mean(g, original, dtype, stride, s->at<double>(s->off_fill), st, &s->launches), "fill mean");
-    else if (!pred0)
+    else if (!pred0 && !fill_kept)
         VP_CUDA(cudaMemcpyAsync(s->at<double>(s->off_fill), fill, (size_t)g.P * sizeof(double), cudaMemcpyHostToDevice, st),
                 "copy fill");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
@@ -994,20 +997,24 @@ size_t vpint_fill_count_offset(int64_t cells_global, int nprob, int value_dtype)
     return ((size_t)vpint_fill_leaf_count(cells_global, nprob) * esz + 255) / 256 * 256;
 }
 
-static int check_ingest(const vpint_solver *s, const vpint_ingest_params *p, const char *who) {
+static int check_ingest(const vpint_solver *s, const vpint_ingest_params *p, const char *who, bool mean_only = false) {
     if (!s || !s->ws) return fail(VPINT_ERR_WORKSPACE, "solver has no workspace bound");
     if (!p || !p->target) return fail(VPINT_ERR_INVALID, std::string(who) + ": null argument");
     if (p->raster_dtype != VPINT_U16 && p->raster_dtype != VPINT_F32 && p->raster_dtype != VPINT_F64)
         return fail(VPINT_ERR_INVALID, std::string(who) + ": raster dtype must be VPINT_U16, VPINT_F32 or VPINT_F64");
     if (p->value_dtype != VPINT_F32 && p->value_dtype != VPINT_F64)
         return fail(VPINT_ERR_INVALID, std::string(who) + ": value dtype must be VPINT_F32 or VPINT_F64");
+    if (mean_only) {                  // the mean init reads the raster only: any 2-D solver
+        if (s->g.ndim != 2) return fail(VPINT_ERR_UNSUPPORTED, std::string(who) + ": needs a 2-D solver");
+        return VPINT_OK;
+    }
     if (s->g.ndim != 2 || s->storage != VPINT_F64 || s->weight_mode != VPINT_W_PLANES)
         return fail(VPINT_ERR_UNSUPPORTED, std::string(who) + ": needs a 2-D fp64 solver with weight planes");
     return VPINT_OK;
 }
 
 int vpint_solver_fill_leaves(vpint_solver *s, const vpint_ingest_params *p, void *stream) {
-    int rc = check_ingest(s, p, "vpint_solver_fill_leaves");
+    int rc = check_ingest(s, p, "vpint_solver_fill_leaves", true);
     if (rc != VPINT_OK) return rc;
     if (!p->scratch) return fail(VPINT_ERR_INVALID, "vpint_solver_fill_leaves: null scratch");
     const Geom &g = s->g;
@@ -1035,6 +1042,7 @@ int vpint_solver_fill_combine(vpint_solver *s, int value_dtype, void *scratch, v
     VP_CUDA(launch_fill_combine(value_dtype, g.P, (int64_t)g.global_H * g.W, scratch, s->at<double>(s->off_fill),
                                 static_cast<cudaStream_t>(stream), &s->launches),
             "fill combine");
+    s->fill_ready = true;
     return VPINT_OK;
 }
 
@@ -1065,6 +1073,7 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
     } else if (p->fill_mode != VPINT_FILL_READY) {
         return fail(VPINT_ERR_INVALID, "vpint_solver_ingest_bands: bad fill_mode");
     }
+    s->fill_ready = false;            // consumed here: a later vpint_solver_load takes its own mean
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_counters), 0, kCntTotal * sizeof(int), st), "memset counters");
     VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme), 0, 2 * sizeof(double), st), "memset range check");
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, sizeof(int), st), "memset flag");

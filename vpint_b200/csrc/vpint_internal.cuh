@@ -176,6 +176,8 @@ cudaError_t launch_init_state(const Geom &g, ProbState *state, int *n_active, in
                               int64_t *launches);
 cudaError_t launch_decide(const DecideArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches);
+bool step2d_ratio_bulk_supported(const StepArgs &a);                      // vpint_step_bulk.cu
+cudaError_t launch_step2d_ratio_bulk(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches);
 cudaError_t launch_to_ratio(const Geom &g, void *const *buf, const double *f, double *save, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_from_ratio(const Geom &g, const ProbState *state, void *const *buf, const double *f,

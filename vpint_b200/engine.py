@@ -226,6 +226,7 @@ class Solver:
             if f.size != self.nprob:
                 raise VPintError("fill needs one value per problem")
             fptr = f.ctypes.data_as(C.POINTER(C.c_double))
+        del self._keep[:-8]            # references only have to outlive the enqueue of the kernels that read them
         self._keep.append(ov)
         N.check(self.lib, self.lib.vpint_solver_load(self._h, C.c_void_p(ov.data_ptr()), pptr, fptr, _code(ov),
                                                       _i64(st), self._stream()), "vpint_solver_load")

@@ -18,9 +18,23 @@ from .errors import VPintError
 from .wp import wp_run_options
 
 
-# Largest grid whose init_strategy='mean' value the library computes on the device (NumPy-exact pairwise
-# nanmean, csrc/vpint_setup.cu fill_mean_kernel); larger scenes take it on the host.
+# Largest grid whose init_strategy='mean' value vpint_solver_load computes itself (one kernel, NumPy-exact pairwise
+# nanmean, csrc/vpint_setup.cu fill_mean_kernel); larger grids take the same value from the leaf / subtree kernels of
+# csrc/vpint_ingest.cu (_device_band_means) -- on the device either way.
 DEVICE_FILL_MAX_CELLS = 131072
+
+
+def _device_band_means(solver, t_dev):
+    """np.nanmean of every band of a large (N, H, W, B) float stack in the band's dtype (VPint/MRP.py:73-77), computed
+    on the device and left in the solver for the next ``load`` (vpint_solver_fill_leaves / _fill_combine)."""
+    import torch
+    vd = {torch.float32: "float32", torch.float64: "float64"}.get(t_dev.dtype)
+    if vd is None:
+        raise VPintError("band stacks must be float32 or float64, got %s" % (t_dev.dtype,))
+    t_dev = t_dev.contiguous()
+    scratch = solver.fill_scratch(vd)
+    solver.fill_leaves(t_dev, None, scratch, value_dtype=vd)
+    solver.fill_combine(scratch, vd)
 
 
 def _band_fill_values(target):
@@ -88,6 +102,8 @@ def _make_solver(nprob, H, W, B, storage, kb, dev, opts, blocking_wait=False):
 
 
 def _solve_chunk(solver, t_dev, f_dev, opts, res_dev, out_layout, fill):
+    if fill is None and t_dev.shape[1] * t_dev.shape[2] > DEVICE_FILL_MAX_CELLS:
+        _device_band_means(solver, t_dev)
     solver.load(t_dev.permute(0, 3, 1, 2), fill=fill)
     solver.weights(f_dev.permute(0, 3, 1, 2).unsqueeze(-1), method=opts["method"],
                    clamp=(opts["method"] != "exact"), min_gamma=0.0, max_gamma=float("inf"))
@@ -121,8 +137,6 @@ def _solve_bands_torch(target, features, opts, out_layout, out_dtype, storage, k
     import torch
     N, H, W, B = target.shape
     kb = _solve.DEFAULT_K_BLOCK if k_block is None else k_block
-    if fill is None and H * W > DEVICE_FILL_MAX_CELLS:
-        fill = _band_fill_values(target.cpu().numpy()).reshape(-1)
     fill = None if fill is None else np.asarray(fill, dtype=np.float64).reshape(N, B)
     chunk = int(chunk_patches or PIPELINE_CHUNK_PATCHES)
     res_shape = (lambda m: (m, B, H, W)) if out_layout == "bhw" else (lambda m: (m, H, W, B))
@@ -247,7 +261,7 @@ def solve_bands(target, features, opts, *, out_dtype=np.float64, out_layout="bhw
             res = res.astype(out_dtype)
         res = res[0] if single else res
         return (res, np.zeros((N, B), dtype=np.int64)[0 if single else slice(None)]) if return_sweeps else res
-    fill = None if H * W <= DEVICE_FILL_MAX_CELLS else _band_fill_values(tgt).reshape(-1)
+    fill = None
     solver = _make_solver(N * B, H, W, B, storage, _solve.DEFAULT_K_BLOCK if k_block is None else k_block, dev, opts)
     try:
         t_dev = to_device(np.ascontiguousarray(tgt), dev)                 # (N, H, W, B) as stored
