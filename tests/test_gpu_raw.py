@@ -288,6 +288,45 @@ def test_single_large_scene_from_raw_through_the_tiled_path():
     assert list(sweeps[0].numpy()) == list(ref_sweeps)
 
 
+@pytest.mark.parametrize("zeros", [False, True], ids=["float32-exact", "zero-features"])
+def test_scene_sweeps_copy_engine_kernel_equals_register_kernel(zeros, monkeypatch):
+    """Rows beyond the cluster-resident kernel: ratio-direct load + the copy-engine-fed ratio stencil (csrc/vpint_step_bulk.cu),
+    with the float32 copy of the feature plane when every feature is a float32 value and the fp64 plane when not (a zero
+    feature becomes 0.01, VPint/WP_MRP.py:143-145) -- bit for bit what the register-fed kernel gives, and the oracle's
+    sweep counts."""
+    import torch
+    rng = np.random.default_rng(515)
+    H, W, B = 600, 300, 3
+    t, f, m = raw_stack(rng, 1, H, W, B, zeros=zeros)
+    td, fd = torch.from_numpy(t).cuda(), torch.from_numpy(f).cuda()
+    cd = torch.from_numpy((m > 10).astype(np.uint8)).cuda()
+
+    def solve():
+        s = Solver(2, B, H, W, nprob_inner=B, planes=True, k_block=1)
+        try:
+            block = torch.zeros(s.peer_bytes(1), dtype=torch.uint8, device="cuda")
+            s.peer_bind(1, 0, [block.data_ptr()])
+            s.ingest_bands(td, fd, cd, value_dtype="float32")
+            s.run_sharded(5000, auto_terminate=True, threshold=1e-4)
+            out, sweeps = s.result()
+            return out.cpu().numpy(), sweeps.cpu().numpy()
+        finally:
+            s.close()
+
+    out5, sw5 = solve()
+    monkeypatch.setenv("VPINT_NO_F32_PLANE", "1")
+    out5d, sw5d = solve()
+    monkeypatch.setenv("VPINT_RATIO_KERNEL", "4")
+    out4, sw4 = solve()
+    assert np.array_equal(sw5, sw4) and np.array_equal(sw5d, sw4)
+    assert np.array_equal(out5, out4) and np.array_equal(out5d, out4)
+    vp = VPint2_interpolator(t[0], f[0], mask=m[0], threshold=10)
+    ref, ref_sweeps = O.vpint2_run(vp.target, vp.features)
+    assert list(sw5) == list(ref_sweeps)
+    err = np.abs(np.moveaxis(out5, 0, -1) - ref) / np.abs(ref)
+    assert err.max() <= 1e-9
+
+
 def test_run_async_then_finish_equals_run():
     """vpint_solver_run_async + run_finish == vpint_solver_run, also when the resident kernel declines (inf feature)."""
     import torch

@@ -125,6 +125,8 @@ struct vpint_solver {
     bool no_nc = false;               // weights carry the priority normalisation (vpint_solver_priority)
     // ratio form of the tiled path (jacobi2d_k1_ratio_kernel): state buffers hold P / f while a run is in flight
     bool state_ratio = false;         // buffers are in ratio space right now
+    bool f32plane_valid = false;      // plane slot 1 holds the feature plane as float32 (ratio-direct load; slots 1-3 are free in ratio space)
+    int f32_exact = -1;               // -1 unknown, 1 every feature is a float32 value (flags[3] == 0 at the range check), 0 not
     bool fill_ready = false;          // vpint_solver_fill_combine left the start values at off_fill; the next load may use them
     bool ratio_fresh = false;         // ... written so by the fused load, no sweep yet: plane slot 0 holds the exact start state
     int ratio_verdict = -1;           // -1 not evaluated since load/weights, 0 declined (extreme data), 1 allowed
@@ -280,7 +282,11 @@ int vpint_solver_create(const vpint_desc *d, vpint_solver **out) {
         s->off_rowchunk = (xc > 1) ? take((size_t)g.P * g.H * xc * 3 * sizeof(double)) : 0;
     }
     // one kernel per launch group unless a problem has so many tiles that its reduction wants many blocks
-    s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !getenv("VPINT_NO_FUSED_FINISH");
+    // fused finish (the last tile block of a problem reduces and decides): saves two small launches per sweep, but the
+    // copy-engine-fed ratio stencil (vpint_step_bulk.cu) only runs with a separate reduction and is ~7 ns per tile faster,
+    // which outweighs the launches from ~2000 tiles on
+    s->can_fuse = ((int64_t)g.S * g.tiles_per_prob < 8192) && !(s->off_partial8 && s->tiles_total >= 2048) &&
+                  !getenv("VPINT_NO_FUSED_FINISH");
     s->has_orig = (d->features & VPINT_FEAT_RESISTANCE) != 0;
     s->blocking_wait = (d->features & VPINT_FEAT_BLOCKING_WAIT) != 0;
     if (s->has_orig) s->off_orig = take(plane);
@@ -309,7 +315,7 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     if (!workspace || bytes < s->ws_bytes) return fail(VPINT_ERR_WORKSPACE, "workspace missing or too small");
     if ((uintptr_t)workspace % 256 != 0) return fail(VPINT_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if (!s->h_counters) {
-        static_assert(kCntTotal * sizeof(int) + 2 * sizeof(double) <= kPinnedBlock, "pinned block too small");
+        static_assert(kCntTotal * sizeof(int) <= 128 && 128 + 32 + sizeof(int) <= kPinnedBlock, "pinned block too small");
         void *blk = nullptr;
         VP_CUDA(pinned_acquire(&blk), "cudaHostAlloc");
         s->h_counters = static_cast<int *>(blk);
@@ -320,6 +326,7 @@ int vpint_solver_bind(vpint_solver *s, void *workspace, size_t bytes) {
     s->ws = static_cast<char *>(workspace);
     s->loaded = s->weights_ready = s->run_begun = false;
     s->planes_valid = s->fplane_valid = false;
+    s->f32plane_valid = false;
     // bind has no stream argument: the memset runs on the legacy default stream and is waited for, so that it is
     // ordered before whatever the caller enqueues next on any (also non-blocking) stream
     VP_CUDA(cudaMemsetAsync(s->at<int>(s->off_flags), 0, 16 * sizeof(int), cudaStreamLegacy), "memset flags");
@@ -388,6 +395,7 @@ int vpint_solver_load(vpint_solver *s, const void *original, const void *pred0, 
     s->state_ratio = false;
     s->ratio_fresh = false;
     s->ratio_verdict = -1;
+    s->f32plane_valid = false;
     VP_CUDA(launch_prepare(g, original, pred0, s->at<double>(s->off_fill), dtype, stride, s->storage,
                            s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1]),
                            s->has_orig ? s->at<void>(s->off_orig) : nullptr, s->at<uint32_t>(s->off_mask),
@@ -422,6 +430,7 @@ int vpint_solver_weights(vpint_solver *s, const void *feat, int dtype, const int
         if (rc != VPINT_OK) return rc;
     }
     s->planes_valid = s->fplane_valid = false;
+    s->f32plane_valid = false;
     s->no_nc = false;
     s->ratio_verdict = -1;
     VP_CUDA(cudaMemsetAsync(s->at<double>(s->off_extreme) + 1, 0, sizeof(double), st), "memset range check");
@@ -572,8 +581,11 @@ static int ratio_allowed(vpint_solver *s, cudaStream_t st, bool *out) {
     if (s->ratio_verdict < 0) {
         VP_CUDA(cudaMemcpyAsync(s->h_extreme, s->at<double>(s->off_extreme), 2 * sizeof(double), cudaMemcpyDeviceToHost, st),
                 "read range check");
+        int *h_wide = reinterpret_cast<int *>(reinterpret_cast<char *>(s->h_extreme) + 32);     // same pinned block
+        VP_CUDA(cudaMemcpyAsync(h_wide, s->at<int>(s->off_flags) + 3, sizeof(int), cudaMemcpyDeviceToHost, st), "read float32 flag");
         VP_CUDA(cudaStreamSynchronize(st), "range check sync");
         s->ratio_verdict = (s->h_extreme[0] == 0.0 && s->h_extreme[1] == 0.0) ? 1 : 0;
+        s->f32_exact = (*h_wide == 0) ? 1 : 0;
     }
     *out = (s->ratio_verdict == 1);
     return VPINT_OK;
@@ -591,6 +603,7 @@ static int ensure_planes(vpint_solver *s, cudaStream_t st) {
     VP_CUDA(launch_planes_from_fplane(s->g, s->at<double>(s->off_w[4]), s->storage, planes, st, &s->launches),
             "planes from feature plane");
     s->planes_valid = true;
+    s->f32plane_valid = false;        // slot 1 is a weight plane again
     return VPINT_OK;
 }
 
@@ -640,6 +653,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
                         "to ratio");
                 s->state_ratio = true;
                 s->planes_valid = false;         // plane slot 0 now holds the saved known values
+                s->f32plane_valid = false;       // (only the ratio-direct load writes the float32 copy)
             }
         } else {
             rc = ensure_planes(s, st);
@@ -654,6 +668,7 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
     a.buf[1] = s->at<void>(s->off_buf[1]);
     a.mask = s->at<uint32_t>(s->off_mask);
     for (int i = 0; i < 5; ++i) a.w[i] = (i < s->n_planes) ? s->at<void>(s->off_w[i]) : nullptr;
+    a.f32plane = (use_ratio && s->f32plane_valid && s->f32_exact == 1 && !getenv("VPINT_NO_F32_PLANE")) ? s->at<float>(s->off_w[1]) : nullptr;
     a.gamma = s->at<double>(s->off_gamma);
     a.tau = s->at<double>(s->off_tau);
     a.partial = s->at<double>(s->off_partial);
@@ -1095,8 +1110,11 @@ int vpint_solver_ingest_bands(vpint_solver *s, const vpint_ingest_params *p, voi
                                 s->at<double>(s->off_w[4]), s->at<double>(s->off_rowpart), s->at<double>(s->off_extreme),
                                 s->at<int>(s->off_flags), p->out, p->out_dtype, p->out_stride,
                                 s->off_rowchunk ? s->at<double>(s->off_rowchunk) : nullptr,
-                                direct ? s->at<double>(s->off_w[0]) : nullptr, st, &s->launches),
+                                direct ? s->at<double>(s->off_w[0]) : nullptr, direct ? s->at<float>(s->off_w[1]) : nullptr, st,
+                                &s->launches),
             "ingest bands");
+    s->f32plane_valid = direct;
+    s->f32_exact = -1;
     if (direct) {
         s->state_ratio = true;
         s->ratio_fresh = true;

@@ -311,6 +311,7 @@ struct IngestArgs {
     int XC;                  // column chunks per row (one warp each)
     double *rowchunk;        // [P][H][XC][3] chunk partials when XC > 1
     double *save;            // ratio-direct load: [P][H][pitch] the start state in value space (bufA / bufB then hold value / f)
+    float *f32plane;         // ratio-direct load: the feature plane once more as float32 (exact unless flags[3] gets set)
 };
 
 // rowpart of a row = its chunk partials added in chunk order (fixed order: the known-cell sums are reproducible).
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_bands_kernel(const I
                     a.bufB[row + e] = ra;
                     a.save[row + e] = va;
                     a.fplane[row + e] = fe;
+                    a.f32plane[row + e] = (float)fe;
                 } else {
                     a.bufA[row + e] = va;
                     if (a.bufB) a.bufB[row + e] = va;
@@ -696,9 +698,11 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, double *rowchunk, double *save, cudaStream_t st, int64_t *launches) {
+                                const int64_t *out_stride, double *rowchunk, double *save, float *f32plane, cudaStream_t st,
+                                int64_t *launches) {
     IngestArgs a;
     a.save = save;
+    a.f32plane = f32plane;
     a.g = g;
     a.target = target; a.features = features; a.cloud = cloud;
     a.clip_t = clip_t; a.clip_f = clip_f; a.t_lo = t_lo; a.t_hi = t_hi; a.f_lo = f_lo; a.f_hi = f_hi;

@@ -62,6 +62,7 @@ struct StepArgs {
     void *buf[2];
     const uint32_t *mask;
     const void *w[5];        // planes: up, right, down, left (, temporal for 3-D)
+    const float *f32plane;   // ratio form: the feature plane as float32 when every feature is exactly one (else null)
     const double *gamma;     // [P] scalar mode
     const double *tau;       // [P] scalar mode, 3-D
     double *partial;         // [tile][KB][kSumSlots]
@@ -215,7 +216,8 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
                                 const uint8_t *cloud, int clip_t, double t_lo, double t_hi, int clip_f, double f_lo,
                                 double f_hi, const double *fill, double *bufA, double *bufB, uint32_t *mask, double *fplane,
                                 double *rowpart, double *extreme, int *flags, void *out, int out_dtype,
-                                const int64_t *out_stride, double *rowchunk, double *save, cudaStream_t st, int64_t *launches);
+                                const int64_t *out_stride, double *rowchunk, double *save, float *f32plane, cudaStream_t st,
+                                int64_t *launches);
 int ingest_row_chunks(const Geom &g);
 bool ingest_direct_supported(const Geom &g, int t_dtype);
 cudaError_t launch_result_unknown(const Geom &g, const ProbState *state, void *const *buf, const uint32_t *mask, void *out,

@@ -20,21 +20,24 @@ namespace vpint {
 namespace {
 
 constexpr int kTW = 128, kTH = 32;          // tile of the 2-D k1 kernels (vpint_step_k1.cu)
-constexpr int kStages = 3;
+// Ring slots: 3 with the fp64 feature plane (3 x 69 KB), 4 with its float32 copy (4 x 53 KB; StepArgs::f32plane, written by
+// the ratio-direct load when every feature is exactly a float32 value -- uint16 rasters always are).
+template <typename FT> struct Slots { static constexpr int n = sizeof(FT) == 4 ? 4 : 3; };
 constexpr int kSW = kTW + 4;                // state row in shared memory: columns x0 - 2 .. x0 + 129 (16-byte aligned start)
 constexpr int kSRows = kTH + 2;             // grid rows y0 - 1 .. y0 + 32
 constexpr int kConsumerWarps = 8;
-constexpr int kProducerWarps = kStages;      // one per ring slot: the latency chains tile -> state -> mask -> copies overlap
-constexpr int kBulkThreads = (kConsumerWarps + kProducerWarps) * 32;
+// one producer warp per ring slot: the latency chains tile -> state -> mask -> copies overlap
+template <typename FT> struct Threads { static constexpr int n = (kConsumerWarps + Slots<FT>::n) * 32; };
 
 struct __align__(16) TileMeta {
     int active, p, y0, x0;
     int cur, pad0, pad1, pad2;
 };
 
+template <typename FT>
 struct __align__(128) Stage {
     double st[kSRows][kSW];                 // 35 904 B
-    double f[kTH][kTW];                     // 32 768 B
+    FT f[kTH][kTW];                         // 32 768 B (fp64) / 16 384 B (float32)
     unsigned long long mw[kTH][2];          // mask words of the tile's rows (0 below the owned band)
     TileMeta meta;
 };
@@ -71,12 +74,18 @@ __device__ __forceinline__ void lds2(const double *p, double &a, double &b) {
     const double2 v = *reinterpret_cast<const double2 *>(p);
     a = v.x; b = v.y;
 }
+__device__ __forceinline__ void lds2(const float *p, double &a, double &b) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    a = (double)v.x; b = (double)v.y;
+}
 
 // ---- producer warps -----------------------------------------------------------------------------------------
 // Producer `slot` owns ring slot `slot`: the tiles it = slot, slot + kStages, ... of this CTA.  The tile reference, the
 // problem state and the mask words are fetched into registers BEFORE the wait for the slot, so their latency runs
 // while the consumers still work on the slot's previous tile.
-__device__ __forceinline__ void produce(const StepArgs &a, Stage &sg, uint64_t *full, uint64_t *empty, int n_tiles, int slot, int lane) {
+template <typename FT>
+__device__ __forceinline__ void produce(const StepArgs &a, Stage<FT> &sg, uint64_t *full, uint64_t *empty, int n_tiles, int slot, int lane) {
+    constexpr int kStages = Slots<FT>::n;
     const Geom &g = a.g;
     const size_t plane = (size_t)g.H * g.pitch;
     const int mp64 = g.mpitch >> 1;
@@ -115,9 +124,9 @@ __device__ __forceinline__ void produce(const StepArgs &a, Stage &sg, uint64_t *
         const unsigned long long need = any64 | (any64 << 1) | (any64 << 2);          // state row i = grid row y0 - 1 + i
         const int xs = max(tile.x0 - 2, 0), xe = min(tile.x0 + kTW + 2, g.pitch);
         const unsigned sbytes = (unsigned)(xe - xs) * 8u;
-        const unsigned fbytes = (unsigned)(min(tile.x0 + kTW, g.pitch) - tile.x0) * 8u;
+        const unsigned fbytes = (unsigned)(min(tile.x0 + kTW, g.pitch) - tile.x0) * (unsigned)sizeof(FT);
         const double *in = reinterpret_cast<const double *>(a.buf[ps.cur]) + (size_t)p * plane;
-        const double *fpl = reinterpret_cast<const double *>(a.w[4]) + (size_t)p * plane;
+        const FT *fpl = (sizeof(FT) == 4 ? reinterpret_cast<const FT *>(a.f32plane) : reinterpret_cast<const FT *>(a.w[4])) + (size_t)p * plane;
         // rows of this lane: state rows lane and lane + 32 (two lanes only), feature row lane
         bool s_on[2];
         unsigned mine = 0;
@@ -200,8 +209,8 @@ __device__ __forceinline__ void commit_pair_fast(double clip, double n0, double 
 // Four rows of one warp (64 columns, two per lane) of a tile with no cell on the border of the global grid: every
 // neighbour exists and counts, every row the producer skipped belongs to cells that are neither stored nor summed,
 // so the loads need no predicates.  sp = &st[R][cx] (state row above the first of the four), fp = &f[R][column].
-template <bool CLIP>
-__device__ __forceinline__ void half_strip_interior(double clip, const double *__restrict__ sp, const double *__restrict__ fp,
+template <bool CLIP, typename FT>
+__device__ __forceinline__ void half_strip_interior(double clip, const double *__restrict__ sp, const FT *__restrict__ fp,
                                                     double *__restrict__ o_base, int pitch, unsigned any, unsigned mine, double &s_abs,
                                                     double &s_old) {
     double v0[6], v1[6], lf[4], rt[4], f0[4], f1[4];
@@ -225,8 +234,8 @@ __device__ __forceinline__ void half_strip_interior(double clip, const double *_
 
 // The same four rows of a tile that touches the border of the global grid (or of the row shard's buffer): rows and
 // columns outside read as 0 and the neighbour count drops, as in ratio_half_strip<false>.
-template <bool CLIP>
-__device__ __forceinline__ void half_strip_border(const StepArgs &a, const Geom &g, const Stage &sg, double *__restrict__ out, int x0,
+template <bool CLIP, typename FT>
+__device__ __forceinline__ void half_strip_border(const StepArgs &a, const Geom &g, const Stage<FT> &sg, double *__restrict__ out, int x0,
                                                   int y0, int xo, int lane, int R, unsigned any, unsigned mine, double &s_abs,
                                                   double &s_old, int &c_abs, int &c_old) {
     const int x = x0 + xo + 2 * lane;
@@ -277,17 +286,18 @@ __device__ __forceinline__ int wsum(int v) {
     return v;
 }
 
-template <bool CLIP>
-__device__ __forceinline__ void consume(const StepArgs &a, Stage *stages, uint64_t *full, uint64_t *empty, int n_tiles, int warp,
+template <bool CLIP, typename FT>
+__device__ __forceinline__ void consume(const StepArgs &a, Stage<FT> *stages, uint64_t *full, uint64_t *empty, int n_tiles, int warp,
                                         int lane) {
     const Geom &g = a.g;
     const size_t plane = (size_t)g.H * g.pitch;
+    constexpr int kStages = Slots<FT>::n;
     const int xo = (warp & 1) * 64, yo = (warp >> 1) * 8;
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int s = it % kStages;
         const unsigned use = (unsigned)(it / kStages);
-        const Stage &sg = stages[s];
+        const Stage<FT> &sg = stages[s];
         bar_wait(&full[s], use & 1u);
         const TileMeta m = sg.meta;
         if (!m.active) {
@@ -314,13 +324,13 @@ __device__ __forceinline__ void consume(const StepArgs &a, Stage *stages, uint64
             if (interior) {
                 // straight code for both halves: every offset is a compile-time constant from these bases
                 const double *sp = &sg.st[yo][cx];
-                const double *fp = &sg.f[yo][xo + 2 * lane];
+                const FT *fp = &sg.f[yo][xo + 2 * lane];
                 double *ob = out + (size_t)(m.y0 + yo) * g.pitch + (m.x0 + xo + 2 * lane);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const unsigned any_h = (any >> (4 * h)) & 15u, mine_h = (mine >> (8 * h)) & 255u;
                     if (any_h == 0) continue;                       // warp-uniform
-                    half_strip_interior<CLIP>(clip, sp + 4 * h * kSW, fp + 4 * h * kTW, ob + (size_t)(4 * h) * g.pitch, g.pitch, any_h, mine_h,
+                    half_strip_interior<CLIP, FT>(clip, sp + 4 * h * kSW, fp + 4 * h * kTW, ob + (size_t)(4 * h) * g.pitch, g.pitch, any_h, mine_h,
                                               s_abs, s_old);
                 }
                 // a NaN term (non-finite data) poisons the sums: redo the tile with the exact nanmean bookkeeping
@@ -332,7 +342,7 @@ __device__ __forceinline__ void consume(const StepArgs &a, Stage *stages, uint64
                 for (int h = 0; h < 2; ++h) {
                     const unsigned any_h = (any >> (4 * h)) & 15u, mine_h = (mine >> (8 * h)) & 255u;
                     if (any_h == 0) continue;
-                    half_strip_border<CLIP>(a, g, sg, out, m.x0, m.y0, xo, lane, yo + 4 * h, any_h, mine_h, s_abs, s_old, c_abs, c_old);
+                    half_strip_border<CLIP, FT>(a, g, sg, out, m.x0, m.y0, xo, lane, yo + 4 * h, any_h, mine_h, s_abs, s_old, c_abs, c_old);
                 }
             }
         }
@@ -348,11 +358,12 @@ __device__ __forceinline__ void consume(const StepArgs &a, Stage *stages, uint64
     }
 }
 
-template <bool CLIP>
-__global__ void __launch_bounds__(kBulkThreads, 1) jacobi2d_ratio_bulk_kernel(const StepArgs a, int n_tiles) {
+template <bool CLIP, typename FT>
+__global__ void __launch_bounds__(Threads<FT>::n, 1) jacobi2d_ratio_bulk_kernel(const StepArgs a, int n_tiles) {
+    constexpr int kStages = Slots<FT>::n;
     extern __shared__ __align__(128) unsigned char bulk_raw[];
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
-    Stage *stages = reinterpret_cast<Stage *>(bulk_raw);
+    Stage<FT> *stages = reinterpret_cast<Stage<FT> *>(bulk_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -365,10 +376,22 @@ __global__ void __launch_bounds__(kBulkThreads, 1) jacobi2d_ratio_bulk_kernel(co
     __syncthreads();
     if (warp >= kConsumerWarps) {
         const int slot = warp - kConsumerWarps;
-        produce(a, stages[slot], &full[slot], &empty[slot], n_tiles, slot, lane);
+        produce<FT>(a, stages[slot], &full[slot], &empty[slot], n_tiles, slot, lane);
     } else {
-        consume<CLIP>(a, stages, full, empty, n_tiles, warp, lane);
+        consume<CLIP, FT>(a, stages, full, empty, n_tiles, warp, lane);
     }
+}
+
+template <bool CLIP, typename FT>
+cudaError_t launch_bulk(const StepArgs &a, int n_tiles, int sms, bool first, cudaStream_t st) {
+    const size_t smem = sizeof(Stage<FT>) * Slots<FT>::n;
+    if (first) {
+        const cudaError_t e = cudaFuncSetAttribute(jacobi2d_ratio_bulk_kernel<CLIP, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    jacobi2d_ratio_bulk_kernel<CLIP, FT><<<grid, Threads<FT>::n, smem, st>>>(a, n_tiles);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -379,28 +402,26 @@ bool step2d_ratio_bulk_supported(const StepArgs &a) {
 
 cudaError_t launch_step2d_ratio_bulk(const StepArgs &a, int64_t n_tiles, cudaStream_t st, int64_t *launches) {
     if (n_tiles <= 0) return cudaSuccess;
-    static int sms_of[64] = {0};                       // per device: the attribute below belongs to the device's context
-    const size_t smem = sizeof(Stage) * kStages;
+    static int sms_of[64] = {0};                       // per device: the shared-memory attribute belongs to the device's context
+    static unsigned char attr_done[64] = {0};          // bit per kernel variant
     int dev = 0;
-    cudaError_t e0 = cudaGetDevice(&dev);
-    if (e0 != cudaSuccess) return e0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (sms_of[dev] == 0) {
         int n = 0;
-        e0 = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (e0 == cudaSuccess)
-            e0 = cudaFuncSetAttribute(jacobi2d_ratio_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e0 == cudaSuccess)
-            e0 = cudaFuncSetAttribute(jacobi2d_ratio_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e0 != cudaSuccess) return e0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
         sms_of[dev] = n > 0 ? n : 148;
     }
-    const int sms = sms_of[dev];
-    const unsigned grid = (unsigned)(n_tiles < (int64_t)sms ? n_tiles : (int64_t)sms);
-    if (a.clip < INFINITY) jacobi2d_ratio_bulk_kernel<true><<<grid, kBulkThreads, smem, st>>>(a, (int)n_tiles);
-    else jacobi2d_ratio_bulk_kernel<false><<<grid, kBulkThreads, smem, st>>>(a, (int)n_tiles);     // clip_val = inf: the default
-    cudaError_t e = cudaGetLastError();
+    const bool clip = a.clip < INFINITY, f32 = a.f32plane != nullptr;       // clip_val = inf is the default
+    const int variant = (clip ? 1 : 0) | (f32 ? 2 : 0);
+    const bool first = !((attr_done[dev] >> variant) & 1);
+    const int nt = (int)n_tiles, sms = sms_of[dev];
+    if (f32) e = clip ? launch_bulk<true, float>(a, nt, sms, first, st) : launch_bulk<false, float>(a, nt, sms, first, st);
+    else e = clip ? launch_bulk<true, double>(a, nt, sms, first, st) : launch_bulk<false, double>(a, nt, sms, first, st);
     if (e != cudaSuccess) return e;
+    attr_done[dev] |= (unsigned char)(1u << variant);
     if (launches) ++*launches;
     return cudaSuccess;
 }

@@ -498,7 +498,8 @@ cudaError_t launch_step2d_ratio(const StepArgs &a, int64_t n_tiles, cudaStream_t
     if (n_tiles <= 0) return cudaSuccess;
     // 5 (default): the copy-engine-fed kernel of vpint_step_bulk.cu wherever the sums are reduced by a separate launch;
     // 4: the register-fed kernel below everywhere; 1: round 1's kernel
-    static const int ver = getenv("VPINT_RATIO_KERNEL") ? atoi(getenv("VPINT_RATIO_KERNEL")) : 5;
+    const char *ver_env = getenv("VPINT_RATIO_KERNEL");           // read per launch: a triage switch, also toggled by the tests
+    const int ver = ver_env ? atoi(ver_env) : 5;
     if (ver >= 5 && step2d_ratio_bulk_supported(a)) return launch_step2d_ratio_bulk(a, n_tiles, st, launches);
     if (ver == 1) jacobi2d_k1_ratio_kernel<0><<<(unsigned)n_tiles, 256, 0, st>>>(a);
     else jacobi2d_k1_ratio4_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(a);
