@@ -127,6 +127,9 @@ struct vpint_solver {
     bool state_ratio = false;         // buffers are in ratio space right now
     bool f32plane_valid = false;      // plane slot 1 holds the feature plane as float32 (ratio-direct load; slots 1-3 are free in ratio space)
     int f32_exact = -1;               // -1 unknown, 1 every feature is a float32 value (flags[3] == 0 at the range check), 0 not
+    std::vector<cudaEvent_t> prof_ev;  // VPINT_SHARD_PROFILE=1: events around the kernels of every sharded sweep (diagnostics)
+    bool prof_on = false;
+    bool early_push = false;          // in-library sharded loop: halo rows leave right after the stencil, before the sums are reduced
     bool fill_ready = false;          // vpint_solver_fill_combine left the start values at off_fill; the next load may use them
     bool ratio_fresh = false;         // ... written so by the fused load, no sweep yet: plane slot 0 holds the exact start state
     int ratio_verdict = -1;           // -1 not evaluated since load/weights, 0 declined (extreme data), 1 allowed
@@ -706,6 +709,18 @@ static int step_begin_impl(vpint_solver *s, void *stream, float *stencil_ms, boo
             VP_CUDA(launch_step2d(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step2d");
     } else {
         VP_CUDA(launch_step3d(a, s->storage, s->weight_mode, s->tiles_active, st, &s->launches), "step3d");
+    }
+    if (s->prof_on) {
+        cudaEvent_t ev;
+        VP_CUDA(cudaEventCreate(&ev), "event create");
+        VP_CUDA(cudaEventRecord(ev, st), "event record");
+        s->prof_ev.push_back(ev);
+    }
+    if (s->early_push) {
+        void *hb[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
+        VP_CUDA(launch_peer_halo(s->g, s->at<ProbState>(s->off_state), hb, s->peer, s->g.KB, s->at<int>(s->off_peerctr),
+                                 s->at<int>(s->off_flags) + 4, 1, st, &s->launches),
+                "peer halo push");
     }
     if (stencil_ms) {
         VP_CUDA(cudaEventRecord(e1, st), "event record");
@@ -1344,14 +1359,33 @@ int vpint_solver_run_sharded(vpint_solver *s, const vpint_run_params *prm, void 
     void *bufs[2] = {s->at<void>(s->off_buf[0]), s->at<void>(s->off_buf[1])};
     const int kDepth = 4;                          // launches the host stays ahead of the device
     const int64_t budget = 2 * (int64_t)prm->max_iter + 8;
+    s->prof_on = getenv("VPINT_SHARD_PROFILE") != nullptr;
+    s->prof_ev.clear();
+    struct EarlyPush {                             // cleared on every way out of the loop
+        vpint_solver *s;
+        ~EarlyPush() { s->early_push = false; }
+    } early_guard{s};
+    s->early_push = !getenv("VPINT_HALO_LATE");
     int64_t n = 0;
     bool done = false;
     while (n < budget && !done) {
-        rc = step_begin_impl(s, stream, nullptr, false);          // sweep + local per-sweep sums
+        auto stamp = [&]() {                                    // diagnostics only (VPINT_SHARD_PROFILE=1)
+            if (!s->prof_on) return;
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) return;
+            cudaEventRecord(ev, st);
+            s->prof_ev.push_back(ev);
+        };
+        stamp();
+        rc = step_begin_impl(s, stream, nullptr, false);          // sweep + local per-sweep sums (stamps after the stencil)
         if (rc != VPINT_OK) return rc;
+        stamp();
         VP_CUDA(launch_peer_commit(d, s->at<double>(s->off_sums), s->peer, ctr, s->d_ring, st, &s->launches), "peer commit");
-        VP_CUDA(launch_peer_halo(s->g, d.state, bufs, s->peer, s->g.KB, ctr, s->at<int>(s->off_flags) + 4, st, &s->launches),
+        stamp();
+        VP_CUDA(launch_peer_halo(s->g, d.state, bufs, s->peer, s->g.KB, ctr, s->at<int>(s->off_flags) + 4, s->early_push ? 2 : 0, st,
+                                 &s->launches),
                 "peer halo");
+        stamp();
         s->first_step_pending = false;
         ++n;
         ++s->peer_t;
@@ -1373,6 +1407,24 @@ int vpint_solver_run_sharded(vpint_solver *s, const vpint_run_params *prm, void 
     }
     VP_CUDA(cudaStreamSynchronize(st), "sharded run sync");
     if (launches_out) *launches_out = n;
+    if (s->prof_on) {
+        // per sweep: [start, after stencil, after reduce, after commit, after halo]
+        double acc[4] = {0, 0, 0, 0};
+        const size_t per = 5, sweeps = s->prof_ev.size() / per;
+        for (size_t i = 0; i < sweeps; ++i)
+            for (int k = 0; k < 4; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, s->prof_ev[i * per + k], s->prof_ev[i * per + k + 1]);
+                acc[k] += ms;
+            }
+        float total = 0.f;
+        if (sweeps) cudaEventElapsedTime(&total, s->prof_ev[0], s->prof_ev[sweeps * per - 1]);
+        fprintf(stderr, "[vpint shard profile] rows %d tiles %lld sweeps %zu: stencil %.3f reduce %.3f commit %.3f halo %.3f total %.3f ms\n",
+                s->g.own_rows, (long long)s->tiles_active, sweeps, acc[0], acc[1], acc[2], acc[3], total);
+        for (cudaEvent_t ev : s->prof_ev) cudaEventDestroy(ev);
+        s->prof_ev.clear();
+        s->prof_on = false;
+    }
     {
         int timed_out = 0;
         VP_CUDA(cudaMemcpy(&timed_out, ctr + 2, sizeof(int), cudaMemcpyDeviceToHost), "read time-out flag");

@@ -16,6 +16,8 @@
 //                          and -- for a full result -- the known cells of the output, from ONE read of the rasters
 //   result_unknown_kernel  the unknown cells of the result only, written as contiguous runs (the caller's array may
 //                          be pinned host memory mapped into the device: only the cloud cells cross the link)
+#include <cstdlib>
+
 #include "vpint_internal.cuh"
 
 namespace vpint {
@@ -711,8 +713,10 @@ cudaError_t launch_ingest_bands(const Geom &g, const void *target, const void *f
     a.out = out; a.out_code = out_dtype;
     a.osd = out ? Strides{out_stride[0], out_stride[1], out_stride[2], out_stride[3]} : Strides{0, 0, 0, 0};
     const size_t tsz = (t_dtype == VPINT_F64) ? 8 : (t_dtype == VPINT_F32 ? 4 : 2);
-    a.TW = g.pitch < kIngestTile ? g.pitch : kIngestTile;
     const bool direct = save != nullptr;
+    // the ratio-direct load stages target AND features: half the tile keeps twice the blocks per SM resident
+    const int tile = (direct && !getenv("VPINT_INGEST_TILE256")) ? kIngestTile / 2 : kIngestTile;
+    a.TW = g.pitch < tile ? g.pitch : tile;
     const size_t smem = (size_t)(direct ? 2 : 1) * kIngestWarps * a.TW * g.Pin * tsz + (size_t)kIngestWarps * a.TW;
     const int64_t n_rows = (int64_t)(g.P / g.Pin) * g.H;
     a.XC = ingest_row_chunks(g);

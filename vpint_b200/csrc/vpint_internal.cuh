@@ -242,7 +242,7 @@ struct PeerCtx {
 cudaError_t launch_peer_commit(const DecideArgs &a, const double *my_sums, const PeerCtx &pc, int *ctr,
                                unsigned long long *host_ring, cudaStream_t st, int64_t *launches);
 cudaError_t launch_peer_halo(const Geom &g, const ProbState *state, void *const *buf, const PeerCtx &pc, int rows, const int *ctr,
-                             int *tickets, cudaStream_t st, int64_t *launches);
+                             int *tickets, int mode, cudaStream_t st, int64_t *launches);
 
 // ---- device helpers -------------------------------------------------------
 #if defined(__CUDACC__)

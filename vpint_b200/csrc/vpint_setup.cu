@@ -875,36 +875,50 @@ __global__ void __launch_bounds__(256) peer_commit_kernel(Geom g, ProbState *sta
     }
 }
 
-// Halo rows of the new state to both row neighbours and the neighbours' rows into the halo rows, one launch (push
-// blocks as halo_push_kernel, pull blocks as halo_pull_kernel); the exchange number is the launch counter
-// peer_commit_kernel has just advanced.  Pull blocks wait for stores of ANOTHER GPU only, and come after all push
-// blocks in dispatch order, so they cannot starve the pushes the neighbour is waiting for.
+// Halo rows of the new state to both row neighbours (push blocks) and the neighbours' rows into the halo rows (pull blocks).
+// A row is moved by kHaloChunks blocks as 16-byte vectors.
+//   mode 1 (push, launched right AFTER THE STENCIL, before the sums are reduced and committed): the exchange number is the
+//          one peer_commit_kernel is about to publish (ctr[0] + 1) and the source is the buffer the stencil has just
+//          written (cur ^ 1 of a running problem) -- the neighbour has the rows while this rank still reduces its sums;
+//   mode 2 (pull, launched after peer_commit_kernel): waits for the neighbours' flags of exchange ctr[0] and copies their
+//          rows into the halo rows of the (now committed) current buffer;
+//   mode 0: both in one launch after the commit (push blocks [0, 2m), pull blocks [2m, 4m): every push block is
+//          dispatched before any spinning pull block).
+constexpr int kHaloChunks = 4;
+
 __global__ void __launch_bounds__(256) peer_halo_kernel(Geom g, const ProbState *__restrict__ state, double *buf0, double *buf1,
-                                                        PeerCtx pc, int rows, const int *__restrict__ ctr, int *tickets) {
-    const int seq = ctr[0];
+                                                        PeerCtx pc, int rows, const int *__restrict__ ctr, int *tickets, int mode) {
+    const int seq = ctr[0] + (mode == 1 ? 1 : 0);
     const int slot = seq & 1;
-    const int n = g.P * rows;
-    // blocks [0, 2n) push, blocks [2n, 4n) pull: every push block is dispatched before any (spinning) pull block
-    const bool pull = (int)blockIdx.x >= 2 * n;
-    const int side = ((int)blockIdx.x / n) & 1;       // 0: the upper neighbour, 1: the lower neighbour
-    const int b = (int)blockIdx.x % n;
+    const int n = g.P * rows, m = n * kHaloChunks;
+    const int bid = (int)blockIdx.x;
+    const bool pull = (mode == 2) || (mode == 0 && bid >= 2 * m);
+    const int local = (mode == 0 && pull) ? bid - 2 * m : bid;
+    const int side = (local / m) & 1;                 // 0: the upper neighbour, 1: the lower neighbour
+    const int b = (local % m) / kHaloChunks, chunk = local % kHaloChunks;
     const int nb = side ? pc.down : pc.up;
     if (nb < 0) return;
     const int p = b / rows, r = b - p * rows;
     const size_t msg = pc.msg_bytes, row_off = ((size_t)p * rows + r) * g.pitch;
-    double *cur = state[p].cur ? buf1 : buf0;
+    const ProbState ps = state[p];
+    // before the commit a running problem's new state is in the other buffer; a finished one keeps its buffer
+    const int which = (mode == 1 && ps.k_run != 0) ? (ps.cur ^ 1) : ps.cur;
+    double *cur = which ? buf1 : buf0;
+    const int v_all = g.pitch >> 1;                    // double2 elements of a row (pitch is a multiple of 64)
+    const int v_per = (v_all + kHaloChunks - 1) / kHaloChunks;
+    const int v0 = chunk * v_per, v1 = min(v_all, v0 + v_per);
     if (!pull) {
         // my first owned rows -> the upper neighbour's "from below" slot; my last owned rows -> the lower one's "from above"
-        double *dst = reinterpret_cast<double *>(pc.base[nb] + (size_t)(2 * slot + (side ? 0 : 1)) * msg) + row_off;
+        double2 *dst = reinterpret_cast<double2 *>(reinterpret_cast<double *>(pc.base[nb] + (size_t)(2 * slot + (side ? 0 : 1)) * msg) + row_off);
         int *flag = reinterpret_cast<int *>(pc.base[nb] + 4 * msg + (side ? 0 : 128));
         const int first = side ? g.own_row0 + g.own_rows - rows : g.own_row0;
-        const double *src = cur + ((size_t)p * g.H + first + r) * g.pitch;
-        for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dst[e] = src[e];
+        const double2 *src = reinterpret_cast<const double2 *>(cur + ((size_t)p * g.H + first + r) * g.pitch);
+        for (int e = v0 + threadIdx.x; e < v1; e += blockDim.x) dst[e] = src[e];
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
             const int done = atomicAdd(&tickets[side], 1);
-            if (done == n - 1) {
+            if (done == m - 1) {
                 tickets[side] = 0;
                 __threadfence_system();
                 asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
@@ -912,13 +926,13 @@ __global__ void __launch_bounds__(256) peer_halo_kernel(Geom g, const ProbState 
         }
     } else {
         char *mine = pc.base[pc.rank];
-        const double *in = reinterpret_cast<const double *>(mine + (size_t)(2 * slot + side) * msg) + row_off;
+        const double2 *in = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(mine + (size_t)(2 * slot + side) * msg) + row_off);
         const int *flag = reinterpret_cast<const int *>(mine + 4 * msg + (side ? 128 : 0));
         if (threadIdx.x == 0 && !wait_flag(flag, seq)) const_cast<int *>(ctr)[2] = 1;
         __syncthreads();
         const int first = side ? g.own_row0 + g.own_rows : g.own_row0 - rows;
-        double *dstrow = cur + ((size_t)p * g.H + first + r) * g.pitch;
-        for (int e = threadIdx.x; e < g.pitch; e += blockDim.x) dstrow[e] = __ldcv(in + e);
+        double2 *dstrow = reinterpret_cast<double2 *>(cur + ((size_t)p * g.H + first + r) * g.pitch);
+        for (int e = v0 + threadIdx.x; e < v1; e += blockDim.x) dstrow[e] = __ldcv(in + e);
     }
 }
 
@@ -1163,10 +1177,11 @@ cudaError_t launch_peer_commit(const DecideArgs &a, const double *my_sums, const
 }
 
 cudaError_t launch_peer_halo(const Geom &g, const ProbState *state, void *const *buf, const PeerCtx &pc, int rows, const int *ctr,
-                             int *tickets, cudaStream_t st, int64_t *launches) {
+                             int *tickets, int mode, cudaStream_t st, int64_t *launches) {
     if (pc.up < 0 && pc.down < 0) return cudaSuccess;
-    peer_halo_kernel<<<(unsigned)(4 * (int64_t)g.P * rows), 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], pc, rows,
-                                                                         ctr, tickets);
+    const int64_t m = (int64_t)g.P * rows * kHaloChunks;
+    peer_halo_kernel<<<(unsigned)((mode == 0 ? 4 : 2) * m), 256, 0, st>>>(g, state, (double *)buf[0], (double *)buf[1], pc, rows, ctr,
+                                                                         tickets, mode);
     VP_LAUNCH_CHECK();
     return cudaSuccess;
 }
