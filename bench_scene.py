@@ -242,6 +242,18 @@ def scene_record(world, rank, dev, size=10980, parity_size=2048, steps=2, bands=
                          "halo_fallback_reason": tiles[3],
                          "protocol": "stop decision lags one sweep (all-reduce overlaps the next sweep)" if os.environ.get("VPINT_SHARD_LAGGED", "1") != "0" else "all-reduce and decision every sweep",
                          "unknown_cell_gbps_48B": 48.0 * pxit * frac / (ms * 1e-3) / 1e9}
+            # roofline of the sweep phase alone: the ratio stencil moves 8 B state in + 4 B feature (the float32 copy of the feature
+            # plane, exact for these uint16 rasters; 8 B otherwise) + 8 B state out per unknown cell per sweep
+            try:
+                peak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json)"
+            except Exception:
+                peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+            if phases.get("sweeps"):
+                ach = 20.0 * pxit * frac / world / (phases["sweeps"] * 1e-3) / 1e9
+                rec["c4"]["roofline_sweeps"] = {"bound": "hbm", "kernel": "jacobi2d_ratio_bulk_kernel (per GPU, sweep phase of rank 0 incl. the "
+                                                "reduction / commit / halo kernels of every sweep)", "bytes_per_unknown_cell_sweep": 20,
+                                                "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak}
     torch.cuda.empty_cache()
     return rec if rank == 0 else None
 

@@ -11,3 +11,7 @@ B="python bench.py --steps 2 --warmup 1 --e2e-steps 2 --roofline-launches 8 --no
 timeout 300 $B > gpurun_out/plain_r02.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_r02.csv $B > gpurun_out/ncu_list_r02.log 2>&1
 echo "list rc=$?"
+S="python scripts/load_probe_raw.py 1373"
+timeout -k 10 300 $S > gpurun_out/plain_shard_r02.log 2>&1 &&
+timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:'ratio_bulk|ingest_bands|fill_leaf' -s 4 -c 6 -f -o gpurun_out/prof_shard_r02 $S > gpurun_out/ncu_shard_r02.log 2>&1
+echo "shard rc=$?"; tail -1 gpurun_out/plain_shard_r02.log
