@@ -91,3 +91,35 @@ def test_unbound_solver_fails_loudly():
 def test_missing_library_is_an_error(tmp_path):
     with pytest.raises(VPintError):
         N.load_library(str(tmp_path / "nope.so"))
+
+
+def test_built_library_is_sm100a_and_uses_the_blackwell_paths():
+    """The shipped .so holds sm_100a code only, and the kernels that claim DSMEM st.async + mbarriers (resident), the
+    copy engine (scene stencil) and TMA tensor loads (temporally blocked kernel) really contain those instructions."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "vpint_b200", "libvpint_b200.so")
+    elfs = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = per_kernel.setdefault(m.group(1), set())
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur is not None:
+            cur.add(m.group(1))
+
+    def ops(fragment):
+        found = [v for k, v in per_kernel.items() if fragment in k]
+        assert found, "kernel not in the library: " + fragment
+        return set.union(*found)
+
+    assert {"STAS", "SYNCS"} <= ops("resident2d_kernel")            # st.async into distributed shared memory, mbarriers
+    assert {"UBLKCP", "SYNCS"} <= ops("jacobi2d_ratio_bulk_kernel")  # cp.async.bulk + mbarrier pipeline
+    assert {"UTMALDG", "SYNCS"} <= ops("jacobi2d_tb_kernel")         # cp.async.bulk.tensor
