@@ -336,3 +336,30 @@ def test_solve_raw_fails_loudly_without_a_device():
     t = np.ones((1, 16, 16, 2), dtype=np.uint16)
     with pytest.raises(VPintError):
         solve_raw(t, t, None)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pairwise_tree_restatement_is_numpy(dtype):
+    """oracle/numpy_pairwise.py -- the leaf / tree decomposition the device mean init implements -- against NumPy
+    itself, bit for bit: sums of ragged sizes around every split rule, and np.nanmean with holes."""
+    from oracle import numpy_pairwise as PW
+    rng = np.random.default_rng(11)
+    sizes = [1, 5, 7, 8, 9, 15, 16, 64, 127, 128, 129, 136, 137, 255, 256, 257, 263, 1000, 1023, 1025, 4097, 10980, 65536, 70001]
+    for n in sizes:
+        a = (rng.uniform(0, 9000, n)).astype(dtype)
+        assert PW.pairwise_sum(a) == np.add.reduce(a), n
+        # every element belongs to exactly one leaf, leaves start at multiples of 8 and hold 64..128 elements (n > 128)
+        lv = PW.leaves(n)
+        assert lv[0][0] == 0 and sum(m for _, m in lv) == n
+        assert all(lo1 + m1 == lo2 for (lo1, m1), (lo2, _) in zip(lv, lv[1:]))
+        if n > 128:
+            assert all(lo % 8 == 0 and 64 <= m <= 128 for lo, m in lv)
+        holes = a.copy()
+        holes[rng.uniform(size=n) < 0.3] = np.nan
+        if np.isnan(holes).all():
+            continue
+        got, want = PW.nanmean(holes), np.nanmean(holes)
+        assert got.dtype == want.dtype and got == want, (n, got, want)
+    grid = rng.uniform(0, 9000, (397, 411)).astype(dtype)
+    grid[rng.uniform(size=grid.shape) < 0.2] = np.nan
+    assert PW.nanmean(grid) == np.nanmean(grid)
